@@ -1,0 +1,148 @@
+/*
+ * nsx_b200.h - C ABI of the B200-native network-simplex engine (libnsx_b200.so).
+ *
+ * The reference (jeffreyhorn/network_flow_solver) is pure Python and defines no FFI;
+ * its boundary for this path is the Python call
+ *     solve_min_cost_flow(problem, options, ...) -> FlowResult      (src/network_solver/solver.py:13-104)
+ * which constructs NetworkSimplex(problem, options) and calls .solve()
+ *                                                                   (src/network_solver/simplex.py:99-265, 1446-1765).
+ * The entry points below are what a ctypes binding placed inside that function would call:
+ * the canonical structure-of-arrays problem in the reference's internal index space goes in,
+ * raw flows / potentials / tree flags / the entering-arc trace come out, and the Python layer does
+ * the dict building and rounding of simplex.py:1703-1765.  See INTEGRATION.md for the stub.
+ *
+ * Conventions: plain pointers and sizes, caller-owned HOST buffers (the *_dev variants take
+ * caller-owned DEVICE buffers), no pointer is kept after return, return value 0 = call completed
+ * (see result->status for the solver outcome), negative = error (nsx_last_error() has the text).
+ * Thread-safe: every call builds its own device state; nsx_last_error() is thread-local.
+ */
+#ifndef NSX_B200_H
+#define NSX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSX_ABI_VERSION 1
+
+/* pricing rules: SolverOptions.pricing_strategy (src/network_solver/data.py:459-488) */
+#define NSX_PRICING_DANTZIG 0 /* DantzigPricing.select_entering_arc, simplex_pricing.py:97-137 */
+#define NSX_PRICING_DEVEX 1   /* DevexPricing._select_entering_arc_vectorized, simplex_pricing.py:310-357 + simplex.py:528-617 */
+
+/* solver outcome (FlowResult.status, data.py:269-322; UnboundedProblemError, simplex.py:1231-1246) */
+#define NSX_STATUS_OPTIMAL 0
+#define NSX_STATUS_INFEASIBLE 1          /* artificial flow left after Phase 1, simplex.py:1600-1624 */
+#define NSX_STATUS_ITERATION_LIMIT 2     /* limit hit in Phase 2 (flows are feasible), simplex.py:1678-1699 */
+#define NSX_STATUS_UNBOUNDED 3           /* theta = +inf in the ratio test */
+#define NSX_STATUS_ITERATION_LIMIT_P1 4  /* limit hit in Phase 1 with artificial flow left, simplex.py:1602-1613 */
+
+/* error codes (negative return values) */
+#define NSX_ERR_INVALID_ARGUMENT (-1)
+#define NSX_ERR_CUDA (-2)
+#define NSX_ERR_NO_DEVICE (-3)
+#define NSX_ERR_INTERNAL (-4)
+
+/* option flags */
+#define NSX_FLAG_FAST_POTENTIALS 1u /* non-parity mode: subtree potentials shifted by a parallel add of delta
+                                       instead of the exact top-down recompute */
+
+/* per-arc state byte returned in nsx_result.state */
+#define NSX_ARC_IN_TREE 1u
+#define NSX_ARC_CAN_FWD 2u  /* upper - flow > tol */
+#define NSX_ARC_CAN_BWD 4u  /* flow > tol */
+#define NSX_ARC_TOUCHED 8u  /* flow was written by a pivot with theta > 0 (drives NumPy-vs-Python rounding
+                               of the result, simplex.py:1703-1721) */
+
+/*
+ * Canonical problem, reference index space (simplex.py:149-163, 392-432, 1431-1440):
+ *   node 0 = artificial root, nodes 1..n_nodes-1 = problem nodes in sorted-id order;
+ *   real arcs 0..n_arcs-1 in stable (tail id, head id) order, lower bounds already shifted out;
+ *   artificial arc n_arcs + (v-1) joins node v and the root (simplex.py:645-698) - built by the engine.
+ */
+typedef struct nsx_problem {
+    int32_t n_nodes;         /* including the root */
+    int64_t n_arcs;          /* real arcs M */
+    const int32_t* tail;     /* [M] */
+    const int32_t* head;     /* [M] */
+    const double* pert_cost; /* [M] perturbed Phase-2 cost  c_i + 1e-10 * 1.00001^i */
+    const double* upper;     /* [M] capacity minus lower bound, +inf = uncapacitated */
+    const double* supply;    /* [n_nodes] after the lower-bound shift; supply[0] ignored */
+    double penalty;          /* artificial-arc cost  max|c| * (n_nodes + 1) */
+} nsx_problem;
+
+typedef struct nsx_options {
+    int32_t pricing;          /* NSX_PRICING_* */
+    int32_t row_scan_first;   /* 1: transportation row-scan rule tried first (specialized_pivots.py:80-120,
+                                 simplex.py:1060-1064); falls through to `pricing` when it finds nothing */
+    int64_t block_size;       /* initial Devex block size (simplex_adaptive.py:70-96 when auto) */
+    int32_t auto_block;       /* 1: x1.5 / x0.75 adaptation every 50 pivots (simplex_adaptive.py:98-151) */
+    int32_t ft_update_limit;  /* Devex weights and pricing block reset on every (limit+1)-th tree change
+                                 (simplex.py:1373-1400) */
+    int64_t max_iterations;   /* > 0 */
+    double tolerance;         /* SolverOptions.tolerance */
+    int64_t trace_capacity;   /* entries available in result->entering_trace (0 = no trace) */
+    int32_t device;           /* CUDA device ordinal */
+    uint32_t flags;           /* NSX_FLAG_* */
+} nsx_options;
+
+typedef struct nsx_result {
+    /* caller-allocated outputs */
+    double* flow;            /* [M + n_nodes - 1] real then artificial arcs */
+    double* potential;       /* [n_nodes] reference sign convention: rc = c + pi[tail] - pi[head] */
+    uint8_t* state;          /* [M + n_nodes - 1] NSX_ARC_* bits */
+    int32_t* entering_trace; /* [trace_capacity] arc * 2 + (direction < 0) per pivot, or NULL */
+    /* scalars written by the call */
+    int64_t trace_len;
+    int64_t iterations;
+    int64_t phase1_iterations;
+    int64_t degenerate_pivots;    /* theta <= tol, simplex.py:1249-1251 */
+    int64_t artificial_with_flow; /* after Phase 1 */
+    int64_t tree_updates;         /* pivots that changed the tree */
+    int64_t weight_resets;        /* Devex reset cadence hits */
+    int64_t final_block_size;
+    int64_t arcs_priced;          /* arcs examined by all pricing sweeps */
+    int64_t unbounded_arc;        /* entering arc when status == NSX_STATUS_UNBOUNDED */
+    double unbounded_rc;
+    int32_t status;               /* NSX_STATUS_* */
+    int32_t reserved;
+    /* device-side timing (milliseconds unless stated) */
+    double solve_ms;              /* CUDA-event time of the resident pivot loop */
+    double h2d_ms, d2h_ms;        /* host<->device copies (host-buffer entry points only) */
+    double pricing_ms;            /* accumulated device clock in pricing sweeps (max over CTAs' leader) */
+    double pivot_ms;              /* accumulated device clock in ratio test + tree/potential update */
+    double sync_ms;               /* accumulated device clock in grid-wide handshakes */
+    int64_t sum_cycle_len;        /* pivot statistics for DESIGN.md / profiles */
+    int64_t sum_subtree;
+    int64_t max_subtree;
+    int64_t sum_rounds;           /* wavefront rounds of the exact potential recompute */
+} nsx_result;
+
+/* Solve one instance on one GPU; all nsx_problem / nsx_result pointers are HOST memory. */
+int nsx_solve(const nsx_problem* problem, const nsx_options* options, nsx_result* result);
+
+/* Same, but tail/head/pert_cost/upper are DEVICE pointers already resident in HBM (supply stays host,
+ * it is n_nodes doubles).  Outputs are still host buffers. Used for the kernel-only throughput figure. */
+int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result);
+
+/* Solve `count` independent instances on one GPU, one CTA per instance (batched config).
+ * problems[i] / results[i] as in nsx_solve; options are shared. */
+int nsx_solve_batch(int64_t count, const nsx_problem* problems, const nsx_options* options,
+                    nsx_result* results);
+
+/* One pricing sweep on a frozen state (parity tests of the sweep kernel and roofline timing):
+ * writes the selected arc (or -1) and direction; `repeat` launches are timed with CUDA events. */
+int nsx_price_once(const nsx_problem* problem, const nsx_options* options, const double* potential,
+                   const double* flow, const uint8_t* in_tree, int32_t phase, int64_t block_start,
+                   int64_t block_end, const double* weight, int32_t excluded_arc, int32_t repeat,
+                   int64_t* out_arc, int32_t* out_dir, double* out_ms_per_sweep);
+
+const char* nsx_last_error(void);
+void nsx_version(int32_t* abi, int32_t* sm_arch);
+int nsx_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSX_B200_H */

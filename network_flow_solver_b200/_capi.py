@@ -1,0 +1,306 @@
+"""ctypes binding of the C ABI in include/nsx_b200.h (libnsx_b200.so).
+
+This is the only door from Python to the CUDA engine.  If the shared library is missing
+or no B200 is visible the call raises DeviceEngineError - there is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from .canonical import CanonicalProblem
+from .exceptions import DeviceEngineError
+
+PRICING_DANTZIG = 0
+PRICING_DEVEX = 1
+
+STATUS_OPTIMAL = 0
+STATUS_INFEASIBLE = 1
+STATUS_ITERATION_LIMIT = 2
+STATUS_UNBOUNDED = 3
+STATUS_ITERATION_LIMIT_P1 = 4
+
+FLAG_FAST_POTENTIALS = 1
+
+ARC_IN_TREE = 1
+ARC_CAN_FWD = 2
+ARC_CAN_BWD = 4
+ARC_TOUCHED = 8
+
+_p_i32 = C.POINTER(C.c_int32)
+_p_f64 = C.POINTER(C.c_double)
+_p_u8 = C.POINTER(C.c_uint8)
+
+
+class NsxProblem(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32),
+        ("n_arcs", C.c_int64),
+        ("tail", _p_i32),
+        ("head", _p_i32),
+        ("pert_cost", _p_f64),
+        ("upper", _p_f64),
+        ("supply", _p_f64),
+        ("penalty", C.c_double),
+    ]
+
+
+class NsxOptions(C.Structure):
+    _fields_ = [
+        ("pricing", C.c_int32),
+        ("row_scan_first", C.c_int32),
+        ("block_size", C.c_int64),
+        ("auto_block", C.c_int32),
+        ("ft_update_limit", C.c_int32),
+        ("max_iterations", C.c_int64),
+        ("tolerance", C.c_double),
+        ("trace_capacity", C.c_int64),
+        ("device", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class NsxResult(C.Structure):
+    _fields_ = [
+        ("flow", _p_f64),
+        ("potential", _p_f64),
+        ("state", _p_u8),
+        ("entering_trace", _p_i32),
+        ("trace_len", C.c_int64),
+        ("iterations", C.c_int64),
+        ("phase1_iterations", C.c_int64),
+        ("degenerate_pivots", C.c_int64),
+        ("artificial_with_flow", C.c_int64),
+        ("tree_updates", C.c_int64),
+        ("weight_resets", C.c_int64),
+        ("final_block_size", C.c_int64),
+        ("arcs_priced", C.c_int64),
+        ("unbounded_arc", C.c_int64),
+        ("unbounded_rc", C.c_double),
+        ("status", C.c_int32),
+        ("reserved", C.c_int32),
+        ("solve_ms", C.c_double),
+        ("h2d_ms", C.c_double),
+        ("d2h_ms", C.c_double),
+        ("pricing_ms", C.c_double),
+        ("pivot_ms", C.c_double),
+        ("sync_ms", C.c_double),
+        ("sum_cycle_len", C.c_int64),
+        ("sum_subtree", C.c_int64),
+        ("max_subtree", C.c_int64),
+        ("sum_rounds", C.c_int64),
+    ]
+
+
+@dataclass
+class EngineOptions:
+    """Flat option record of the C ABI (nsx_options)."""
+
+    pricing: int = PRICING_DANTZIG
+    row_scan_first: bool = False
+    block_size: int = 1
+    auto_block: bool = False
+    ft_update_limit: int = 64
+    max_iterations: int = 100
+    tolerance: float = 1e-6
+    trace_capacity: int = 0
+    device: int = 0
+    flags: int = 0
+
+    def to_c(self) -> NsxOptions:
+        return NsxOptions(
+            int(self.pricing),
+            int(bool(self.row_scan_first)),
+            int(self.block_size),
+            int(bool(self.auto_block)),
+            int(self.ft_update_limit),
+            int(self.max_iterations),
+            float(self.tolerance),
+            int(self.trace_capacity),
+            int(self.device),
+            int(self.flags),
+        )
+
+
+@dataclass
+class RawSolution:
+    """What comes back over the C ABI, in the engine's index space."""
+
+    status: int
+    iterations: int
+    phase1_iterations: int
+    flow: np.ndarray  # float64[M + N]
+    potential: np.ndarray  # float64[n_nodes]
+    state: np.ndarray  # uint8[M + N]
+    trace: np.ndarray  # int32[trace_len] arc*2 + (dir<0)
+    degenerate_pivots: int = 0
+    artificial_with_flow: int = 0
+    tree_updates: int = 0
+    weight_resets: int = 0
+    final_block_size: int = 0
+    arcs_priced: int = 0
+    unbounded_arc: int = -1
+    unbounded_rc: float = 0.0
+    timing: dict = field(default_factory=dict)
+    stats: dict = field(default_factory=dict)
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+class CallFrame:
+    """Owns the numpy buffers behind one nsx_problem / nsx_result pair."""
+
+    def __init__(self, cp: CanonicalProblem, opts: EngineOptions):
+        self.cp = cp
+        m = cp.n_arcs
+        ma = m + cp.n_nodes - 1
+        self.tail = np.ascontiguousarray(cp.tail, dtype=np.int32)
+        self.head = np.ascontiguousarray(cp.head, dtype=np.int32)
+        self.pert = np.ascontiguousarray(cp.pert_cost, dtype=np.float64)
+        self.upper = np.ascontiguousarray(cp.upper, dtype=np.float64)
+        self.supply = np.ascontiguousarray(cp.supply, dtype=np.float64)
+        self.problem = NsxProblem(
+            int(cp.n_nodes),
+            int(m),
+            _ptr(self.tail, _p_i32),
+            _ptr(self.head, _p_i32),
+            _ptr(self.pert, _p_f64),
+            _ptr(self.upper, _p_f64),
+            _ptr(self.supply, _p_f64),
+            float(cp.penalty),
+        )
+        self.options = opts.to_c()
+        self.flow = np.zeros(ma, dtype=np.float64)
+        self.potential = np.zeros(cp.n_nodes, dtype=np.float64)
+        self.state = np.zeros(ma, dtype=np.uint8)
+        cap = max(int(opts.trace_capacity), 0)
+        self.trace = np.zeros(max(cap, 1), dtype=np.int32)
+        self.result = NsxResult()
+        self.result.flow = _ptr(self.flow, _p_f64)
+        self.result.potential = _ptr(self.potential, _p_f64)
+        self.result.state = _ptr(self.state, _p_u8)
+        self.result.entering_trace = _ptr(self.trace, _p_i32) if cap > 0 else None
+        self.trace_capacity = cap
+
+    def harvest(self) -> RawSolution:
+        r = self.result
+        n_tr = int(min(r.trace_len, self.trace_capacity))
+        return RawSolution(
+            status=int(r.status),
+            iterations=int(r.iterations),
+            phase1_iterations=int(r.phase1_iterations),
+            flow=self.flow,
+            potential=self.potential,
+            state=self.state,
+            trace=self.trace[:n_tr].copy(),
+            degenerate_pivots=int(r.degenerate_pivots),
+            artificial_with_flow=int(r.artificial_with_flow),
+            tree_updates=int(r.tree_updates),
+            weight_resets=int(r.weight_resets),
+            final_block_size=int(r.final_block_size),
+            arcs_priced=int(r.arcs_priced),
+            unbounded_arc=int(r.unbounded_arc),
+            unbounded_rc=float(r.unbounded_rc),
+            timing={
+                "solve_ms": float(r.solve_ms),
+                "h2d_ms": float(r.h2d_ms),
+                "d2h_ms": float(r.d2h_ms),
+                "pricing_ms": float(r.pricing_ms),
+                "pivot_ms": float(r.pivot_ms),
+                "sync_ms": float(r.sync_ms),
+            },
+            stats={
+                "sum_cycle_len": int(r.sum_cycle_len),
+                "sum_subtree": int(r.sum_subtree),
+                "max_subtree": int(r.max_subtree),
+                "sum_rounds": int(r.sum_rounds),
+            },
+        )
+
+
+# ----------------------------------------------------------------------------------------------
+# library loading
+# ----------------------------------------------------------------------------------------------
+_LIB_NAME = "libnsx_b200.so"
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / "csrc" / _LIB_NAME
+
+
+def load_library():
+    """dlopen libnsx_b200.so (built in-tree by __graft_entry__.build()); raise if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = Path(os.environ.get("NSX_B200_LIB", str(library_path())))
+        if not path.exists():
+            raise DeviceEngineError(
+                f"CUDA engine {path} is not built. Run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` from the repo root. There is no CPU fallback."
+            )
+        try:
+            lib = C.CDLL(str(path))
+        except OSError as exc:  # missing libcudart etc.
+            raise DeviceEngineError(f"cannot load {path}: {exc}") from exc
+        for name in ("nsx_solve", "nsx_solve_resident"):
+            fn = getattr(lib, name)
+            fn.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult)]
+            fn.restype = C.c_int
+        lib.nsx_solve_batch.argtypes = [
+            C.c_int64,
+            C.POINTER(NsxProblem),
+            C.POINTER(NsxOptions),
+            C.POINTER(NsxResult),
+        ]
+        lib.nsx_solve_batch.restype = C.c_int
+        lib.nsx_last_error.restype = C.c_char_p
+        lib.nsx_version.argtypes = [_p_i32, _p_i32]
+        lib.nsx_device_count.restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    msg = load_library().nsx_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise DeviceEngineError(f"{what} failed with code {rc}: {last_error()}")
+
+
+def solve_canonical(cp: CanonicalProblem, opts: EngineOptions) -> RawSolution:
+    """One instance, host buffers in, host buffers out (nsx_solve). Releases the GIL."""
+    lib = load_library()
+    frame = CallFrame(cp, opts)
+    rc = lib.nsx_solve(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result))
+    _check(rc, "nsx_solve")
+    return frame.harvest()
+
+
+def solve_batch_canonical(cps: list[CanonicalProblem], opts: EngineOptions) -> list[RawSolution]:
+    """Independent instances, one CTA each (nsx_solve_batch)."""
+    lib = load_library()
+    frames = [CallFrame(cp, opts) for cp in cps]
+    n = len(frames)
+    probs = (NsxProblem * n)(*[f.problem for f in frames])
+    ress = (NsxResult * n)(*[f.result for f in frames])
+    o = opts.to_c()
+    rc = lib.nsx_solve_batch(n, probs, C.byref(o), ress)
+    _check(rc, "nsx_solve_batch")
+    for f, r in zip(frames, ress):
+        f.result = r
+    return [f.harvest() for f in frames]

@@ -1,0 +1,262 @@
+"""Drop-in entry point: ``solve_min_cost_flow`` backed by the device-resident pivot loop.
+
+Same signature, option meaning, statuses and error behaviour as the reference façade
+(reference: src/network_solver/solver.py:13-104 -> simplex.py:99-265,1446-1765).  The host does
+exactly three things: resolve the options the way ``NetworkSimplex.__init__`` does, canonicalise
+the problem into the engine's structure-of-arrays, and turn the raw arrays that come back over
+the C ABI into a ``FlowResult`` with the reference's rounding (simplex.py:1703-1765).  Pricing,
+ratio test, flow / tree / potential updates all run inside libnsx_b200.so on the GPU.
+"""
+
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from .canonical import (
+    NET_GENERAL,
+    NET_TRANSPORTATION,
+    PERTURB_EPS_BASE,
+    CanonicalProblem,
+    canonicalize,
+    initial_block_size,
+    is_likely_goto,
+)
+from .data import Basis, FlowResult, NetworkProblem, ProgressCallback, SolverOptions
+from .exceptions import SolverConfigurationError, UnboundedProblemError
+
+_log = logging.getLogger(__name__)
+
+_STATUS_TEXT = {
+    _capi.STATUS_OPTIMAL: "optimal",
+    _capi.STATUS_INFEASIBLE: "infeasible",
+    _capi.STATUS_ITERATION_LIMIT: "iteration_limit",
+    _capi.STATUS_ITERATION_LIMIT_P1: "iteration_limit",
+}
+
+
+@dataclass
+class ResolvedPlan:
+    """Outcome of option resolution: what the engine is asked to do."""
+
+    strategy: str
+    engine: _capi.EngineOptions
+
+
+def resolve_plan(
+    cp: CanonicalProblem,
+    options: SolverOptions,
+    max_iterations: int | None,
+    *,
+    goto_like: bool = False,
+    trace_capacity: int = 0,
+    device: int = 0,
+    flags: int = 0,
+) -> ResolvedPlan:
+    """Mirror of the decisions taken in NetworkSimplex.__init__ / solve().
+
+    * pricing rule: explicit choice, else Dantzig on grid-on-torus structure
+      (simplex.py:312-377);
+    * structure override: transportation instances are priced by the row-scan rule first
+      (simplex.py:259-261,1060-1064; specialized_pivots.py:80-120);
+    * Devex block size: fixed int, or the static heuristic plus runtime adaptation
+      (simplex.py:195-211; simplex_adaptive.py:70-151);
+    * iteration budget: argument, else options, else max(100, 20*(arcs incl. artificial))
+      (simplex.py:1465-1470).
+    """
+    strategy = options.pricing_strategy
+    if not options.explicit_pricing_strategy and goto_like:
+        strategy = "dantzig"
+    if strategy == "dantzig":
+        pricing = _capi.PRICING_DANTZIG
+    elif strategy == "devex":
+        if not options.use_vectorized_pricing:
+            raise SolverConfigurationError(
+                "use_vectorized_pricing=False selects the reference's loop-based Devex rule "
+                "(simplex_pricing.py:205-269), which the device engine does not implement; "
+                "only the vectorised block search is on the accelerated path."
+            )
+        pricing = _capi.PRICING_DEVEX
+    else:
+        raise SolverConfigurationError(
+            f"pricing_strategy='{strategy}' is not on the accelerated path yet (SURVEY.md "
+            f"section 8f: candidate_list / adaptive are 'next' rows). Pass 'dantzig' or 'devex'."
+        )
+    if cp.network_type == NET_TRANSPORTATION:
+        row_scan = True
+    elif cp.network_type == NET_GENERAL:
+        row_scan = False
+    else:
+        raise SolverConfigurationError(
+            f"detected network type '{cp.network_type}': the reference overrides pricing with a "
+            f"specialised pivot rule here (specialized_pivots.py:150-450) that is outside the "
+            f"accelerated path (SURVEY.md section 2 row 7)."
+        )
+    auto = options.block_size is None or isinstance(options.block_size, str)
+    block = initial_block_size(cp.n_arcs) if auto else int(options.block_size)
+    if max_iterations is None:
+        if options.max_iterations is not None:
+            max_iterations = options.max_iterations
+        else:
+            max_iterations = max(100, 20 * (cp.n_arcs + cp.n_nodes - 1))
+    eng = _capi.EngineOptions(
+        pricing=pricing,
+        row_scan_first=row_scan,
+        block_size=block,
+        auto_block=auto,
+        ft_update_limit=options.ft_update_limit,
+        max_iterations=int(max_iterations),
+        tolerance=options.tolerance,
+        trace_capacity=trace_capacity,
+        device=device,
+        flags=flags,
+    )
+    return ResolvedPlan(strategy=strategy, engine=eng)
+
+
+def _np_round12(x: float) -> float:
+    """NumPy's scale-rint-unscale rounding, which the reference applies to np.float64 values
+    (6749969302.0 comes back as 6749969301.999999)."""
+    return float(round(np.float64(x), 12))
+
+
+def objective_value(cp: CanonicalProblem, raw: _capi.RawSolution) -> float:
+    """Sum over real arcs in index order of (flow+shift)*original cost, rounded like the
+    reference (simplex.py:1703-1714,1759)."""
+    m = cp.n_arcs
+    if m == 0:
+        return 0.0
+    values = raw.flow[:m] + cp.shift
+    total = float(np.cumsum(values * cp.orig_cost)[-1])  # cumsum folds left to right
+    touched = bool(np.any(raw.state[:m] & _capi.ARC_TOUCHED))
+    return _np_round12(total) if touched else float(round(total, 12))
+
+
+def finish(
+    cp: CanonicalProblem, raw: _capi.RawSolution, options: SolverOptions
+) -> FlowResult:
+    """Raw engine arrays -> FlowResult (simplex.py:1600-1624,1703-1765)."""
+    if raw.status == _capi.STATUS_UNBOUNDED:
+        key = cp.arc_keys[raw.unbounded_arc] if cp.arc_keys is not None else None
+        raise UnboundedProblemError(
+            "Unbounded problem detected: entering arc can increase indefinitely without "
+            "hitting any capacity constraint. This indicates a negative-cost cycle with "
+            "infinite capacity.",
+            entering_arc=key,
+            reduced_cost=raw.unbounded_rc,
+        )
+    status = _STATUS_TEXT[raw.status]
+    if raw.status in (_capi.STATUS_INFEASIBLE, _capi.STATUS_ITERATION_LIMIT_P1):
+        return FlowResult(
+            objective=0.0, flows={}, status=status, iterations=raw.iterations, duals={}
+        )
+    tol = options.tolerance
+    m = cp.n_arcs
+    values = raw.flow[:m] + cp.shift
+    touched = (raw.state[:m] & _capi.ARC_TOUCHED) != 0
+    flows: dict[tuple[str, str], float] = {}
+    if cp.arc_keys is not None:
+        np_typed: dict[tuple[str, str], bool] = {}
+        keys = cp.arc_keys
+        for i in np.flatnonzero((values != 0.0) | touched).tolist():
+            k = keys[i]
+            if k in flows:
+                flows[k] += float(values[i])
+                np_typed[k] = np_typed[k] or bool(touched[i])
+            else:
+                flows[k] = float(values[i])
+                np_typed[k] = bool(touched[i])
+        for k, v in list(flows.items()):
+            if abs(v) <= tol:
+                del flows[k]
+            else:
+                flows[k] = _np_round12(v) if np_typed[k] else float(round(v, 12))
+    duals: dict[str, float] = {}
+    if cp.node_ids is not None:
+        pot = raw.potential.tolist()
+        for i in range(1, cp.n_nodes):
+            duals[cp.node_ids[i]] = float(round(pot[i], 12))
+    basis = None
+    if cp.arc_keys is not None:
+        in_tree = np.flatnonzero(raw.state[:m] & _capi.ARC_IN_TREE).tolist()
+        basis = Basis(
+            tree_arcs={cp.arc_keys[i] for i in in_tree},
+            arc_flows={cp.arc_keys[i]: float(raw.flow[i]) for i in in_tree},
+        )
+    return FlowResult(
+        objective=objective_value(cp, raw),
+        flows=flows,
+        status=status,
+        iterations=raw.iterations,
+        duals=duals,
+        basis=basis,
+    )
+
+
+def prepare(
+    problem: NetworkProblem,
+    options: SolverOptions | None = None,
+    max_iterations: int | None = None,
+    *,
+    trace_capacity: int = 0,
+    device: int = 0,
+    flags: int = 0,
+    eps_base: float = PERTURB_EPS_BASE,
+) -> tuple[CanonicalProblem, ResolvedPlan, SolverOptions]:
+    """Host-side half of the call: options + canonical arrays, no device work."""
+    options = options if options is not None else SolverOptions()
+    if options.auto_scale:
+        from .scaling import should_scale_problem
+
+        if should_scale_problem(problem):
+            raise SolverConfigurationError(
+                "auto_scale=True would rescale this problem (value ranges differ by more than "
+                "1e6, scaling.py:37-95); automatic scaling is a host pre/post step outside the "
+                "accelerated path - pass SolverOptions(auto_scale=False)."
+            )
+    cp = canonicalize(problem, options.tolerance, eps_base)
+    goto = is_likely_goto(problem, cp.n_arcs, options.tolerance)
+    plan = resolve_plan(
+        cp,
+        options,
+        max_iterations,
+        goto_like=goto,
+        trace_capacity=trace_capacity,
+        device=device,
+        flags=flags,
+    )
+    return cp, plan, options
+
+
+def solve_min_cost_flow(
+    problem: NetworkProblem,
+    options: SolverOptions | None = None,
+    max_iterations: int | None = None,
+    progress_callback: ProgressCallback | None = None,
+    progress_interval: int = 100,
+    warm_start_basis: Basis | None = None,
+    *,
+    device: int = 0,
+) -> FlowResult:
+    """Solve a minimum-cost flow problem on the GPU; drop-in for the reference call
+    (solver.py:13-104).  Raises DeviceEngineError when the CUDA engine is unavailable."""
+    if warm_start_basis is not None:
+        raise SolverConfigurationError(
+            "warm_start_basis is not on the accelerated path yet (SURVEY.md section 8f row 3)."
+        )
+    if progress_callback is not None:
+        _log.info(
+            "progress_callback is not invoked: the pivot loop is device-resident with no host "
+            "round-trip per pivot"
+        )
+    cp, plan, options = prepare(problem, options, max_iterations, device=device)
+    raw = _capi.solve_canonical(cp, plan.engine)
+    result = finish(cp, raw, options)
+    if raw.status in (_capi.STATUS_OPTIMAL, _capi.STATUS_ITERATION_LIMIT):
+        rate = (raw.degenerate_pivots / raw.iterations * 100) if raw.iterations > 0 else 0.0
+        # the reference prints this line unconditionally (simplex.py:1672-1674)
+        print(f"  > Degeneracy: {raw.degenerate_pivots}/{raw.iterations} pivots ({rate:.1f}%)")
+    return result
