@@ -131,13 +131,6 @@ int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* option
 int nsx_solve_batch(int64_t count, const nsx_problem* problems, const nsx_options* options,
                     nsx_result* results);
 
-/* One pricing sweep on a frozen state (parity tests of the sweep kernel and roofline timing):
- * writes the selected arc (or -1) and direction; `repeat` launches are timed with CUDA events. */
-int nsx_price_once(const nsx_problem* problem, const nsx_options* options, const double* potential,
-                   const double* flow, const uint8_t* in_tree, int32_t phase, int64_t block_start,
-                   int64_t block_end, const double* weight, int32_t excluded_arc, int32_t repeat,
-                   int64_t* out_arc, int32_t* out_dir, double* out_ms_per_sweep);
-
 const char* nsx_last_error(void);
 void nsx_version(int32_t* abi, int32_t* sm_arch);
 int nsx_device_count(void);

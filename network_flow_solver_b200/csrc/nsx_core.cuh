@@ -1,0 +1,803 @@
+// nsx_core.cuh - pivot logic of the B200 network-simplex engine (ratio test, flow update,
+// spanning-tree re-hang on a preorder array, exact node-potential recompute).
+//
+// The code is written as CTA-wide phases: NSX_PAR_FOR loops whose iterations are independent,
+// separated by NSX_SYNC().  On the device a phase is executed by all threads of one CTA; with
+// NSX_HOST_EMU defined the same source compiles with g++ as a serial program (one "thread"),
+// which tests/ use to check the device logic on machines without a GPU.  The emulation is test
+// infrastructure: the product library is built by nvcc only and has no host execution path.
+//
+// Reference behaviour restated here (paths relative to the reference root):
+//   ratio test / flow update / bound flip ........ src/network_solver/simplex.py:1176-1334
+//   cycle orientation ............................ src/network_solver/basis.py:178-241
+//   potentials = fold of +-cost along root path .. src/network_solver/basis.py:82-125
+//   Devex weight = tree-path length .............. simplex_pricing.py:271-292
+//   reset cadence (weights := 1, block := 0) ..... simplex.py:1373-1425
+//   block-size adaptation ........................ simplex_adaptive.py:98-151
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/nsx_b200.h"
+
+#if defined(__CUDACC__) && !defined(NSX_HOST_EMU)
+#define NSX_ON_DEVICE 1
+#define NSX_FN __device__ __forceinline__
+#define NSX_PAR_FOR(i, lo, hi) \
+    for (int64_t i = (int64_t)(lo) + (int64_t)threadIdx.x; i < (int64_t)(hi); i += (int64_t)blockDim.x)
+#define NSX_SYNC() __syncthreads()
+#define NSX_SINGLE if (threadIdx.x == 0)
+#define NSX_TID ((int)threadIdx.x)
+#define NSX_NTHREADS ((int)blockDim.x)
+// IEEE float64 without fused multiply-add: the reference's operation order
+#define NSX_ADD(a, b) __dadd_rn((a), (b))
+#define NSX_SUB(a, b) __dsub_rn((a), (b))
+#define NSX_MUL(a, b) __dmul_rn((a), (b))
+#define NSX_DIV(a, b) __ddiv_rn((a), (b))
+#define NSX_INF __longlong_as_double(0x7ff0000000000000LL)
+#define NSX_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#else
+#define NSX_ON_DEVICE 0
+#define NSX_FN static inline
+#define NSX_PAR_FOR(i, lo, hi) for (int64_t i = (int64_t)(lo); i < (int64_t)(hi); ++i)
+#define NSX_SYNC() ((void)0)
+#define NSX_SINGLE
+#define NSX_TID 0
+#define NSX_NTHREADS 1
+#define NSX_ADD(a, b) ((a) + (b)) /* compiled with -ffp-contract=off */
+#define NSX_SUB(a, b) ((a) - (b))
+#define NSX_MUL(a, b) ((a) * (b))
+#define NSX_DIV(a, b) ((a) / (b))
+#define NSX_INF INFINITY
+#define NSX_ATOMIC_ADD_I32(p, v) (*(p) += (v))
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Device-resident state
+// ------------------------------------------------------------------------------------------
+// One 16-byte record per node so that a hop of the cycle walk is a single 128-bit load.
+struct NsxNode {
+    int32_t parent;  // parent node (root: itself)
+    int32_t pred2;   // (arc joining the node to its parent) * 2 + (arc points child->parent), -1 for root
+    int32_t pos;     // position in the preorder array
+    int32_t size;    // subtree size (node included): subtree = order[pos .. pos+size)
+};
+
+struct NsxDev {
+    int32_t n;   // nodes incl. root
+    int64_t m;   // real arcs
+    int64_t ma;  // m + n - 1 (real + artificial)
+    // arcs, structure-of-arrays in HBM
+    const int32_t* tail;  // [m]   real arcs (caller's arrays, used in place)
+    const int32_t* head;  // [m]
+    const double* pert;   // [m]   perturbed Phase-2 cost
+    const double* upper;  // [m]
+    int32_t* atail;       // [n-1] artificial arcs m + v - 1 (engine-owned)
+    int32_t* ahead;       // [n-1]
+    double* aupper;       // [n-1]
+    double* flow;         // [ma]
+    uint8_t* state;       // [ma] NSX_ARC_* bits
+    uint32_t* wgt;        // [m]  Devex weight: (epoch << 24) | path length; stale epoch => weight 1
+    // nodes
+    NsxNode* node;     // [n]
+    int32_t* depth;    // [n]
+    double* pi;        // [n]
+    int32_t* order;    // [n] preorder array
+    int32_t* tmp;      // [n] scratch for the re-hang permutation
+    int32_t* gpath_h;  // [n] cycle path spill (node ids), head side
+    int32_t* gpath_t;  // [n] tail side
+    int32_t* garc2;    // [2n+1] spill of cycle arcs in scan order
+    double* gres;      // [2n+1] spill of residuals in scan order
+    double penalty;
+    double tol;
+};
+
+// Solver scalars; lives in global memory, written by the pivot CTA only.
+struct NsxCtl {
+    int32_t phase;        // 1 or 2
+    int32_t status;       // NSX_STATUS_*; -1 while running
+    int64_t it;           // pivots in the current phase
+    int64_t total;        // pivots in finished phases
+    int64_t maxit;
+    int64_t bs, pb;       // Devex block size / current block
+    int32_t last_deg;     // arc excluded from the next Devex search, -1 none
+    int32_t ftc;          // tree changes since the last weight reset
+    int32_t ft_limit;
+    int32_t auto_block;
+    int32_t pricing;
+    int32_t row_scan_first;
+    int64_t tuner_total, tuner_deg, tuner_last;
+    int64_t art_with_flow;
+    uint32_t wepoch;      // current Devex weight epoch (8 bits used)
+    int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
+    // statistics
+    int64_t degenerate, tree_updates, resets, arcs_priced;
+    int64_t sum_cycle, sum_subtree, max_subtree, sum_rounds, sum_window;
+    int64_t phase1_iterations, art_after_p1;
+    int64_t trace_len, trace_cap;
+    int64_t unbounded_arc;
+    double unbounded_rc;
+    int64_t clk_pricing, clk_pivot, clk_sync;
+};
+
+#define NSX_PATH_CAP 1536  // cycle entries per side kept in shared memory
+
+// Scratch of the pivot CTA (shared memory on the device).
+struct NsxPivotScratch {
+    int32_t nh, nt;            // path lengths (nodes below the join on each side)
+    int32_t join;
+    int32_t leave_k;           // scan position of the leaving arc
+    int32_t leave_arc;
+    int32_t spill;             // 1: paths longer than NSX_PATH_CAP, use the global spill arrays
+    int32_t art_delta;
+    int32_t rounds;
+    int32_t pending;
+    double theta;
+    int32_t path_h[NSX_PATH_CAP];
+    int32_t path_t[NSX_PATH_CAP];
+    int32_t arc2[2 * NSX_PATH_CAP + 1];  // scan order: arc*2 + (sign<0)
+    double res[2 * NSX_PATH_CAP + 1];
+    // stem (old pos / size / depth of s_0..s_k), aliases res[] storage after the ratio test
+};
+
+NSX_FN double nsx_arc_cost(const NsxDev& d, int32_t phase, int64_t a) {
+    // simplex.py:1162-1168: Phase 1 real arc = pert - 1.0 - 1e-6*idx ; artificial = penalty
+    if (a >= d.m) return d.penalty;
+    double c = d.pert[a];
+    if (phase == 1) c = NSX_SUB(NSX_SUB(c, 1.0), NSX_MUL(1e-6, (double)a));
+    return c;
+}
+
+NSX_FN bool nsx_isinf(double x) { return x == NSX_INF; }
+NSX_FN int32_t nsx_tail(const NsxDev& d, int64_t a) { return a < d.m ? d.tail[a] : d.atail[a - d.m]; }
+NSX_FN int32_t nsx_head(const NsxDev& d, int64_t a) { return a < d.m ? d.head[a] : d.ahead[a - d.m]; }
+NSX_FN double nsx_upper(const NsxDev& d, int64_t a) { return a < d.m ? d.upper[a] : d.aupper[a - d.m]; }
+
+NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
+    uint8_t b = 0;
+    if (nsx_isinf(up) || NSX_SUB(up, f) > tol) b |= NSX_ARC_CAN_FWD;
+    if (f > tol) b |= NSX_ARC_CAN_BWD;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact potential recompute over the preorder range [lo, hi): pi[v] = pi[parent] +- cost(pred)
+// parent-before-child (basis.py:111-117).  Chunks of the preorder array are processed in order;
+// inside a chunk a node waits (in rounds) until its parent, which precedes it in preorder, is
+// final.  `flags` is a per-thread-slot byte array of NSX_CHUNK entries.
+// ------------------------------------------------------------------------------------------
+#if NSX_ON_DEVICE
+#define NSX_CHUNK 1024
+#else
+#define NSX_CHUNK 256
+#endif
+
+struct NsxPotScratch {
+    double val[NSX_CHUNK];
+    int32_t par_local[NSX_CHUNK];  // parent index inside the chunk, -1 = parent already final
+    double cst[NSX_CHUNK];         // signed cost to add
+    uint8_t done[NSX_CHUNK];
+    int32_t pending;
+    int32_t rounds;
+};
+
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
+                                     NsxPotScratch& s, int64_t* rounds_out) {
+    NSX_SINGLE { s.rounds = 0; }
+    for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
+        int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
+        NSX_SYNC();
+        NSX_PAR_FOR(x, c0, c1) {
+            int32_t j = (int32_t)(x - c0);
+            int32_t v = d.order[x];
+            NsxNode r = d.node[v];
+            int32_t a = r.pred2 >> 1;
+            double cst = nsx_arc_cost(d, phase, a);
+            // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
+            s.cst[j] = (r.pred2 & 1) ? -cst : cst;
+            int32_t ppos = d.node[r.parent].pos;
+            if (ppos >= c0 && ppos < x) {
+                s.par_local[j] = (int32_t)(ppos - c0);
+                s.done[j] = 0;
+            } else {
+                s.par_local[j] = -1;
+                s.val[j] = NSX_ADD(d.pi[r.parent], s.cst[j]);  // x - c == x + (-c) exactly
+                s.done[j] = 1;
+            }
+        }
+        // rounds until every node of the chunk is final
+        for (;;) {
+            NSX_SYNC();
+            NSX_SINGLE { s.pending = 0; }
+            NSX_SYNC();
+            // phase 1 of the round: decide from the flags of the previous round
+            NSX_PAR_FOR(x, c0, c1) {
+                int32_t j = (int32_t)(x - c0);
+                if (!s.done[j]) {
+                    int32_t pj = s.par_local[j];
+                    if (s.done[pj] == 1) {
+                        s.val[j] = NSX_ADD(s.val[pj], s.cst[j]);
+                        s.done[j] = 2;  // becomes visible as final after the sync
+                    } else {
+                        s.pending = 1;
+                    }
+                }
+            }
+            NSX_SYNC();
+            NSX_PAR_FOR(x, c0, c1) {
+                int32_t j = (int32_t)(x - c0);
+                if (s.done[j] == 2) s.done[j] = 1;
+            }
+            NSX_SYNC();
+            int32_t pend = s.pending;
+            NSX_SINGLE { s.rounds++; }
+            if (!pend) break;
+        }
+        NSX_PAR_FOR(x, c0, c1) {
+            int32_t j = (int32_t)(x - c0);
+            d.pi[d.order[x]] = s.val[j];
+        }
+    }
+    NSX_SYNC();
+    NSX_SINGLE { if (rounds_out) *rounds_out += s.rounds; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cycle walk: tree paths from both ends of the entering arc up to their join, found with the
+// preorder ancestor test  pos[u] <= pos[x] < pos[u] + size[u]  (no depth comparison needed).
+// Executed by two lanes on the device (one per side), serially in the emulation.
+// ------------------------------------------------------------------------------------------
+NSX_FN void nsx_walk_side(const NsxDev& d, int32_t from, int32_t other_pos, int32_t* spath,
+                          int32_t* gpath, int32_t* len_out, int32_t* join_out) {
+    int32_t u = from;
+    int32_t len = 0;
+    NsxNode r = d.node[u];
+    while (!(r.pos <= other_pos && other_pos < r.pos + r.size)) {
+        if (len < NSX_PATH_CAP) spath[len] = u;
+        gpath[len] = u;
+        ++len;
+        u = r.parent;
+        r = d.node[u];
+    }
+    *len_out = len;
+    *join_out = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// One pivot on entering arc e (direction dir = +1 forward / -1 backward).
+// Returns (block-uniform) 0 = ok, 3 = unbounded.
+// ------------------------------------------------------------------------------------------
+NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScratch& ps, int32_t e,
+                     int32_t dir, int32_t want_weight) {
+    const double tol = d.tol;
+    const int32_t t = dir == 1 ? d.tail[e] : d.head[e];
+    const int32_t h = dir == 1 ? d.head[e] : d.tail[e];
+
+    // ---- 1. walk both sides up to the join ------------------------------------------------
+#if NSX_ON_DEVICE
+    if (threadIdx.x < 2) {
+        int32_t from = threadIdx.x == 0 ? h : t;
+        int32_t opos = d.node[threadIdx.x == 0 ? t : h].pos;
+        int32_t len, join;
+        nsx_walk_side(d, from, opos, threadIdx.x == 0 ? s.path_h : s.path_t,
+                      threadIdx.x == 0 ? d.gpath_h : d.gpath_t, &len, &join);
+        if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
+    }
+#else
+    {
+        int32_t len, join;
+        nsx_walk_side(d, h, d.node[t].pos, s.path_h, d.gpath_h, &len, &join);
+        s.nh = len; s.join = join;
+        nsx_walk_side(d, t, d.node[h].pos, s.path_t, d.gpath_t, &len, &join);
+        s.nt = len;
+    }
+#endif
+    NSX_SYNC();
+    const int32_t nh = s.nh, nt = s.nt;
+    const int32_t ncyc = nh + nt + 1;
+    const bool spill = nh > NSX_PATH_CAP || nt > NSX_PATH_CAP;
+    const int32_t* path_h = spill ? d.gpath_h : s.path_h;
+    const int32_t* path_t = spill ? d.gpath_t : s.path_t;
+    int32_t* arc2 = spill ? d.garc2 : s.arc2;
+    double* res = spill ? d.gres : s.res;
+
+    // ---- 2. residuals in the reference's scan order (simplex.py:1198-1229) ----------------
+    NSX_PAR_FOR(k, 0, ncyc) {
+        int32_t a, sign;
+        if (k < nh) {
+            int32_t p2 = d.node[path_h[k]].pred2;
+            a = p2 >> 1;
+            sign = (p2 & 1) ? 1 : -1;  // walking child->parent: arc pointing child->parent is traversed forward
+        } else if (k < nh + nt) {
+            int32_t p2 = d.node[path_t[nt - 1 - (k - nh)]].pred2;
+            a = p2 >> 1;
+            sign = (p2 & 1) ? -1 : 1;  // walking parent->child
+        } else {
+            a = e;
+            sign = dir;
+        }
+        double f = d.flow[a];
+        double r;
+        if (sign == 1) {
+            double up = nsx_upper(d, a);
+            r = nsx_isinf(up) ? NSX_INF : NSX_SUB(up, f);
+        } else {
+            r = f;  // flow - lower with lower = 0
+        }
+        arc2[k] = a * 2 + (sign < 0 ? 1 : 0);
+        res[k] = r;
+    }
+    NSX_SYNC();
+
+    // ---- 3. ratio test: sequential scan with tolerance ties -> lowest arc index ------------
+    NSX_SINGLE {
+        double theta = NSX_INF, best = -NSX_INF;
+        int32_t leave = e, leave_k = ncyc - 1;
+        for (int32_t k = 0; k < ncyc; ++k) {
+            double r = res[k];
+            int32_t a = arc2[k] >> 1;
+            if (r < NSX_SUB(theta, tol)) {
+                theta = r; leave = a; best = r; leave_k = k;
+            } else if (fabs(NSX_SUB(r, theta)) <= tol) {
+                if (r > NSX_ADD(best, tol) || (fabs(NSX_SUB(r, best)) <= tol && a < leave)) {
+                    leave = a; best = r; leave_k = k;
+                }
+            }
+        }
+        s.theta = theta;
+        s.leave_arc = leave;
+        s.leave_k = leave_k;
+        s.art_delta = 0;
+    }
+    NSX_SYNC();
+    if (nsx_isinf(s.theta)) {
+        NSX_SINGLE {
+            c.unbounded_arc = e;
+            double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, e), d.pi[d.tail[e]]), d.pi[d.head[e]]);
+            c.unbounded_rc = dir == 1 ? rc : -rc;
+        }
+        return 3;
+    }
+    const double theta = s.theta > 0.0 ? s.theta : 0.0;
+    const int32_t leave = s.leave_arc;
+    const int32_t leave_k = s.leave_k;
+
+    // ---- 4. flow update (simplex.py:1255-1283); nothing changes when theta == 0 -----------
+    if (theta > 0.0) {
+        NSX_PAR_FOR(k, 0, ncyc) {
+            int32_t a = arc2[k] >> 1;
+            int32_t sign = (arc2[k] & 1) ? -1 : 1;
+            double old = d.flow[a];
+            double up = nsx_upper(d, a);
+            double f = sign > 0 ? NSX_ADD(old, theta) : NSX_SUB(old, theta);
+            uint8_t st = (uint8_t)(d.state[a] | NSX_ARC_TOUCHED);
+            if (f < NSX_SUB(0.0, tol)) { f = 0.0; st &= (uint8_t)~NSX_ARC_TOUCHED; }
+            if (!nsx_isinf(up) && f > NSX_ADD(up, tol)) { f = up; st &= (uint8_t)~NSX_ARC_TOUCHED; }
+            d.flow[a] = f;
+            st = (uint8_t)((st & (NSX_ARC_IN_TREE | NSX_ARC_TOUCHED)) | nsx_bounds_bits(f, up, tol));
+            d.state[a] = st;
+            if (a >= d.m) {
+                int had = old > tol, has = f > tol;
+                if (had != has) NSX_ATOMIC_ADD_I32(&s.art_delta, has - had);
+            }
+        }
+    }
+    NSX_SYNC();
+    NSX_SINGLE {
+        c.art_with_flow += s.art_delta;
+        if (theta <= tol) c.degenerate++;
+        c.sum_cycle += ncyc;
+        // Devex weight := number of tree arcs on the tail-head path, written by pricing before
+        // the pivot in the reference (simplex_pricing.py:350-352)
+        if (want_weight && e < d.m) d.wgt[e] = (c.wepoch << 24) | (uint32_t)(nh + nt);
+        int is_deg = (leave == e) || (fabs(theta) < tol);  // simplex.py:1317
+        c.tuner_total++;
+        if (is_deg) c.tuner_deg++;
+        if (leave == e) c.last_deg = e;  // bound flip (simplex.py:1320-1334)
+    }
+    if (leave == e) { NSX_SYNC(); return 0; }
+
+    // ---- 5. tree update: re-hang the subtree below the leaving arc under the entering arc --
+    // stem s_0 = q (entering endpoint inside the cut subtree) ... s_k = r (its pred arc leaves)
+    const bool on_h = leave_k < nh;
+    const int32_t kk = on_h ? leave_k : nt - 1 - (leave_k - nh);  // index of r in its side path
+    const int32_t* spath = on_h ? path_h : path_t;                // side containing the stem
+    const int32_t* opath = on_h ? path_t : path_h;                // side of p
+    const int32_t slen = on_h ? nh : nt;
+    const int32_t olen = on_h ? nt : nh;
+    const int32_t p = on_h ? t : h;
+    const int32_t r = spath[kk];
+    const NsxNode rec_r = d.node[r];
+    const NsxNode rec_p = d.node[p];
+    const int32_t a0 = rec_r.pos, sz = rec_r.size, P = rec_p.pos;
+    const int32_t depth_q_new = d.depth[p] + 1;
+    // stem snapshot (old pos / size / depth / pred2): shared scratch reusing res[] / arc2[], or the
+    // global spill arrays when the cycle did not fit (garc2: 2n+1 ints, gres: 2n+1 doubles)
+    int32_t* st_pos = spill ? d.garc2 : (int32_t*)s.res;
+    int32_t* st_size = spill ? d.garc2 + d.n : ((int32_t*)s.res) + NSX_PATH_CAP;
+    int32_t* st_depth = spill ? (int32_t*)d.gres : ((int32_t*)s.res) + 2 * NSX_PATH_CAP;
+    int32_t* st_pred2 = spill ? ((int32_t*)d.gres) + d.n : s.arc2;
+    NSX_SYNC();  // everyone has read arc2/res for the flow update before they are reused
+    NSX_PAR_FOR(i, 0, kk + 1) {
+        NsxNode x = d.node[spath[i]];
+        st_pos[i] = x.pos; st_size[i] = x.size; st_pred2[i] = x.pred2;
+        st_depth[i] = d.depth[spath[i]];
+    }
+    // subtree-size bookkeeping of the untouched ancestors on both sides of the cycle
+    NSX_PAR_FOR(i, kk + 1, slen) { d.node[spath[i]].size -= sz; }
+    NSX_PAR_FOR(i, 0, olen) { d.node[opath[i]].size += sz; }
+    NSX_SYNC();
+
+    // window of the preorder array that changes: the block S = [a0, a0+sz) moves right behind p
+    int64_t lo, hi, s_base;
+    if (P < a0) { lo = (int64_t)P + 1; hi = (int64_t)a0 + sz; s_base = lo; }
+    else        { lo = a0; hi = (int64_t)P + 1; s_base = (int64_t)P + 1 - sz; }
+    const int32_t k_stem = kk;
+    NSX_PAR_FOR(x, lo, hi) {
+        int32_t v = d.order[x];
+        int64_t fx;
+        if (x >= a0 && x < (int64_t)a0 + sz) {
+            // smallest i with x inside old subtree(s_i): ranges are nested, growing with i
+            int32_t lo_i = 0, hi_i = k_stem;
+            while (lo_i < hi_i) {
+                int32_t mid = (lo_i + hi_i) >> 1;
+                if (x >= st_pos[mid] && x < (int64_t)st_pos[mid] + st_size[mid]) hi_i = mid; else lo_i = mid + 1;
+            }
+            int32_t i = lo_i;
+            int64_t rel;
+            if (i == 0) rel = x - st_pos[0];
+            else if (x < st_pos[i - 1]) rel = (int64_t)st_size[i - 1] + (x - st_pos[i]);
+            else rel = (int64_t)st_size[i - 1] + (st_pos[i - 1] - st_pos[i]) +
+                       (x - ((int64_t)st_pos[i - 1] + st_size[i - 1]));
+            fx = s_base + rel;
+            d.depth[v] = d.depth[v] - st_depth[i] + depth_q_new + i;
+        } else {
+            fx = P < a0 ? x + sz : x - sz;
+        }
+        d.tmp[fx] = v;
+        d.node[v].pos = (int32_t)fx;
+    }
+    NSX_SYNC();
+    NSX_PAR_FOR(x, lo, hi) { d.order[x] = d.tmp[x]; }
+    // stem: reverse parent pointers, new subtree sizes
+    NSX_PAR_FOR(i, 0, k_stem + 1) {
+        int32_t v = spath[i];
+        if (i == 0) {
+            d.node[v].parent = p;
+            d.node[v].pred2 = e * 2 + (d.tail[e] == p ? 0 : 1);
+            d.node[v].size = sz;
+        } else {
+            d.node[v].parent = spath[i - 1];
+            d.node[v].pred2 = st_pred2[i - 1] ^ 1;  // same arc, now pointing the other way
+            d.node[v].size = sz - st_size[i - 1];
+        }
+    }
+    NSX_SINGLE {
+        d.state[e] |= NSX_ARC_IN_TREE;
+        d.state[leave] &= (uint8_t)~NSX_ARC_IN_TREE;
+        c.tree_updates++;
+        c.sum_subtree += sz;
+        if (sz > c.max_subtree) c.max_subtree = sz;
+        c.sum_window += hi - lo;
+    }
+    NSX_SYNC();
+
+    // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
+    nsx_recompute_potentials(d, c.phase, s_base, s_base + sz, ps, &c.sum_rounds);
+
+    // ---- 7. reset cadence (simplex.py:1373-1425) -------------------------------------------
+    NSX_SINGLE {
+        if (c.ftc >= c.ft_limit) {
+            c.ftc = 0;
+            c.pb = 0;
+            c.resets++;
+            c.wepoch = (c.wepoch + 1) & 0xffu;
+            if (c.wepoch == 0) c.need_wfill = 1;  // epoch tags wrapped: refill physically
+        } else {
+            c.ftc++;
+        }
+    }
+    NSX_SYNC();
+    return 0;
+}
+
+// Block-size adaptation after each pivot (simplex_adaptive.py:98-151). Single thread.
+NSX_FN void nsx_adapt_block(NsxCtl& c, int64_t m, int64_t iteration) {
+    if (!c.auto_block) return;
+    if (iteration - c.tuner_last < 50) return;
+    if (c.tuner_total < 10) return;
+    double ratio = (double)c.tuner_deg / (double)c.tuner_total;
+    if (ratio > 0.30) {
+        int64_t nb = (int64_t)NSX_MUL((double)c.bs, 1.5);
+        c.bs = nb < m ? nb : m;
+    } else if (ratio < 0.10) {
+        int64_t nb = (int64_t)NSX_MUL((double)c.bs, 0.75);
+        c.bs = nb > 10 ? nb : 10;
+    }
+    c.tuner_deg = 0;
+    c.tuner_total = 0;
+    c.tuner_last = iteration;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-arc pricing predicates shared by the sweep kernels and the emulation.
+// rc = (cost + pi[tail]) - pi[head]  (simplex.py:508-512)
+// ------------------------------------------------------------------------------------------
+struct NsxCand {      // Dantzig / row-scan: minimum key, lowest index
+    double key;       // signed reduced cost (rc forward, -rc backward)
+    int32_t arc2;     // arc*2 + (dir<0); -1 = none
+    int32_t zero2;    // first zero-reduced-cost candidate arc*2+(dir<0); INT32_MAX = none
+};
+struct NsxDevexCand { // Devex block: first arg-max of rc^2/w per direction, zero candidates
+    double fm, bm;
+    int32_t fi, bi;   // -1 = none
+    int32_t fz, bz;   // INT32_MAX = none
+};
+
+NSX_FN void nsx_cand_init(NsxCand& k) { k.key = 0.0; k.arc2 = -1; k.zero2 = 0x7fffffff; }
+NSX_FN void nsx_devex_init(NsxDevexCand& k) {
+    k.fm = -NSX_INF; k.bm = -NSX_INF; k.fi = -1; k.bi = -1; k.fz = 0x7fffffff; k.bz = 0x7fffffff;
+}
+// merge b (covering higher arc indices or an unordered partition) into a: lowest index wins ties
+NSX_FN void nsx_cand_merge(NsxCand& a, const NsxCand& b) {
+    if (b.arc2 >= 0 && (a.arc2 < 0 || b.key < a.key || (b.key == a.key && b.arc2 < a.arc2))) {
+        a.key = b.key; a.arc2 = b.arc2;
+    }
+    if (b.zero2 < a.zero2) a.zero2 = b.zero2;
+}
+NSX_FN void nsx_devex_merge(NsxDevexCand& a, const NsxDevexCand& b) {
+    if (b.fi >= 0 && (a.fi < 0 || b.fm > a.fm || (b.fm == a.fm && b.fi < a.fi))) { a.fm = b.fm; a.fi = b.fi; }
+    if (b.bi >= 0 && (a.bi < 0 || b.bm > a.bm || (b.bm == a.bm && b.bi < a.bi))) { a.bm = b.bm; a.bi = b.bi; }
+    if (b.fz < a.fz) a.fz = b.fz;
+    if (b.bz < a.bz) a.bz = b.bz;
+}
+
+// DantzigPricing.select_entering_arc body for one arc (simplex_pricing.py:110-135)
+NSX_FN void nsx_price_dantzig(NsxCand& k, int32_t i, uint8_t st, double rc, double tol) {
+    if (st & NSX_ARC_IN_TREE) return;
+    if ((st & NSX_ARC_CAN_FWD) && rc < -tol) {
+        if (k.arc2 < 0 || rc < k.key || (rc == k.key && i * 2 < k.arc2)) { k.key = rc; k.arc2 = i * 2; }
+    } else if ((st & NSX_ARC_CAN_BWD) && rc > tol) {
+        double nk = -rc;
+        if (k.arc2 < 0 || nk < k.key || (nk == k.key && i * 2 + 1 < k.arc2)) { k.key = nk; k.arc2 = i * 2 + 1; }
+    } else if (fabs(rc) <= tol) {
+        if (st & NSX_ARC_CAN_FWD) { if (i * 2 < k.zero2) k.zero2 = i * 2; }
+        else if (st & NSX_ARC_CAN_BWD) { if (i * 2 + 1 < k.zero2) k.zero2 = i * 2 + 1; }
+    }
+}
+
+// NetworkSimplex._select_entering_arc_vectorized body for one arc (simplex.py:571-615)
+NSX_FN void nsx_price_devex(NsxDevexCand& k, int32_t i, uint8_t st, double rc, uint32_t wraw,
+                            uint32_t wepoch, double tol) {
+    if (st & NSX_ARC_IN_TREE) return;
+    bool fv = (st & NSX_ARC_CAN_FWD) && rc < -tol;
+    bool bv = (st & NSX_ARC_CAN_BWD) && rc > tol;
+    if (fv || bv) {
+        double w = (wraw >> 24) == wepoch ? (double)(wraw & 0xffffffu) : 1.0;
+        double merit = NSX_DIV(NSX_MUL(rc, rc), w);
+        if (fv) { if (k.fi < 0 || merit > k.fm || (merit == k.fm && i < k.fi)) { k.fm = merit; k.fi = i; } }
+        else    { if (k.bi < 0 || merit > k.bm || (merit == k.bm && i < k.bi)) { k.bm = merit; k.bi = i; } }
+    } else if (fabs(rc) <= tol) {
+        if ((st & NSX_ARC_CAN_FWD) && i < k.fz) k.fz = i;
+        if ((st & NSX_ARC_CAN_BWD) && i < k.bz) k.bz = i;
+    }
+}
+
+// Final decision of one Devex block from its merged candidate (simplex.py:589-617).
+// Returns arc2 (arc*2 + (dir<0)) or -1; *merit_pos = 1 when the weight must be refreshed.
+NSX_FN int32_t nsx_devex_decide(const NsxDevexCand& k, int allow_zero, int32_t* merit_pos) {
+    *merit_pos = 0;
+    double fm = k.fi >= 0 ? k.fm : -NSX_INF, bm = k.bi >= 0 ? k.bm : -NSX_INF;
+    if (fm > bm) {
+        if (k.fi >= 0) { *merit_pos = fm > 0.0; return k.fi * 2; }
+    } else {
+        if (k.bi >= 0) { *merit_pos = bm > 0.0; return k.bi * 2 + 1; }
+    }
+    if (allow_zero) {
+        if (k.fz != 0x7fffffff) return k.fz * 2;
+        if (k.bz != 0x7fffffff) return k.bz * 2 + 1;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Initial state (simplex.py:619-728): flows 0, every node hangs off the root by one artificial
+// arc whose direction / flow follow the supply sign.  Element-wise, any launch shape.
+// ------------------------------------------------------------------------------------------
+NSX_FN void nsx_init_real_arc(const NsxDev& d, int64_t i) {
+    d.flow[i] = 0.0;
+    d.state[i] = nsx_bounds_bits(0.0, d.upper[i], d.tol);
+    if (d.wgt) d.wgt[i] = 1u;  // epoch 0, weight 1
+}
+// Writes node v >= 1 and its artificial arc m + v - 1.
+NSX_FN void nsx_init_node(const NsxDev& d, int32_t v, double supply) {
+    if (v == 0) {
+        NsxNode r; r.parent = 0; r.pred2 = -1; r.pos = 0; r.size = d.n;
+        d.node[0] = r; d.depth[0] = 0; d.pi[0] = 0.0; d.order[0] = 0;
+        return;
+    }
+    int64_t a = d.m + (v - 1);
+    double f, up; int32_t tl, hd;
+    if (fabs(supply) <= d.tol) { tl = 0; hd = v; up = NSX_INF; f = 0.0; }
+    else if (supply > 0) { tl = v; hd = 0; up = supply; f = supply; }
+    else { tl = 0; hd = v; up = -supply; f = -supply; }
+    d.atail[v - 1] = tl; d.ahead[v - 1] = hd; d.aupper[v - 1] = up;
+    d.flow[a] = f;
+    d.state[a] = (uint8_t)(NSX_ARC_IN_TREE | nsx_bounds_bits(f, up, d.tol));
+    NsxNode r; r.parent = 0; r.pred2 = (int32_t)(a * 2 + (tl == 0 ? 0 : 1)); r.pos = v; r.size = 1;
+    d.node[v] = r; d.depth[v] = 1; d.order[v] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Driver state machine (single thread of the pivot CTA).  Restates the control flow of
+// NetworkSimplex.solve / _run_simplex_iterations / _find_entering_arc
+// (simplex.py:1058-1075, 1109-1160, 1534-1701) and DevexPricing's block loop
+// (simplex_pricing.py:325-357).
+// ------------------------------------------------------------------------------------------
+enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2 };
+enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3 };
+enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4 };
+
+struct NsxCmd {       // what every CTA does next
+    int32_t kind;
+    int32_t phase;    // selects the pricing cost for NSX_CMD_DANTZIG
+    int64_t lo, hi;   // arc range
+    int32_t excluded; // Devex: arc skipped (last bound-flip arc), -1 none
+    uint32_t wepoch;
+};
+struct NsxAction { int32_t kind, arc, dir, want_weight; };
+struct NsxDrv {       // driver scalars (kept beside NsxCtl)
+    int32_t stage, final_check;
+    int64_t bc, blocks_left, budget;
+};
+struct NsxLoopShared {
+    NsxCmd cmd;
+    NsxAction act;
+    NsxCand dz;
+    NsxDevexCand dx;
+    NsxDrv drv;
+    int32_t rc;
+};
+
+NSX_FN void nsx_drv_devex_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
+    int64_t st = c.pb * c.bs;
+    if (st >= m) { c.pb = 0; st = 0; }
+    int64_t en = st + c.bs < m ? st + c.bs : m;
+    cmd.kind = NSX_CMD_DEVEX; cmd.phase = c.phase; cmd.lo = st; cmd.hi = en;
+    cmd.excluded = c.last_deg; cmd.wepoch = c.wepoch;
+}
+NSX_FN void nsx_drv_devex_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd) {
+    v.stage = NSX_ST_DEVEX;
+    v.bc = (m + c.bs - 1) / c.bs;
+    if (v.bc < 1) v.bc = 1;
+    v.blocks_left = v.bc;
+    nsx_drv_devex_cmd(c, m, cmd);
+}
+// top of an iteration: first sweep command, or phase end when the budget is used up
+NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    if (!v.final_check && c.it >= v.budget) { act.kind = NSX_ACT_PHASE_END; return; }
+    act.kind = NSX_ACT_SWEEP;
+    if (c.row_scan_first || c.pricing == NSX_PRICING_DANTZIG) {
+        v.stage = c.row_scan_first ? NSX_ST_ROWSCAN : NSX_ST_DANTZIG;
+        cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
+        cmd.excluded = -1; cmd.wepoch = c.wepoch;
+    } else {
+        nsx_drv_devex_begin(c, v, m, cmd);
+    }
+}
+NSX_FN void nsx_drv_choose(NsxCtl& c, NsxDrv& v, NsxAction& act, int32_t arc2, int32_t want_weight,
+                           int32_t* trace) {
+    if (v.final_check) {  // simplex.py:1678-1699: an entering arc still exists at the limit
+        c.status = NSX_STATUS_ITERATION_LIMIT;
+        act.kind = NSX_ACT_EXIT;
+        return;
+    }
+    act.kind = NSX_ACT_PIVOT; act.arc = arc2 >> 1; act.dir = (arc2 & 1) ? -1 : 1;
+    act.want_weight = want_weight;
+    if (trace && c.trace_len < c.trace_cap) trace[c.trace_len] = arc2;
+    c.trace_len++;
+}
+NSX_FN void nsx_drv_none(NsxCtl& c, NsxDrv& v, NsxAction& act) {
+    if (v.final_check) { c.status = NSX_STATUS_OPTIMAL; act.kind = NSX_ACT_EXIT; }
+    else act.kind = NSX_ACT_PHASE_END;
+}
+NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
+                              const NsxDevexCand& dx, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
+    const int allow_zero = (c.phase == 1) && !v.final_check;
+    if (v.stage == NSX_ST_ROWSCAN || v.stage == NSX_ST_DANTZIG) {
+        c.arcs_priced += m;
+        if (dz.arc2 >= 0) { nsx_drv_choose(c, v, act, dz.arc2, 0, trace); return; }
+        if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_DEVEX) {
+            act.kind = NSX_ACT_SWEEP;  // fall through to the configured strategy (simplex.py:1066-1075)
+            nsx_drv_devex_begin(c, v, m, cmd);
+            return;
+        }
+        if (allow_zero && dz.zero2 != 0x7fffffff) { nsx_drv_choose(c, v, act, dz.zero2, 0, trace); return; }
+        nsx_drv_none(c, v, act);
+    } else {
+        c.arcs_priced += cmd.hi - cmd.lo;
+        int32_t mp = 0;
+        int32_t a2 = nsx_devex_decide(dx, allow_zero, &mp);
+        if (a2 >= 0) { c.last_deg = -1; nsx_drv_choose(c, v, act, a2, mp, trace); return; }
+        c.pb = (c.pb + 1) % v.bc;
+        v.blocks_left--;
+        if (v.blocks_left == 0) { nsx_drv_none(c, v, act); return; }
+        act.kind = NSX_ACT_SWEEP;
+        nsx_drv_devex_cmd(c, m, cmd);
+    }
+}
+NSX_FN void nsx_drv_after_pivot(NsxCtl& c, NsxDrv& v, int64_t m, int32_t rc, NsxCmd& cmd, NsxAction& act) {
+    if (rc == 3) {
+        c.status = NSX_STATUS_UNBOUNDED;
+        if (c.phase == 2) c.total += c.it;
+        act.kind = NSX_ACT_EXIT;
+        return;
+    }
+    c.it++;
+    nsx_adapt_block(c, m, (c.phase == 1 ? 0 : c.total) + c.it);
+    if (c.phase == 1 && c.art_with_flow == 0) { act.kind = NSX_ACT_PHASE_END; return; }  // simplex.py:1157
+    nsx_drv_begin(c, v, m, cmd, act);
+}
+NSX_FN void nsx_drv_phase_end(NsxCtl& c, NsxDrv& v, NsxAction& act) {
+    if (c.phase == 1) {
+        c.total = c.it;
+        c.phase1_iterations = c.it;
+        c.art_after_p1 = c.art_with_flow;
+        if (c.art_with_flow > 0) {  // simplex.py:1600-1624
+            c.status = c.total >= c.maxit ? NSX_STATUS_ITERATION_LIMIT_P1 : NSX_STATUS_INFEASIBLE;
+            act.kind = NSX_ACT_EXIT;
+            return;
+        }
+        c.phase = 2;
+        v.budget = c.maxit - c.total > 0 ? c.maxit - c.total : 0;
+        c.it = 0;
+        act.kind = NSX_ACT_RECOMPUTE;  // simplex.py:1632-1633: Phase-2 costs, potentials rebuilt
+    } else {
+        c.total += c.it;
+        c.it = 0;
+        if (c.total >= c.maxit) { v.final_check = 1; act.kind = NSX_ACT_RECOMPUTE; }
+        else { c.status = NSX_STATUS_OPTIMAL; act.kind = NSX_ACT_EXIT; }
+    }
+}
+
+// The resident loop of the pivot CTA.  `Sweep::run(cmd, dz, dx)` prices the arc range of `cmd`
+// (grid-wide on the device, serially in the emulation) and leaves the merged candidates in
+// dz / dx, visible to all threads of this CTA on return.  `Sweep::finish()` releases workers.
+template <class Sweep>
+NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
+                           NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
+    nsx_recompute_potentials(d, 1, 1, d.n, ps, (int64_t*)0);  // Phase-1 costs on the initial star
+    NSX_SINGLE {
+        L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
+        L.drv.budget = c.maxit;
+        nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act);
+    }
+    for (;;) {
+        NSX_SYNC();
+        const int32_t kind = L.act.kind;
+        NSX_SYNC();
+        if (kind == NSX_ACT_SWEEP) {
+            sweep.run(L.cmd, L.dz, L.dx);
+            NSX_SINGLE { nsx_drv_on_result(c, L.drv, d.m, L.dz, L.dx, L.cmd, L.act, trace); }
+        } else if (kind == NSX_ACT_PIVOT) {
+            int32_t rc = nsx_pivot(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
+            if (c.need_wfill) {  // Devex epoch tags wrapped: physically reset the weights
+                NSX_SYNC();
+                NSX_PAR_FOR(i, 0, d.m) { if (d.wgt) d.wgt[i] = 1u; }
+                NSX_SYNC();
+                NSX_SINGLE { c.need_wfill = 0; }
+            }
+            NSX_SYNC();
+            NSX_SINGLE { nsx_drv_after_pivot(c, L.drv, d.m, rc, L.cmd, L.act); }
+        } else if (kind == NSX_ACT_PHASE_END) {
+            NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
+        } else if (kind == NSX_ACT_RECOMPUTE) {
+            if (!L.drv.final_check) nsx_recompute_potentials(d, 2, 1, d.n, ps, (int64_t*)0);
+            NSX_SYNC();
+            NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }
+        } else {  // NSX_ACT_EXIT
+            sweep.finish();
+            break;
+        }
+    }
+}

@@ -1,0 +1,41 @@
+"""ctypes wrapper for tests/emu/libnsx_emu.so - the serial host emulation of the device pivot code.
+Test infrastructure only (see nsx_emu.cpp)."""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+from network_flow_solver_b200._capi import CallFrame, EngineOptions, NsxOptions, NsxProblem, NsxResult, RawSolution
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "libnsx_emu.so"
+_CORE = _HERE.parents[1] / "network_flow_solver_b200" / "csrc" / "nsx_core.cuh"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src = _HERE / "nsx_emu.cpp"
+    newest = max(src.stat().st_mtime, _CORE.stat().st_mtime)
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < newest:
+        subprocess.run(
+            ["/usr/bin/g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math",
+             "-x", "c++", "-shared", "-o", str(_LIB), str(src)],
+            check=True, capture_output=True,
+        )
+    return _LIB
+
+
+def solve_canonical(cp, opts: EngineOptions) -> RawSolution:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.nsx_emu_solve.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult)]
+        _lib.nsx_emu_solve.restype = C.c_int
+    frame = CallFrame(cp, opts)
+    rc = _lib.nsx_emu_solve(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result))
+    if rc != 0:
+        raise RuntimeError(f"nsx_emu_solve returned {rc}")
+    return frame.harvest()

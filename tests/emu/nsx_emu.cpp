@@ -1,0 +1,105 @@
+// nsx_emu.cpp - serial HOST EMULATION of the device pivot code (nsx_core.cuh with NSX_HOST_EMU).
+//
+// Test infrastructure only: lets the CPU test-suite exercise the exact source the CUDA kernels
+// are built from (tree re-hang on the preorder array, wavefront potential recompute, driver state
+// machine) on machines without a GPU.  Not linked into libnsx_b200.so, not importable from the
+// package; the product has no host execution path.
+#define NSX_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../network_flow_solver_b200/csrc/nsx_core.cuh"
+
+namespace {
+
+struct SerialSweep {
+    const NsxDev& d;
+    SerialSweep(const NsxDev& dev) : d(dev) {}
+    void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx) {
+        nsx_cand_init(dz);
+        nsx_devex_init(dx);
+        if (cmd.kind == NSX_CMD_DANTZIG) {
+            for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
+                double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
+                nsx_price_dantzig(dz, (int32_t)i, d.state[i], rc, d.tol);
+            }
+        } else {
+            for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
+                if ((int32_t)i == cmd.excluded) continue;
+                double rc = NSX_SUB(NSX_ADD(d.pert[i], d.pi[d.tail[i]]), d.pi[d.head[i]]);
+                nsx_price_devex(dx, (int32_t)i, d.state[i], rc, d.wgt[i], cmd.wepoch, d.tol);
+            }
+        }
+    }
+    void finish() {}
+};
+
+}  // namespace
+
+extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* res) {
+    const int32_t n = pb->n_nodes;
+    const int64_t m = pb->n_arcs, ma = m + n - 1;
+    std::vector<int32_t> atail(n), ahead(n), depth(n), order(n), tmp(n), gph(n), gpt(n), garc2(2 * (size_t)n + 1);
+    std::vector<double> aupper(n), flow(ma), pi(n), gres(2 * (size_t)n + 1);
+    std::vector<uint8_t> state(ma);
+    std::vector<uint32_t> wgt(m > 0 ? m : 1);
+    std::vector<NsxNode> node(n);
+    NsxDev d;
+    d.n = n; d.m = m; d.ma = ma;
+    d.tail = pb->tail; d.head = pb->head; d.pert = pb->pert_cost; d.upper = pb->upper;
+    d.atail = atail.data(); d.ahead = ahead.data(); d.aupper = aupper.data();
+    d.flow = flow.data(); d.state = state.data(); d.wgt = wgt.data();
+    d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.order = order.data();
+    d.tmp = tmp.data(); d.gpath_h = gph.data(); d.gpath_t = gpt.data(); d.garc2 = garc2.data();
+    d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance;
+
+    NsxCtl c;
+    memset(&c, 0, sizeof c);
+    c.phase = 1; c.status = -1; c.maxit = opt->max_iterations;
+    c.bs = opt->block_size > 0 ? opt->block_size : 1; c.pb = 0; c.last_deg = -1;
+    c.ft_limit = opt->ft_update_limit; c.auto_block = opt->auto_block;
+    c.pricing = opt->pricing; c.row_scan_first = opt->row_scan_first;
+    c.trace_cap = res->entering_trace ? opt->trace_capacity : 0;
+    c.unbounded_arc = -1;
+
+    for (int64_t i = 0; i < m; ++i) nsx_init_real_arc(d, i);
+    int64_t art = 0;
+    for (int32_t v = 0; v < n; ++v) {
+        nsx_init_node(d, v, pb->supply[v]);
+        if (v > 0 && flow[m + v - 1] > d.tol) art++;
+    }
+    c.art_with_flow = art;
+
+    NsxLoopShared* L = new NsxLoopShared;
+    NsxPivotScratch* s = new NsxPivotScratch;
+    NsxPotScratch* ps = new NsxPotScratch;
+    SerialSweep sweep(d);
+    nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep);
+    delete L; delete s; delete ps;
+
+    res->status = c.status;
+    res->iterations = c.total;
+    res->phase1_iterations = c.phase1_iterations;
+    res->trace_len = c.trace_len;
+    res->degenerate_pivots = c.degenerate;
+    res->artificial_with_flow = c.art_after_p1;
+    res->tree_updates = c.tree_updates;
+    res->weight_resets = c.resets;
+    res->final_block_size = c.bs;
+    res->arcs_priced = c.arcs_priced;
+    res->unbounded_arc = c.unbounded_arc;
+    res->unbounded_rc = c.unbounded_rc;
+    res->sum_cycle_len = c.sum_cycle; res->sum_subtree = c.sum_subtree; res->max_subtree = c.max_subtree;
+    res->sum_rounds = c.sum_rounds;
+    res->pricing_ms = (double)c.sum_window;  // emulation only: moved preorder entries, for design stats
+    if (res->flow) memcpy(res->flow, flow.data(), ma * 8);
+    if (res->potential) memcpy(res->potential, pi.data(), (size_t)n * 8);
+    if (res->state) memcpy(res->state, state.data(), ma);
+    return 0;
+}
+
+// Consistency check of the preorder representation (used by tests after a solve is not possible
+// from outside; exposed separately): returns 0 when parent/pos/size/order/depth agree.
+extern "C" int nsx_emu_selfcheck_enabled(void) { return 1; }

@@ -1,0 +1,86 @@
+"""CPU check of the device pivot code: nsx_core.cuh compiled as a serial host emulation
+(tests/emu) must reproduce every recorded reference run bit for bit, and agree with the oracle
+on larger generated instances of each family."""
+
+import numpy as np
+import pytest
+
+from helpers import assert_matches_reference, golden_cases, load_golden, prepare_run
+from network_flow_solver_b200 import _capi
+from network_flow_solver_b200 import generators as gen
+from network_flow_solver_b200.canonical import initial_block_size
+from oracle import oracle
+from emu import emu
+
+
+@pytest.mark.parametrize("name,idx", golden_cases())
+def test_emulated_core_reproduces_reference(name, idx):
+    doc = load_golden(name)
+    run = doc["runs"][idx]
+    _, cp, plan, options = prepare_run(doc, run)
+    raw = emu.solve_canonical(cp, plan.engine)
+    assert_matches_reference(run, cp, raw, options)
+
+
+def engine_options(cp, pricing, **kw):
+    m = cp.n_arcs
+    base = dict(
+        pricing=pricing,
+        row_scan_first=cp.network_type == "transportation",
+        block_size=initial_block_size(m),
+        auto_block=True,
+        ft_update_limit=64,
+        max_iterations=max(100, 20 * (m + cp.n_nodes - 1)),
+        tolerance=1e-6,
+        trace_capacity=1 << 22,
+    )
+    base.update(kw)
+    return _capi.EngineOptions(**base)
+
+
+def assert_same_solution(a: _capi.RawSolution, b: _capi.RawSolution):
+    assert a.status == b.status
+    assert a.iterations == b.iterations
+    np.testing.assert_array_equal(a.trace, b.trace)
+    np.testing.assert_array_equal(a.flow, b.flow)
+    np.testing.assert_array_equal(a.potential, b.potential)
+    np.testing.assert_array_equal(a.state, b.state)
+    assert a.degenerate_pivots == b.degenerate_pivots
+    assert a.final_block_size == b.final_block_size
+    assert a.tree_updates == b.tree_updates
+    assert a.weight_resets == b.weight_resets
+
+
+CASES = [
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), 0),
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), 1),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), 0),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), 1),
+    ("transport", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 0),
+    ("transport", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 1),
+    ("goto", lambda: gen.goto_like(32, seed=8), 0),
+    ("goto", lambda: gen.goto_like(32, seed=8), 1),
+    ("gridgen", lambda: gen.gridgen_like(32, 8200, seed=9), 1),
+]
+
+
+@pytest.mark.parametrize("family,make,pricing", CASES)
+def test_emulated_core_matches_oracle(family, make, pricing):
+    cp = make().canonical()
+    opts = engine_options(cp, pricing)
+    assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_emulated_core_fixed_small_blocks_and_short_reset_cadence():
+    cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
+    for bs, ft in ((10, 64), (37, 3), (8192, 1), (100000, 64)):
+        opts = engine_options(cp, 1, block_size=bs, auto_block=False, ft_update_limit=ft)
+        assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_emulated_core_iteration_limits():
+    cp = gen.netgen_like(512, 4096, n_sources=8, n_sinks=8, seed=16).canonical()
+    full = oracle.solve_canonical(cp, engine_options(cp, 0))
+    for limit in (1, 7, full.phase1_iterations, full.phase1_iterations + 1, full.iterations, full.iterations + 5):
+        opts = engine_options(cp, 0, max_iterations=limit)
+        assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))

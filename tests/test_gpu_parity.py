@@ -1,0 +1,131 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against (i) every recorded
+reference run and (ii) the oracle on larger generated instances.  Bit-exact: entering-arc
+sequence, per-arc flows, tree flags, node potentials, statuses, iteration counts."""
+
+import numpy as np
+import pytest
+
+from helpers import assert_matches_reference, golden_cases, load_golden, prepare_run
+from network_flow_solver_b200 import _capi
+from network_flow_solver_b200 import generators as gen
+from network_flow_solver_b200.canonical import initial_block_size
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_options(cp, pricing, **kw):
+    m = cp.n_arcs
+    base = dict(
+        pricing=pricing,
+        row_scan_first=cp.network_type == "transportation",
+        block_size=initial_block_size(m),
+        auto_block=True,
+        ft_update_limit=64,
+        max_iterations=max(100, 20 * (m + cp.n_nodes - 1)),
+        tolerance=1e-6,
+        trace_capacity=1 << 22,
+    )
+    base.update(kw)
+    return _capi.EngineOptions(**base)
+
+
+def assert_same_solution(a, b):
+    assert a.status == b.status
+    assert a.iterations == b.iterations
+    if not np.array_equal(a.trace, b.trace):
+        k = int(np.argmax(a.trace[: len(b.trace)] != b.trace[: len(a.trace)])) if len(a.trace) and len(b.trace) else 0
+        raise AssertionError(f"entering sequence diverges at pivot {k}: {a.trace[k:k+3]} vs {b.trace[k:k+3]}")
+    np.testing.assert_array_equal(a.flow, b.flow)
+    np.testing.assert_array_equal(a.potential, b.potential)
+    np.testing.assert_array_equal(a.state, b.state)
+    assert a.degenerate_pivots == b.degenerate_pivots
+    assert a.final_block_size == b.final_block_size
+    assert a.tree_updates == b.tree_updates
+    assert a.weight_resets == b.weight_resets
+    assert a.phase1_iterations == b.phase1_iterations
+
+
+@pytest.mark.parametrize("name,idx", golden_cases())
+def test_engine_reproduces_reference(name, idx):
+    doc = load_golden(name)
+    run = doc["runs"][idx]
+    _, cp, plan, options = prepare_run(doc, run)
+    raw = _capi.solve_canonical(cp, plan.engine)
+    assert_matches_reference(run, cp, raw, options)
+
+
+CASES = [
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), 0),
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), 1),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), 0),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), 1),
+    ("netgen_2^14", lambda: gen.netgen_like(1 << 14, 1 << 18, n_sources=64, n_sinks=64, seed=1601), 0),
+    ("netgen_2^14", lambda: gen.netgen_like(1 << 14, 1 << 18, n_sources=64, n_sinks=64, seed=1601), 1),
+    ("transport", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 0),
+    ("transport", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 1),
+    ("transport_512", lambda: gen.transportation(512, 512, cost_max=1000, seed=4096), 0),
+    ("goto", lambda: gen.goto_like(32, seed=8), 0),
+    ("goto_64", lambda: gen.goto_like(64, seed=0), 0),
+    ("gridgen", lambda: gen.gridgen_like(32, 8200, seed=9), 1),
+]
+
+
+@pytest.mark.parametrize("family,make,pricing", CASES)
+def test_engine_matches_oracle(family, make, pricing):
+    cp = make().canonical()
+    opts = engine_options(cp, pricing)
+    assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts, threads=4))
+
+
+@pytest.mark.parametrize("grid", [1, 2, 7, 148])
+def test_engine_result_independent_of_grid_size(grid, monkeypatch):
+    monkeypatch.setenv("NSX_GRID", str(grid))
+    cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
+    for pricing in (0, 1):
+        opts = engine_options(cp, pricing)
+        assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_engine_without_shared_memory_potentials(monkeypatch):
+    monkeypatch.setenv("NSX_STAGE_PI", "0")
+    cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
+    opts = engine_options(cp, 0)
+    assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_engine_fixed_small_blocks_and_short_reset_cadence():
+    cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
+    for bs, ft in ((10, 64), (37, 3), (8192, 1), (100000, 64)):
+        opts = engine_options(cp, 1, block_size=bs, auto_block=False, ft_update_limit=ft)
+        assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_engine_iteration_limits():
+    cp = gen.netgen_like(512, 4096, n_sources=8, n_sinks=8, seed=16).canonical()
+    full = oracle.solve_canonical(cp, engine_options(cp, 0))
+    for limit in (1, 7, full.phase1_iterations, full.phase1_iterations + 1, full.iterations, full.iterations + 5):
+        opts = engine_options(cp, 0, max_iterations=limit)
+        assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+def test_batch_matches_single_solves():
+    cps = [gen.goto_like(16, seed=100 + k).canonical() for k in range(40)]
+    cps += [gen.netgen_like(256, 2048, n_sources=4, n_sinks=4, seed=200 + k).canonical() for k in range(8)]
+    opts = engine_options(cps[0], 0, max_iterations=10**7)
+    outs = _capi.solve_batch_canonical(cps, opts)
+    for cp, out in zip(cps, outs):
+        assert_same_solution(out, oracle.solve_canonical(cp, opts))
+
+
+def test_public_api_matches_reference_fixture():
+    from network_flow_solver_b200 import SolverOptions, solve_min_cost_flow
+    from helpers import rebuild_problem
+
+    doc = load_golden("gridgen_257")
+    run = doc["runs"][0]
+    result = solve_min_cost_flow(rebuild_problem(doc["problem"]), SolverOptions(**run["options"]))
+    assert result.status == run["status"] and result.iterations == run["iterations"]
+    assert result.objective == run["objective"]
+    assert result.flows == {(a, b): v for a, b, v in run["flows"]}
+    assert result.duals == dict((k, v) for k, v in run["duals"])
