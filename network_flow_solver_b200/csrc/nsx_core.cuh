@@ -25,7 +25,14 @@
 #define NSX_FN __device__ __forceinline__
 #define NSX_PAR_FOR(i, lo, hi) \
     for (int64_t i = (int64_t)(lo) + (int64_t)threadIdx.x; i < (int64_t)(hi); i += (int64_t)blockDim.x)
-#define NSX_SYNC() __syncthreads()
+// __syncwarp() first: bar.sync is an *aligned* barrier and nvcc may thread a preceding
+// thread-0-only block into code that reaches the barrier un-converged (observed on sm_100a:
+// warp 0 arrived twice and the CTA slipped one barrier phase).
+#define NSX_SYNC()        \
+    do {                  \
+        __syncwarp();     \
+        __syncthreads();  \
+    } while (0)
 #define NSX_SINGLE if (threadIdx.x == 0)
 #define NSX_TID ((int)threadIdx.x)
 #define NSX_NTHREADS ((int)blockDim.x)
@@ -395,7 +402,8 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (is_deg) c.tuner_deg++;
         if (leave == e) c.last_deg = e;  // bound flip (simplex.py:1320-1334)
     }
-    if (leave == e) { NSX_SYNC(); return 0; }
+    NSX_SYNC();
+    if (leave == e) return 0;  // tree unchanged
 
     // ---- 5. tree update: re-hang the subtree below the leaving arc under the entering arc --
     // stem s_0 = q (entering endpoint inside the cut subtree) ... s_k = r (its pred arc leaves)

@@ -95,9 +95,9 @@ template <class T>
 __device__ __forceinline__ void nsx_block_reduce(T& k, T* buf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
     nsx_warp_reduce(k);
-    __syncthreads();  // buf may still be read from a previous reduction
+    NSX_SYNC();  // buf may still be read from a previous reduction
     if (lane == 0) buf[warp] = k;
-    __syncthreads();
+    NSX_SYNC();
     if (warp == 0) {
         if (lane < nwarp) k = buf[lane]; else nsx_init(k);
         nsx_warp_reduce(k);
@@ -206,9 +206,9 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxCmd& cmd
     nsx_cand_init(dz);
     nsx_devex_init(dx);
     if (stage) {
-        __syncthreads();
+        NSX_SYNC();
         for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) pis[v] = __ldcg(d.pi + v);
-        __syncthreads();
+        NSX_SYNC();
     }
     const double* p = stage ? pis : nullptr;
     if (cmd.kind == NSX_CMD_DEVEX) {
@@ -244,7 +244,7 @@ struct GridSweep {
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
-        __syncthreads();  // pivot writes of all threads precede thread 0's fence + release
+        NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
         publish(cmd_in);
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
@@ -256,7 +256,7 @@ struct GridSweep {
             __threadfence();
             t_sync += nsx_globaltimer() - t1;
         }
-        __syncthreads();
+        NSX_SYNC();
         // merge the candidates of the other CTAs (one per thread), then reduce across the block
         if (cmd.kind == NSX_CMD_DEVEX) {
             NsxDevexCand k; nsx_devex_init(k);
@@ -281,12 +281,12 @@ struct GridSweep {
             if (threadIdx.x == 0) out_dz = k;
         }
         if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
-        __syncthreads();
+        NSX_SYNC();
     }
     __device__ void finish() {
         NsxCmd cmd;
         cmd.kind = NSX_CMD_EXIT; cmd.phase = 0; cmd.lo = cmd.hi = 0; cmd.excluded = -1; cmd.wepoch = 0;
-        __syncthreads();
+        NSX_SYNC();
         publish(cmd);
     }
 };
@@ -340,7 +340,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
             tmp.v[1] = __ldcg(((const int4*)&a.grid->cmd) + 1);
             sh.cmd = tmp.c;
         }
-        __syncthreads();
+        NSX_SYNC();
         const NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
@@ -351,7 +351,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
             __threadfence();
             atomicAdd(&a.grid->arrived, 1ull);
         }
-        __syncthreads();
+        NSX_SYNC();
     }
 }
 
@@ -388,7 +388,7 @@ struct LocalSweep {
         NsxCand dz; NsxDevexCand dx;
         nsx_cta_sweep(d, cmd, pis, stage, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
         if (threadIdx.x == 0) { if (cmd.kind == NSX_CMD_DEVEX) out_dx = dx; else out_dz = dz; }
-        __syncthreads();
+        NSX_SYNC();
     }
     __device__ void finish() {}
 };
@@ -400,22 +400,22 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
     double* pis = reinterpret_cast<double*>(smem_raw + ((sizeof(NsxCtaShared) + 15) & ~(size_t)15));
     __shared__ unsigned long long my_item;
     for (;;) {
-        __syncthreads();
+        NSX_SYNC();
         if (threadIdx.x == 0) my_item = atomicAdd(next, 1ull);
-        __syncthreads();
+        NSX_SYNC();
         const unsigned long long it = my_item;
         if (it >= (unsigned long long)count) return;
         const NsxBatchItem& item = items[it];
         const NsxDev& d = item.d;
         for (int64_t i = threadIdx.x; i < d.m; i += blockDim.x) nsx_init_real_arc(d, i);
         for (int64_t v = threadIdx.x; v < d.n; v += blockDim.x) nsx_init_node(d, (int32_t)v, item.supply[v]);
-        __syncthreads();
+        NSX_SYNC();
         if (threadIdx.x == 0) {
             int64_t art = 0;
             for (int32_t v = 1; v < d.n; ++v) art += d.flow[d.m + v - 1] > d.tol;
             item.ctl->art_with_flow = art;
         }
-        __syncthreads();
+        NSX_SYNC();
         LocalSweep sweep{d, sh, pis, stage_pi != 0 && d.n <= NSX_PI_SMEM_MAX_NODES};
         nsx_solve_loop(d, *item.ctl, sh.L, sh.u.p.piv, sh.u.p.pot, item.trace, sweep);
     }
