@@ -95,6 +95,7 @@ class NsxResult(C.Structure):
         ("sum_subtree", C.c_int64),
         ("max_subtree", C.c_int64),
         ("sum_rounds", C.c_int64),
+        ("phase_cycles", C.c_int64 * 12),
     ]
 
 
@@ -158,29 +159,38 @@ def _ptr(a: np.ndarray, typ):
 class CallFrame:
     """Owns the numpy buffers behind one nsx_problem / nsx_result pair."""
 
-    def __init__(self, cp: CanonicalProblem, opts: EngineOptions):
+    def __init__(self, cp: CanonicalProblem, opts: EngineOptions, device_arrays=None, out=None):
+        """device_arrays: optional (tail, head, pert_cost, upper) DEVICE addresses (ints) for the
+        resident entry point; out: optional dict of preallocated (e.g. pinned) flow / potential /
+        state arrays."""
         self.cp = cp
         m = cp.n_arcs
         ma = m + cp.n_nodes - 1
-        self.tail = np.ascontiguousarray(cp.tail, dtype=np.int32)
-        self.head = np.ascontiguousarray(cp.head, dtype=np.int32)
-        self.pert = np.ascontiguousarray(cp.pert_cost, dtype=np.float64)
-        self.upper = np.ascontiguousarray(cp.upper, dtype=np.float64)
         self.supply = np.ascontiguousarray(cp.supply, dtype=np.float64)
+        if device_arrays is None:
+            self.tail = np.ascontiguousarray(cp.tail, dtype=np.int32)
+            self.head = np.ascontiguousarray(cp.head, dtype=np.int32)
+            self.pert = np.ascontiguousarray(cp.pert_cost, dtype=np.float64)
+            self.upper = np.ascontiguousarray(cp.upper, dtype=np.float64)
+            ptrs = (
+                _ptr(self.tail, _p_i32),
+                _ptr(self.head, _p_i32),
+                _ptr(self.pert, _p_f64),
+                _ptr(self.upper, _p_f64),
+            )
+        else:
+            t, h, c, u = (int(x) for x in device_arrays)
+            ptrs = (C.cast(t, _p_i32), C.cast(h, _p_i32), C.cast(c, _p_f64), C.cast(u, _p_f64))
         self.problem = NsxProblem(
-            int(cp.n_nodes),
-            int(m),
-            _ptr(self.tail, _p_i32),
-            _ptr(self.head, _p_i32),
-            _ptr(self.pert, _p_f64),
-            _ptr(self.upper, _p_f64),
-            _ptr(self.supply, _p_f64),
-            float(cp.penalty),
+            int(cp.n_nodes), int(m), *ptrs, _ptr(self.supply, _p_f64), float(cp.penalty)
         )
         self.options = opts.to_c()
-        self.flow = np.zeros(ma, dtype=np.float64)
-        self.potential = np.zeros(cp.n_nodes, dtype=np.float64)
-        self.state = np.zeros(ma, dtype=np.uint8)
+        out = out or {}
+        self.flow = out.get("flow") if out.get("flow") is not None else np.zeros(ma, dtype=np.float64)
+        self.potential = (
+            out.get("potential") if out.get("potential") is not None else np.zeros(cp.n_nodes, dtype=np.float64)
+        )
+        self.state = out.get("state") if out.get("state") is not None else np.zeros(ma, dtype=np.uint8)
         cap = max(int(opts.trace_capacity), 0)
         self.trace = np.zeros(max(cap, 1), dtype=np.int32)
         self.result = NsxResult()
@@ -218,10 +228,12 @@ class CallFrame:
                 "sync_ms": float(r.sync_ms),
             },
             stats={
+                "grid": int(r.reserved),
                 "sum_cycle_len": int(r.sum_cycle_len),
                 "sum_subtree": int(r.sum_subtree),
                 "max_subtree": int(r.max_subtree),
                 "sum_rounds": int(r.sum_rounds),
+                "phase_cycles": [int(x) for x in r.phase_cycles],
             },
         )
 
@@ -282,12 +294,24 @@ def _check(rc: int, what: str) -> None:
         raise DeviceEngineError(f"{what} failed with code {rc}: {last_error()}")
 
 
-def solve_canonical(cp: CanonicalProblem, opts: EngineOptions) -> RawSolution:
+def solve_canonical(cp: CanonicalProblem, opts: EngineOptions, out=None) -> RawSolution:
     """One instance, host buffers in, host buffers out (nsx_solve). Releases the GIL."""
     lib = load_library()
-    frame = CallFrame(cp, opts)
+    frame = CallFrame(cp, opts, out=out)
     rc = lib.nsx_solve(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result))
     _check(rc, "nsx_solve")
+    return frame.harvest()
+
+
+def solve_resident(cp: CanonicalProblem, opts: EngineOptions, device_arrays, out=None) -> RawSolution:
+    """Arc arrays already resident in HBM: device_arrays = (tail, head, pert_cost, upper) device
+    addresses, 16-byte aligned (nsx_solve_resident)."""
+    lib = load_library()
+    frame = CallFrame(cp, opts, device_arrays=device_arrays, out=out)
+    rc = lib.nsx_solve_resident(
+        C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result)
+    )
+    _check(rc, "nsx_solve_resident")
     return frame.harvest()
 
 

@@ -275,6 +275,9 @@ def canonicalize_arrays(
     """
     tail = np.asarray(tail)
     head = np.asarray(head)
+    if not presorted and tail.shape[0] > 1:
+        key = tail.astype(np.int64) * (n_problem_nodes + 1) + head.astype(np.int64)
+        presorted = bool(np.all(key[1:] >= key[:-1]))
     if not presorted:
         order = np.lexsort((head, tail))  # stable, primary key = tail
         tail, head = tail[order], head[order]

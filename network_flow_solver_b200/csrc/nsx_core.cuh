@@ -43,6 +43,9 @@
 #define NSX_DIV(a, b) __ddiv_rn((a), (b))
 #define NSX_INF __longlong_as_double(0x7ff0000000000000LL)
 #define NSX_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#define NSX_CLOCK() clock64()
+#define NSX_ATOMIC_MIN_I32(p, v) atomicMin((p), (v))
+#define NSX_ATOMIC_MAX_I32(p, v) atomicMax((p), (v))
 #else
 #define NSX_ON_DEVICE 0
 #define NSX_FN static inline
@@ -57,6 +60,9 @@
 #define NSX_DIV(a, b) ((a) / (b))
 #define NSX_INF INFINITY
 #define NSX_ATOMIC_ADD_I32(p, v) (*(p) += (v))
+#define NSX_CLOCK() 0ll
+#define NSX_ATOMIC_MIN_I32(p, v) (*(p) = (v) < *(p) ? (v) : *(p))
+#define NSX_ATOMIC_MAX_I32(p, v) (*(p) = (v) > *(p) ? (v) : *(p))
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -89,6 +95,8 @@ struct NsxDev {
     NsxNode* node;     // [n]
     int32_t* depth;    // [n]
     double* pi;        // [n]
+    double* pi_mirror; // optional second copy of pi kept in step (global copy read by the sweep
+                       // CTAs when the pivot CTA keeps its own node state in shared memory)
     int32_t* order;    // [n] preorder array
     int32_t* tmp;      // [n] scratch for the re-hang permutation
     int32_t* gpath_h;  // [n] cycle path spill (node ids), head side
@@ -125,9 +133,12 @@ struct NsxCtl {
     int64_t unbounded_arc;
     double unbounded_rc;
     int64_t clk_pricing, clk_pivot, clk_sync;
+    int64_t ph[12];       // SM-clock cycles per pivot phase (thread 0): walk, residuals, ratio, flow,
+                          // bookkeeping, snapshot+sizes, window, copy+stem, potentials, cadence, driver
 };
+#define NSX_PH(c, k, t0) NSX_SINGLE { long long t1__ = NSX_CLOCK(); (c).ph[k] += t1__ - (t0); (t0) = t1__; }
 
-#define NSX_PATH_CAP 1536  // cycle entries per side kept in shared memory
+#define NSX_PATH_CAP 512  // cycle entries per side kept in shared memory (longer cycles spill to HBM)
 
 // Scratch of the pivot CTA (shared memory on the device).
 struct NsxPivotScratch {
@@ -174,25 +185,30 @@ NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
 // final.  `flags` is a per-thread-slot byte array of NSX_CHUNK entries.
 // ------------------------------------------------------------------------------------------
 #if NSX_ON_DEVICE
-#define NSX_CHUNK 1024
+#define NSX_CHUNK 512
 #else
 #define NSX_CHUNK 256
 #endif
 
 struct NsxPotScratch {
     double val[NSX_CHUNK];
-    int32_t par_local[NSX_CHUNK];  // parent index inside the chunk, -1 = parent already final
     double cst[NSX_CHUNK];         // signed cost to add
-    uint8_t done[NSX_CHUNK];
-    int32_t pending;
+    int32_t par_local[NSX_CHUNK];  // parent index inside the chunk, -1 = parent already final
+    int32_t dep[NSX_CHUNK];        // tree depth of a node that still waits for its parent, -1 = final
+    int32_t dmin, dmax;            // depth range of the waiting nodes of the chunk
     int32_t rounds;
 };
 
+// A chunk is finished level by level: a waiting node of depth L has its parent at depth L-1, which
+// is either outside the chunk (final), or final from the chunk set-up, or was computed in the
+// previous level step.  One barrier per tree level present in the chunk.
 NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
                                      NsxPotScratch& s, int64_t* rounds_out) {
     NSX_SINGLE { s.rounds = 0; }
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
         int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
+        NSX_SYNC();
+        NSX_SINGLE { s.dmin = 0x7fffffff; s.dmax = -1; }
         NSX_SYNC();
         NSX_PAR_FOR(x, c0, c1) {
             int32_t j = (int32_t)(x - c0);
@@ -201,48 +217,36 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
             int32_t a = r.pred2 >> 1;
             double cst = nsx_arc_cost(d, phase, a);
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
-            s.cst[j] = (r.pred2 & 1) ? -cst : cst;
+            cst = (r.pred2 & 1) ? -cst : cst;
+            s.cst[j] = cst;
             int32_t ppos = d.node[r.parent].pos;
-            if (ppos >= c0 && ppos < x) {
+            if (ppos >= c0) {
+                int32_t dep = d.depth[v];
                 s.par_local[j] = (int32_t)(ppos - c0);
-                s.done[j] = 0;
+                s.dep[j] = dep;
+                NSX_ATOMIC_MIN_I32(&s.dmin, dep);
+                NSX_ATOMIC_MAX_I32(&s.dmax, dep);
             } else {
                 s.par_local[j] = -1;
-                s.val[j] = NSX_ADD(d.pi[r.parent], s.cst[j]);  // x - c == x + (-c) exactly
-                s.done[j] = 1;
+                s.dep[j] = -1;
+                s.val[j] = NSX_ADD(d.pi[r.parent], cst);  // x - c == x + (-c) exactly
             }
         }
-        // rounds until every node of the chunk is final
-        for (;;) {
-            NSX_SYNC();
-            NSX_SINGLE { s.pending = 0; }
-            NSX_SYNC();
-            // phase 1 of the round: decide from the flags of the previous round
+        NSX_SYNC();
+        const int32_t dmin = s.dmin, dmax = s.dmax;
+        for (int32_t lev = dmin; lev <= dmax; ++lev) {
             NSX_PAR_FOR(x, c0, c1) {
                 int32_t j = (int32_t)(x - c0);
-                if (!s.done[j]) {
-                    int32_t pj = s.par_local[j];
-                    if (s.done[pj] == 1) {
-                        s.val[j] = NSX_ADD(s.val[pj], s.cst[j]);
-                        s.done[j] = 2;  // becomes visible as final after the sync
-                    } else {
-                        s.pending = 1;
-                    }
-                }
+                if (s.dep[j] == lev) s.val[j] = NSX_ADD(s.val[s.par_local[j]], s.cst[j]);
             }
             NSX_SYNC();
-            NSX_PAR_FOR(x, c0, c1) {
-                int32_t j = (int32_t)(x - c0);
-                if (s.done[j] == 2) s.done[j] = 1;
-            }
-            NSX_SYNC();
-            int32_t pend = s.pending;
-            NSX_SINGLE { s.rounds++; }
-            if (!pend) break;
         }
+        NSX_SINGLE { if (dmax >= dmin) s.rounds += dmax - dmin + 1; }
         NSX_PAR_FOR(x, c0, c1) {
             int32_t j = (int32_t)(x - c0);
-            d.pi[d.order[x]] = s.val[j];
+            int32_t v = d.order[x];
+            d.pi[v] = s.val[j];
+            if (d.pi_mirror) d.pi_mirror[v] = s.val[j];
         }
     }
     NSX_SYNC();
@@ -260,14 +264,65 @@ NSX_FN void nsx_walk_side(const NsxDev& d, int32_t from, int32_t other_pos, int3
     int32_t len = 0;
     NsxNode r = d.node[u];
     while (!(r.pos <= other_pos && other_pos < r.pos + r.size)) {
-        if (len < NSX_PATH_CAP) spath[len] = u;
-        gpath[len] = u;
+        if (len < NSX_PATH_CAP) spath[len] = u; else gpath[len] = u;
         ++len;
         u = r.parent;
         r = d.node[u];
     }
     *len_out = len;
     *join_out = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// Ratio-test reduction record: m1 = smallest residual, a1 / k1 = lowest arc index (and its scan
+// position) among residuals equal to m1, m2 = smallest residual strictly above m1.
+// ------------------------------------------------------------------------------------------
+struct NsxRatio { double m1, m2; int32_t a1, k1; };
+NSX_FN void nsx_ratio_init(NsxRatio& r) { r.m1 = NSX_INF; r.m2 = NSX_INF; r.a1 = 0x7fffffff; r.k1 = -1; }
+NSX_FN void nsx_ratio_add(NsxRatio& r, double v, int32_t a, int32_t k) {
+    if (v < r.m1) { r.m2 = r.m1; r.m1 = v; r.a1 = a; r.k1 = k; }
+    else if (v == r.m1) { if (a < r.a1) { r.a1 = a; r.k1 = k; } }
+    else if (v < r.m2) r.m2 = v;
+}
+NSX_FN void nsx_ratio_merge(NsxRatio& x, const NsxRatio& y) {
+    if (y.m1 < x.m1) {
+        x.m2 = x.m1 < y.m2 ? x.m1 : y.m2;
+        x.m1 = y.m1; x.a1 = y.a1; x.k1 = y.k1;
+    } else if (y.m1 == x.m1) {
+        if (y.m2 < x.m2) x.m2 = y.m2;
+        if (y.a1 < x.a1) { x.a1 = y.a1; x.k1 = y.k1; }
+    } else if (y.m1 < x.m2) {
+        x.m2 = y.m1;
+    }
+}
+// Decide from the reduced record, or replay the reference's sequential scan (single thread).
+NSX_FN void nsx_ratio_finish(const NsxRatio& rr, const double* res, const int32_t* arc2, int32_t ncyc,
+                             int32_t e, double tol, NsxPivotScratch& s) {
+    double theta; int32_t leave, leave_k;
+    const bool safe = nsx_isinf(rr.m1) || NSX_SUB(rr.m2, rr.m1) > NSX_MUL(4.0, tol);
+    if (safe) {
+        theta = rr.m1;
+        leave = nsx_isinf(rr.m1) ? e : rr.a1;
+        leave_k = nsx_isinf(rr.m1) ? ncyc - 1 : rr.k1;
+    } else {
+        double best = -NSX_INF;
+        theta = NSX_INF; leave = e; leave_k = ncyc - 1;
+        for (int32_t k = 0; k < ncyc; ++k) {
+            double r = res[k];
+            int32_t a = arc2[k] >> 1;
+            if (r < NSX_SUB(theta, tol)) {
+                theta = r; leave = a; best = r; leave_k = k;
+            } else if (fabs(NSX_SUB(r, theta)) <= tol) {
+                if (r > NSX_ADD(best, tol) || (fabs(NSX_SUB(r, best)) <= tol && a < leave)) {
+                    leave = a; best = r; leave_k = k;
+                }
+            }
+        }
+    }
+    s.theta = theta;
+    s.leave_arc = leave;
+    s.leave_k = leave_k;
+    s.art_delta = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -280,6 +335,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t t = dir == 1 ? d.tail[e] : d.head[e];
     const int32_t h = dir == 1 ? d.head[e] : d.tail[e];
 
+    long long tph = NSX_CLOCK();
     // ---- 1. walk both sides up to the join ------------------------------------------------
 #if NSX_ON_DEVICE
     if (threadIdx.x < 2) {
@@ -300,9 +356,15 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     }
 #endif
     NSX_SYNC();
+    NSX_PH(c, 0, tph);
     const int32_t nh = s.nh, nt = s.nt;
     const int32_t ncyc = nh + nt + 1;
     const bool spill = nh > NSX_PATH_CAP || nt > NSX_PATH_CAP;
+    if (spill) {  // long cycle: the shared-memory prefixes join the rest of the paths in HBM
+        NSX_PAR_FOR(i, 0, nh < NSX_PATH_CAP ? nh : NSX_PATH_CAP) { d.gpath_h[i] = s.path_h[i]; }
+        NSX_PAR_FOR(i, 0, nt < NSX_PATH_CAP ? nt : NSX_PATH_CAP) { d.gpath_t[i] = s.path_t[i]; }
+        NSX_SYNC();
+    }
     const int32_t* path_h = spill ? d.gpath_h : s.path_h;
     const int32_t* path_t = spill ? d.gpath_t : s.path_t;
     int32_t* arc2 = spill ? d.garc2 : s.arc2;
@@ -335,28 +397,39 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         res[k] = r;
     }
     NSX_SYNC();
+    NSX_PH(c, 1, tph);
 
-    // ---- 3. ratio test: sequential scan with tolerance ties -> lowest arc index ------------
-    NSX_SINGLE {
-        double theta = NSX_INF, best = -NSX_INF;
-        int32_t leave = e, leave_k = ncyc - 1;
-        for (int32_t k = 0; k < ncyc; ++k) {
-            double r = res[k];
-            int32_t a = arc2[k] >> 1;
-            if (r < NSX_SUB(theta, tol)) {
-                theta = r; leave = a; best = r; leave_k = k;
-            } else if (fabs(NSX_SUB(r, theta)) <= tol) {
-                if (r > NSX_ADD(best, tol) || (fabs(NSX_SUB(r, best)) <= tol && a < leave)) {
-                    leave = a; best = r; leave_k = k;
-                }
-            }
+    // ---- 3. ratio test -------------------------------------------------------------------
+    // The reference scans the cycle sequentially with tolerance comparisons (simplex.py:1205-1229).
+    // When no residual lies within (theta*, theta* + 4 tol] of the minimum theta*, that scan provably
+    // returns theta* and the lowest arc index among the residuals equal to theta*, which one warp
+    // finds with a shuffle reduction; otherwise thread 0 replays the sequential scan.
+#if NSX_ON_DEVICE
+    if (threadIdx.x < 32) {
+        NsxRatio rr; nsx_ratio_init(rr);
+        for (int32_t k = threadIdx.x; k < ncyc; k += 32) nsx_ratio_add(rr, res[k], arc2[k] >> 1, k);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            NsxRatio o;
+            o.m1 = __shfl_down_sync(0xffffffffu, rr.m1, off);
+            o.m2 = __shfl_down_sync(0xffffffffu, rr.m2, off);
+            o.a1 = __shfl_down_sync(0xffffffffu, rr.a1, off);
+            o.k1 = __shfl_down_sync(0xffffffffu, rr.k1, off);
+            nsx_ratio_merge(rr, o);
         }
-        s.theta = theta;
-        s.leave_arc = leave;
-        s.leave_k = leave_k;
-        s.art_delta = 0;
+        if (threadIdx.x == 0) nsx_ratio_finish(rr, res, arc2, ncyc, e, tol, s);
     }
+#else
+    {
+        NsxRatio lanes[4];
+        for (int l = 0; l < 4; ++l) nsx_ratio_init(lanes[l]);
+        for (int32_t k = 0; k < ncyc; ++k) nsx_ratio_add(lanes[k & 3], res[k], arc2[k] >> 1, k);
+        for (int l = 1; l < 4; ++l) nsx_ratio_merge(lanes[0], lanes[l]);
+        nsx_ratio_finish(lanes[0], res, arc2, ncyc, e, tol, s);
+    }
+#endif
     NSX_SYNC();
+    NSX_PH(c, 2, tph);
     if (nsx_isinf(s.theta)) {
         NSX_SINGLE {
             c.unbounded_arc = e;
@@ -390,6 +463,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
     }
     NSX_SYNC();
+    NSX_PH(c, 3, tph);
     NSX_SINGLE {
         c.art_with_flow += s.art_delta;
         if (theta <= tol) c.degenerate++;
@@ -403,6 +477,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (leave == e) c.last_deg = e;  // bound flip (simplex.py:1320-1334)
     }
     NSX_SYNC();
+    NSX_PH(c, 4, tph);
     if (leave == e) return 0;  // tree unchanged
 
     // ---- 5. tree update: re-hang the subtree below the leaving arc under the entering arc --
@@ -435,38 +510,72 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_PAR_FOR(i, kk + 1, slen) { d.node[spath[i]].size -= sz; }
     NSX_PAR_FOR(i, 0, olen) { d.node[opath[i]].size += sz; }
     NSX_SYNC();
+    NSX_PH(c, 5, tph);
 
-    // window of the preorder array that changes: the block S = [a0, a0+sz) moves right behind p
-    int64_t lo, hi, s_base;
-    if (P < a0) { lo = (int64_t)P + 1; hi = (int64_t)a0 + sz; s_base = lo; }
-    else        { lo = a0; hi = (int64_t)P + 1; s_base = (int64_t)P + 1 - sz; }
+    // The block S = [a0, a0+sz) of the preorder array is re-rooted at q and moved under p: either
+    // right behind p or to the end of p's old subtree, whichever shifts fewer entries (both are
+    // valid preorders).  `ins` is the insertion point in old coordinates.
+    const int64_t S0 = a0, S1 = (int64_t)a0 + sz;
+    const int64_t insA = (int64_t)P + 1, insB = (int64_t)P + rec_p.size;
+    const int64_t dA = insA <= S0 ? S0 - insA : insA - S1;
+    const int64_t dB = insB <= S0 ? S0 - insB : insB - S1;
+    const int64_t ins = dB < dA ? insB : insA;
+    int64_t lo, hi, s_base, xshift;
+    if (ins <= S0) { lo = ins; hi = S1; s_base = ins; xshift = sz; }        // [ins, S0) moves right
+    else           { lo = S0; hi = ins; s_base = ins - sz; xshift = -(int64_t)sz; }  // [S1, ins) moves left
     const int32_t k_stem = kk;
-    NSX_PAR_FOR(x, lo, hi) {
-        int32_t v = d.order[x];
-        int64_t fx;
-        if (x >= a0 && x < (int64_t)a0 + sz) {
-            // smallest i with x inside old subtree(s_i): ranges are nested, growing with i
-            int32_t lo_i = 0, hi_i = k_stem;
-            while (lo_i < hi_i) {
-                int32_t mid = (lo_i + hi_i) >> 1;
-                if (x >= st_pos[mid] && x < (int64_t)st_pos[mid] + st_size[mid]) hi_i = mid; else lo_i = mid + 1;
+    {
+        // four entries per thread and step: the loads of all four are issued before any store
+        const int64_t T = NSX_NTHREADS;
+        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+            int32_t v[4], dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.order[x] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int64_t x = x0 + u * T;
+                dv[u] = (v[u] >= 0 && x >= S0 && x < S1) ? d.depth[v[u]] : 0;
             }
-            int32_t i = lo_i;
-            int64_t rel;
-            if (i == 0) rel = x - st_pos[0];
-            else if (x < st_pos[i - 1]) rel = (int64_t)st_size[i - 1] + (x - st_pos[i]);
-            else rel = (int64_t)st_size[i - 1] + (st_pos[i - 1] - st_pos[i]) +
-                       (x - ((int64_t)st_pos[i - 1] + st_size[i - 1]));
-            fx = s_base + rel;
-            d.depth[v] = d.depth[v] - st_depth[i] + depth_q_new + i;
-        } else {
-            fx = P < a0 ? x + sz : x - sz;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t x = x0 + u * T;
+                if (v[u] < 0) continue;
+                int64_t fx;
+                if (x >= S0 && x < S1) {
+                    // smallest i with x inside old subtree(s_i): ranges are nested, growing with i
+                    int32_t lo_i = 0, hi_i = k_stem;
+                    while (lo_i < hi_i) {
+                        int32_t mid = (lo_i + hi_i) >> 1;
+                        if (x >= st_pos[mid] && x < (int64_t)st_pos[mid] + st_size[mid]) hi_i = mid; else lo_i = mid + 1;
+                    }
+                    const int32_t i = lo_i;
+                    int64_t rel;
+                    if (i == 0) rel = x - st_pos[0];
+                    else if (x < st_pos[i - 1]) rel = (int64_t)st_size[i - 1] + (x - st_pos[i]);
+                    else rel = (int64_t)st_size[i - 1] + (st_pos[i - 1] - st_pos[i]) +
+                               (x - ((int64_t)st_pos[i - 1] + st_size[i - 1]));
+                    fx = s_base + rel;
+                    d.depth[v[u]] = dv[u] - st_depth[i] + depth_q_new + i;
+                } else {
+                    fx = x + xshift;
+                }
+                d.tmp[fx] = v[u];
+                d.node[v[u]].pos = (int32_t)fx;
+            }
         }
-        d.tmp[fx] = v;
-        d.node[v].pos = (int32_t)fx;
     }
     NSX_SYNC();
-    NSX_PAR_FOR(x, lo, hi) { d.order[x] = d.tmp[x]; }
+    NSX_PH(c, 6, tph);
+    {
+        const int64_t T = NSX_NTHREADS;
+        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+            int32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.tmp[x] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < hi) d.order[x] = v[u]; }
+        }
+    }
     // stem: reverse parent pointers, new subtree sizes
     NSX_PAR_FOR(i, 0, k_stem + 1) {
         int32_t v = spath[i];
@@ -489,9 +598,11 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         c.sum_window += hi - lo;
     }
     NSX_SYNC();
+    NSX_PH(c, 7, tph);
 
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
     nsx_recompute_potentials(d, c.phase, s_base, s_base + sz, ps, &c.sum_rounds);
+    NSX_PH(c, 8, tph);
 
     // ---- 7. reset cadence (simplex.py:1373-1425) -------------------------------------------
     NSX_SINGLE {
@@ -506,6 +617,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
     }
     NSX_SYNC();
+    NSX_PH(c, 9, tph);
     return 0;
 }
 

@@ -26,7 +26,7 @@
 #include "nsx_core.cuh"
 
 #ifndef NSX_THREADS
-#define NSX_THREADS 1024
+#define NSX_THREADS 512
 #endif
 #define NSX_PI_SMEM_MAX_NODES 12288  // node potentials staged in shared memory up to this many nodes
 
@@ -53,6 +53,30 @@ __device__ __forceinline__ unsigned long long nsx_ld_acquire_u64(const unsigned 
 __device__ __forceinline__ void nsx_st_release(int32_t* p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk), completion on an mbarrier.
+__device__ __forceinline__ uint32_t nsx_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nsx_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nsx_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(nsx_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(nsx_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void nsx_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NSX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NSX_DONE;\n"
+        "bra NSX_WAIT;\n"
+        "NSX_DONE:\n"
+        "}\n" ::"r"(nsx_smem_addr(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long nsx_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -131,105 +155,168 @@ __device__ __forceinline__ void nsx_price_arc(const NsxDev& d, const NsxCmd& cmd
     }
 }
 
+// One quad (4 consecutive arcs, 16-byte aligned columns) held in registers.
+struct NsxQuad {
+    int4 t, h;
+    double2 c0, c1;
+    uint32_t st;
+    uint4 w;
+};
+
+template <bool DEVEX>
+__device__ __forceinline__ void nsx_load_quad(const NsxDev& d, int64_t base, NsxQuad& q) {
+    q.t = __ldg((const int4*)(d.tail + base));
+    q.h = __ldg((const int4*)(d.head + base));
+    q.c0 = __ldg((const double2*)(d.pert + base));
+    q.c1 = __ldg((const double2*)(d.pert + base + 2));
+    q.st = __ldcg((const unsigned int*)(d.state + base));
+    if (DEVEX) q.w = __ldcg((const uint4*)(d.wgt + base)); else q.w = make_uint4(1u, 1u, 1u, 1u);
+}
+
+template <bool DEVEX>
+__device__ __forceinline__ void nsx_price_quad(const NsxDev& d, const NsxCmd& cmd, const double* pis,
+                                               int64_t base, const NsxQuad& q, NsxCand& dz,
+                                               NsxDevexCand& dx) {
+    // fast reject: nothing to do when every arc of the quad is in the tree or has no residual
+    const uint32_t st = q.st;
+    const uint32_t live = ((st >> 1) | (st >> 2)) & ~st & 0x01010101u;
+    if (!live) return;
+    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 0, q.t.x, q.h.x, q.c0.x, st & 0xffu, q.w.x, dz, dx);
+    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 1, q.t.y, q.h.y, q.c0.y, (st >> 8) & 0xffu, q.w.y, dz, dx);
+    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 2, q.t.z, q.h.z, q.c1.x, (st >> 16) & 0xffu, q.w.z, dz, dx);
+    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 3, q.t.w, q.h.w, q.c1.y, (st >> 24) & 0xffu, q.w.w, dz, dx);
+}
+
+template <bool DEVEX>
+__device__ __forceinline__ void nsx_price_scalar(const NsxDev& d, const NsxCmd& cmd, const double* pis,
+                                                 int64_t lo, int64_t hi, NsxCand& dz, NsxDevexCand& dx) {
+    for (int64_t i = lo; i < hi; ++i)
+        nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)i, __ldg(d.tail + i), __ldg(d.head + i),
+                             __ldg(d.pert + i), __ldcg(d.state + i), DEVEX ? __ldcg(d.wgt + i) : 1u, dz, dx);
+}
+
+#ifndef NSX_UNROLL
+#define NSX_UNROLL 2
+#endif
+
+// Thread g of T handles quads g, g+T, g+2T, ... of the aligned interior; NSX_UNROLL quads are
+// loaded before the first one is priced so that several 128-bit requests are in flight per thread.
 template <bool DEVEX>
 __device__ __forceinline__ void nsx_sweep(const NsxDev& d, const NsxCmd& cmd, const double* pis,
                                           int64_t g, int64_t T, NsxCand& dz, NsxDevexCand& dx) {
     const int64_t lo = cmd.lo, hi = cmd.hi;
-    const int64_t q0 = lo >> 2, q1 = (hi + 3) >> 2;
-    for (int64_t q = q0 + g; q < q1; q += 2 * T) {
-        // two quads per iteration: all loads of both are issued before any is consumed
-        const int64_t qa = q, qb = q + T;
-        const int64_t ba = qa << 2, bb = qb << 2;
-        const bool fa = ba >= lo && ba + 4 <= hi;
-        const bool fb = qb < q1 && bb >= lo && bb + 4 <= hi;
-        int4 ta, ha, tb, hb;
-        double2 ca0, ca1, cb0, cb1;
-        uint32_t sa = 0, sb = 0;
-        uint4 wa = make_uint4(1, 1, 1, 1), wb = make_uint4(1, 1, 1, 1);
-        if (fa) {
-            ta = __ldg((const int4*)(d.tail + ba));
-            ha = __ldg((const int4*)(d.head + ba));
-            ca0 = __ldg((const double2*)(d.pert + ba));
-            ca1 = __ldg((const double2*)(d.pert + ba + 2));
-            sa = __ldcg((const unsigned int*)(d.state + ba));
-            if (DEVEX) wa = __ldcg((const uint4*)(d.wgt + ba));
-        }
-        if (fb) {
-            tb = __ldg((const int4*)(d.tail + bb));
-            hb = __ldg((const int4*)(d.head + bb));
-            cb0 = __ldg((const double2*)(d.pert + bb));
-            cb1 = __ldg((const double2*)(d.pert + bb + 2));
-            sb = __ldcg((const unsigned int*)(d.state + bb));
-            if (DEVEX) wb = __ldcg((const uint4*)(d.wgt + bb));
-        }
-        if (fa) {
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)ba + 0, ta.x, ha.x, ca0.x, sa & 0xffu, wa.x, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)ba + 1, ta.y, ha.y, ca0.y, (sa >> 8) & 0xffu, wa.y, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)ba + 2, ta.z, ha.z, ca1.x, (sa >> 16) & 0xffu, wa.z, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)ba + 3, ta.w, ha.w, ca1.y, (sa >> 24) & 0xffu, wa.w, dz, dx);
-        } else {
-            for (int64_t i = (ba > lo ? ba : lo); i < ba + 4 && i < hi; ++i)
-                nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)i, __ldg(d.tail + i), __ldg(d.head + i),
-                                     __ldg(d.pert + i), __ldcg(d.state + i), DEVEX ? __ldcg(d.wgt + i) : 1u, dz, dx);
-        }
-        if (fb) {
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)bb + 0, tb.x, hb.x, cb0.x, sb & 0xffu, wb.x, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)bb + 1, tb.y, hb.y, cb0.y, (sb >> 8) & 0xffu, wb.y, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)bb + 2, tb.z, hb.z, cb1.x, (sb >> 16) & 0xffu, wb.z, dz, dx);
-            nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)bb + 3, tb.w, hb.w, cb1.y, (sb >> 24) & 0xffu, wb.w, dz, dx);
-        } else if (qb < q1) {
-            for (int64_t i = (bb > lo ? bb : lo); i < bb + 4 && i < hi; ++i)
-                nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)i, __ldg(d.tail + i), __ldg(d.head + i),
-                                     __ldg(d.pert + i), __ldcg(d.state + i), DEVEX ? __ldcg(d.wgt + i) : 1u, dz, dx);
-        }
+    const int64_t a0 = (lo + 3) & ~(int64_t)3;          // first aligned arc
+    const int64_t a1 = hi & ~(int64_t)3;                // end of the aligned interior
+    if (a1 <= a0) {                                     // tiny range: scalar only
+        if (g == 0) nsx_price_scalar<DEVEX>(d, cmd, pis, lo, hi, dz, dx);
+        return;
+    }
+    if (g == 0) {                                       // ragged head / tail (at most 3 arcs each)
+        nsx_price_scalar<DEVEX>(d, cmd, pis, lo, a0, dz, dx);
+        nsx_price_scalar<DEVEX>(d, cmd, pis, a1, hi, dz, dx);
+    }
+    const int64_t nq = (a1 - a0) >> 2;
+    int64_t q = g;
+    for (; q + (NSX_UNROLL - 1) * T < nq; q += NSX_UNROLL * T) {
+        NsxQuad quad[NSX_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NSX_UNROLL; ++u) nsx_load_quad<DEVEX>(d, a0 + ((q + u * T) << 2), quad[u]);
+#pragma unroll
+        for (int u = 0; u < NSX_UNROLL; ++u)
+            nsx_price_quad<DEVEX>(d, cmd, pis, a0 + ((q + u * T) << 2), quad[u], dz, dx);
+    }
+    for (; q < nq; q += T) {
+        NsxQuad quad;
+        nsx_load_quad<DEVEX>(d, a0 + (q << 2), quad);
+        nsx_price_quad<DEVEX>(d, cmd, pis, a0 + (q << 2), quad, dz, dx);
     }
 }
 
-// Shared-memory layout of one CTA of the resident kernel.
+// Shared-memory layout of one CTA: fixed part, then (dynamic) the staged / resident node state.
 struct NsxCtaShared {
     NsxLoopShared L;
+    NsxCtl ctl;  // solver scalars live here during the solve (copied in / out of HBM once)
     NsxCmd cmd;  // worker copy of the command
     NsxCand dz_buf[32];
     NsxDevexCand dx_buf[32];
-    union {
-        struct {
-            NsxPivotScratch piv;
-            NsxPotScratch pot;
-        } p;
-    } u;
+    unsigned long long mbar;  // completion barrier of the potentials bulk copy
+    NsxPivotScratch piv;
+    NsxPotScratch pot;
 };
 
+// How much node state the pivot CTA keeps in shared memory (chosen by the host from n and the
+// opt-in shared-memory limit): the cycle walk is a chain of dependent 16-byte record loads, so
+// holding the records on-chip turns ~L2 latency per hop into shared-memory latency.
+enum { NSX_RES_NONE = 0,   // tree in HBM/L2; potentials optionally staged per sweep
+       NSX_RES_NODES = 1,  // node records + potentials resident (24 B / node)
+       NSX_RES_ALL = 2 };  // + depth, preorder array, permutation scratch (36 B / node)
+
+struct NsxSmemPlan {
+    int32_t mode;      // NSX_RES_*
+    int32_t stage_pi;  // workers (and NSX_RES_NONE pivot CTAs) copy pi into shared memory per sweep
+};
+
+__device__ __forceinline__ size_t nsx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Redirect the node arrays of `d` into shared memory according to the plan and fill them.
+__device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSmemPlan plan,
+                                                    unsigned char* dyn, double** pis_out) {
+    NsxDev dl = d;
+    double* pis = reinterpret_cast<double*>(dyn);
+    *pis_out = pis;
+    if (plan.mode == NSX_RES_NONE) return dl;
+    size_t off = nsx_align16((size_t)d.n * 8);
+    NsxNode* node_s = reinterpret_cast<NsxNode*>(dyn + off);
+    off += (size_t)d.n * sizeof(NsxNode);
+    for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) { node_s[v] = d.node[v]; pis[v] = d.pi[v]; }
+    dl.node = node_s; dl.pi = pis; dl.pi_mirror = d.pi;
+    if (plan.mode == NSX_RES_ALL) {
+        int32_t* depth_s = reinterpret_cast<int32_t*>(dyn + off); off += (size_t)d.n * 4;
+        int32_t* order_s = reinterpret_cast<int32_t*>(dyn + off); off += (size_t)d.n * 4;
+        int32_t* tmp_s = reinterpret_cast<int32_t*>(dyn + off);
+        for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) { depth_s[v] = d.depth[v]; order_s[v] = d.order[v]; }
+        dl.depth = depth_s; dl.order = order_s; dl.tmp = tmp_s;
+    }
+    NSX_SYNC();
+    return dl;
+}
+
 // One sweep of this CTA: stage potentials (optional), price, block-reduce into thread 0.
-__device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxCmd& cmd, double* pis, bool stage,
-                                              int64_t g, int64_t T, NsxCtaShared& sh, NsxCand& dz,
-                                              NsxDevexCand& dx) {
+// `stage_count` is a per-thread register copy of the number of bulk copies issued so far by this
+// CTA (all threads count alike); its low bit is the mbarrier phase to wait for.
+__device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxCmd& cmd, const double* pi_src,
+                                              double* pis, bool stage, uint32_t& stage_count, int64_t g,
+                                              int64_t T, NsxCtaShared& sh, NsxCand& dz, NsxDevexCand& dx) {
     nsx_cand_init(dz);
     nsx_devex_init(dx);
     if (stage) {
+        // refresh the shared-memory copy of the node potentials: one TMA bulk copy, every thread
+        // waits on the mbarrier phase (no register staging, no per-thread loads)
         NSX_SYNC();
-        for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) pis[v] = __ldcg(d.pi + v);
-        NSX_SYNC();
+        if (threadIdx.x == 0)
+            nsx_bulk_load(pis, pi_src, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
+        nsx_mbar_wait(&sh.mbar, stage_count & 1u);
+        stage_count++;
     }
-    const double* p = stage ? pis : nullptr;
     if (cmd.kind == NSX_CMD_DEVEX) {
-        nsx_sweep<true>(d, cmd, p, g, T, dz, dx);
+        nsx_sweep<true>(d, cmd, pis, g, T, dz, dx);
         nsx_block_reduce(dx, sh.dx_buf);
     } else {
-        nsx_sweep<false>(d, cmd, p, g, T, dz, dx);
+        nsx_sweep<false>(d, cmd, pis, g, T, dz, dx);
         nsx_block_reduce(dz, sh.dz_buf);
     }
 }
 
 // Sweep functor of CTA 0 in the grid-resident kernel.
 struct GridSweep {
-    const NsxDev& d;
-    NsxCtl& c;
+    const NsxDev& d;      // global view (arc arrays, global pi mirror)
     NsxGridCtl* g;
     NsxCand* dzc;
     NsxDevexCand* dxc;
     NsxCtaShared& sh;
-    double* pis;
-    bool stage;
+    double* pis;          // potentials in shared memory (resident master copy, or staging buffer), or null
+    bool stage;           // this CTA must refresh `pis` from HBM before each sweep
+    uint32_t& stage_count;
     int32_t seq;
     unsigned long long target;
     unsigned long long t_price, t_sync;
@@ -245,10 +332,21 @@ struct GridSweep {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
-        publish(cmd_in);
+        if (gridDim.x > 1) publish(cmd_in);
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
-        nsx_cta_sweep(d, cmd, pis, stage, (int64_t)threadIdx.x, (int64_t)gridDim.x * blockDim.x, sh, dz, dx);
+        nsx_cand_init(dz); nsx_devex_init(dx);
+        // with workers present this CTA only pivots and merges; alone it prices everything itself
+        if (gridDim.x == 1)
+            nsx_cta_sweep(d, cmd, d.pi, pis, stage, stage_count, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
+        if (gridDim.x == 1) {
+            if (threadIdx.x == 0) {
+                if (cmd.kind == NSX_CMD_DEVEX) out_dx = dx; else out_dz = dz;
+                t_price += nsx_globaltimer() - t0;
+            }
+            NSX_SYNC();
+            return;
+        }
         if (threadIdx.x == 0) {
             unsigned long long t1 = nsx_globaltimer();
             target += gridDim.x - 1;
@@ -287,7 +385,7 @@ struct GridSweep {
         NsxCmd cmd;
         cmd.kind = NSX_CMD_EXIT; cmd.phase = 0; cmd.lo = cmd.hi = 0; cmd.excluded = -1; cmd.wepoch = 0;
         NSX_SYNC();
-        publish(cmd);
+        if (gridDim.x > 1) publish(cmd);
     }
 };
 
@@ -303,36 +401,54 @@ struct NsxKernelArgs {
     NsxCand* dzc;
     NsxDevexCand* dxc;
     int32_t* trace;
-    int32_t stage_pi;
+    NsxSmemPlan plan;
 };
+
+__device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
+    const int32_t* s = reinterpret_cast<const int32_t*>(src);
+    int32_t* t = reinterpret_cast<int32_t*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(NsxCtl) / 4); i += blockDim.x) t[i] = s[i];
+}
 
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
 nsx_resident_kernel(const NsxKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
-    double* pis = reinterpret_cast<double*>(smem_raw + ((sizeof(NsxCtaShared) + 15) & ~(size_t)15));
+    unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
     const NsxDev& d = a.d;
-    const bool stage = a.stage_pi != 0;
+    if (threadIdx.x == 0) nsx_mbar_init(&sh.mbar, 1);
+    uint32_t stage_count = 0;
+    NSX_SYNC();
 
     if (blockIdx.x == 0) {
-        GridSweep sweep{d, *a.ctl, a.grid, a.dzc, a.dxc, sh, pis, stage, 0, 0ull, 0ull, 0ull};
         unsigned long long t_begin = 0;
         if (threadIdx.x == 0) t_begin = nsx_globaltimer();
-        nsx_solve_loop(d, *a.ctl, sh.L, sh.u.p.piv, sh.u.p.pot, a.trace, sweep);
+        nsx_copy_ctl(&sh.ctl, a.ctl);
+        double* pis = nullptr;
+        const NsxDev dl = nsx_make_resident(d, a.plan, dyn, &pis);
+        NSX_SYNC();
+        const bool resident = a.plan.mode != NSX_RES_NONE;
+        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, (resident || a.plan.stage_pi) ? pis : nullptr,
+                        !resident && a.plan.stage_pi != 0, stage_count, 0, 0ull, 0ull, 0ull};
+        nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
+        NSX_SYNC();
         if (threadIdx.x == 0) {
             unsigned long long total = nsx_globaltimer() - t_begin;
-            a.ctl->clk_pricing = (int64_t)sweep.t_price;
-            a.ctl->clk_sync = (int64_t)sweep.t_sync;
-            a.ctl->clk_pivot = (int64_t)(total - sweep.t_price);
+            sh.ctl.clk_pricing = (int64_t)sweep.t_price;
+            sh.ctl.clk_sync = (int64_t)sweep.t_sync;
+            sh.ctl.clk_pivot = (int64_t)(total - sweep.t_price);
         }
+        NSX_SYNC();
+        nsx_copy_ctl(a.ctl, &sh.ctl);
         return;
     }
     // worker CTAs: wait for a command, price, deliver, repeat
+    double* pis = a.plan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     int32_t seen = 0;
     for (;;) {
         if (threadIdx.x == 0) {
             int32_t s;
-            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(64); }
+            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(32); }
             seen = s;
             __threadfence();
             union { NsxCmd c; int4 v[2]; } tmp;
@@ -344,8 +460,8 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
-        nsx_cta_sweep(d, cmd, pis, stage, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
-                      (int64_t)gridDim.x * blockDim.x, sh, dz, dx);
+        nsx_cta_sweep(d, cmd, d.pi, pis, pis != nullptr, stage_count, (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x,
+                      (int64_t)(gridDim.x - 1) * blockDim.x, sh, dz, dx);
         if (threadIdx.x == 0) {
             if (cmd.kind == NSX_CMD_DEVEX) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
             __threadfence();
@@ -383,22 +499,27 @@ struct LocalSweep {
     NsxCtaShared& sh;
     double* pis;
     bool stage;
+    uint32_t& stage_count;
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
-        nsx_cta_sweep(d, cmd, pis, stage, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
+        nsx_cta_sweep(d, cmd, d.pi, pis, stage, stage_count, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
         if (threadIdx.x == 0) { if (cmd.kind == NSX_CMD_DEVEX) out_dx = dx; else out_dz = dz; }
         NSX_SYNC();
     }
     __device__ void finish() {}
 };
 
+// per-item smem need is decided on the host from the largest instance; smaller instances simply
+// use less of it.  `limit_bytes` = dynamic bytes available after the fixed part.
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
-nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, int32_t stage_pi) {
+nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
-    double* pis = reinterpret_cast<double*>(smem_raw + ((sizeof(NsxCtaShared) + 15) & ~(size_t)15));
+    unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
     __shared__ unsigned long long my_item;
+    if (threadIdx.x == 0) nsx_mbar_init(&sh.mbar, 1);
+    uint32_t stage_count = 0;
     for (;;) {
         NSX_SYNC();
         if (threadIdx.x == 0) my_item = atomicAdd(next, 1ull);
@@ -409,15 +530,26 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
         const NsxDev& d = item.d;
         for (int64_t i = threadIdx.x; i < d.m; i += blockDim.x) nsx_init_real_arc(d, i);
         for (int64_t v = threadIdx.x; v < d.n; v += blockDim.x) nsx_init_node(d, (int32_t)v, item.supply[v]);
+        nsx_copy_ctl(&sh.ctl, item.ctl);
         NSX_SYNC();
         if (threadIdx.x == 0) {
             int64_t art = 0;
             for (int32_t v = 1; v < d.n; ++v) art += d.flow[d.m + v - 1] > d.tol;
-            item.ctl->art_with_flow = art;
+            sh.ctl.art_with_flow = art;
         }
         NSX_SYNC();
-        LocalSweep sweep{d, sh, pis, stage_pi != 0 && d.n <= NSX_PI_SMEM_MAX_NODES};
-        nsx_solve_loop(d, *item.ctl, sh.L, sh.u.p.piv, sh.u.p.pot, item.trace, sweep);
+        NsxSmemPlan plan;
+        const size_t n = (size_t)d.n;
+        plan.mode = (36 * n + 64 <= limit_bytes) ? NSX_RES_ALL : (24 * n + 64 <= limit_bytes) ? NSX_RES_NODES : NSX_RES_NONE;
+        plan.stage_pi = (plan.mode == NSX_RES_NONE && 8 * n + 64 <= limit_bytes) ? 1 : 0;
+        double* pis = nullptr;
+        const NsxDev dl = nsx_make_resident(d, plan, dyn, &pis);
+        NSX_SYNC();
+        const bool resident = plan.mode != NSX_RES_NONE;
+        LocalSweep sweep{d, sh, (resident || plan.stage_pi) ? pis : nullptr, !resident && plan.stage_pi != 0, stage_count};
+        nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, item.trace, sweep);
+        NSX_SYNC();
+        nsx_copy_ctl(item.ctl, &sh.ctl);
     }
 }
 
@@ -493,6 +625,7 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
     res->pricing_ms = (double)c.clk_pricing * 1e-6;
     res->pivot_ms = (double)c.clk_pivot * 1e-6;
     res->sync_ms = (double)c.clk_sync * 1e-6;
+    for (int i = 0; i < 12; ++i) res->phase_cycles[i] = c.ph[i];
 }
 
 struct DeviceInfo { int sms = 0; int coop = 0; size_t smem_optin = 0; bool ok = false; };
@@ -507,14 +640,25 @@ static int nsx_device_info(int dev, DeviceInfo& info) {
     return 0;
 }
 
-static size_t nsx_smem_bytes(int32_t n, bool stage) {
-    size_t base = (sizeof(NsxCtaShared) + 15) & ~(size_t)15;
-    return base + (stage ? (size_t)n * 8 : 0) + 16;
-}
-
 static int nsx_env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+static size_t nsx_smem_fixed() { return (sizeof(NsxCtaShared) + 15) & ~(size_t)15; }
+// Choose how much node state lives in shared memory for an n-node instance under `limit` bytes.
+static NsxSmemPlan nsx_plan_smem(int32_t n, size_t limit, size_t* bytes) {
+    NsxSmemPlan plan; plan.mode = NSX_RES_NONE; plan.stage_pi = 0;
+    const size_t fixed = nsx_smem_fixed(), nn = (size_t)n;
+    const int want = nsx_env_int("NSX_RESIDENT", 2);
+    size_t dyn = 0;
+    if (want >= 2 && fixed + 36 * nn + 64 <= limit) { plan.mode = NSX_RES_ALL; plan.stage_pi = 1; dyn = 36 * nn + 64; }
+    else if (want >= 1 && fixed + 24 * nn + 64 <= limit) { plan.mode = NSX_RES_NODES; plan.stage_pi = 1; dyn = 24 * nn + 64; }
+    else if (nsx_env_int("NSX_STAGE_PI", 1) != 0 && fixed + 8 * nn + 64 <= limit && n <= NSX_PI_SMEM_MAX_NODES) {
+        plan.stage_pi = 1; dyn = 8 * nn + 64;
+    }
+    *bytes = fixed + dyn;
+    return plan;
 }
 
 // Common implementation; `resident` = arc arrays are device pointers.
@@ -546,7 +690,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_flow = arena.plan((size_t)(ma + 4) * 8), o_state = arena.plan((size_t)ma + 16);
     size_t o_wgt = devex ? arena.plan((size_t)(m + 4) * 4) : 0;
     size_t o_node = arena.plan((size_t)n * sizeof(NsxNode)), o_depth = arena.plan((size_t)n * 4);
-    size_t o_pi = arena.plan((size_t)n * 8), o_order = arena.plan((size_t)n * 4), o_tmp = arena.plan((size_t)n * 4);
+    size_t o_pi = arena.plan((size_t)n * 8 + 16), o_order = arena.plan((size_t)n * 4), o_tmp = arena.plan((size_t)n * 4);
     size_t o_gph = arena.plan((size_t)n * 4), o_gpt = arena.plan((size_t)n * 4);
     size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
     size_t o_supply = arena.plan((size_t)n * 8);
@@ -585,7 +729,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.atail = arena.at<int32_t>(o_atail); d.ahead = arena.at<int32_t>(o_ahead); d.aupper = arena.at<double>(o_aupper);
     d.flow = arena.at<double>(o_flow); d.state = arena.at<uint8_t>(o_state);
     d.wgt = devex ? arena.at<uint32_t>(o_wgt) : nullptr;
-    d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi);
+    d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi); d.pi_mirror = nullptr;
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
@@ -601,17 +745,18 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
     // ---- launch shape ----
-    const bool stage = n <= NSX_PI_SMEM_MAX_NODES && nsx_env_int("NSX_STAGE_PI", 1) != 0;
-    const size_t smem = nsx_smem_bytes(n, stage);
+    size_t smem = 0;
+    ka.plan = nsx_plan_smem(n, info.smem_optin, &smem);
     if (smem > info.smem_optin) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
-    ka.stage_pi = stage ? 1 : 0;
     NSX_CUDA(cudaFuncSetAttribute(nsx_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_resident_kernel, NSX_THREADS, smem));
     if (per_sm < 1) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "resident kernel does not fit on an SM"); }
-    int64_t arcs_per_cta = nsx_env_int("NSX_ARCS_PER_CTA", 32768);
-    int64_t want = (m + arcs_per_cta - 1) / arcs_per_cta;
-    int grid = (int)(want < 1 ? 1 : (want > info.sms ? info.sms : want));
+    // one pivot CTA + sweep workers; small instances are priced by the pivot CTA alone
+    int64_t arcs_per_cta = nsx_env_int("NSX_ARCS_PER_CTA", 8192);
+    int64_t workers = (m + arcs_per_cta - 1) / arcs_per_cta;
+    if (workers > info.sms - 1) workers = info.sms - 1;
+    int grid = m < nsx_env_int("NSX_SINGLE_CTA_ARCS", 65536) || workers < 2 ? 1 : (int)workers + 1;
     int forced = nsx_env_int("NSX_GRID", 0);
     if (forced > 0) grid = forced < info.sms * per_sm ? forced : info.sms * per_sm;
     if (grid > 1024) grid = 1024;
@@ -689,7 +834,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         o.atail = arena.plan(n * 4); o.ahead = arena.plan(n * 4); o.aupper = arena.plan(n * 8);
         o.flow = arena.plan((ma + 4) * 8); o.state = arena.plan(ma + 16);
         o.wgt = devex ? arena.plan((m + 4) * 4) : 0;
-        o.node = arena.plan(n * sizeof(NsxNode)); o.depth = arena.plan(n * 4); o.pi = arena.plan(n * 8);
+        o.node = arena.plan(n * sizeof(NsxNode)); o.depth = arena.plan(n * 4); o.pi = arena.plan(n * 8 + 16);
         o.order = arena.plan(n * 4); o.tmp = arena.plan(n * 4); o.gph = arena.plan(n * 4); o.gpt = arena.plan(n * 4);
         o.garc2 = arena.plan((2 * n + 1) * 4); o.gres = arena.plan((2 * n + 1) * 8);
         o.supply = arena.plan(n * 8); o.ctl = arena.plan(sizeof(NsxCtl));
@@ -718,7 +863,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.atail = arena.at<int32_t>(o.atail); d.ahead = arena.at<int32_t>(o.ahead); d.aupper = arena.at<double>(o.aupper);
         d.flow = arena.at<double>(o.flow); d.state = arena.at<uint8_t>(o.state);
         d.wgt = devex ? arena.at<uint32_t>(o.wgt) : nullptr;
-        d.node = arena.at<NsxNode>(o.node); d.depth = arena.at<int32_t>(o.depth); d.pi = arena.at<double>(o.pi);
+        d.node = arena.at<NsxNode>(o.node); d.depth = arena.at<int32_t>(o.depth); d.pi = arena.at<double>(o.pi); d.pi_mirror = nullptr;
         d.order = arena.at<int32_t>(o.order); d.tmp = arena.at<int32_t>(o.tmp);
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
@@ -742,8 +887,8 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     NSX_CUDA(cudaMemsetAsync(d_next, 0, 8, stream));
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
-    const bool stage = max_n <= NSX_PI_SMEM_MAX_NODES && nsx_env_int("NSX_STAGE_PI", 1) != 0;
-    const size_t smem = nsx_smem_bytes(max_n, stage);
+    size_t smem = 0;
+    (void)nsx_plan_smem(max_n, info.smem_optin, &smem);
     if (smem > info.smem_optin) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
     NSX_CUDA(cudaFuncSetAttribute(nsx_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -751,7 +896,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)info.sms * per_sm;
     if (grid > count) grid = count;
-    nsx_batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, stage ? 1 : 0);
+    nsx_batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, smem - nsx_smem_fixed());
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(ev[2], stream));
     for (int64_t i = 0; i < count; ++i) {

@@ -51,7 +51,7 @@ extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_
     d.tail = pb->tail; d.head = pb->head; d.pert = pb->pert_cost; d.upper = pb->upper;
     d.atail = atail.data(); d.ahead = ahead.data(); d.aupper = aupper.data();
     d.flow = flow.data(); d.state = state.data(); d.wgt = wgt.data();
-    d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.order = order.data();
+    d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.pi_mirror = nullptr; d.order = order.data();
     d.tmp = tmp.data(); d.gpath_h = gph.data(); d.gpath_t = gpt.data(); d.garc2 = garc2.data();
     d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance;
 
