@@ -103,9 +103,16 @@ typedef struct nsx_result {
     int64_t weight_resets;        /* Devex reset cadence hits */
     int64_t final_block_size;
     int64_t arcs_priced;          /* arcs examined by all pricing sweeps */
+    int64_t sweeps;               /* pricing sweeps (grid-wide command rounds) */
     int64_t unbounded_arc;        /* entering arc when status == NSX_STATUS_UNBOUNDED */
     double unbounded_rc;
     int32_t status;               /* NSX_STATUS_* */
+    int32_t grid_ctas;            /* CTAs of the resident kernel (1 pivot CTA + sweep workers) */
+    int32_t bytes_per_arc;        /* bytes a sweep streams per arc in the layout chosen for this instance
+                                     (2 * node id + cost + 1 state byte; Devex adds 4) */
+    int32_t ring_stages;          /* depth of the shared-memory tile ring of a sweeping CTA */
+    int32_t resident_mode;        /* node state held in the pivot CTA's shared memory: 0 none, 1 records +
+                                     potentials, 2 everything */
     int32_t reserved;
     /* device-side timing (milliseconds unless stated) */
     double solve_ms;              /* CUDA-event time of the resident pivot loop */
@@ -128,6 +135,12 @@ int nsx_solve(const nsx_problem* problem, const nsx_options* options, nsx_result
 /* Same, but tail/head/pert_cost/upper are DEVICE pointers already resident in HBM (supply stays host,
  * it is n_nodes doubles).  Outputs are still host buffers. Used for the kernel-only throughput figure. */
 int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result);
+
+/* Measurement aid: `sweeps` full pricing sweeps over the initial state of the instance (device arrays as in
+ * nsx_solve_resident) through the command / arrival protocol of a solve, without pivoting.  result->solve_ms,
+ * arcs_priced and pricing_ms describe the sweeps; flows / potentials are the initial ones. */
+int nsx_sweep_probe(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
+                    nsx_result* result);
 
 /* Solve `count` independent instances on one GPU, one CTA per instance (batched config).
  * problems[i] / results[i] as in nsx_solve; options are shared. */

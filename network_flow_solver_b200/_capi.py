@@ -81,9 +81,14 @@ class NsxResult(C.Structure):
         ("weight_resets", C.c_int64),
         ("final_block_size", C.c_int64),
         ("arcs_priced", C.c_int64),
+        ("sweeps", C.c_int64),
         ("unbounded_arc", C.c_int64),
         ("unbounded_rc", C.c_double),
         ("status", C.c_int32),
+        ("grid_ctas", C.c_int32),
+        ("bytes_per_arc", C.c_int32),
+        ("ring_stages", C.c_int32),
+        ("resident_mode", C.c_int32),
         ("reserved", C.c_int32),
         ("solve_ms", C.c_double),
         ("h2d_ms", C.c_double),
@@ -228,7 +233,11 @@ class CallFrame:
                 "sync_ms": float(r.sync_ms),
             },
             stats={
-                "grid": int(r.reserved),
+                "grid": int(r.grid_ctas),
+                "bytes_per_arc": int(r.bytes_per_arc),
+                "ring_stages": int(r.ring_stages),
+                "resident_mode": int(r.resident_mode),
+                "sweeps": int(r.sweeps),
                 "sum_cycle_len": int(r.sum_cycle_len),
                 "sum_subtree": int(r.sum_subtree),
                 "max_subtree": int(r.max_subtree),
@@ -270,6 +279,9 @@ def load_library():
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult)]
             fn.restype = C.c_int
+        lib.nsx_sweep_probe.argtypes = [
+            C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.c_int32, C.POINTER(NsxResult)]
+        lib.nsx_sweep_probe.restype = C.c_int
         lib.nsx_solve_batch.argtypes = [
             C.c_int64,
             C.POINTER(NsxProblem),
@@ -312,6 +324,17 @@ def solve_resident(cp: CanonicalProblem, opts: EngineOptions, device_arrays, out
         C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result)
     )
     _check(rc, "nsx_solve_resident")
+    return frame.harvest()
+
+
+def sweep_probe(cp: CanonicalProblem, opts: EngineOptions, device_arrays, sweeps: int) -> RawSolution:
+    """Measurement aid: `sweeps` pricing sweeps of the initial state, no pivots (nsx_sweep_probe)."""
+    lib = load_library()
+    frame = CallFrame(cp, opts, device_arrays=device_arrays)
+    rc = lib.nsx_sweep_probe(
+        C.byref(frame.problem), C.byref(frame.options), int(sweeps), C.byref(frame.result)
+    )
+    _check(rc, "nsx_sweep_probe")
     return frame.harvest()
 
 

@@ -126,7 +126,7 @@ struct NsxCtl {
     uint32_t wepoch;      // current Devex weight epoch (8 bits used)
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     // statistics
-    int64_t degenerate, tree_updates, resets, arcs_priced;
+    int64_t degenerate, tree_updates, resets, arcs_priced, sweeps;
     int64_t sum_cycle, sum_subtree, max_subtree, sum_rounds, sum_window;
     int64_t phase1_iterations, art_after_p1;
     int64_t trace_len, trace_cap;
@@ -754,8 +754,10 @@ NSX_FN void nsx_init_node(const NsxDev& d, int32_t v, double supply) {
 // (simplex.py:1058-1075, 1109-1160, 1534-1701) and DevexPricing's block loop
 // (simplex_pricing.py:325-357).
 // ------------------------------------------------------------------------------------------
-enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2 };
-enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3 };
+// *_ZERO commands look for zero-reduced-cost candidates only (Phase 1, after the improving sweep of
+// the same range found nothing): the hot sweeps then carry no zero bookkeeping.
+enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2, NSX_CMD_DANTZIG_ZERO = 3, NSX_CMD_DEVEX_ZERO = 4 };
+enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_ZERO = 4, NSX_ST_DEVEX_ZERO = 5 };
 enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4 };
 
 struct NsxCmd {       // what every CTA does next
@@ -764,6 +766,9 @@ struct NsxCmd {       // what every CTA does next
     int64_t lo, hi;   // arc range
     int32_t excluded; // Devex: arc skipped (last bound-flip arc), -1 none
     uint32_t wepoch;
+    int32_t reverse;  // tiles visited in descending order (alternates per sweep: the tail of the
+                      // previous sweep is still in L2 / shared memory when the next one starts)
+    int32_t pad[3];
 };
 struct NsxAction { int32_t kind, arc, dir, want_weight; };
 struct NsxDrv {       // driver scalars (kept beside NsxCtl)
@@ -784,7 +789,7 @@ NSX_FN void nsx_drv_devex_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
     if (st >= m) { c.pb = 0; st = 0; }
     int64_t en = st + c.bs < m ? st + c.bs : m;
     cmd.kind = NSX_CMD_DEVEX; cmd.phase = c.phase; cmd.lo = st; cmd.hi = en;
-    cmd.excluded = c.last_deg; cmd.wepoch = c.wepoch;
+    cmd.excluded = c.last_deg; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
 }
 NSX_FN void nsx_drv_devex_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd) {
     v.stage = NSX_ST_DEVEX;
@@ -800,7 +805,7 @@ NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxActio
     if (c.row_scan_first || c.pricing == NSX_PRICING_DANTZIG) {
         v.stage = c.row_scan_first ? NSX_ST_ROWSCAN : NSX_ST_DANTZIG;
         cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
-        cmd.excluded = -1; cmd.wepoch = c.wepoch;
+        cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
     } else {
         nsx_drv_devex_begin(c, v, m, cmd);
     }
@@ -821,29 +826,52 @@ NSX_FN void nsx_drv_none(NsxCtl& c, NsxDrv& v, NsxAction& act) {
     if (v.final_check) { c.status = NSX_STATUS_OPTIMAL; act.kind = NSX_ACT_EXIT; }
     else act.kind = NSX_ACT_PHASE_END;
 }
+// Devex: the current block yielded nothing; move to the next block or give up
+NSX_FN void nsx_drv_devex_next(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    c.pb = (c.pb + 1) % v.bc;
+    v.blocks_left--;
+    if (v.blocks_left == 0) { nsx_drv_none(c, v, act); return; }
+    v.stage = NSX_ST_DEVEX;
+    act.kind = NSX_ACT_SWEEP;
+    nsx_drv_devex_cmd(c, m, cmd);
+}
 NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
                               const NsxDevexCand& dx, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
     const int allow_zero = (c.phase == 1) && !v.final_check;
+    c.arcs_priced += cmd.hi - cmd.lo;
+    c.sweeps++;
     if (v.stage == NSX_ST_ROWSCAN || v.stage == NSX_ST_DANTZIG) {
-        c.arcs_priced += m;
         if (dz.arc2 >= 0) { nsx_drv_choose(c, v, act, dz.arc2, 0, trace); return; }
         if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_DEVEX) {
             act.kind = NSX_ACT_SWEEP;  // fall through to the configured strategy (simplex.py:1066-1075)
             nsx_drv_devex_begin(c, v, m, cmd);
             return;
         }
-        if (allow_zero && dz.zero2 != 0x7fffffff) { nsx_drv_choose(c, v, act, dz.zero2, 0, trace); return; }
+        if (allow_zero) {  // simplex_pricing.py:132-135: zero-reduced-cost candidates, second pass
+            v.stage = NSX_ST_DANTZIG_ZERO;
+            act.kind = NSX_ACT_SWEEP;
+            cmd.kind = NSX_CMD_DANTZIG_ZERO; cmd.reverse ^= 1;
+            return;
+        }
         nsx_drv_none(c, v, act);
-    } else {
-        c.arcs_priced += cmd.hi - cmd.lo;
+    } else if (v.stage == NSX_ST_DANTZIG_ZERO) {
+        if (dz.zero2 != 0x7fffffff) { nsx_drv_choose(c, v, act, dz.zero2, 0, trace); return; }
+        nsx_drv_none(c, v, act);
+    } else if (v.stage == NSX_ST_DEVEX) {
         int32_t mp = 0;
-        int32_t a2 = nsx_devex_decide(dx, allow_zero, &mp);
+        int32_t a2 = nsx_devex_decide(dx, 0, &mp);
         if (a2 >= 0) { c.last_deg = -1; nsx_drv_choose(c, v, act, a2, mp, trace); return; }
-        c.pb = (c.pb + 1) % v.bc;
-        v.blocks_left--;
-        if (v.blocks_left == 0) { nsx_drv_none(c, v, act); return; }
-        act.kind = NSX_ACT_SWEEP;
-        nsx_drv_devex_cmd(c, m, cmd);
+        if (allow_zero) {  // simplex.py:603-615: zero candidates of the same block, second pass
+            v.stage = NSX_ST_DEVEX_ZERO;
+            act.kind = NSX_ACT_SWEEP;
+            cmd.kind = NSX_CMD_DEVEX_ZERO; cmd.reverse ^= 1;
+            return;
+        }
+        nsx_drv_devex_next(c, v, m, cmd, act);
+    } else {  // NSX_ST_DEVEX_ZERO
+        int32_t a2 = dx.fz != 0x7fffffff ? dx.fz * 2 : (dx.bz != 0x7fffffff ? dx.bz * 2 + 1 : -1);
+        if (a2 >= 0) { c.last_deg = -1; nsx_drv_choose(c, v, act, a2, 0, trace); return; }
+        nsx_drv_devex_next(c, v, m, cmd, act);
     }
 }
 NSX_FN void nsx_drv_after_pivot(NsxCtl& c, NsxDrv& v, int64_t m, int32_t rc, NsxCmd& cmd, NsxAction& act) {
@@ -890,6 +918,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
     NSX_SINGLE {
         L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
         L.drv.budget = c.maxit;
+        L.cmd.reverse = 0;
         nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act);
     }
     for (;;) {

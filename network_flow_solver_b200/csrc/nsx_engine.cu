@@ -53,28 +53,45 @@ __device__ __forceinline__ unsigned long long nsx_ld_acquire_u64(const unsigned 
 __device__ __forceinline__ void nsx_st_release(int32_t* p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk), completion on an mbarrier.
+// 1-D bulk copies global -> shared through the TMA unit (cp.async.bulk), completion on an mbarrier.
 __device__ __forceinline__ uint32_t nsx_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nsx_mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nsx_mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// copy only: the caller has already posted the expected byte count on `bar`
+__device__ __forceinline__ void nsx_bulk_copy(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(nsx_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(nsx_smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void nsx_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                               unsigned long long* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(nsx_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(nsx_smem_addr(bar)) : "memory");
+    nsx_bulk_copy(dst_smem, src_gmem, bytes, bar);
 }
-__device__ __forceinline__ void nsx_mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ void nsx_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nsx_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool nsx_mbar_try(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "NSX_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra NSX_DONE;\n"
-        "bra NSX_WAIT;\n"
-        "NSX_DONE:\n"
-        "}\n" ::"r"(nsx_smem_addr(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(nsx_smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void nsx_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    while (!nsx_mbar_try(bar, parity)) { }
+}
+// orders earlier generic-proxy accesses (the acquired writes of other CTAs) before later
+// async-proxy (TMA) reads issued by this thread
+__device__ __forceinline__ void nsx_fence_proxy_async() {
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __device__ __forceinline__ unsigned long long nsx_globaltimer() {
@@ -129,134 +146,114 @@ __device__ __forceinline__ void nsx_block_reduce(T& k, T* buf) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Pricing sweep over [cmd.lo, cmd.hi): thread `g` of `T` takes quads (4 consecutive arcs)
-// g, g+T, ... so that a warp streams 128 consecutive arcs with 128-bit loads.
-// Algorithmic bytes per arc: tail 4 + head 4 + cost 8 + state 1 = 17 (Dantzig / row scan),
-// + 4 Devex weight = 21.  Potentials are gathered from `pis` (shared memory) when staged,
-// otherwise from L2 (ld.global.cg: they are rewritten between sweeps by the pivot CTA).
+// Pricing store: the arrays a sweep streams, held tile-padded in HBM in the narrowest exact
+// encoding the instance allows (chosen on the host side of the C ABI, see nsx_choose_layout):
+//   node ids   int32, or uint16 holding id-1 when n-1 <= 65536 (real arcs never touch the root);
+//   cost       float64 perturbed cost, or int32 / int16 when every cost is an integer of that
+//              range (perturbation off) - converted to float64 exactly before any arithmetic;
+//   state      one byte per arc (NSX_ARC_* bits), shared with the pivot code;
+//   weight     uint32 epoch-tagged Devex weight (Devex solves only).
+// Algorithmic bytes per arc = 2*node + cost + 1 (+4 Devex): 17 / 13 / 7 for the three layouts
+// used by the BASELINE configs.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double nsx_pi_at(const NsxDev& d, const double* pis, int32_t v) {
-    return pis ? pis[v] : __ldcg(d.pi + v);
-}
+#define NSX_TILE (4 * NSX_THREADS)  // arcs per tile: one quad (4 consecutive arcs) per thread
+#define NSX_MAX_STAGES 8
 
-template <bool DEVEX>
-__device__ __forceinline__ void nsx_price_arc(const NsxDev& d, const NsxCmd& cmd, const double* pis,
-                                              int32_t i, int32_t tl, int32_t hd, double pert,
-                                              uint32_t st, uint32_t wraw, NsxCand& dz, NsxDevexCand& dx) {
-    if ((st & NSX_ARC_IN_TREE) || !(st & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD))) return;
-    double cost = pert;
-    if (!DEVEX && cmd.phase == 1) cost = NSX_SUB(NSX_SUB(pert, 1.0), NSX_MUL(1e-6, (double)i));
-    double rc = NSX_SUB(NSX_ADD(cost, nsx_pi_at(d, pis, tl)), nsx_pi_at(d, pis, hd));
-    if (DEVEX) {
-        if (i == cmd.excluded) return;
-        nsx_price_devex(dx, i, (uint8_t)st, rc, wraw, cmd.wepoch, d.tol);
-    } else {
-        nsx_price_dantzig(dz, i, (uint8_t)st, rc, d.tol);
-    }
-}
+enum { NSX_NODE_I32 = 0, NSX_NODE_U16 = 1 };
+enum { NSX_COST_F64 = 0, NSX_COST_I32 = 1, NSX_COST_I16 = 2 };
 
-// One quad (4 consecutive arcs, 16-byte aligned columns) held in registers.
-struct NsxQuad {
-    int4 t, h;
-    double2 c0, c1;
-    uint32_t st;
-    uint4 w;
+struct NsxStore {
+    const unsigned char* tail;  // [tiles * b_node]
+    const unsigned char* head;
+    const unsigned char* cost;  // [tiles * b_cost]
+    int32_t node_kind, cost_kind;
+    uint32_t b_node, b_cost;    // bytes per tile of a node-id array / of the cost array
+    uint32_t off_head, off_cost, off_state, off_wgt, stage_bytes;  // layout of one ring stage
+    int32_t has_wgt;
 };
 
-template <bool DEVEX>
-__device__ __forceinline__ void nsx_load_quad(const NsxDev& d, int64_t base, NsxQuad& q) {
-    q.t = __ldg((const int4*)(d.tail + base));
-    q.h = __ldg((const int4*)(d.head + base));
-    q.c0 = __ldg((const double2*)(d.pert + base));
-    q.c1 = __ldg((const double2*)(d.pert + base + 2));
-    q.st = __ldcg((const unsigned int*)(d.state + base));
-    if (DEVEX) q.w = __ldcg((const uint4*)(d.wgt + base)); else q.w = make_uint4(1u, 1u, 1u, 1u);
+static inline __host__ __device__ uint32_t nsx_node_bytes(int kind) { return kind == NSX_NODE_U16 ? 2u : 4u; }
+static inline __host__ __device__ uint32_t nsx_cost_bytes(int kind) {
+    return kind == NSX_COST_F64 ? 8u : kind == NSX_COST_I32 ? 4u : 2u;
+}
+static inline __host__ __device__ void nsx_store_layout(NsxStore& st, int node_kind, int cost_kind, int has_wgt) {
+    st.node_kind = node_kind; st.cost_kind = cost_kind; st.has_wgt = has_wgt;
+    st.b_node = NSX_TILE * nsx_node_bytes(node_kind);
+    st.b_cost = NSX_TILE * nsx_cost_bytes(cost_kind);
+    st.off_head = st.b_node;
+    st.off_cost = 2 * st.b_node;
+    st.off_state = st.off_cost + st.b_cost;
+    st.off_wgt = st.off_state + NSX_TILE;
+    st.stage_bytes = st.off_wgt + (has_wgt ? 4u * NSX_TILE : 0u);
 }
 
-template <bool DEVEX>
-__device__ __forceinline__ void nsx_price_quad(const NsxDev& d, const NsxCmd& cmd, const double* pis,
-                                               int64_t base, const NsxQuad& q, NsxCand& dz,
-                                               NsxDevexCand& dx) {
-    // fast reject: nothing to do when every arc of the quad is in the tree or has no residual
-    const uint32_t st = q.st;
-    const uint32_t live = ((st >> 1) | (st >> 2)) & ~st & 0x01010101u;
-    if (!live) return;
-    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 0, q.t.x, q.h.x, q.c0.x, st & 0xffu, q.w.x, dz, dx);
-    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 1, q.t.y, q.h.y, q.c0.y, (st >> 8) & 0xffu, q.w.y, dz, dx);
-    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 2, q.t.z, q.h.z, q.c1.x, (st >> 16) & 0xffu, q.w.z, dz, dx);
-    nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)base + 3, q.t.w, q.h.w, q.c1.y, (st >> 24) & 0xffu, q.w.w, dz, dx);
+// How much node state the pivot CTA keeps in shared memory: the cycle walk is a chain of
+// dependent 16-byte record loads, so holding the records on-chip turns ~L2 latency per hop into
+// shared-memory latency.
+enum { NSX_RES_NONE = 0,   // tree in HBM/L2
+       NSX_RES_NODES = 1,  // node records + potentials resident (24 B / node)
+       NSX_RES_ALL = 2 };  // + depth, preorder array, permutation scratch (36 B / node)
+
+// Dynamic shared memory of one CTA: [potentials | resident node state][ring of tile stages].
+struct NsxSmemPlan {
+    int32_t mode;       // NSX_RES_* (pivot CTA only)
+    int32_t stage_pi;   // potentials are copied into shared memory before each sweep (TMA bulk copy)
+    uint32_t ring_off;  // byte offset of the tile ring inside the dynamic part
+    int32_t stages;     // ring depth (0: this CTA never sweeps)
+};
+
+static inline __host__ __device__ size_t nsx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+static inline __host__ __device__ size_t nsx_resident_bytes(int mode, size_t n) {
+    if (mode == NSX_RES_ALL) return nsx_align16(nsx_align16(8 * n) + 16 * n + 12 * n) + 16;
+    if (mode == NSX_RES_NODES) return nsx_align16(8 * n) + 16 * n;
+    return 0;
+}
+// Plan for a CTA that pivots (and, when `sweeps`, also prices: single-CTA and batch modes).
+static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t limit, uint32_t stage_bytes,
+                                                             bool sweeps, int want_mode, int want_stage) {
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0;
+    const size_t ring_min = sweeps ? 2 * (size_t)stage_bytes : 0;
+    for (int mode = want_mode; mode >= NSX_RES_NODES; --mode) {
+        if (nsx_resident_bytes(mode, n) + ring_min <= limit) { p.mode = mode; break; }
+    }
+    size_t used = nsx_resident_bytes(p.mode, n);
+    if (p.mode == NSX_RES_NONE && sweeps && want_stage && nsx_align16(8 * n) + ring_min <= limit) {
+        p.stage_pi = 1; used = nsx_align16(8 * n);
+    }
+    p.ring_off = (uint32_t)used;
+    if (sweeps) {
+        size_t s = (limit - used) / stage_bytes;
+        p.stages = (int32_t)(s > NSX_MAX_STAGES ? NSX_MAX_STAGES : s);
+    }
+    return p;
+}
+// Plan for a sweep-only worker CTA.
+static inline __host__ __device__ NsxSmemPlan nsx_plan_worker(size_t n, size_t limit, uint32_t stage_bytes, int want_stage) {
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0;
+    size_t used = 0;
+    if (want_stage && nsx_align16(8 * n) + 3 * (size_t)stage_bytes <= limit) { p.stage_pi = 1; used = nsx_align16(8 * n); }
+    p.ring_off = (uint32_t)used;
+    size_t s = (limit - used) / stage_bytes;
+    p.stages = (int32_t)(s > NSX_MAX_STAGES ? NSX_MAX_STAGES : s);
+    return p;
+}
+static inline __host__ __device__ size_t nsx_plan_bytes(const NsxSmemPlan& p, uint32_t stage_bytes) {
+    return (size_t)p.ring_off + (size_t)p.stages * stage_bytes;
 }
 
-template <bool DEVEX>
-__device__ __forceinline__ void nsx_price_scalar(const NsxDev& d, const NsxCmd& cmd, const double* pis,
-                                                 int64_t lo, int64_t hi, NsxCand& dz, NsxDevexCand& dx) {
-    for (int64_t i = lo; i < hi; ++i)
-        nsx_price_arc<DEVEX>(d, cmd, pis, (int32_t)i, __ldg(d.tail + i), __ldg(d.head + i),
-                             __ldg(d.pert + i), __ldcg(d.state + i), DEVEX ? __ldcg(d.wgt + i) : 1u, dz, dx);
-}
-
-#ifndef NSX_UNROLL
-#define NSX_UNROLL 2
-#endif
-
-// Thread g of T handles quads g, g+T, g+2T, ... of the aligned interior; NSX_UNROLL quads are
-// loaded before the first one is priced so that several 128-bit requests are in flight per thread.
-template <bool DEVEX>
-__device__ __forceinline__ void nsx_sweep(const NsxDev& d, const NsxCmd& cmd, const double* pis,
-                                          int64_t g, int64_t T, NsxCand& dz, NsxDevexCand& dx) {
-    const int64_t lo = cmd.lo, hi = cmd.hi;
-    const int64_t a0 = (lo + 3) & ~(int64_t)3;          // first aligned arc
-    const int64_t a1 = hi & ~(int64_t)3;                // end of the aligned interior
-    if (a1 <= a0) {                                     // tiny range: scalar only
-        if (g == 0) nsx_price_scalar<DEVEX>(d, cmd, pis, lo, hi, dz, dx);
-        return;
-    }
-    if (g == 0) {                                       // ragged head / tail (at most 3 arcs each)
-        nsx_price_scalar<DEVEX>(d, cmd, pis, lo, a0, dz, dx);
-        nsx_price_scalar<DEVEX>(d, cmd, pis, a1, hi, dz, dx);
-    }
-    const int64_t nq = (a1 - a0) >> 2;
-    int64_t q = g;
-    for (; q + (NSX_UNROLL - 1) * T < nq; q += NSX_UNROLL * T) {
-        NsxQuad quad[NSX_UNROLL];
-#pragma unroll
-        for (int u = 0; u < NSX_UNROLL; ++u) nsx_load_quad<DEVEX>(d, a0 + ((q + u * T) << 2), quad[u]);
-#pragma unroll
-        for (int u = 0; u < NSX_UNROLL; ++u)
-            nsx_price_quad<DEVEX>(d, cmd, pis, a0 + ((q + u * T) << 2), quad[u], dz, dx);
-    }
-    for (; q < nq; q += T) {
-        NsxQuad quad;
-        nsx_load_quad<DEVEX>(d, a0 + (q << 2), quad);
-        nsx_price_quad<DEVEX>(d, cmd, pis, a0 + (q << 2), quad, dz, dx);
-    }
-}
-
-// Shared-memory layout of one CTA: fixed part, then (dynamic) the staged / resident node state.
+// Shared-memory layout of one CTA: fixed part, then (dynamic) node state and the tile ring.
 struct NsxCtaShared {
     NsxLoopShared L;
     NsxCtl ctl;  // solver scalars live here during the solve (copied in / out of HBM once)
     NsxCmd cmd;  // worker copy of the command
     NsxCand dz_buf[32];
     NsxDevexCand dx_buf[32];
-    unsigned long long mbar;  // completion barrier of the potentials bulk copy
+    unsigned long long mbar;                    // completion barrier of the potentials bulk copy
+    unsigned long long full[NSX_MAX_STAGES];    // tile landed in the stage (TMA complete_tx)
+    unsigned long long empty[NSX_MAX_STAGES];   // every warp is done with the stage
     NsxPivotScratch piv;
     NsxPotScratch pot;
 };
-
-// How much node state the pivot CTA keeps in shared memory (chosen by the host from n and the
-// opt-in shared-memory limit): the cycle walk is a chain of dependent 16-byte record loads, so
-// holding the records on-chip turns ~L2 latency per hop into shared-memory latency.
-enum { NSX_RES_NONE = 0,   // tree in HBM/L2; potentials optionally staged per sweep
-       NSX_RES_NODES = 1,  // node records + potentials resident (24 B / node)
-       NSX_RES_ALL = 2 };  // + depth, preorder array, permutation scratch (36 B / node)
-
-struct NsxSmemPlan {
-    int32_t mode;      // NSX_RES_*
-    int32_t stage_pi;  // workers (and NSX_RES_NONE pivot CTAs) copy pi into shared memory per sweep
-};
-
-__device__ __forceinline__ size_t nsx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Redirect the node arrays of `d` into shared memory according to the plan and fill them.
 __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSmemPlan plan,
@@ -281,49 +278,264 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
     return dl;
 }
 
-// One sweep of this CTA: stage potentials (optional), price, block-reduce into thread 0.
-// `stage_count` is a per-thread register copy of the number of bulk copies issued so far by this
-// CTA (all threads count alike); its low bit is the mbarrier phase to wait for.
-__device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxCmd& cmd, const double* pi_src,
-                                              double* pis, bool stage, uint32_t& stage_count, int64_t g,
-                                              int64_t T, NsxCtaShared& sh, NsxCand& dz, NsxDevexCand& dx) {
-    nsx_cand_init(dz);
-    nsx_devex_init(dx);
-    if (stage) {
-        // refresh the shared-memory copy of the node potentials: one TMA bulk copy, every thread
-        // waits on the mbarrier phase (no register staging, no per-thread loads)
-        NSX_SYNC();
-        if (threadIdx.x == 0)
-            nsx_bulk_load(pis, pi_src, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
-        nsx_mbar_wait(&sh.mbar, stage_count & 1u);
-        stage_count++;
-    }
-    if (cmd.kind == NSX_CMD_DEVEX) {
-        nsx_sweep<true>(d, cmd, pis, g, T, dz, dx);
-        nsx_block_reduce(dx, sh.dx_buf);
-    } else {
-        nsx_sweep<false>(d, cmd, pis, g, T, dz, dx);
-        nsx_block_reduce(dz, sh.dz_buf);
+// ------------------------------------------------------------------------------------------
+// Tile ring: thread 0 keeps `stages` tiles in flight with TMA bulk copies (one mbarrier per
+// stage counts the bytes of the 4-5 column copies of a tile); all warps consume a landed tile
+// straight from shared memory and release the stage through a second mbarrier.  No registers
+// hold data in flight, so the depth of the memory pipeline is set by shared memory alone.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nsx_ring_issue(const NsxDev& d, const NsxStore& st, unsigned char* ring,
+                                               NsxCtaShared& sh, uint32_t stage, int32_t tile, bool with_wgt) {
+    unsigned char* dst = ring + (size_t)stage * st.stage_bytes;
+    unsigned long long* bar = &sh.full[stage];
+    const uint32_t total = 2 * st.b_node + st.b_cost + NSX_TILE + (with_wgt ? 4u * NSX_TILE : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(total) : "memory");
+    nsx_bulk_copy(dst, st.tail + (size_t)tile * st.b_node, st.b_node, bar);
+    nsx_bulk_copy(dst + st.off_head, st.head + (size_t)tile * st.b_node, st.b_node, bar);
+    nsx_bulk_copy(dst + st.off_cost, st.cost + (size_t)tile * st.b_cost, st.b_cost, bar);
+    nsx_bulk_copy(dst + st.off_state, d.state + (size_t)tile * NSX_TILE, NSX_TILE, bar);
+    if (with_wgt) nsx_bulk_copy(dst + st.off_wgt, d.wgt + (size_t)tile * NSX_TILE, 4u * NSX_TILE, bar);
+}
+
+// improving candidates of DantzigPricing.select_entering_arc (simplex_pricing.py:110-131)
+__device__ __forceinline__ void nsx_dantzig_improving(NsxCand& k, int32_t i, uint32_t st, double rc, double tol) {
+    if ((st & NSX_ARC_CAN_FWD) && rc < -tol) {
+        if (k.arc2 < 0 || rc < k.key || (rc == k.key && i * 2 < k.arc2)) { k.key = rc; k.arc2 = i * 2; }
+    } else if ((st & NSX_ARC_CAN_BWD) && rc > tol) {
+        const double nk = -rc;
+        if (k.arc2 < 0 || nk < k.key || (nk == k.key && i * 2 + 1 < k.arc2)) { k.key = nk; k.arc2 = i * 2 + 1; }
     }
 }
 
-// Sweep functor of CTA 0 in the grid-resident kernel.
+enum { NSX_MODE_DANTZIG = 0, NSX_MODE_DEVEX = 1, NSX_MODE_DANTZIG_ZERO = 2, NSX_MODE_DEVEX_ZERO = 3 };
+
+// One landed tile.  Thread t prices arcs t, t + T, t + 2T, t + 3T of the tile (T = block size):
+// consecutive lanes take consecutive arcs, so the column reads from the stage and - on instances
+// whose arcs are sorted by endpoint, such as the dense transportation case - the potential
+// gathers are free of shared-memory bank conflicts.  `gate` caches the key a Dantzig candidate
+// has to reach (-tol while there is none): a single compare rejects almost every arc.
+// PISMEM: potentials are gathered from shared memory (`pis`), else from L2.
+template <int MODE, bool PHASE1, bool PISMEM>
+__device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
+                                               const double* pis, const unsigned char* sp, int32_t tile_base,
+                                               NsxCand& dz, NsxDevexCand& dx, double& gate) {
+    const int tid = threadIdx.x;
+    uint32_t sb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sb[u] = sp[st.off_state + u * NSX_THREADS + tid];
+    if ((int64_t)tile_base < cmd.lo || (int64_t)tile_base + NSX_TILE > cmd.hi) {  // ragged first / last tile
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = (int64_t)tile_base + u * NSX_THREADS + tid;
+            if (i < cmd.lo || i >= cmd.hi) sb[u] = 0;
+        }
+    }
+    // nothing to do when every arc of the thread is in the tree or has no residual either way
+    uint32_t any = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (sb[u] & NSX_ARC_IN_TREE) sb[u] = 0;
+        any |= sb[u] & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD);
+    }
+    if (!any) return;
+    int32_t tl[4], hd[4];
+    double c[4];
+    if (st.node_kind == NSX_NODE_U16) {
+        const uint16_t* pt = reinterpret_cast<const uint16_t*>(sp);
+        const uint16_t* ph = reinterpret_cast<const uint16_t*>(sp + st.off_head);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid] + 1; hd[u] = ph[u * NSX_THREADS + tid] + 1; }
+    } else {
+        const int32_t* pt = reinterpret_cast<const int32_t*>(sp);
+        const int32_t* ph = reinterpret_cast<const int32_t*>(sp + st.off_head);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid]; hd[u] = ph[u * NSX_THREADS + tid]; }
+    }
+    if (st.cost_kind == NSX_COST_F64) {
+        const double* pc = reinterpret_cast<const double*>(sp + st.off_cost);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = pc[u * NSX_THREADS + tid];
+    } else if (st.cost_kind == NSX_COST_I32) {
+        const int32_t* pc = reinterpret_cast<const int32_t*>(sp + st.off_cost);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = (double)pc[u * NSX_THREADS + tid];
+    } else {
+        const int16_t* pc = reinterpret_cast<const int16_t*>(sp + st.off_cost);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_THREADS + tid];
+    }
+    uint32_t wv[4] = {1u, 1u, 1u, 1u};
+    if (MODE == NSX_MODE_DEVEX) {
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(sp + st.off_wgt);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_THREADS + tid];
+    }
+    const double tol = d.tol;
+    const double* pig = d.pi;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int32_t i = tile_base + u * NSX_THREADS + tid;
+        double cost = c[u];
+        // Phase-1 tree cost  pert - 1 - 1e-6*idx  (simplex.py:1162-1168); Devex prices with the
+        // perturbed Phase-2 cost in both phases
+        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, (double)i));
+        const double pt = PISMEM ? pis[tl[u]] : __ldcg(pig + tl[u]);
+        const double ph = PISMEM ? pis[hd[u]] : __ldcg(pig + hd[u]);
+        const double rc = NSX_SUB(NSX_ADD(cost, pt), ph);
+        const uint32_t s = sb[u];
+        if (MODE == NSX_MODE_DANTZIG) {
+            const bool hit = ((s & NSX_ARC_CAN_FWD) && rc <= gate) || ((s & NSX_ARC_CAN_BWD) && -rc <= gate);
+            if (hit) {
+                nsx_dantzig_improving(dz, i, s, rc, tol);
+                gate = dz.arc2 >= 0 ? dz.key : -tol;
+            }
+        } else if (MODE == NSX_MODE_DANTZIG_ZERO) {
+            if ((s & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD)) && fabs(rc) <= tol) {  // simplex_pricing.py:132-135
+                const int32_t cand = i * 2 + ((s & NSX_ARC_CAN_FWD) ? 0 : 1);
+                if (cand < dz.zero2) dz.zero2 = cand;
+            }
+        } else {
+            if (i == cmd.excluded) continue;
+            const bool fv = (s & NSX_ARC_CAN_FWD) && rc < -tol;
+            const bool bv = (s & NSX_ARC_CAN_BWD) && rc > tol;
+            if (MODE == NSX_MODE_DEVEX) {
+                if (fv || bv) {
+                    const double wd = (wv[u] >> 24) == cmd.wepoch ? (double)(wv[u] & 0xffffffu) : 1.0;
+                    const double merit = NSX_DIV(NSX_MUL(rc, rc), wd);
+                    if (fv) { if (dx.fi < 0 || merit > dx.fm || (merit == dx.fm && i < dx.fi)) { dx.fm = merit; dx.fi = i; } }
+                    else    { if (dx.bi < 0 || merit > dx.bm || (merit == dx.bm && i < dx.bi)) { dx.bm = merit; dx.bi = i; } }
+                }
+            } else {  // NSX_MODE_DEVEX_ZERO, simplex.py:603-615
+                if (!(fv || bv) && fabs(rc) <= tol) {
+                    if ((s & NSX_ARC_CAN_FWD) && i < dx.fz) dx.fz = i;
+                    if ((s & NSX_ARC_CAN_BWD) && i < dx.bz) dx.bz = i;
+                }
+            }
+        }
+    }
+}
+
+// Sweep of [cmd.lo, cmd.hi) by sweeper `worker` of `nworkers`: tiles worker, worker + nworkers, ...
+// of the range, ascending or (cmd.reverse) descending.  `pos` is the ring position of this CTA
+// (register copy, identical in all threads): bits 0-15 = stage of the next tile, bit 16 = mbarrier
+// phase parity of that stage.
+template <int MODE, bool PHASE1, bool PISMEM>
+__device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
+                                               const double* pis, unsigned char* ring, int stages,
+                                               NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
+                                               bool wait_pi, uint32_t& stage_count, NsxCand& dz,
+                                               NsxDevexCand& dx) {
+    const int32_t t0 = (int32_t)(cmd.lo / NSX_TILE), t1 = (int32_t)((cmd.hi + NSX_TILE - 1) / NSX_TILE);
+    const int32_t ntiles = t1 - t0;
+    const int32_t my_n = ntiles > worker ? (ntiles - worker + nworkers - 1) / nworkers : 0;
+    const bool with_wgt = MODE == NSX_MODE_DEVEX;
+    const int lane = threadIdx.x & 31;
+    const int32_t step = cmd.reverse ? -nworkers : nworkers;
+    const int32_t first = t0 + worker + (cmd.reverse ? (my_n - 1) * nworkers : 0);
+    uint32_t stage = pos & 0xffffu, parity = pos >> 16;
+    if (threadIdx.x == 0) {
+        const int32_t pre = my_n < stages ? my_n : stages;
+        uint32_t s = stage;
+        for (int32_t j = 0; j < pre; ++j) {
+            nsx_ring_issue(d, st, ring, sh, s, first + j * step, with_wgt);
+            if (++s == (uint32_t)stages) s = 0;
+        }
+    }
+    if (wait_pi) {  // potentials of this sweep have landed (their copy was issued before the tiles)
+        nsx_mbar_wait(&sh.mbar, stage_count & 1u);
+        stage_count++;
+    }
+    double gate = -d.tol;
+    int32_t tile = first;
+    for (int32_t j = 0; j < my_n; ++j) {
+        nsx_mbar_wait(&sh.full[stage], parity);
+        nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + stage * st.stage_bytes, tile * NSX_TILE, dz, dx, gate);
+        __syncwarp();
+        if (lane == 0) nsx_mbar_arrive(&sh.empty[stage]);
+        if (threadIdx.x == 0 && j + stages < my_n) {
+            nsx_mbar_wait(&sh.empty[stage], parity);  // every warp has read the stage
+            nsx_ring_issue(d, st, ring, sh, stage, tile + stages * step, with_wgt);
+        }
+        tile += step;
+        if (++stage == (uint32_t)stages) { stage = 0; parity ^= 1u; }
+    }
+    pos = stage | (parity << 16);
+}
+
+template <int MODE, bool PHASE1>
+__device__ __forceinline__ void nsx_sweep_ring_pi(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
+                                                  const double* pis, unsigned char* ring, int stages,
+                                                  NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
+                                                  bool wait_pi, uint32_t& stage_count, NsxCand& dz,
+                                                  NsxDevexCand& dx) {
+    if (pis) nsx_sweep_ring<MODE, PHASE1, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
+    else nsx_sweep_ring<MODE, PHASE1, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
+}
+
+// One sweep of this CTA: refresh the staged potentials (optional), price, block-reduce into
+// thread 0.  `stage_count` is the per-thread register copy of the number of potential copies this
+// CTA has issued (its low bit is the mbarrier phase to wait for).
+__device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
+                                              double* pis, bool stage, uint32_t& stage_count,
+                                              unsigned char* ring, int stages, uint32_t& pos, int worker,
+                                              int nworkers, NsxCtaShared& sh, NsxCand& dz, NsxDevexCand& dx) {
+    nsx_cand_init(dz);
+    nsx_devex_init(dx);
+    NSX_SYNC();  // the command is visible; reduction buffers / staged potentials are free again
+    if (threadIdx.x == 0) {
+        // writes of the pivot CTA (state bytes, weights, potentials) were acquired through the
+        // generic proxy; the bulk copies below read them through the async proxy
+        nsx_fence_proxy_async();
+        if (stage) nsx_bulk_load(pis, d.pi, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
+    }
+    if (cmd.kind == NSX_CMD_DANTZIG) {
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_block_reduce(dz, sh.dz_buf);
+    } else if (cmd.kind == NSX_CMD_DEVEX) {
+        nsx_sweep_ring_pi<NSX_MODE_DEVEX, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_block_reduce(dx, sh.dx_buf);
+    } else if (cmd.kind == NSX_CMD_DANTZIG_ZERO) {
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_block_reduce(dz, sh.dz_buf);
+    } else {
+        nsx_sweep_ring_pi<NSX_MODE_DEVEX_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_block_reduce(dx, sh.dx_buf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Grid-resident kernel: CTA 0 pivots, the other CTAs price.
+// ------------------------------------------------------------------------------------------
+struct NsxSweepCtx {       // what a CTA needs to run sweeps
+    const NsxStore* st;
+    double* pis;           // potentials in shared memory (resident master copy or staging buffer), or null
+    bool stage;            // refresh `pis` from HBM before each sweep
+    unsigned char* ring;
+    int stages;
+};
+
+// Sweep functor of CTA 0.
 struct GridSweep {
-    const NsxDev& d;      // global view (arc arrays, global pi mirror)
+    const NsxDev& d;      // global view (state bytes, weights, global potentials)
     NsxGridCtl* g;
     NsxCand* dzc;
     NsxDevexCand* dxc;
     NsxCtaShared& sh;
-    double* pis;          // potentials in shared memory (resident master copy, or staging buffer), or null
-    bool stage;           // this CTA must refresh `pis` from HBM before each sweep
+    NsxSweepCtx cx;
     uint32_t& stage_count;
+    uint32_t& q0;
     int32_t seq;
     unsigned long long target;
     unsigned long long t_price, t_sync;
 
     __device__ void publish(const NsxCmd& cmd) {
         if (threadIdx.x == 0) {
-            g->cmd = cmd;
+            union { NsxCmd c; int4 v[3]; } tmp;
+            tmp.c = cmd;
+            int4* dst = reinterpret_cast<int4*>(&g->cmd);
+            dst[0] = tmp.v[0]; dst[1] = tmp.v[1]; dst[2] = tmp.v[2];
             __threadfence();
             nsx_st_release(&g->seq, ++seq);
         }
@@ -332,21 +544,20 @@ struct GridSweep {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
-        if (gridDim.x > 1) publish(cmd_in);
         const NsxCmd cmd = cmd_in;
-        NsxCand dz; NsxDevexCand dx;
-        nsx_cand_init(dz); nsx_devex_init(dx);
-        // with workers present this CTA only pivots and merges; alone it prices everything itself
-        if (gridDim.x == 1)
-            nsx_cta_sweep(d, cmd, d.pi, pis, stage, stage_count, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
-        if (gridDim.x == 1) {
+        const bool devex = cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO;
+        if (gridDim.x == 1) {  // alone: this CTA prices everything itself
+            NsxCand dz; NsxDevexCand dx;
+            if (threadIdx.x == 0) __threadfence();
+            nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
             if (threadIdx.x == 0) {
-                if (cmd.kind == NSX_CMD_DEVEX) out_dx = dx; else out_dz = dz;
+                if (devex) out_dx = dx; else out_dz = dz;
                 t_price += nsx_globaltimer() - t0;
             }
             NSX_SYNC();
             return;
         }
+        publish(cmd);
         if (threadIdx.x == 0) {
             unsigned long long t1 = nsx_globaltimer();
             target += gridDim.x - 1;
@@ -356,9 +567,8 @@ struct GridSweep {
         }
         NSX_SYNC();
         // merge the candidates of the other CTAs (one per thread), then reduce across the block
-        if (cmd.kind == NSX_CMD_DEVEX) {
+        if (devex) {
             NsxDevexCand k; nsx_devex_init(k);
-            if (threadIdx.x == 0) k = dx;
             for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
                 const int4* src = (const int4*)(dxc + b);
                 union { NsxDevexCand c; int4 v[2]; } tmp;
@@ -369,7 +579,6 @@ struct GridSweep {
             if (threadIdx.x == 0) out_dx = k;
         } else {
             NsxCand k; nsx_cand_init(k);
-            if (threadIdx.x == 0) k = dz;
             for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
                 union { NsxCand c; int4 v; } tmp;
                 tmp.v = __ldcg((const int4*)(dzc + b));
@@ -384,24 +593,28 @@ struct GridSweep {
     __device__ void finish() {
         NsxCmd cmd;
         cmd.kind = NSX_CMD_EXIT; cmd.phase = 0; cmd.lo = cmd.hi = 0; cmd.excluded = -1; cmd.wepoch = 0;
+        cmd.reverse = 0; cmd.pad[0] = cmd.pad[1] = cmd.pad[2] = 0;
         NSX_SYNC();
         if (gridDim.x > 1) publish(cmd);
     }
 };
 
 static_assert(sizeof(NsxCand) == 16, "NsxCand is moved as one int4");
-static_assert(sizeof(NsxCmd) == 32, "NsxCmd is moved as two int4");
+static_assert(sizeof(NsxCmd) == 48, "NsxCmd is moved as three int4");
 static_assert(offsetof(NsxGridCtl, cmd) % 16 == 0, "command block must be 16-byte aligned");
 static_assert(sizeof(NsxDevexCand) == 32, "NsxDevexCand is moved as two int4");
 
 struct NsxKernelArgs {
     NsxDev d;
+    NsxStore st;
     NsxCtl* ctl;
     NsxGridCtl* grid;
     NsxCand* dzc;
     NsxDevexCand* dxc;
     int32_t* trace;
-    NsxSmemPlan plan;
+    NsxSmemPlan plan;    // CTA 0
+    NsxSmemPlan wplan;   // sweep workers
+    int32_t probe_sweeps;  // > 0: measurement aid, run this many sweeps of the initial state and stop
 };
 
 __device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
@@ -410,14 +623,53 @@ __device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
     for (int i = threadIdx.x; i < (int)(sizeof(NsxCtl) / 4); i += blockDim.x) t[i] = s[i];
 }
 
+__device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
+    if (threadIdx.x == 0) {
+        nsx_mbar_init(&sh.mbar, 1);
+        for (int s = 0; s < NSX_MAX_STAGES; ++s) {
+            nsx_mbar_init(&sh.full[s], 1);
+            nsx_mbar_init(&sh.empty[s], blockDim.x >> 5);
+        }
+        nsx_mbar_init_fence();
+    }
+}
+
+// Measurement aid (nsx_sweep_probe): `count` sweeps of the initial state through exactly the
+// command / arrival protocol of a solve, no pivots.
+template <class Sweep>
+__device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPotScratch& ps,
+                                               Sweep& sweep, int32_t count) {
+    nsx_recompute_potentials(d, 1, 1, d.n, ps, (int64_t*)0);
+    for (int32_t k = 0; k < count; ++k) {
+        NSX_SYNC();
+        if (threadIdx.x == 0) {
+            NsxCmd& cmd = L.cmd;
+            if (c.pricing == NSX_PRICING_DEVEX && !c.row_scan_first) {
+                int64_t st = (k % ((d.m + c.bs - 1) / c.bs)) * c.bs;
+                cmd.kind = NSX_CMD_DEVEX; cmd.lo = st; cmd.hi = st + c.bs < d.m ? st + c.bs : d.m;
+            } else {
+                cmd.kind = NSX_CMD_DANTZIG; cmd.lo = 0; cmd.hi = d.m;
+            }
+            cmd.phase = 1; cmd.excluded = -1; cmd.wepoch = 0; cmd.reverse = k & 1;
+            c.arcs_priced += cmd.hi - cmd.lo;
+            c.sweeps++;
+        }
+        NSX_SYNC();
+        sweep.run(L.cmd, L.dz, L.dx);
+    }
+    NSX_SYNC();
+    if (threadIdx.x == 0) { c.status = NSX_STATUS_OPTIMAL; c.total = 0; }
+    sweep.finish();
+}
+
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
 nsx_resident_kernel(const NsxKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
     unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
     const NsxDev& d = a.d;
-    if (threadIdx.x == 0) nsx_mbar_init(&sh.mbar, 1);
-    uint32_t stage_count = 0;
+    nsx_init_barriers(sh);
+    uint32_t stage_count = 0, q0 = 0;
     NSX_SYNC();
 
     if (blockIdx.x == 0) {
@@ -428,9 +680,11 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const NsxDev dl = nsx_make_resident(d, a.plan, dyn, &pis);
         NSX_SYNC();
         const bool resident = a.plan.mode != NSX_RES_NONE;
-        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, (resident || a.plan.stage_pi) ? pis : nullptr,
-                        !resident && a.plan.stage_pi != 0, stage_count, 0, 0ull, 0ull, 0ull};
-        nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
+        NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
+                       dyn + a.plan.ring_off, a.plan.stages};
+        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull};
+        if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.pot, sweep, a.probe_sweeps);
+        else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
         if (threadIdx.x == 0) {
             unsigned long long total = nsx_globaltimer() - t_begin;
@@ -443,31 +697,31 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         return;
     }
     // worker CTAs: wait for a command, price, deliver, repeat
-    double* pis = a.plan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
+    double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
+    unsigned char* ring = dyn + a.wplan.ring_off;
     int32_t seen = 0;
     for (;;) {
         if (threadIdx.x == 0) {
             int32_t s;
-            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(32); }
+            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(20); }
             seen = s;
             __threadfence();
-            union { NsxCmd c; int4 v[2]; } tmp;
-            tmp.v[0] = __ldcg((const int4*)&a.grid->cmd);
-            tmp.v[1] = __ldcg(((const int4*)&a.grid->cmd) + 1);
+            union { NsxCmd c; int4 v[3]; } tmp;
+            const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
+            tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1); tmp.v[2] = __ldcg(src + 2);
             sh.cmd = tmp.c;
         }
         NSX_SYNC();
         const NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
-        nsx_cta_sweep(d, cmd, d.pi, pis, pis != nullptr, stage_count, (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x,
-                      (int64_t)(gridDim.x - 1) * blockDim.x, sh, dz, dx);
+        nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
+                      (int)blockIdx.x - 1, (int)gridDim.x - 1, sh, dz, dx);
         if (threadIdx.x == 0) {
-            if (cmd.kind == NSX_CMD_DEVEX) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
+            if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
             __threadfence();
             atomicAdd(&a.grid->arrived, 1ull);
         }
-        NSX_SYNC();
     }
 }
 
@@ -484,11 +738,51 @@ extern "C" __global__ void nsx_init_kernel(const NsxDev d, const double* supply,
     if (art) atomicAdd((unsigned long long*)&ctl->art_with_flow, art);
 }
 
+// Which compact cost encodings are exact for this instance: bit 0 set = some cost is not an
+// int32-valued integer, bit 1 set = some cost is not an int16-valued integer.
+extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, int64_t m, unsigned int* flags) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    unsigned int f = 0;
+    for (int64_t i = g; i < m; i += T) {
+        const double c = pert[i];
+        if (!(c == rint(c)) || fabs(c) > 2147483000.0) f |= 3u;
+        else if (fabs(c) > 32767.0) f |= 2u;
+    }
+    if (f) atomicOr(flags, f);
+}
+
+// Canonical arrays (int32 tail / head, float64 perturbed cost) -> tile-padded pricing store.
+extern "C" __global__ void nsx_pack_kernel(const int32_t* tail, const int32_t* head, const double* pert,
+                                           int64_t m, int64_t mpad, NsxStore st) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    unsigned char* ptail = const_cast<unsigned char*>(st.tail);
+    unsigned char* phead = const_cast<unsigned char*>(st.head);
+    unsigned char* pcost = const_cast<unsigned char*>(st.cost);
+    for (int64_t i = g; i < mpad; i += T) {
+        const bool in = i < m;
+        const int32_t tl = in ? tail[i] : 1, hd = in ? head[i] : 1;
+        const double c = in ? pert[i] : 0.0;
+        if (st.node_kind == NSX_NODE_U16) {
+            reinterpret_cast<uint16_t*>(ptail)[i] = (uint16_t)(tl - 1);
+            reinterpret_cast<uint16_t*>(phead)[i] = (uint16_t)(hd - 1);
+        } else {
+            reinterpret_cast<int32_t*>(ptail)[i] = tl;
+            reinterpret_cast<int32_t*>(phead)[i] = hd;
+        }
+        if (st.cost_kind == NSX_COST_F64) reinterpret_cast<double*>(pcost)[i] = c;
+        else if (st.cost_kind == NSX_COST_I32) reinterpret_cast<int32_t*>(pcost)[i] = (int32_t)c;
+        else reinterpret_cast<int16_t*>(pcost)[i] = (int16_t)c;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Batched variant: one CTA solves one independent instance end to end (config 4).
 // ------------------------------------------------------------------------------------------
 struct NsxBatchItem {
     NsxDev d;
+    NsxStore st;
     NsxCtl* ctl;
     int32_t* trace;
     const double* supply;
@@ -497,29 +791,34 @@ struct NsxBatchItem {
 struct LocalSweep {
     const NsxDev& d;
     NsxCtaShared& sh;
-    double* pis;
-    bool stage;
+    NsxSweepCtx cx;
     uint32_t& stage_count;
+    uint32_t& q0;
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
-        nsx_cta_sweep(d, cmd, d.pi, pis, stage, stage_count, (int64_t)threadIdx.x, (int64_t)blockDim.x, sh, dz, dx);
-        if (threadIdx.x == 0) { if (cmd.kind == NSX_CMD_DEVEX) out_dx = dx; else out_dz = dz; }
+        NSX_SYNC();
+        if (threadIdx.x == 0) __threadfence();  // this CTA's own state / potential writes reach L2 before the bulk reads
+        nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
+        if (threadIdx.x == 0) {
+            if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) out_dx = dx; else out_dz = dz;
+        }
         NSX_SYNC();
     }
     __device__ void finish() {}
 };
 
-// per-item smem need is decided on the host from the largest instance; smaller instances simply
-// use less of it.  `limit_bytes` = dynamic bytes available after the fixed part.
+// The shared-memory plan of an item is made in the kernel from its node count; `limit_bytes` =
+// dynamic bytes available after the fixed part (sized by the host for the largest instance).
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
-nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes) {
+nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes,
+                 int want_mode, int want_stage) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
     unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
     __shared__ unsigned long long my_item;
-    if (threadIdx.x == 0) nsx_mbar_init(&sh.mbar, 1);
-    uint32_t stage_count = 0;
+    nsx_init_barriers(sh);
+    uint32_t stage_count = 0, q0 = 0;
     for (;;) {
         NSX_SYNC();
         if (threadIdx.x == 0) my_item = atomicAdd(next, 1ull);
@@ -538,15 +837,14 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
             sh.ctl.art_with_flow = art;
         }
         NSX_SYNC();
-        NsxSmemPlan plan;
-        const size_t n = (size_t)d.n;
-        plan.mode = (36 * n + 64 <= limit_bytes) ? NSX_RES_ALL : (24 * n + 64 <= limit_bytes) ? NSX_RES_NODES : NSX_RES_NONE;
-        plan.stage_pi = (plan.mode == NSX_RES_NONE && 8 * n + 64 <= limit_bytes) ? 1 : 0;
+        const NsxSmemPlan plan = nsx_plan_pivot((size_t)d.n, limit_bytes, item.st.stage_bytes, true, want_mode, want_stage);
         double* pis = nullptr;
         const NsxDev dl = nsx_make_resident(d, plan, dyn, &pis);
         NSX_SYNC();
         const bool resident = plan.mode != NSX_RES_NONE;
-        LocalSweep sweep{d, sh, (resident || plan.stage_pi) ? pis : nullptr, !resident && plan.stage_pi != 0, stage_count};
+        NsxSweepCtx cx{&item.st, (resident || plan.stage_pi) ? pis : nullptr, !resident && plan.stage_pi != 0,
+                       dyn + plan.ring_off, plan.stages};
+        LocalSweep sweep{d, sh, cx, stage_count, q0};
         nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, item.trace, sweep);
         NSX_SYNC();
         nsx_copy_ctl(item.ctl, &sh.ctl);
@@ -566,12 +864,12 @@ static int nsx_fail(int code, const std::string& msg) {
     do {                                                                                        \
         cudaError_t err__ = (call);                                                             \
         if (err__ != cudaSuccess) {                                                             \
-            arena.release();                                                                    \
+            arena.release(); inputs.release();                                                  \
             return nsx_fail(NSX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
         }                                                                                       \
     } while (0)
 
-// One cudaMalloc per call; sub-allocations are 256-byte aligned.
+// One cudaMalloc per arena; sub-allocations are 256-byte aligned.
 struct Arena {
     unsigned char* base = nullptr;
     size_t size = 0, used = 0;
@@ -616,6 +914,7 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
     res->weight_resets = c.resets;
     res->final_block_size = c.bs;
     res->arcs_priced = c.arcs_priced;
+    res->sweeps = c.sweeps;
     res->unbounded_arc = c.unbounded_arc;
     res->unbounded_rc = c.unbounded_rc;
     res->sum_cycle_len = c.sum_cycle;
@@ -646,24 +945,26 @@ static int nsx_env_int(const char* name, int dflt) {
 }
 
 static size_t nsx_smem_fixed() { return (sizeof(NsxCtaShared) + 15) & ~(size_t)15; }
-// Choose how much node state lives in shared memory for an n-node instance under `limit` bytes.
-static NsxSmemPlan nsx_plan_smem(int32_t n, size_t limit, size_t* bytes) {
-    NsxSmemPlan plan; plan.mode = NSX_RES_NONE; plan.stage_pi = 0;
-    const size_t fixed = nsx_smem_fixed(), nn = (size_t)n;
-    const int want = nsx_env_int("NSX_RESIDENT", 2);
-    size_t dyn = 0;
-    if (want >= 2 && fixed + 36 * nn + 64 <= limit) { plan.mode = NSX_RES_ALL; plan.stage_pi = 1; dyn = 36 * nn + 64; }
-    else if (want >= 1 && fixed + 24 * nn + 64 <= limit) { plan.mode = NSX_RES_NODES; plan.stage_pi = 1; dyn = 24 * nn + 64; }
-    else if (nsx_env_int("NSX_STAGE_PI", 1) != 0 && fixed + 8 * nn + 64 <= limit && n <= NSX_PI_SMEM_MAX_NODES) {
-        plan.stage_pi = 1; dyn = 8 * nn + 64;
-    }
-    *bytes = fixed + dyn;
-    return plan;
+static int64_t nsx_pad_tiles(int64_t m) {
+    int64_t t = (m + NSX_TILE - 1) / NSX_TILE;
+    return (t < 1 ? 1 : t) * (int64_t)NSX_TILE;
 }
 
-// Common implementation; `resident` = arc arrays are device pointers.
-static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_result* res, bool resident) {
-    Arena arena;
+// Narrowest exact encoding of the pricing store (see the NsxStore comment).  `cost_flags` is the
+// result of nsx_classify_costs_kernel.  NSX_LAYOUT=wide forces int32 ids + float64 costs.
+static void nsx_choose_layout(int32_t n, unsigned int cost_flags, bool devex, NsxStore& st) {
+    int node_kind = (n - 1 <= 65536) ? NSX_NODE_U16 : NSX_NODE_I32;
+    int cost_kind = !(cost_flags & 2u) ? NSX_COST_I16 : !(cost_flags & 1u) ? NSX_COST_I32 : NSX_COST_F64;
+    const char* force = getenv("NSX_LAYOUT");
+    if (force && !strcmp(force, "wide")) { node_kind = NSX_NODE_I32; cost_kind = NSX_COST_F64; }
+    if (force && !strcmp(force, "i32")) { node_kind = NSX_NODE_I32; if (cost_kind == NSX_COST_I16) cost_kind = NSX_COST_I32; }
+    nsx_store_layout(st, node_kind, cost_kind, devex ? 1 : 0);
+}
+
+// Common implementation; `resident` = arc arrays are device pointers; probe_sweeps > 0 = sweep probe.
+static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_result* res, bool resident,
+                          int32_t probe_sweeps) {
+    Arena arena, inputs;
     int rc = nsx_validate(pb, opt, res);
     if (rc) return rc;
     int ndev = 0;
@@ -676,47 +977,32 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     if (!info.coop) return nsx_fail(NSX_ERR_NO_DEVICE, "device lacks cooperative launch");
 
     const int32_t n = pb->n_nodes;
-    const int64_t m = pb->n_arcs, ma = m + n - 1;
+    const int64_t m = pb->n_arcs, ma = m + n - 1, mpad = nsx_pad_tiles(m);
     const bool devex = opt->pricing == NSX_PRICING_DEVEX;
     const bool want_trace = res->entering_trace && opt->trace_capacity > 0;
-
-    // ---- device memory plan ----
-    size_t o_tail = 0, o_head = 0, o_pert = 0, o_upper = 0;
-    if (!resident) {
-        o_tail = arena.plan((size_t)(m + 4) * 4); o_head = arena.plan((size_t)(m + 4) * 4);
-        o_pert = arena.plan((size_t)(m + 4) * 8); o_upper = arena.plan((size_t)(m + 4) * 8);
-    }
-    size_t o_atail = arena.plan((size_t)n * 4), o_ahead = arena.plan((size_t)n * 4), o_aupper = arena.plan((size_t)n * 8);
-    size_t o_flow = arena.plan((size_t)(ma + 4) * 8), o_state = arena.plan((size_t)ma + 16);
-    size_t o_wgt = devex ? arena.plan((size_t)(m + 4) * 4) : 0;
-    size_t o_node = arena.plan((size_t)n * sizeof(NsxNode)), o_depth = arena.plan((size_t)n * 4);
-    size_t o_pi = arena.plan((size_t)n * 8 + 16), o_order = arena.plan((size_t)n * 4), o_tmp = arena.plan((size_t)n * 4);
-    size_t o_gph = arena.plan((size_t)n * 4), o_gpt = arena.plan((size_t)n * 4);
-    size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
-    size_t o_supply = arena.plan((size_t)n * 8);
-    size_t o_ctl = arena.plan(sizeof(NsxCtl)), o_grid = arena.plan(sizeof(NsxGridCtl));
-    size_t o_dzc = arena.plan(sizeof(NsxCand) * 1024), o_dxc = arena.plan(sizeof(NsxDevexCand) * 1024);
-    size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
-    NSX_CUDA(arena.commit());
 
     cudaStream_t stream;
     NSX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     cudaEvent_t ev[4];
     for (auto& e : ev) NSX_CUDA(cudaEventCreate(&e));
 
+    // ---- inputs: canonical arrays in HBM (uploaded, or the caller's resident copies) ----
+    size_t i_tail = 0, i_head = 0, i_pert = 0, i_upper = 0;
+    if (!resident) {
+        i_tail = inputs.plan((size_t)(m + 4) * 4); i_head = inputs.plan((size_t)(m + 4) * 4);
+        i_pert = inputs.plan((size_t)(m + 4) * 8); i_upper = inputs.plan((size_t)(m + 4) * 8);
+    }
+    size_t i_supply = inputs.plan((size_t)n * 8), i_flags = inputs.plan(16);
+    NSX_CUDA(inputs.commit());
     NsxKernelArgs ka;
     NsxDev& d = ka.d;
     d.n = n; d.m = m; d.ma = ma;
     NSX_CUDA(cudaEventRecord(ev[0], stream));
     if (resident) {
         d.tail = pb->tail; d.head = pb->head; d.pert = pb->pert_cost; d.upper = pb->upper;
-        if (((uintptr_t)d.tail | (uintptr_t)d.head | (uintptr_t)d.pert | (uintptr_t)d.upper) & 15) {
-            arena.release();
-            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "resident arc arrays must be 16-byte aligned");
-        }
     } else {
-        d.tail = arena.at<int32_t>(o_tail); d.head = arena.at<int32_t>(o_head);
-        d.pert = arena.at<double>(o_pert); d.upper = arena.at<double>(o_upper);
+        d.tail = inputs.at<int32_t>(i_tail); d.head = inputs.at<int32_t>(i_head);
+        d.pert = inputs.at<double>(i_pert); d.upper = inputs.at<double>(i_upper);
         if (m > 0) {
             NSX_CUDA(cudaMemcpyAsync((void*)d.tail, pb->tail, (size_t)m * 4, cudaMemcpyHostToDevice, stream));
             NSX_CUDA(cudaMemcpyAsync((void*)d.head, pb->head, (size_t)m * 4, cudaMemcpyHostToDevice, stream));
@@ -724,8 +1010,38 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
             NSX_CUDA(cudaMemcpyAsync((void*)d.upper, pb->upper, (size_t)m * 8, cudaMemcpyHostToDevice, stream));
         }
     }
-    double* d_supply = arena.at<double>(o_supply);
+    double* d_supply = inputs.at<double>(i_supply);
+    unsigned int* d_flags = inputs.at<unsigned int>(i_flags);
     NSX_CUDA(cudaMemcpyAsync(d_supply, pb->supply, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+    NSX_CUDA(cudaMemsetAsync(d_flags, 0, 16, stream));
+    const int util_blocks = info.sms * 8;
+    if (m > 0) {
+        nsx_classify_costs_kernel<<<util_blocks, 256, 0, stream>>>(d.pert, m, d_flags);
+        NSX_CUDA(cudaGetLastError());
+    }
+    unsigned int cost_flags = 3u;
+    NSX_CUDA(cudaMemcpyAsync(&cost_flags, d_flags, 4, cudaMemcpyDeviceToHost, stream));
+    NSX_CUDA(cudaStreamSynchronize(stream));
+    NsxStore& st = ka.st;
+    nsx_choose_layout(n, cost_flags, devex, st);
+
+    // ---- engine-owned device memory ----
+    const size_t state_len = (size_t)(ma > mpad ? ma : mpad) + 16;
+    size_t o_stail = arena.plan((size_t)mpad * nsx_node_bytes(st.node_kind)), o_shead = arena.plan((size_t)mpad * nsx_node_bytes(st.node_kind));
+    size_t o_scost = arena.plan((size_t)mpad * nsx_cost_bytes(st.cost_kind));
+    size_t o_atail = arena.plan((size_t)n * 4), o_ahead = arena.plan((size_t)n * 4), o_aupper = arena.plan((size_t)n * 8);
+    size_t o_flow = arena.plan((size_t)(ma + 4) * 8), o_state = arena.plan(state_len);
+    size_t o_wgt = devex ? arena.plan((size_t)mpad * 4) : 0;
+    size_t o_node = arena.plan((size_t)n * sizeof(NsxNode)), o_depth = arena.plan((size_t)n * 4);
+    size_t o_pi = arena.plan((size_t)n * 8 + 16), o_order = arena.plan((size_t)n * 4), o_tmp = arena.plan((size_t)n * 4);
+    size_t o_gph = arena.plan((size_t)n * 4), o_gpt = arena.plan((size_t)n * 4);
+    size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
+    size_t o_ctl = arena.plan(sizeof(NsxCtl)), o_grid = arena.plan(sizeof(NsxGridCtl));
+    size_t o_dzc = arena.plan(sizeof(NsxCand) * 1024), o_dxc = arena.plan(sizeof(NsxDevexCand) * 1024);
+    size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
+    NSX_CUDA(arena.commit());
+
+    st.tail = arena.at<unsigned char>(o_stail); st.head = arena.at<unsigned char>(o_shead); st.cost = arena.at<unsigned char>(o_scost);
     d.atail = arena.at<int32_t>(o_atail); d.ahead = arena.at<int32_t>(o_ahead); d.aupper = arena.at<double>(o_aupper);
     d.flow = arena.at<double>(o_flow); d.state = arena.at<uint8_t>(o_state);
     d.wgt = devex ? arena.at<uint32_t>(o_wgt) : nullptr;
@@ -737,29 +1053,47 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.dzc = arena.at<NsxCand>(o_dzc); ka.dxc = arena.at<NsxDevexCand>(o_dxc);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
+    ka.probe_sweeps = probe_sweeps;
 
     NsxCtl hctl;
     nsx_fill_ctl(hctl, opt, want_trace);
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
+    NSX_CUDA(cudaMemsetAsync(d.state, 0, state_len, stream));
+    if (devex) NSX_CUDA(cudaMemsetAsync(d.wgt, 0, (size_t)mpad * 4, stream));
+    nsx_pack_kernel<<<util_blocks, 256, 0, stream>>>(d.tail, d.head, d.pert, m, mpad, st);
+    NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
     // ---- launch shape ----
-    size_t smem = 0;
-    ka.plan = nsx_plan_smem(n, info.smem_optin, &smem);
-    if (smem > info.smem_optin) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
-    NSX_CUDA(cudaFuncSetAttribute(nsx_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_resident_kernel, NSX_THREADS, smem));
-    if (per_sm < 1) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "resident kernel does not fit on an SM"); }
     // one pivot CTA + sweep workers; small instances are priced by the pivot CTA alone
     int64_t arcs_per_cta = nsx_env_int("NSX_ARCS_PER_CTA", 8192);
     int64_t workers = (m + arcs_per_cta - 1) / arcs_per_cta;
     if (workers > info.sms - 1) workers = info.sms - 1;
     int grid = m < nsx_env_int("NSX_SINGLE_CTA_ARCS", 65536) || workers < 2 ? 1 : (int)workers + 1;
     int forced = nsx_env_int("NSX_GRID", 0);
-    if (forced > 0) grid = forced < info.sms * per_sm ? forced : info.sms * per_sm;
-    if (grid > 1024) grid = 1024;
+    if (forced > 0) grid = forced < info.sms ? forced : info.sms;
+    const size_t fixed = nsx_smem_fixed();
+    if (fixed + 2 * (size_t)st.stage_bytes > info.smem_optin) { arena.release(); inputs.release(); return nsx_fail(NSX_ERR_INTERNAL, "tile ring does not fit in shared memory"); }
+    const size_t limit = info.smem_optin - fixed;
+    const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
+    ka.plan = nsx_plan_pivot((size_t)n, limit, st.stage_bytes, grid == 1, want_mode, want_stage);
+    ka.wplan = nsx_plan_worker((size_t)n, limit, st.stage_bytes, want_stage);
+    int max_stages = nsx_env_int("NSX_STAGES", NSX_MAX_STAGES);
+    if (max_stages < 2) max_stages = 2;
+    if (ka.plan.stages > max_stages) ka.plan.stages = max_stages;
+    if (ka.wplan.stages > max_stages) ka.wplan.stages = max_stages;
+    size_t dyn = nsx_plan_bytes(ka.plan, st.stage_bytes);
+    if (grid > 1 && nsx_plan_bytes(ka.wplan, st.stage_bytes) > dyn) dyn = nsx_plan_bytes(ka.wplan, st.stage_bytes);
+    const size_t smem = fixed + dyn;
+    if (smem > info.smem_optin || (grid == 1 ? ka.plan.stages : ka.wplan.stages) < 2) {
+        arena.release(); inputs.release();
+        return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit");
+    }
+    NSX_CUDA(cudaFuncSetAttribute(nsx_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_resident_kernel, NSX_THREADS, smem));
+    if (per_sm < 1) { arena.release(); inputs.release(); return nsx_fail(NSX_ERR_INTERNAL, "resident kernel does not fit on an SM"); }
 
     {
         int ib = (int)((m + n + 1023) / 1024);
@@ -788,23 +1122,32 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     cudaEventElapsedTime(&ms, ev[0], ev[1]); res->h2d_ms = ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); res->solve_ms = ms;
     cudaEventElapsedTime(&ms, ev[2], ev[3]); res->d2h_ms = ms;
-    res->reserved = grid;
+    res->grid_ctas = grid;
+    res->bytes_per_arc = (int32_t)(2 * nsx_node_bytes(st.node_kind) + nsx_cost_bytes(st.cost_kind) + 1);
+    res->ring_stages = grid == 1 ? ka.plan.stages : ka.wplan.stages;
+    res->resident_mode = ka.plan.mode;
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream);
     arena.release();
+    inputs.release();
     if (hctl.status < 0) return nsx_fail(NSX_ERR_INTERNAL, "resident kernel ended without a status");
     return 0;
 }
 
 extern "C" int nsx_solve(const nsx_problem* problem, const nsx_options* options, nsx_result* result) {
-    return nsx_solve_impl(problem, options, result, false);
+    return nsx_solve_impl(problem, options, result, false, 0);
 }
 extern "C" int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result) {
-    return nsx_solve_impl(problem_dev, options, result, true);
+    return nsx_solve_impl(problem_dev, options, result, true, 0);
+}
+extern "C" int nsx_sweep_probe(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
+                               nsx_result* result) {
+    if (sweeps < 1) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "sweeps must be positive");
+    return nsx_solve_impl(problem_dev, options, result, true, sweeps);
 }
 
 extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const nsx_options* opt, nsx_result* results) {
-    Arena arena;
+    Arena arena, inputs;
     if (count < 0 || (count > 0 && (!problems || !results)) || !opt) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
     if (count == 0) return 0;
     for (int64_t i = 0; i < count; ++i) {
@@ -821,19 +1164,23 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     if (rc) return rc;
     const bool devex = opt->pricing == NSX_PRICING_DEVEX;
 
+    // batch instances keep the wide encoding (int32 ids, float64 costs): the canonical arrays,
+    // uploaded tile-padded, are the pricing store
+    NsxStore layout;
+    nsx_store_layout(layout, NSX_NODE_I32, NSX_COST_F64, devex ? 1 : 0);
     struct Off { size_t tail, head, pert, upper, atail, ahead, aupper, flow, state, wgt, node, depth, pi, order, tmp, gph, gpt, garc2, gres, supply, ctl, trace; };
     std::vector<Off> off(count);
     int32_t max_n = 1;
     for (int64_t i = 0; i < count; ++i) {
         const nsx_problem& p = problems[i];
-        const size_t n = p.n_nodes, m = p.n_arcs, ma = m + n - 1;
+        const size_t n = p.n_nodes, m = p.n_arcs, ma = m + n - 1, mpad = (size_t)nsx_pad_tiles((int64_t)m);
         if ((int32_t)n > max_n) max_n = (int32_t)n;
         Off& o = off[i];
-        o.tail = arena.plan((m + 4) * 4); o.head = arena.plan((m + 4) * 4);
-        o.pert = arena.plan((m + 4) * 8); o.upper = arena.plan((m + 4) * 8);
+        o.tail = arena.plan(mpad * 4); o.head = arena.plan(mpad * 4);
+        o.pert = arena.plan(mpad * 8); o.upper = arena.plan((m + 4) * 8);
         o.atail = arena.plan(n * 4); o.ahead = arena.plan(n * 4); o.aupper = arena.plan(n * 8);
-        o.flow = arena.plan((ma + 4) * 8); o.state = arena.plan(ma + 16);
-        o.wgt = devex ? arena.plan((m + 4) * 4) : 0;
+        o.flow = arena.plan((ma + 4) * 8); o.state = arena.plan((ma > mpad ? ma : mpad) + 16);
+        o.wgt = devex ? arena.plan(mpad * 4) : 0;
         o.node = arena.plan(n * sizeof(NsxNode)); o.depth = arena.plan(n * 4); o.pi = arena.plan(n * 8 + 16);
         o.order = arena.plan(n * 4); o.tmp = arena.plan(n * 4); o.gph = arena.plan(n * 4); o.gpt = arena.plan(n * 4);
         o.garc2 = arena.plan((2 * n + 1) * 4); o.gres = arena.plan((2 * n + 1) * 8);
@@ -851,6 +1198,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     std::vector<NsxBatchItem> items(count);
     std::vector<NsxCtl> ctls(count);
     NSX_CUDA(cudaEventRecord(ev[0], stream));
+    NSX_CUDA(cudaMemsetAsync(arena.base, 0, arena.size, stream));  // tile padding reads as "no arc"
     for (int64_t i = 0; i < count; ++i) {
         const nsx_problem& p = problems[i];
         const size_t n = p.n_nodes, m = p.n_arcs;
@@ -868,6 +1216,9 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance;
+        items[i].st = layout;
+        items[i].st.tail = arena.at<unsigned char>(o.tail); items[i].st.head = arena.at<unsigned char>(o.head);
+        items[i].st.cost = arena.at<unsigned char>(o.pert);
         items[i].ctl = arena.at<NsxCtl>(o.ctl);
         items[i].trace = tr ? arena.at<int32_t>(o.trace) : nullptr;
         items[i].supply = arena.at<double>(o.supply);
@@ -887,16 +1238,23 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     NSX_CUDA(cudaMemsetAsync(d_next, 0, 8, stream));
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
-    size_t smem = 0;
-    (void)nsx_plan_smem(max_n, info.smem_optin, &smem);
-    if (smem > info.smem_optin) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
+    const size_t fixed = nsx_smem_fixed();
+    const size_t limit_all = info.smem_optin - fixed;
+    const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
+    NsxSmemPlan plan = nsx_plan_pivot((size_t)max_n, limit_all, layout.stage_bytes, true, want_mode, want_stage);
+    if (plan.stages < 2) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
+    int max_stages = nsx_env_int("NSX_BATCH_STAGES", 4);
+    if (max_stages < 2) max_stages = 2;
+    if (plan.stages > max_stages) plan.stages = max_stages;
+    const size_t dyn = nsx_plan_bytes(plan, layout.stage_bytes);
+    const size_t smem = fixed + dyn;
     NSX_CUDA(cudaFuncSetAttribute(nsx_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_batch_kernel, NSX_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)info.sms * per_sm;
     if (grid > count) grid = count;
-    nsx_batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, smem - nsx_smem_fixed());
+    nsx_batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, dyn, want_mode, want_stage);
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(ev[2], stream));
     for (int64_t i = 0; i < count; ++i) {
@@ -917,7 +1275,8 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     for (int64_t i = 0; i < count; ++i) {
         nsx_result& r = results[i];
         nsx_harvest(ctls[i], &r);
-        r.h2d_ms = h2d; r.solve_ms = solve; r.d2h_ms = d2h; r.reserved = (int32_t)grid;
+        r.h2d_ms = h2d; r.solve_ms = solve; r.d2h_ms = d2h; r.grid_ctas = (int32_t)grid;
+        r.bytes_per_arc = 17; r.ring_stages = plan.stages; r.resident_mode = plan.mode;
         if (items[i].trace) {
             int64_t cnt = ctls[i].trace_len < opt->trace_capacity ? ctls[i].trace_len : opt->trace_capacity;
             if (cnt > 0) NSX_CUDA(cudaMemcpy(r.entering_trace, items[i].trace, (size_t)cnt * 4, cudaMemcpyDeviceToHost));

@@ -28,7 +28,8 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     src = _HERE / "nsx_oracle.c"
-    if force or not _LIB.exists() or _LIB.stat().st_mtime < src.stat().st_mtime:
+    header = _HERE.parent / "include" / "nsx_b200.h"
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < max(src.stat().st_mtime, header.stat().st_mtime):
         subprocess.run(["make", "-C", str(_HERE), "-B", "libnsx_oracle.so"], check=True,
                        capture_output=True)
     return _LIB

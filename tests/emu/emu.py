@@ -17,7 +17,8 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     src = _HERE / "nsx_emu.cpp"
-    newest = max(src.stat().st_mtime, _CORE.stat().st_mtime)
+    header = _HERE.parents[1] / "include" / "nsx_b200.h"
+    newest = max(src.stat().st_mtime, _CORE.stat().st_mtime, header.stat().st_mtime)
     if force or not _LIB.exists() or _LIB.stat().st_mtime < newest:
         subprocess.run(
             ["/usr/bin/g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math",

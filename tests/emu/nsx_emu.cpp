@@ -20,7 +20,7 @@ struct SerialSweep {
     void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx) {
         nsx_cand_init(dz);
         nsx_devex_init(dx);
-        if (cmd.kind == NSX_CMD_DANTZIG) {
+        if (cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO) {
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
                 double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
                 nsx_price_dantzig(dz, (int32_t)i, d.state[i], rc, d.tol);

@@ -87,6 +87,50 @@ def test_engine_result_independent_of_grid_size(grid, monkeypatch):
         assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
 
 
+LAYOUT_CASES = [
+    # (label, generator, eps_base, pricing, expected bytes per arc, NSX_LAYOUT)
+    ("u16_i16", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 0.0, 0, 7, None),
+    ("u16_i16_devex", lambda: gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15), 0.0, 1, 7, None),
+    ("u16_i32", lambda: gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, cost_max=100000, seed=17), 0.0, 0, 9, None),
+    ("u16_f64", lambda: gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15), 1e-10, 0, 13, None),
+    ("i32_f64_forced", lambda: gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15), 1e-10, 1, 17, "wide"),
+    ("i32_i32_forced", lambda: gen.transportation(300, 300, cost_max=1000, seed=3), 0.0, 0, 13, "i32"),
+    ("multi_cta_u16_i16", lambda: gen.transportation(384, 512, cost_max=1000, seed=4), 0.0, 0, 7, None),
+]
+
+
+@pytest.mark.parametrize("label,make,eps,pricing,bpa,force", LAYOUT_CASES)
+def test_engine_packed_store_layouts(label, make, eps, pricing, bpa, force, monkeypatch):
+    """Every encoding of the pricing store (uint16 / int32 node ids, int16 / int32 / float64 costs)
+    gives the oracle's pivots bit for bit."""
+    if force:
+        monkeypatch.setenv("NSX_LAYOUT", force)
+    cp = make().canonical(eps_base=eps)
+    opts = engine_options(cp, pricing)
+    got = _capi.solve_canonical(cp, opts)
+    assert got.stats["bytes_per_arc"] == bpa
+    assert_same_solution(got, oracle.solve_canonical(cp, opts, threads=4))
+
+
+@pytest.mark.parametrize("stages", [2, 3])
+def test_engine_shallow_tile_ring(stages, monkeypatch):
+    monkeypatch.setenv("NSX_STAGES", str(stages))
+    cp = gen.netgen_like(1 << 12, 1 << 17, n_sources=16, n_sinks=16, seed=21).canonical()
+    for pricing in (0, 1):
+        opts = engine_options(cp, pricing)
+        assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts, threads=4))
+
+
+def test_sweep_probe_prices_every_arc():
+    import torch
+
+    cp = gen.transportation(512, 512, cost_max=1000, seed=4096).canonical(eps_base=0.0)
+    opts = engine_options(cp, 0)
+    dev = [torch.from_numpy(getattr(cp, k)).cuda() for k in ("tail", "head", "pert_cost", "upper")]
+    r = _capi.sweep_probe(cp, opts, [t.data_ptr() for t in dev], 10)
+    assert r.status == 0 and r.arcs_priced == 10 * cp.n_arcs and r.stats["sweeps"] == 10
+
+
 def test_engine_without_shared_memory_potentials(monkeypatch):
     monkeypatch.setenv("NSX_STAGE_PI", "0")
     cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
