@@ -127,6 +127,9 @@ typedef struct nsx_result {
     int64_t phase_cycles[12];     /* SM-clock cycles spent per pivot phase (walk, residuals, ratio test, flow
                                      update, bookkeeping, stem snapshot, window permutation, copy-back + stem,
                                      potentials, reset cadence, spare, spare) */
+    int64_t handshake_ns[8];      /* grid handshake timeline, ns after the command is published, summed over all
+                                     sweeps: worker 1 saw the command, entered the sweep, potentials staged,
+                                     tiles done, reduced, arrived; pivot CTA saw all arrivals, merged */
 } nsx_result;
 
 /* Solve one instance on one GPU; all nsx_problem / nsx_result pointers are HOST memory. */

@@ -101,6 +101,7 @@ class NsxResult(C.Structure):
         ("max_subtree", C.c_int64),
         ("sum_rounds", C.c_int64),
         ("phase_cycles", C.c_int64 * 12),
+        ("handshake_ns", C.c_int64 * 8),
     ]
 
 
@@ -243,6 +244,7 @@ class CallFrame:
                 "max_subtree": int(r.max_subtree),
                 "sum_rounds": int(r.sum_rounds),
                 "phase_cycles": [int(x) for x in r.phase_cycles],
+                "handshake_ns": [int(x) for x in r.handshake_ns],
             },
         )
 

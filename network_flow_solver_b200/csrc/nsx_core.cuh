@@ -69,7 +69,7 @@
 // Device-resident state
 // ------------------------------------------------------------------------------------------
 // One 16-byte record per node so that a hop of the cycle walk is a single 128-bit load.
-struct NsxNode {
+struct alignas(16) NsxNode {
     int32_t parent;  // parent node (root: itself)
     int32_t pred2;   // (arc joining the node to its parent) * 2 + (arc points child->parent), -1 for root
     int32_t pos;     // position in the preorder array
@@ -105,6 +105,7 @@ struct NsxDev {
     double* gres;      // [2n+1] spill of residuals in scan order
     double penalty;
     double tol;
+    int32_t scan_walk;  // node records are in shared memory: find the cycle by a parallel ancestor scan
 };
 
 // Solver scalars; lives in global memory, written by the pivot CTA only.
@@ -150,6 +151,7 @@ struct NsxPivotScratch {
     int32_t art_delta;
     int32_t rounds;
     int32_t pending;
+    int32_t jkey;              // scan walk: min over common ancestors of (size << 16 | node)
     double theta;
     int32_t path_h[NSX_PATH_CAP];
     int32_t path_t[NSX_PATH_CAP];
@@ -185,7 +187,10 @@ NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
 // final.  `flags` is a per-thread-slot byte array of NSX_CHUNK entries.
 // ------------------------------------------------------------------------------------------
 #if NSX_ON_DEVICE
-#define NSX_CHUNK 512
+#ifndef NSX_THREADS
+#define NSX_THREADS 512
+#endif
+#define NSX_CHUNK NSX_THREADS  // one preorder entry per thread
 #else
 #define NSX_CHUNK 256
 #endif
@@ -199,6 +204,65 @@ struct NsxPotScratch {
     int32_t rounds;
 };
 
+#if NSX_ON_DEVICE
+// Device version: one preorder entry per thread.  An entry whose parent lies inside the chunk
+// waits until the parent's value is published in shared memory (value, block-scope fence, flag);
+// warps retry in rounds of their own, so a chain of k tree levels costs k shared-memory round
+// trips and no CTA-wide barrier.  The parent precedes the child in preorder, hence sits in the
+// same or an earlier warp and the rounds terminate.
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
+                                     NsxPotScratch& s, int64_t* rounds_out) {
+    int32_t rounds = 0;
+    volatile double* vval = s.val;
+    volatile int32_t* vflag = s.dep;
+    for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
+        const int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
+        NSX_SYNC();  // scratch is free; potentials written for earlier chunks are visible
+        const int32_t j = NSX_TID;
+        const int64_t x = c0 + j;
+        const bool active = j < NSX_CHUNK && x < c1;
+        bool done = true;
+        int32_t v = 0, par = -1;
+        double cst = 0.0, val = 0.0;
+        if (active) {
+            v = d.order[x];
+            const NsxNode r = d.node[v];
+            cst = nsx_arc_cost(d, phase, r.pred2 >> 1);
+            // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
+            cst = (r.pred2 & 1) ? -cst : cst;
+            const int32_t ppos = d.node[r.parent].pos;
+            if (ppos >= c0) { par = (int32_t)(ppos - c0); done = false; }
+            else val = NSX_ADD(d.pi[r.parent], cst);  // x - c == x + (-c) exactly
+            vval[j] = val;
+            vflag[j] = done ? 1 : 0;
+        }
+        NSX_SYNC();
+        while (!__all_sync(0xffffffffu, done)) {
+            if (!done && vflag[par]) {
+                val = NSX_ADD(vval[par], cst);
+                vval[j] = val;
+                __threadfence_block();
+                vflag[j] = 1;
+                done = true;
+            }
+            ++rounds;
+        }
+        if (active) {
+            d.pi[v] = val;
+            if (d.pi_mirror) d.pi_mirror[v] = val;
+        }
+    }
+    NSX_SYNC();
+    if (rounds_out) {
+        // statistics only: rounds of the slowest warp, summed over chunks
+        NSX_SINGLE { s.rounds = 0; }
+        NSX_SYNC();
+        if ((NSX_TID & 31) == 0) NSX_ATOMIC_MAX_I32(&s.rounds, rounds);
+        NSX_SYNC();
+        NSX_SINGLE { *rounds_out += s.rounds; }
+    }
+}
+#else
 // A chunk is finished level by level: a waiting node of depth L has its parent at depth L-1, which
 // is either outside the chunk (final), or final from the chunk set-up, or was computed in the
 // previous level step.  One barrier per tree level present in the chunk.
@@ -252,6 +316,8 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
     NSX_SYNC();
     NSX_SINGLE { if (rounds_out) *rounds_out += s.rounds; }
 }
+
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Cycle walk: tree paths from both ends of the entering arc up to their join, found with the
@@ -338,7 +404,35 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     long long tph = NSX_CLOCK();
     // ---- 1. walk both sides up to the join ------------------------------------------------
 #if NSX_ON_DEVICE
-    if (threadIdx.x < 2) {
+    if (d.scan_walk) {
+        // Every node tests in parallel whether it is an ancestor of h / of t (preorder interval
+        // test).  Ancestors of exactly one endpoint are the cycle; their slot in the path is the
+        // depth difference to that endpoint.  The join is the common ancestor of smallest size.
+        NSX_SINGLE { s.jkey = 0x7fffffff; }
+        const int32_t ph = d.node[h].pos, pt = d.node[t].pos;
+        const int32_t dh = d.depth[h], dt = d.depth[t];
+        NSX_SYNC();
+        NSX_PAR_FOR(w, 0, d.n) {
+            const NsxNode rec = d.node[w];
+            const bool in_h = rec.pos <= ph && ph < rec.pos + rec.size;
+            const bool in_t = rec.pos <= pt && pt < rec.pos + rec.size;
+            if (in_h && in_t) {
+                NSX_ATOMIC_MIN_I32(&s.jkey, (rec.size << 16) | (int32_t)w);
+            } else if (in_h) {
+                const int32_t k = dh - d.depth[w];
+                if (k < NSX_PATH_CAP) s.path_h[k] = (int32_t)w; else d.gpath_h[k] = (int32_t)w;
+            } else if (in_t) {
+                const int32_t k = dt - d.depth[w];
+                if (k < NSX_PATH_CAP) s.path_t[k] = (int32_t)w; else d.gpath_t[k] = (int32_t)w;
+            }
+        }
+        NSX_SYNC();
+        NSX_SINGLE {
+            const int32_t join = s.jkey & 0xffff;
+            const int32_t dj = d.depth[join];
+            s.join = join; s.nh = dh - dj; s.nt = dt - dj;
+        }
+    } else if (threadIdx.x < 2) {
         int32_t from = threadIdx.x == 0 ? h : t;
         int32_t opos = d.node[threadIdx.x == 0 ? t : h].pos;
         int32_t len, join;

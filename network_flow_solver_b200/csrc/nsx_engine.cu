@@ -23,22 +23,26 @@
 #include <string>
 #include <vector>
 
-#include "nsx_core.cuh"
-
 #ifndef NSX_THREADS
 #define NSX_THREADS 512
 #endif
+#include "nsx_core.cuh"
+
 #define NSX_PI_SMEM_MAX_NODES 12288  // node potentials staged in shared memory up to this many nodes
 
 // ------------------------------------------------------------------------------------------
 // Grid-wide command / arrival handshake
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long nsx_globaltimer();
 struct NsxGridCtl {
     int32_t seq;  // command sequence number, release-published by CTA 0
     int32_t pad;
     unsigned long long arrived;  // CTAs (other than 0) that delivered their candidate, cumulative
     NsxCmd cmd;
+    unsigned long long t_pub;    // globaltimer at the publication of the current command
+    unsigned long long tl[8];    // handshake timeline of worker 1, ns after t_pub, accumulated over sweeps
 };
+#define NSX_TL(grid, k) do { if (blockIdx.x == 1 && threadIdx.x == 0) (grid)->tl[k] += nsx_globaltimer() - (grid)->t_pub; } while (0)
 
 __device__ __forceinline__ int32_t nsx_ld_acquire(const int32_t* p) {
     int32_t v;
@@ -248,6 +252,7 @@ struct NsxCtaShared {
     NsxCmd cmd;  // worker copy of the command
     NsxCand dz_buf[32];
     NsxDevexCand dx_buf[32];
+    NsxGridCtl* tl_grid;                        // handshake timeline sink (worker CTAs of the grid kernel), or null
     unsigned long long mbar;                    // completion barrier of the potentials bulk copy
     unsigned long long full[NSX_MAX_STAGES];    // tile landed in the stage (TMA complete_tx)
     unsigned long long empty[NSX_MAX_STAGES];   // every warp is done with the stage
@@ -274,6 +279,7 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
         for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) { depth_s[v] = d.depth[v]; order_s[v] = d.order[v]; }
         dl.depth = depth_s; dl.order = order_s; dl.tmp = tmp_s;
     }
+    dl.scan_walk = d.n <= 32767 ? 1 : 0;
     NSX_SYNC();
     return dl;
 }
@@ -318,33 +324,36 @@ enum { NSX_MODE_DANTZIG = 0, NSX_MODE_DEVEX = 1, NSX_MODE_DANTZIG_ZERO = 2, NSX_
 template <int MODE, bool PHASE1, bool PISMEM>
 __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
                                                const double* pis, const unsigned char* sp, int32_t tile_base,
-                                               NsxCand& dz, NsxDevexCand& dx, double& gate) {
+                                               int32_t lo, int32_t hi, NsxCand& dz, NsxDevexCand& dx,
+                                               double& gate) {
     const int tid = threadIdx.x;
     uint32_t sb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) sb[u] = sp[st.off_state + u * NSX_THREADS + tid];
-    if ((int64_t)tile_base < cmd.lo || (int64_t)tile_base + NSX_TILE > cmd.hi) {  // ragged first / last tile
+    if (tile_base < lo || tile_base + NSX_TILE > hi) {  // ragged first / last tile of the range
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int64_t i = (int64_t)tile_base + u * NSX_THREADS + tid;
-            if (i < cmd.lo || i >= cmd.hi) sb[u] = 0;
+            const int32_t i = tile_base + u * NSX_THREADS + tid;
+            if (i < lo || i >= hi) sb[u] = 0;
         }
     }
-    // nothing to do when every arc of the thread is in the tree or has no residual either way
+    // eligibility bits: residual forward / backward and not in the tree
     uint32_t any = 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        if (sb[u] & NSX_ARC_IN_TREE) sb[u] = 0;
-        any |= sb[u] & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD);
+        sb[u] = sb[u] & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD) & ((sb[u] & NSX_ARC_IN_TREE) - 1u);
+        any |= sb[u];
     }
     if (!any) return;
+    // node ids are stored zero-based from node 1 (uint16 layout) - `pi1` points at pi[1]
     int32_t tl[4], hd[4];
     double c[4];
+    const int bias = st.node_kind == NSX_NODE_U16 ? 1 : 0;
     if (st.node_kind == NSX_NODE_U16) {
         const uint16_t* pt = reinterpret_cast<const uint16_t*>(sp);
         const uint16_t* ph = reinterpret_cast<const uint16_t*>(sp + st.off_head);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid] + 1; hd[u] = ph[u * NSX_THREADS + tid] + 1; }
+        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid]; hd[u] = ph[u * NSX_THREADS + tid]; }
     } else {
         const int32_t* pt = reinterpret_cast<const int32_t*>(sp);
         const int32_t* ph = reinterpret_cast<const int32_t*>(sp + st.off_head);
@@ -364,49 +373,63 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
 #pragma unroll
         for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_THREADS + tid];
     }
-    uint32_t wv[4] = {1u, 1u, 1u, 1u};
-    if (MODE == NSX_MODE_DEVEX) {
-        const uint32_t* pw = reinterpret_cast<const uint32_t*>(sp + st.off_wgt);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_THREADS + tid];
-    }
     const double tol = d.tol;
-    const double* pig = d.pi;
+    const double* pi1 = (PISMEM ? pis : d.pi) + bias;
+    // all four reduced costs first (independent dependency chains), decisions after
+    double rc[4];
+    const double i0 = (double)(tile_base + tid);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int32_t i = tile_base + u * NSX_THREADS + tid;
         double cost = c[u];
         // Phase-1 tree cost  pert - 1 - 1e-6*idx  (simplex.py:1162-1168); Devex prices with the
-        // perturbed Phase-2 cost in both phases
-        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, (double)i));
-        const double pt = PISMEM ? pis[tl[u]] : __ldcg(pig + tl[u]);
-        const double ph = PISMEM ? pis[hd[u]] : __ldcg(pig + hd[u]);
-        const double rc = NSX_SUB(NSX_ADD(cost, pt), ph);
-        const uint32_t s = sb[u];
-        if (MODE == NSX_MODE_DANTZIG) {
-            const bool hit = ((s & NSX_ARC_CAN_FWD) && rc <= gate) || ((s & NSX_ARC_CAN_BWD) && -rc <= gate);
-            if (hit) {
-                nsx_dantzig_improving(dz, i, s, rc, tol);
-                gate = dz.arc2 >= 0 ? dz.key : -tol;
-            }
-        } else if (MODE == NSX_MODE_DANTZIG_ZERO) {
-            if ((s & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD)) && fabs(rc) <= tol) {  // simplex_pricing.py:132-135
-                const int32_t cand = i * 2 + ((s & NSX_ARC_CAN_FWD) ? 0 : 1);
+        // perturbed Phase-2 cost in both phases.  idx as a double:
+        // i0 + u*T is exact
+        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, NSX_ADD(i0, (double)(u * NSX_THREADS))));
+        const double pt = PISMEM ? pi1[tl[u]] : __ldcg(pi1 + tl[u]);
+        const double ph = PISMEM ? pi1[hd[u]] : __ldcg(pi1 + hd[u]);
+        rc[u] = NSX_SUB(NSX_ADD(cost, pt), ph);
+    }
+    if (MODE == NSX_MODE_DANTZIG) {
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            hit |= ((sb[u] & NSX_ARC_CAN_FWD) && rc[u] <= gate) || ((sb[u] & NSX_ARC_CAN_BWD) && -rc[u] <= gate);
+        if (hit) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nsx_dantzig_improving(dz, tile_base + u * NSX_THREADS + tid, sb[u], rc[u], tol);
+            gate = dz.arc2 >= 0 ? dz.key : -tol;
+        }
+    } else if (MODE == NSX_MODE_DANTZIG_ZERO) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (sb[u] && fabs(rc[u]) <= tol) {  // simplex_pricing.py:132-135
+                const int32_t cand = (tile_base + u * NSX_THREADS + tid) * 2 + ((sb[u] & NSX_ARC_CAN_FWD) ? 0 : 1);
                 if (cand < dz.zero2) dz.zero2 = cand;
             }
-        } else {
+        }
+    } else {
+        uint32_t wv[4] = {1u, 1u, 1u, 1u};
+        if (MODE == NSX_MODE_DEVEX) {
+            const uint32_t* pw = reinterpret_cast<const uint32_t*>(sp + st.off_wgt);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_THREADS + tid];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t i = tile_base + u * NSX_THREADS + tid;
+            const uint32_t s = sb[u];
             if (i == cmd.excluded) continue;
-            const bool fv = (s & NSX_ARC_CAN_FWD) && rc < -tol;
-            const bool bv = (s & NSX_ARC_CAN_BWD) && rc > tol;
+            const bool fv = (s & NSX_ARC_CAN_FWD) && rc[u] < -tol;
+            const bool bv = (s & NSX_ARC_CAN_BWD) && rc[u] > tol;
             if (MODE == NSX_MODE_DEVEX) {
                 if (fv || bv) {
                     const double wd = (wv[u] >> 24) == cmd.wepoch ? (double)(wv[u] & 0xffffffu) : 1.0;
-                    const double merit = NSX_DIV(NSX_MUL(rc, rc), wd);
+                    const double merit = NSX_DIV(NSX_MUL(rc[u], rc[u]), wd);
                     if (fv) { if (dx.fi < 0 || merit > dx.fm || (merit == dx.fm && i < dx.fi)) { dx.fm = merit; dx.fi = i; } }
                     else    { if (dx.bi < 0 || merit > dx.bm || (merit == dx.bm && i < dx.bi)) { dx.bm = merit; dx.bi = i; } }
                 }
             } else {  // NSX_MODE_DEVEX_ZERO, simplex.py:603-615
-                if (!(fv || bv) && fabs(rc) <= tol) {
+                if (!(fv || bv) && fabs(rc[u]) <= tol) {
                     if ((s & NSX_ARC_CAN_FWD) && i < dx.fz) dx.fz = i;
                     if ((s & NSX_ARC_CAN_BWD) && i < dx.bz) dx.bz = i;
                 }
@@ -445,11 +468,13 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         nsx_mbar_wait(&sh.mbar, stage_count & 1u);
         stage_count++;
     }
+    if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
     double gate = -d.tol;
     int32_t tile = first;
+    const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
     for (int32_t j = 0; j < my_n; ++j) {
         nsx_mbar_wait(&sh.full[stage], parity);
-        nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + stage * st.stage_bytes, tile * NSX_TILE, dz, dx, gate);
+        nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + stage * st.stage_bytes, tile * NSX_TILE, lo, hi, dz, dx, gate);
         __syncwarp();
         if (lane == 0) nsx_mbar_arrive(&sh.empty[stage]);
         if (threadIdx.x == 0 && j + stages < my_n) {
@@ -460,6 +485,7 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         if (++stage == (uint32_t)stages) { stage = 0; parity ^= 1u; }
     }
     pos = stage | (parity << 16);
+    if (sh.tl_grid) NSX_TL(sh.tl_grid, 3);
 }
 
 template <int MODE, bool PHASE1>
@@ -482,6 +508,7 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
     nsx_cand_init(dz);
     nsx_devex_init(dx);
     NSX_SYNC();  // the command is visible; reduction buffers / staged potentials are free again
+    if (sh.tl_grid) NSX_TL(sh.tl_grid, 1);
     if (threadIdx.x == 0) {
         // writes of the pivot CTA (state bytes, weights, potentials) were acquired through the
         // generic proxy; the bulk copies below read them through the async proxy
@@ -536,6 +563,7 @@ struct GridSweep {
             tmp.c = cmd;
             int4* dst = reinterpret_cast<int4*>(&g->cmd);
             dst[0] = tmp.v[0]; dst[1] = tmp.v[1]; dst[2] = tmp.v[2];
+            g->t_pub = nsx_globaltimer();
             __threadfence();
             nsx_st_release(&g->seq, ++seq);
         }
@@ -564,6 +592,7 @@ struct GridSweep {
             while (nsx_ld_acquire_u64(&g->arrived) < target) { }
             __threadfence();
             t_sync += nsx_globaltimer() - t1;
+            g->tl[6] += nsx_globaltimer() - g->t_pub;
         }
         NSX_SYNC();
         // merge the candidates of the other CTAs (one per thread), then reduce across the block
@@ -587,7 +616,7 @@ struct GridSweep {
             nsx_block_reduce(k, sh.dz_buf);
             if (threadIdx.x == 0) out_dz = k;
         }
-        if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
+        if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
     }
     __device__ void finish() {
@@ -625,6 +654,7 @@ __device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
 
 __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
     if (threadIdx.x == 0) {
+        sh.tl_grid = nullptr;
         nsx_mbar_init(&sh.mbar, 1);
         for (int s = 0; s < NSX_MAX_STAGES; ++s) {
             nsx_mbar_init(&sh.full[s], 1);
@@ -697,6 +727,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         return;
     }
     // worker CTAs: wait for a command, price, deliver, repeat
+    if (threadIdx.x == 0) sh.tl_grid = a.grid;
     double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     unsigned char* ring = dyn + a.wplan.ring_off;
     int32_t seen = 0;
@@ -706,6 +737,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
             while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(20); }
             seen = s;
             __threadfence();
+            NSX_TL(a.grid, 0);
             union { NsxCmd c; int4 v[3]; } tmp;
             const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
             tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1); tmp.v[2] = __ldcg(src + 2);
@@ -718,9 +750,11 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
                       (int)blockIdx.x - 1, (int)gridDim.x - 1, sh, dz, dx);
         if (threadIdx.x == 0) {
+            NSX_TL(a.grid, 4);
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
             __threadfence();
             atomicAdd(&a.grid->arrived, 1ull);
+            NSX_TL(a.grid, 5);
         }
     }
 }
@@ -1049,7 +1083,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
-    d.penalty = pb->penalty; d.tol = opt->tolerance;
+    d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0;
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.dzc = arena.at<NsxCand>(o_dzc); ka.dxc = arena.at<NsxDevexCand>(o_dxc);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
@@ -1111,8 +1145,11 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     if (res->potential) NSX_CUDA(cudaMemcpyAsync(res->potential, d.pi, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
     if (res->state) NSX_CUDA(cudaMemcpyAsync(res->state, d.state, (size_t)ma, cudaMemcpyDeviceToHost, stream));
     NSX_CUDA(cudaMemcpyAsync(&hctl, ka.ctl, sizeof hctl, cudaMemcpyDeviceToHost, stream));
+    NsxGridCtl hgrid;
+    NSX_CUDA(cudaMemcpyAsync(&hgrid, ka.grid, sizeof hgrid, cudaMemcpyDeviceToHost, stream));
     NSX_CUDA(cudaEventRecord(ev[3], stream));
     NSX_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 8; ++i) res->handshake_ns[i] = (int64_t)hgrid.tl[i];
     if (want_trace) {
         int64_t cnt = hctl.trace_len < opt->trace_capacity ? hctl.trace_len : opt->trace_capacity;
         if (cnt > 0) NSX_CUDA(cudaMemcpy(res->entering_trace, ka.trace, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
@@ -1215,7 +1252,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.order = arena.at<int32_t>(o.order); d.tmp = arena.at<int32_t>(o.tmp);
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
-        d.penalty = p.penalty; d.tol = opt->tolerance;
+        d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0;
         items[i].st = layout;
         items[i].st.tail = arena.at<unsigned char>(o.tail); items[i].st.head = arena.at<unsigned char>(o.head);
         items[i].st.cost = arena.at<unsigned char>(o.pert);

@@ -17,3 +17,5 @@ us = r.timing["solve_ms"] * 1e3 / sweeps
 print(f"{name}: {sweeps} sweeps, {us:.2f} us/sweep, {r.arcs_priced / sweeps:.0f} arcs/sweep, {bpa} B/arc -> "
       f"{r.arcs_priced * bpa / (r.timing['solve_ms'] * 1e-3) / 1e9:.0f} GB/s; grid {r.stats['grid']} stages {r.stats['ring_stages']} "
       f"sync_wait {r.timing['sync_ms'] * 1e3 / sweeps:.2f} us/sweep")
+print("  handshake us/sweep [seen, enter, pi, tiles, reduced, arrived | all_arrived, merged]:",
+      [round(x / 1e3 / sweeps, 2) for x in r.stats["handshake_ns"]])

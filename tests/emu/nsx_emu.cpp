@@ -53,7 +53,7 @@ extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_
     d.flow = flow.data(); d.state = state.data(); d.wgt = wgt.data();
     d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.pi_mirror = nullptr; d.order = order.data();
     d.tmp = tmp.data(); d.gpath_h = gph.data(); d.gpath_t = gpt.data(); d.garc2 = garc2.data();
-    d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance;
+    d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0;
 
     NsxCtl c;
     memset(&c, 0, sizeof c);
