@@ -160,16 +160,17 @@ __device__ __forceinline__ void nsx_block_reduce(T& k, T* buf) {
 // Algorithmic bytes per arc = 2*node + cost + 1 (+4 Devex): 17 / 13 / 7 for the three layouts
 // used by the BASELINE configs.
 // ------------------------------------------------------------------------------------------
-#define NSX_TILE (4 * NSX_THREADS)  // arcs per tile: one quad (4 consecutive arcs) per thread
+// The last warp of a CTA is the TMA producer of the tile ring during sweeps; the others consume.
+#define NSX_CONSUMERS (NSX_THREADS - 32)
+#define NSX_TILE (4 * NSX_CONSUMERS)  // arcs per tile: four arcs per consumer thread
 #define NSX_MAX_STAGES 8
 
 enum { NSX_NODE_I32 = 0, NSX_NODE_U16 = 1 };
 enum { NSX_COST_F64 = 0, NSX_COST_I32 = 1, NSX_COST_I16 = 2 };
 
 struct NsxStore {
-    const unsigned char* tail;  // [tiles * b_node]
-    const unsigned char* head;
-    const unsigned char* cost;  // [tiles * b_cost]
+    const unsigned char* base;  // [tiles][tail column | head column | cost column], tile_bytes each
+    uint32_t tile_bytes;        // 2 * b_node + b_cost
     int32_t node_kind, cost_kind;
     uint32_t b_node, b_cost;    // bytes per tile of a node-id array / of the cost array
     uint32_t off_head, off_cost, off_state, off_wgt, stage_bytes;  // layout of one ring stage
@@ -186,6 +187,7 @@ static inline __host__ __device__ void nsx_store_layout(NsxStore& st, int node_k
     st.b_cost = NSX_TILE * nsx_cost_bytes(cost_kind);
     st.off_head = st.b_node;
     st.off_cost = 2 * st.b_node;
+    st.tile_bytes = 2 * st.b_node + st.b_cost;
     st.off_state = st.off_cost + st.b_cost;
     st.off_wgt = st.off_state + NSX_TILE;
     st.stage_bytes = st.off_wgt + (has_wgt ? 4u * NSX_TILE : 0u);
@@ -252,6 +254,8 @@ struct NsxCtaShared {
     NsxCmd cmd;  // worker copy of the command
     NsxCand dz_buf[32];
     NsxDevexCand dx_buf[32];
+    unsigned long long gate_bits;               // Dantzig sweep: raw bits of the best (most negative) key any
+                                                // thread of this CTA has found so far in the current sweep
     NsxGridCtl* tl_grid;                        // handshake timeline sink (worker CTAs of the grid kernel), or null
     unsigned long long mbar;                    // completion barrier of the potentials bulk copy
     unsigned long long full[NSX_MAX_STAGES];    // tile landed in the stage (TMA complete_tx)
@@ -294,11 +298,9 @@ __device__ __forceinline__ void nsx_ring_issue(const NsxDev& d, const NsxStore& 
                                                NsxCtaShared& sh, uint32_t stage, int32_t tile, bool with_wgt) {
     unsigned char* dst = ring + (size_t)stage * st.stage_bytes;
     unsigned long long* bar = &sh.full[stage];
-    const uint32_t total = 2 * st.b_node + st.b_cost + NSX_TILE + (with_wgt ? 4u * NSX_TILE : 0u);
+    const uint32_t total = st.tile_bytes + NSX_TILE + (with_wgt ? 4u * NSX_TILE : 0u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(total) : "memory");
-    nsx_bulk_copy(dst, st.tail + (size_t)tile * st.b_node, st.b_node, bar);
-    nsx_bulk_copy(dst + st.off_head, st.head + (size_t)tile * st.b_node, st.b_node, bar);
-    nsx_bulk_copy(dst + st.off_cost, st.cost + (size_t)tile * st.b_cost, st.b_cost, bar);
+    nsx_bulk_copy(dst, st.base + (size_t)tile * st.tile_bytes, st.tile_bytes, bar);  // tail | head | cost
     nsx_bulk_copy(dst + st.off_state, d.state + (size_t)tile * NSX_TILE, NSX_TILE, bar);
     if (with_wgt) nsx_bulk_copy(dst + st.off_wgt, d.wgt + (size_t)tile * NSX_TILE, 4u * NSX_TILE, bar);
 }
@@ -325,15 +327,15 @@ template <int MODE, bool PHASE1, bool PISMEM>
 __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
                                                const double* pis, const unsigned char* sp, int32_t tile_base,
                                                int32_t lo, int32_t hi, NsxCand& dz, NsxDevexCand& dx,
-                                               double& gate) {
+                                               NsxCtaShared& sh) {
     const int tid = threadIdx.x;
     uint32_t sb[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sb[u] = sp[st.off_state + u * NSX_THREADS + tid];
+    for (int u = 0; u < 4; ++u) sb[u] = sp[st.off_state + u * NSX_CONSUMERS + tid];
     if (tile_base < lo || tile_base + NSX_TILE > hi) {  // ragged first / last tile of the range
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int32_t i = tile_base + u * NSX_THREADS + tid;
+            const int32_t i = tile_base + u * NSX_CONSUMERS + tid;
             if (i < lo || i >= hi) sb[u] = 0;
         }
     }
@@ -353,25 +355,25 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         const uint16_t* pt = reinterpret_cast<const uint16_t*>(sp);
         const uint16_t* ph = reinterpret_cast<const uint16_t*>(sp + st.off_head);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid]; hd[u] = ph[u * NSX_THREADS + tid]; }
+        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_CONSUMERS + tid]; hd[u] = ph[u * NSX_CONSUMERS + tid]; }
     } else {
         const int32_t* pt = reinterpret_cast<const int32_t*>(sp);
         const int32_t* ph = reinterpret_cast<const int32_t*>(sp + st.off_head);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_THREADS + tid]; hd[u] = ph[u * NSX_THREADS + tid]; }
+        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_CONSUMERS + tid]; hd[u] = ph[u * NSX_CONSUMERS + tid]; }
     }
     if (st.cost_kind == NSX_COST_F64) {
         const double* pc = reinterpret_cast<const double*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = pc[u * NSX_THREADS + tid];
+        for (int u = 0; u < 4; ++u) c[u] = pc[u * NSX_CONSUMERS + tid];
     } else if (st.cost_kind == NSX_COST_I32) {
         const int32_t* pc = reinterpret_cast<const int32_t*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (double)pc[u * NSX_THREADS + tid];
+        for (int u = 0; u < 4; ++u) c[u] = (double)pc[u * NSX_CONSUMERS + tid];
     } else {
         const int16_t* pc = reinterpret_cast<const int16_t*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_THREADS + tid];
+        for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_CONSUMERS + tid];
     }
     const double tol = d.tol;
     const double* pi1 = (PISMEM ? pis : d.pi) + bias;
@@ -384,26 +386,40 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         // Phase-1 tree cost  pert - 1 - 1e-6*idx  (simplex.py:1162-1168); Devex prices with the
         // perturbed Phase-2 cost in both phases.  idx as a double:
         // i0 + u*T is exact
-        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, NSX_ADD(i0, (double)(u * NSX_THREADS))));
+        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, NSX_ADD(i0, (double)(u * NSX_CONSUMERS))));
         const double pt = PISMEM ? pi1[tl[u]] : __ldcg(pi1 + tl[u]);
         const double ph = PISMEM ? pi1[hd[u]] : __ldcg(pi1 + hd[u]);
         rc[u] = NSX_SUB(NSX_ADD(cost, pt), ph);
     }
     if (MODE == NSX_MODE_DANTZIG) {
-        bool hit = false;
+        // Candidate keys are negative doubles (key <= -tol), so "key a <= key b" is "raw bits of a >=
+        // raw bits of b" as unsigned integers, and a non-negative rc never passes.  The gate is the
+        // best key found so far by ANY thread of the CTA (shared memory, atomicMax on the raw
+        // bits): it only filters - the exact rule runs in nsx_dantzig_improving on the few arcs that
+        // reach it, so a stale gate costs time, never correctness.
+        const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(&sh.gate_bits);
+        const unsigned long long sign = 0x8000000000000000ull;
+        uint32_t hit = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            hit |= ((sb[u] & NSX_ARC_CAN_FWD) && rc[u] <= gate) || ((sb[u] & NSX_ARC_CAN_BWD) && -rc[u] <= gate);
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(rc[u]);
+            const uint32_t f = (b >= g) ? NSX_ARC_CAN_FWD : 0u;
+            const uint32_t r = ((b ^ sign) >= g) ? NSX_ARC_CAN_BWD : 0u;
+            hit |= sb[u] & (f | r);
+        }
         if (hit) {
+            const int32_t before = dz.arc2;
+            const double kbefore = dz.key;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nsx_dantzig_improving(dz, tile_base + u * NSX_THREADS + tid, sb[u], rc[u], tol);
-            gate = dz.arc2 >= 0 ? dz.key : -tol;
+            for (int u = 0; u < 4; ++u) nsx_dantzig_improving(dz, tile_base + u * NSX_CONSUMERS + tid, sb[u], rc[u], tol);
+            if (dz.arc2 >= 0 && (before < 0 || dz.key < kbefore))
+                atomicMax(&sh.gate_bits, (unsigned long long)__double_as_longlong(dz.key));
         }
     } else if (MODE == NSX_MODE_DANTZIG_ZERO) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (sb[u] && fabs(rc[u]) <= tol) {  // simplex_pricing.py:132-135
-                const int32_t cand = (tile_base + u * NSX_THREADS + tid) * 2 + ((sb[u] & NSX_ARC_CAN_FWD) ? 0 : 1);
+                const int32_t cand = (tile_base + u * NSX_CONSUMERS + tid) * 2 + ((sb[u] & NSX_ARC_CAN_FWD) ? 0 : 1);
                 if (cand < dz.zero2) dz.zero2 = cand;
             }
         }
@@ -412,11 +428,11 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         if (MODE == NSX_MODE_DEVEX) {
             const uint32_t* pw = reinterpret_cast<const uint32_t*>(sp + st.off_wgt);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_THREADS + tid];
+            for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_CONSUMERS + tid];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int32_t i = tile_base + u * NSX_THREADS + tid;
+            const int32_t i = tile_base + u * NSX_CONSUMERS + tid;
             const uint32_t s = sb[u];
             if (i == cmd.excluded) continue;
             const bool fv = (s & NSX_ARC_CAN_FWD) && rc[u] < -tol;
@@ -444,9 +460,9 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
 // phase parity of that stage.
 template <int MODE, bool PHASE1, bool PISMEM>
 __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
-                                               const double* pis, unsigned char* ring, int stages,
+                                               double* pis, unsigned char* ring, int stages,
                                                NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
-                                               bool wait_pi, uint32_t& stage_count, NsxCand& dz,
+                                               bool stage_pi, uint32_t& stage_count, NsxCand& dz,
                                                NsxDevexCand& dx) {
     const int32_t t0 = (int32_t)(cmd.lo / NSX_TILE), t1 = (int32_t)((cmd.hi + NSX_TILE - 1) / NSX_TILE);
     const int32_t ntiles = t1 - t0;
@@ -456,41 +472,47 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
     const int32_t step = cmd.reverse ? -nworkers : nworkers;
     const int32_t first = t0 + worker + (cmd.reverse ? (my_n - 1) * nworkers : 0);
     uint32_t stage = pos & 0xffffu, parity = pos >> 16;
-    if (threadIdx.x == 0) {
-        const int32_t pre = my_n < stages ? my_n : stages;
-        uint32_t s = stage;
-        for (int32_t j = 0; j < pre; ++j) {
-            nsx_ring_issue(d, st, ring, sh, s, first + j * step, with_wgt);
-            if (++s == (uint32_t)stages) s = 0;
+    if (threadIdx.x >= NSX_CONSUMERS) {
+        // ---- producer warp: one lane keeps the ring full ----
+        if (lane == 0) {
+            // writes of the pivot CTA (state bytes, weights, potentials) were acquired through the
+            // generic proxy; the bulk copies below read them through the async proxy
+            nsx_fence_proxy_async();
+            if (stage_pi) nsx_bulk_load(pis, d.pi, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
+            int32_t tile = first;
+            uint32_t s = stage, par = parity;
+            for (int32_t j = 0; j < my_n; ++j) {
+                if (j >= stages) nsx_mbar_wait(&sh.empty[s], par ^ 1u);  // previous tenant of the stage was read by every warp
+                nsx_ring_issue(d, st, ring, sh, s, tile, with_wgt);
+                tile += step;
+                if (++s == (uint32_t)stages) { s = 0; par ^= 1u; }
+            }
         }
-    }
-    if (wait_pi) {  // potentials of this sweep have landed (their copy was issued before the tiles)
-        nsx_mbar_wait(&sh.mbar, stage_count & 1u);
-        stage_count++;
-    }
-    if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
-    double gate = -d.tol;
-    int32_t tile = first;
-    const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
-    for (int32_t j = 0; j < my_n; ++j) {
-        nsx_mbar_wait(&sh.full[stage], parity);
-        nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + stage * st.stage_bytes, tile * NSX_TILE, lo, hi, dz, dx, gate);
-        __syncwarp();
-        if (lane == 0) nsx_mbar_arrive(&sh.empty[stage]);
-        if (threadIdx.x == 0 && j + stages < my_n) {
-            nsx_mbar_wait(&sh.empty[stage], parity);  // every warp has read the stage
-            nsx_ring_issue(d, st, ring, sh, stage, tile + stages * step, with_wgt);
+    } else {
+        // ---- consumer warps ----
+        if (stage_pi) nsx_mbar_wait(&sh.mbar, stage_count & 1u);  // potentials of this sweep have landed
+        if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
+        int32_t tile = first;
+        const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
+        uint32_t s = stage, par = parity;
+        for (int32_t j = 0; j < my_n; ++j) {
+            nsx_mbar_wait(&sh.full[s], par);
+            nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + s * st.stage_bytes, tile * NSX_TILE, lo, hi, dz, dx, sh);
+            __syncwarp();
+            if (lane == 0) nsx_mbar_arrive(&sh.empty[s]);
+            tile += step;
+            if (++s == (uint32_t)stages) { s = 0; par ^= 1u; }
         }
-        tile += step;
-        if (++stage == (uint32_t)stages) { stage = 0; parity ^= 1u; }
+        if (sh.tl_grid) NSX_TL(sh.tl_grid, 3);
     }
-    pos = stage | (parity << 16);
-    if (sh.tl_grid) NSX_TL(sh.tl_grid, 3);
+    if (stage_pi) stage_count++;
+    const uint32_t adv = stage + (uint32_t)my_n;
+    pos = (adv % (uint32_t)stages) | ((parity ^ ((adv / (uint32_t)stages) & 1u)) << 16);
 }
 
 template <int MODE, bool PHASE1>
 __device__ __forceinline__ void nsx_sweep_ring_pi(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
-                                                  const double* pis, unsigned char* ring, int stages,
+                                                  double* pis, unsigned char* ring, int stages,
                                                   NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
                                                   bool wait_pi, uint32_t& stage_count, NsxCand& dz,
                                                   NsxDevexCand& dx) {
@@ -507,14 +529,10 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
                                               int nworkers, NsxCtaShared& sh, NsxCand& dz, NsxDevexCand& dx) {
     nsx_cand_init(dz);
     nsx_devex_init(dx);
+    // first candidate must satisfy rc < -tol: start the gate at the largest double below -tol
+    if (threadIdx.x == 0) sh.gate_bits = (unsigned long long)__double_as_longlong(-d.tol) + 1ull;
     NSX_SYNC();  // the command is visible; reduction buffers / staged potentials are free again
     if (sh.tl_grid) NSX_TL(sh.tl_grid, 1);
-    if (threadIdx.x == 0) {
-        // writes of the pivot CTA (state bytes, weights, potentials) were acquired through the
-        // generic proxy; the bulk copies below read them through the async proxy
-        nsx_fence_proxy_async();
-        if (stage) nsx_bulk_load(pis, d.pi, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
-    }
     if (cmd.kind == NSX_CMD_DANTZIG) {
         if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
         else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
@@ -658,7 +676,7 @@ __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
         nsx_mbar_init(&sh.mbar, 1);
         for (int s = 0; s < NSX_MAX_STAGES; ++s) {
             nsx_mbar_init(&sh.full[s], 1);
-            nsx_mbar_init(&sh.empty[s], blockDim.x >> 5);
+            nsx_mbar_init(&sh.empty[s], NSX_CONSUMERS / 32);
         }
         nsx_mbar_init_fence();
     }
@@ -787,28 +805,33 @@ extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, int64_t
 }
 
 // Canonical arrays (int32 tail / head, float64 perturbed cost) -> tile-padded pricing store.
-extern "C" __global__ void nsx_pack_kernel(const int32_t* tail, const int32_t* head, const double* pert,
-                                           int64_t m, int64_t mpad, NsxStore st) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    unsigned char* ptail = const_cast<unsigned char*>(st.tail);
-    unsigned char* phead = const_cast<unsigned char*>(st.head);
-    unsigned char* pcost = const_cast<unsigned char*>(st.cost);
+// Element i of tile i / NSX_TILE; any launch shape (g = first element, T = stride).
+__device__ __forceinline__ void nsx_pack_range(const int32_t* tail, const int32_t* head, const double* pert,
+                                               int64_t m, int64_t mpad, const NsxStore& st, int64_t g, int64_t T) {
+    unsigned char* base = const_cast<unsigned char*>(st.base);
     for (int64_t i = g; i < mpad; i += T) {
         const bool in = i < m;
         const int32_t tl = in ? tail[i] : 1, hd = in ? head[i] : 1;
         const double c = in ? pert[i] : 0.0;
+        const int64_t tile = i / NSX_TILE;
+        const int32_t r = (int32_t)(i - tile * NSX_TILE);
+        unsigned char* tb = base + (size_t)tile * st.tile_bytes;
         if (st.node_kind == NSX_NODE_U16) {
-            reinterpret_cast<uint16_t*>(ptail)[i] = (uint16_t)(tl - 1);
-            reinterpret_cast<uint16_t*>(phead)[i] = (uint16_t)(hd - 1);
+            reinterpret_cast<uint16_t*>(tb)[r] = (uint16_t)(tl - 1);
+            reinterpret_cast<uint16_t*>(tb + st.off_head)[r] = (uint16_t)(hd - 1);
         } else {
-            reinterpret_cast<int32_t*>(ptail)[i] = tl;
-            reinterpret_cast<int32_t*>(phead)[i] = hd;
+            reinterpret_cast<int32_t*>(tb)[r] = tl;
+            reinterpret_cast<int32_t*>(tb + st.off_head)[r] = hd;
         }
-        if (st.cost_kind == NSX_COST_F64) reinterpret_cast<double*>(pcost)[i] = c;
-        else if (st.cost_kind == NSX_COST_I32) reinterpret_cast<int32_t*>(pcost)[i] = (int32_t)c;
-        else reinterpret_cast<int16_t*>(pcost)[i] = (int16_t)c;
+        if (st.cost_kind == NSX_COST_F64) reinterpret_cast<double*>(tb + st.off_cost)[r] = c;
+        else if (st.cost_kind == NSX_COST_I32) reinterpret_cast<int32_t*>(tb + st.off_cost)[r] = (int32_t)c;
+        else reinterpret_cast<int16_t*>(tb + st.off_cost)[r] = (int16_t)c;
     }
+}
+extern "C" __global__ void nsx_pack_kernel(const int32_t* tail, const int32_t* head, const double* pert,
+                                           int64_t m, int64_t mpad, NsxStore st) {
+    nsx_pack_range(tail, head, pert, m, mpad, st, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                   (int64_t)gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -817,6 +840,7 @@ extern "C" __global__ void nsx_pack_kernel(const int32_t* tail, const int32_t* h
 struct NsxBatchItem {
     NsxDev d;
     NsxStore st;
+    int64_t mpad;
     NsxCtl* ctl;
     int32_t* trace;
     const double* supply;
@@ -863,6 +887,7 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
         const NsxDev& d = item.d;
         for (int64_t i = threadIdx.x; i < d.m; i += blockDim.x) nsx_init_real_arc(d, i);
         for (int64_t v = threadIdx.x; v < d.n; v += blockDim.x) nsx_init_node(d, (int32_t)v, item.supply[v]);
+        nsx_pack_range(d.tail, d.head, d.pert, d.m, item.mpad, item.st, threadIdx.x, blockDim.x);
         nsx_copy_ctl(&sh.ctl, item.ctl);
         NSX_SYNC();
         if (threadIdx.x == 0) {
@@ -1061,8 +1086,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
 
     // ---- engine-owned device memory ----
     const size_t state_len = (size_t)(ma > mpad ? ma : mpad) + 16;
-    size_t o_stail = arena.plan((size_t)mpad * nsx_node_bytes(st.node_kind)), o_shead = arena.plan((size_t)mpad * nsx_node_bytes(st.node_kind));
-    size_t o_scost = arena.plan((size_t)mpad * nsx_cost_bytes(st.cost_kind));
+    size_t o_store = arena.plan((size_t)(mpad / NSX_TILE) * st.tile_bytes);
     size_t o_atail = arena.plan((size_t)n * 4), o_ahead = arena.plan((size_t)n * 4), o_aupper = arena.plan((size_t)n * 8);
     size_t o_flow = arena.plan((size_t)(ma + 4) * 8), o_state = arena.plan(state_len);
     size_t o_wgt = devex ? arena.plan((size_t)mpad * 4) : 0;
@@ -1075,7 +1099,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     NSX_CUDA(arena.commit());
 
-    st.tail = arena.at<unsigned char>(o_stail); st.head = arena.at<unsigned char>(o_shead); st.cost = arena.at<unsigned char>(o_scost);
+    st.base = arena.at<unsigned char>(o_store);
     d.atail = arena.at<int32_t>(o_atail); d.ahead = arena.at<int32_t>(o_ahead); d.aupper = arena.at<double>(o_aupper);
     d.flow = arena.at<double>(o_flow); d.state = arena.at<uint8_t>(o_state);
     d.wgt = devex ? arena.at<uint32_t>(o_wgt) : nullptr;
@@ -1201,11 +1225,13 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     if (rc) return rc;
     const bool devex = opt->pricing == NSX_PRICING_DEVEX;
 
-    // batch instances keep the wide encoding (int32 ids, float64 costs): the canonical arrays,
-    // uploaded tile-padded, are the pricing store
+    // batch instances keep float64 costs; node ids are narrowed when every instance allows it.
+    // Each CTA packs the store of its instance itself before the first sweep.
+    bool narrow = !(getenv("NSX_LAYOUT") && !strcmp(getenv("NSX_LAYOUT"), "wide"));
+    for (int64_t i = 0; i < count; ++i) if (problems[i].n_nodes - 1 > 65536) narrow = false;
     NsxStore layout;
-    nsx_store_layout(layout, NSX_NODE_I32, NSX_COST_F64, devex ? 1 : 0);
-    struct Off { size_t tail, head, pert, upper, atail, ahead, aupper, flow, state, wgt, node, depth, pi, order, tmp, gph, gpt, garc2, gres, supply, ctl, trace; };
+    nsx_store_layout(layout, narrow ? NSX_NODE_U16 : NSX_NODE_I32, NSX_COST_F64, devex ? 1 : 0);
+    struct Off { size_t store; size_t tail, head, pert, upper, atail, ahead, aupper, flow, state, wgt, node, depth, pi, order, tmp, gph, gpt, garc2, gres, supply, ctl, trace; };
     std::vector<Off> off(count);
     int32_t max_n = 1;
     for (int64_t i = 0; i < count; ++i) {
@@ -1213,8 +1239,9 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         const size_t n = p.n_nodes, m = p.n_arcs, ma = m + n - 1, mpad = (size_t)nsx_pad_tiles((int64_t)m);
         if ((int32_t)n > max_n) max_n = (int32_t)n;
         Off& o = off[i];
-        o.tail = arena.plan(mpad * 4); o.head = arena.plan(mpad * 4);
-        o.pert = arena.plan(mpad * 8); o.upper = arena.plan((m + 4) * 8);
+        o.tail = arena.plan((m + 4) * 4); o.head = arena.plan((m + 4) * 4);
+        o.pert = arena.plan((m + 4) * 8); o.upper = arena.plan((m + 4) * 8);
+        o.store = arena.plan((mpad / NSX_TILE) * layout.tile_bytes);
         o.atail = arena.plan(n * 4); o.ahead = arena.plan(n * 4); o.aupper = arena.plan(n * 8);
         o.flow = arena.plan((ma + 4) * 8); o.state = arena.plan((ma > mpad ? ma : mpad) + 16);
         o.wgt = devex ? arena.plan(mpad * 4) : 0;
@@ -1254,8 +1281,8 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0;
         items[i].st = layout;
-        items[i].st.tail = arena.at<unsigned char>(o.tail); items[i].st.head = arena.at<unsigned char>(o.head);
-        items[i].st.cost = arena.at<unsigned char>(o.pert);
+        items[i].st.base = arena.at<unsigned char>(o.store);
+        items[i].mpad = nsx_pad_tiles((int64_t)m);
         items[i].ctl = arena.at<NsxCtl>(o.ctl);
         items[i].trace = tr ? arena.at<int32_t>(o.trace) : nullptr;
         items[i].supply = arena.at<double>(o.supply);
@@ -1313,7 +1340,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         nsx_result& r = results[i];
         nsx_harvest(ctls[i], &r);
         r.h2d_ms = h2d; r.solve_ms = solve; r.d2h_ms = d2h; r.grid_ctas = (int32_t)grid;
-        r.bytes_per_arc = 17; r.ring_stages = plan.stages; r.resident_mode = plan.mode;
+        r.bytes_per_arc = (int32_t)(2 * nsx_node_bytes(layout.node_kind) + 9); r.ring_stages = plan.stages; r.resident_mode = plan.mode;
         if (items[i].trace) {
             int64_t cnt = ctls[i].trace_len < opt->trace_capacity ? ctls[i].trace_len : opt->trace_capacity;
             if (cnt > 0) NSX_CUDA(cudaMemcpy(r.entering_trace, items[i].trace, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
