@@ -34,7 +34,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-BYTES_PER_ARC = {0: 17, 1: 21}  # tail 4 + head 4 + cost f64 8 + state 1 (+ Devex weight 4)
+# bytes a sweep streams per arc = nsx_result.bytes_per_arc (layout chosen by the engine for the instance:
+# 2 * node id + cost + 1 state byte) + 4 for the Devex weight
 
 
 def env_int(name: str, default: int) -> int:
@@ -153,7 +154,7 @@ def main() -> int:
 
     batch_mode = args.workload == "goto_batch"
     wl = WORKLOADS["goto_64" if batch_mode else args.workload]
-    bpa = BYTES_PER_ARC[wl.pricing]
+    bpa = None  # known after the first solve (the engine reports the layout it chose)
     config = {
         "workload": args.workload,
         "description": wl.description,
@@ -229,6 +230,7 @@ def main() -> int:
             dev_ms += t["solve_ms"]; e2e_ms += t["h2d_ms"] + t["solve_ms"] + t["d2h_ms"]
             pivots += sum(o.iterations for o in outs); arcs += sum(o.arcs_priced for o in outs)
         barrier(); clocks = sampler.stop()
+        bpa = outs[0].stats["bytes_per_arc"] + (4 if wl.pricing == 1 else 0)
         h2d = sum(cp.n_arcs * 24 + cp.n_nodes * 8 for cp in cps)
         d2h = sum((cp.n_arcs + cp.n_nodes) * 9 + cp.n_nodes * 8 for cp in cps)
         launches = 1
@@ -260,6 +262,7 @@ def main() -> int:
             dev_ms += last.timing["solve_ms"]; pivots += last.iterations; arcs += last.arcs_priced
             pricing_ms += last.timing["pricing_ms"]; pivot_ms += last.timing["pivot_ms"]; sync_ms += last.timing["sync_ms"]
         barrier()
+        bpa = last.stats["bytes_per_arc"] + (4 if wl.pricing == 1 else 0)
         # end to end through the host-buffer entry point (pinned inputs, results read back)
         e2e_ms = 0.0; wall = 0.0
         for _ in range(args.steps):
@@ -278,6 +281,9 @@ def main() -> int:
             "avg_cycle_len": last.stats["sum_cycle_len"] / max(last.iterations, 1),
             "avg_rehung_subtree": last.stats["sum_subtree"] / max(last.tree_updates, 1),
             "avg_potential_levels": last.stats["sum_rounds"] / max(last.tree_updates, 1),
+            "avg_preorder_window": last.stats["sum_window"] / max(last.tree_updates, 1),
+            "bytes_per_arc": last.stats["bytes_per_arc"], "ring_stages": last.stats["ring_stages"],
+            "resident_mode": last.stats["resident_mode"], "sweeps_per_solve": last.stats["sweeps"],
             "phase_ms_per_step": {"pricing": pricing_ms / args.steps, "pivot_and_tree": pivot_ms / args.steps,
                                   "of_which_grid_wait": sync_ms / args.steps},
             "sweep_only_GBps": arcs * bpa / max(pricing_ms, 1e-9) / 1e6,

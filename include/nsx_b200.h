@@ -124,6 +124,7 @@ typedef struct nsx_result {
     int64_t sum_subtree;
     int64_t max_subtree;
     int64_t sum_rounds;           /* wavefront rounds of the exact potential recompute */
+    int64_t sum_window;           /* preorder-array entries moved by all tree updates */
     int64_t phase_cycles[12];     /* SM-clock cycles spent per pivot phase (walk, residuals, ratio test, flow
                                      update, bookkeeping, stem snapshot, window permutation, copy-back + stem,
                                      potentials, reset cadence, spare, spare) */

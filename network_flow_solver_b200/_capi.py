@@ -100,6 +100,7 @@ class NsxResult(C.Structure):
         ("sum_subtree", C.c_int64),
         ("max_subtree", C.c_int64),
         ("sum_rounds", C.c_int64),
+        ("sum_window", C.c_int64),
         ("phase_cycles", C.c_int64 * 12),
         ("handshake_ns", C.c_int64 * 8),
     ]
@@ -243,6 +244,7 @@ class CallFrame:
                 "sum_subtree": int(r.sum_subtree),
                 "max_subtree": int(r.max_subtree),
                 "sum_rounds": int(r.sum_rounds),
+                "sum_window": int(r.sum_window),
                 "phase_cycles": [int(x) for x in r.phase_cycles],
                 "handshake_ns": [int(x) for x in r.handshake_ns],
             },

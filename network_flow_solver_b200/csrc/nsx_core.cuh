@@ -59,7 +59,7 @@
 #define NSX_MUL(a, b) ((a) * (b))
 #define NSX_DIV(a, b) ((a) / (b))
 #define NSX_INF INFINITY
-#define NSX_ATOMIC_ADD_I32(p, v) (*(p) += (v))
+#define NSX_ATOMIC_ADD_I32(p, v) ((*(p) += (v)) - (v))
 #define NSX_CLOCK() 0ll
 #define NSX_ATOMIC_MIN_I32(p, v) (*(p) = (v) < *(p) ? (v) : *(p))
 #define NSX_ATOMIC_MAX_I32(p, v) (*(p) = (v) > *(p) ? (v) : *(p))
@@ -128,6 +128,7 @@ struct NsxCtl {
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     // statistics
     int64_t degenerate, tree_updates, resets, arcs_priced, sweeps;
+    int64_t avg_cycle;    // running mean of the cycle length * 16 (chooses the cycle-walk variant)
     int64_t sum_cycle, sum_subtree, max_subtree, sum_rounds, sum_window;
     int64_t phase1_iterations, art_after_p1;
     int64_t trace_len, trace_cap;
@@ -205,16 +206,17 @@ struct NsxPotScratch {
 };
 
 #if NSX_ON_DEVICE
-// Device version: one preorder entry per thread.  An entry whose parent lies inside the chunk
-// waits until the parent's value is published in shared memory (value, block-scope fence, flag);
-// warps retry in rounds of their own, so a chain of k tree levels costs k shared-memory round
-// trips and no CTA-wide barrier.  The parent precedes the child in preorder, hence sits in the
-// same or an earlier warp and the rounds terminate.
+// Device version: one preorder entry per thread.  An entry whose parent lies inside the chunk polls
+// the parent's slot in shared memory until it holds a value (slots start as a NaN bit pattern that
+// no potential can take; 8-byte shared-memory stores are single transactions, so no flag or fence
+// is needed).  Warps retry in rounds of their own: a chain of k tree levels costs k shared-memory
+// round trips and no CTA-wide barrier.  The parent precedes the child in preorder, hence sits in
+// the same or an earlier warp and the rounds terminate.
+#define NSX_POT_EMPTY 0x7ff8dead0badc0deLL
 NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
                                      NsxPotScratch& s, int64_t* rounds_out) {
     int32_t rounds = 0;
-    volatile double* vval = s.val;
-    volatile int32_t* vflag = s.dep;
+    volatile long long* vbits = reinterpret_cast<volatile long long*>(s.val);
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
         const int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
         NSX_SYNC();  // scratch is free; potentials written for earlier chunks are visible
@@ -222,7 +224,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
         const int64_t x = c0 + j;
         const bool active = j < NSX_CHUNK && x < c1;
         bool done = true;
-        int32_t v = 0, par = -1;
+        int32_t v = 0, par = 0;
         double cst = 0.0, val = 0.0;
         if (active) {
             v = d.order[x];
@@ -231,19 +233,18 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
             const int32_t ppos = d.node[r.parent].pos;
-            if (ppos >= c0) { par = (int32_t)(ppos - c0); done = false; }
-            else val = NSX_ADD(d.pi[r.parent], cst);  // x - c == x + (-c) exactly
-            vval[j] = val;
-            vflag[j] = done ? 1 : 0;
+            if (ppos >= c0) { par = (int32_t)(ppos - c0); done = false; vbits[j] = NSX_POT_EMPTY; }
+            else { val = NSX_ADD(d.pi[r.parent], cst); vbits[j] = __double_as_longlong(val); }  // x - c == x + (-c) exactly
         }
         NSX_SYNC();
         while (!__all_sync(0xffffffffu, done)) {
-            if (!done && vflag[par]) {
-                val = NSX_ADD(vval[par], cst);
-                vval[j] = val;
-                __threadfence_block();
-                vflag[j] = 1;
-                done = true;
+            if (!done) {
+                const long long pb = vbits[par];
+                if (pb != NSX_POT_EMPTY) {
+                    val = NSX_ADD(__longlong_as_double(pb), cst);
+                    vbits[j] = __double_as_longlong(val);
+                    done = true;
+                }
             }
             ++rounds;
         }
@@ -404,33 +405,55 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     long long tph = NSX_CLOCK();
     // ---- 1. walk both sides up to the join ------------------------------------------------
 #if NSX_ON_DEVICE
-    if (d.scan_walk) {
+    if (d.scan_walk && c.avg_cycle > 40 * 16) {
+        // (long cycles expected: recent average, in 1/16 arcs, above 40)
         // Every node tests in parallel whether it is an ancestor of h / of t (preorder interval
-        // test).  Ancestors of exactly one endpoint are the cycle; their slot in the path is the
-        // depth difference to that endpoint.  The join is the common ancestor of smallest size.
-        NSX_SINGLE { s.jkey = 0x7fffffff; }
+        // test).  Ancestors of exactly one endpoint are the cycle: they are collected per side,
+        // then ordered by subtree size (strictly increasing from the endpoint towards the join), so
+        // no depth lookup and no dependent load chain is involved.  The join is the common
+        // ancestor of smallest size.
+        int32_t* list_n = s.arc2;                          // [2 * CAP] nodes, head side then tail side
+        int32_t* list_s = reinterpret_cast<int32_t*>(s.res);  // [2 * CAP] their subtree sizes
+        NSX_SINGLE { s.jkey = 0x7fffffff; s.nh = 0; s.nt = 0; }
         const int32_t ph = d.node[h].pos, pt = d.node[t].pos;
-        const int32_t dh = d.depth[h], dt = d.depth[t];
         NSX_SYNC();
+        int32_t jk = 0x7fffffff;
         NSX_PAR_FOR(w, 0, d.n) {
             const NsxNode rec = d.node[w];
             const bool in_h = rec.pos <= ph && ph < rec.pos + rec.size;
             const bool in_t = rec.pos <= pt && pt < rec.pos + rec.size;
             if (in_h && in_t) {
-                NSX_ATOMIC_MIN_I32(&s.jkey, (rec.size << 16) | (int32_t)w);
+                const int32_t key = (rec.size << 16) | (int32_t)w;
+                jk = key < jk ? key : jk;
             } else if (in_h) {
-                const int32_t k = dh - d.depth[w];
-                if (k < NSX_PATH_CAP) s.path_h[k] = (int32_t)w; else d.gpath_h[k] = (int32_t)w;
+                const int32_t k = NSX_ATOMIC_ADD_I32(&s.nh, 1);
+                if (k < NSX_PATH_CAP) { list_n[k] = (int32_t)w; list_s[k] = rec.size; }
             } else if (in_t) {
-                const int32_t k = dt - d.depth[w];
-                if (k < NSX_PATH_CAP) s.path_t[k] = (int32_t)w; else d.gpath_t[k] = (int32_t)w;
+                const int32_t k = NSX_ATOMIC_ADD_I32(&s.nt, 1);
+                if (k < NSX_PATH_CAP) { list_n[NSX_PATH_CAP + k] = (int32_t)w; list_s[NSX_PATH_CAP + k] = rec.size; }
             }
         }
+        jk = __reduce_min_sync(0xffffffffu, jk);
+        if ((threadIdx.x & 31) == 0 && jk != 0x7fffffff) NSX_ATOMIC_MIN_I32(&s.jkey, jk);
         NSX_SYNC();
-        NSX_SINGLE {
-            const int32_t join = s.jkey & 0xffff;
-            const int32_t dj = d.depth[join];
-            s.join = join; s.nh = dh - dj; s.nt = dt - dj;
+        const int32_t cnt_h = s.nh, cnt_t = s.nt;
+        if (cnt_h <= NSX_PATH_CAP && cnt_t <= NSX_PATH_CAP) {
+            NSX_PAR_FOR(idx, 0, cnt_h + cnt_t) {
+                const bool hs = idx < cnt_h;
+                const int32_t base = hs ? 0 : NSX_PATH_CAP, cnt = hs ? cnt_h : cnt_t;
+                const int32_t me = hs ? (int32_t)idx : (int32_t)idx - cnt_h;
+                const int32_t my_size = list_s[base + me];
+                int32_t k = 0;
+                for (int32_t o = 0; o < cnt; ++o) k += list_s[base + o] < my_size;
+                (hs ? s.path_h : s.path_t)[k] = list_n[base + me];
+            }
+            NSX_SINGLE { s.join = s.jkey & 0xffff; }
+        } else if (threadIdx.x < 2) {  // a side longer than the shared-memory lists: serial walk
+            int32_t from = threadIdx.x == 0 ? h : t;
+            int32_t len, join;
+            nsx_walk_side(d, from, threadIdx.x == 0 ? pt : ph, threadIdx.x == 0 ? s.path_h : s.path_t,
+                          threadIdx.x == 0 ? d.gpath_h : d.gpath_t, &len, &join);
+            if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
         }
     } else if (threadIdx.x < 2) {
         int32_t from = threadIdx.x == 0 ? h : t;
@@ -562,6 +585,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         c.art_with_flow += s.art_delta;
         if (theta <= tol) c.degenerate++;
         c.sum_cycle += ncyc;
+        c.avg_cycle += ncyc - (c.avg_cycle >> 4);  // running mean of the cycle length, scaled by 16
         // Devex weight := number of tree arcs on the tail-head path, written by pricing before
         // the pivot in the reference (simplex_pricing.py:350-352)
         if (want_weight && e < d.m) d.wgt[e] = (c.wepoch << 24) | (uint32_t)(nh + nt);

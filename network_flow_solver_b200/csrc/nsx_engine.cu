@@ -980,6 +980,7 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
     res->sum_subtree = c.sum_subtree;
     res->max_subtree = c.max_subtree;
     res->sum_rounds = c.sum_rounds;
+    res->sum_window = c.sum_window;
     res->pricing_ms = (double)c.clk_pricing * 1e-6;
     res->pivot_ms = (double)c.clk_pivot * 1e-6;
     res->sync_ms = (double)c.clk_sync * 1e-6;

@@ -92,7 +92,7 @@ extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_
     res->unbounded_arc = c.unbounded_arc;
     res->unbounded_rc = c.unbounded_rc;
     res->sum_cycle_len = c.sum_cycle; res->sum_subtree = c.sum_subtree; res->max_subtree = c.max_subtree;
-    res->sum_rounds = c.sum_rounds;
+    res->sum_rounds = c.sum_rounds; res->sum_window = c.sum_window;
     res->pricing_ms = (double)c.sum_window;  // emulation only: moved preorder entries, for design stats
     if (res->flow) memcpy(res->flow, flow.data(), ma * 8);
     if (res->potential) memcpy(res->potential, pi.data(), (size_t)n * 8);
