@@ -143,6 +143,8 @@ def main() -> int:
     ap.add_argument("--batch", type=int, default=8192, help="instances in the goto_batch workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--probe-sweeps", type=int, default=200)
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
@@ -161,7 +163,7 @@ def main() -> int:
         "pricing": "devex" if wl.pricing == 1 else ("row_scan" if "transport" in wl.name else "dantzig"),
         "perturbation_eps": wl.eps_base,
         "parallelism": f"replicas x{world}" if not batch_mode else f"batch round-robin x{world}",
-        "l2_policy": "inputs larger than L2 (arc arrays re-streamed every pivot)",
+        "l2_policy": "256 MB memset (> 126 MB L2) between timed steps; within a step the arc store is re-streamed once per pivot",
     }
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -253,27 +255,48 @@ def main() -> int:
                  "potential": torch.empty(cp0.n_nodes, dtype=torch.float64).pin_memory(),
                  "state": torch.empty(ma, dtype=torch.uint8).pin_memory()}
         out = {k: v.numpy() for k, v in out_t.items()}
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")  # > 126 MB L2
         for _ in range(args.warmup):
             last = _capi.solve_resident(cp0, opts, ptrs, out=out)
         barrier(); sampler.start()
         dev_ms = 0.0; pivots = 0; arcs = 0; pricing_ms = pivot_ms = sync_ms = 0.0
         for _ in range(args.steps):
+            flush.zero_(); torch.cuda.synchronize()
             last = _capi.solve_resident(cp0, opts, ptrs, out=out)
             dev_ms += last.timing["solve_ms"]; pivots += last.iterations; arcs += last.arcs_priced
             pricing_ms += last.timing["pricing_ms"]; pivot_ms += last.timing["pivot_ms"]; sync_ms += last.timing["sync_ms"]
         barrier()
         bpa = last.stats["bytes_per_arc"] + (4 if wl.pricing == 1 else 0)
         # end to end through the host-buffer entry point (pinned inputs, results read back)
-        e2e_ms = 0.0; wall = 0.0
+        e2e_ms = 0.0; e2e_dev_ms = 0.0
         for _ in range(args.steps):
+            flush.zero_(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-            r = _capi.solve_canonical(cp0, opts, out=out)
-            wall += time.perf_counter() - t0
-            e2e_ms += r.timing["h2d_ms"] + r.timing["solve_ms"] + r.timing["d2h_ms"]
+            r = _capi.solve_canonical(cp0, opts, out=out)   # pinned host arrays in, pinned host results out
+            e2e_ms += 1e3 * (time.perf_counter() - t0)       # wall clock of the C-ABI call: alloc + H2D + solve + D2H
+            e2e_dev_ms += r.timing["h2d_ms"] + r.timing["solve_ms"] + r.timing["d2h_ms"]
         barrier(); clocks = sampler.stop()
+        # the sweep kernel alone: K sweeps of the initial state through the real command / arrival protocol
+        probe = {}
+        if rank == 0 and not args.no_probe:
+            for label, env in (("engine_layout", None), ("wide_layout", "wide")):
+                old = os.environ.get("NSX_LAYOUT")
+                if env: os.environ["NSX_LAYOUT"] = env
+                try:
+                    _capi.sweep_probe(cp0, opts, ptrs, 20)
+                    pr = _capi.sweep_probe(cp0, opts, ptrs, args.probe_sweeps)
+                finally:
+                    if env:
+                        if old is None: os.environ.pop("NSX_LAYOUT", None)
+                        else: os.environ["NSX_LAYOUT"] = old
+                b = pr.stats["bytes_per_arc"] + (4 if wl.pricing == 1 else 0)
+                gbs = pr.arcs_priced * b / (pr.timing["solve_ms"] * 1e-3) / 1e9
+                probe[label] = {"bytes_per_arc": b, "us_per_sweep": 1e3 * pr.timing["solve_ms"] / args.probe_sweeps,
+                                "arcs_per_sweep": pr.arcs_priced / args.probe_sweeps, "GBps": gbs, "frac_of_peak": gbs / peak,
+                                "handshake_us": [round(x / 1e3 / args.probe_sweeps, 2) for x in pr.stats["handshake_ns"]]}
         h2d = m * 24 + cp0.n_nodes * 8
         d2h = ma * 9 + cp0.n_nodes * 8
-        launches = 2  # nsx_init_kernel + nsx_resident_kernel per step
+        launches = 4  # nsx_classify_costs_kernel, nsx_pack_kernel, nsx_init_kernel, nsx_resident_kernel per step
         stats = {
             "status": last.status, "pivots_per_solve": last.iterations,
             "phase1_pivots": last.phase1_iterations, "degenerate_pivots": last.degenerate_pivots,
@@ -290,7 +313,8 @@ def main() -> int:
             "pivot_phase_us": {k: round(v / 1.9e3 / max(last.iterations, 1), 3) for k, v in zip(
                 ["walk", "residuals", "ratio", "flow", "bookkeeping", "snapshot", "window", "copy_stem",
                  "potentials", "cadence"], last.stats["phase_cycles"])},
-            "e2e_wall_ms_per_step": 1e3 * wall / args.steps,
+            "e2e_device_events_ms_per_step": e2e_dev_ms / args.steps,
+            "sweep_probe": probe,
         }
 
     # max over ranks of the device time, sum of the work
@@ -320,6 +344,13 @@ def main() -> int:
         dist.destroy_process_group()
     if rank != 0:
         return 0
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     line = {
         "metric": "pivots_per_second", "value": value, "unit": "pivots/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -330,9 +361,10 @@ def main() -> int:
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "nsx_resident_kernel (whole resident pivot loop: sweeps + pivots)",
-                     "bytes_per_arc": bpa, "arcs_priced_per_launch": arcs / args.steps},
+                     "bytes_per_arc": bpa, "arcs_priced_per_launch": arcs / args.steps,
+                     "algorithmic_bytes_per_launch": arcs / args.steps * bpa},
         "cpu_baseline": cpu,
         "detail": stats,
     }
