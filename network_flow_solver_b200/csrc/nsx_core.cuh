@@ -106,6 +106,8 @@ struct NsxDev {
     double penalty;
     double tol;
     int32_t scan_walk;  // node records are in shared memory: find the cycle by a parallel ancestor scan
+    int32_t lazy_pos;   // preorder positions are updated lazily through the shift log (large trees in HBM)
+    int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
 };
 
 // Solver scalars; lives in global memory, written by the pivot CTA only.
@@ -138,9 +140,12 @@ struct NsxCtl {
     int64_t ph[12];       // SM-clock cycles per pivot phase (thread 0): walk, residuals, ratio, flow,
                           // bookkeeping, snapshot+sizes, window, copy+stem, potentials, cadence, driver
 };
-#define NSX_PH(c, k, t0) NSX_SINGLE { long long t1__ = NSX_CLOCK(); (c).ph[k] += t1__ - (t0); (t0) = t1__; }
+// bar.sync blocks lazily (at the next access to barrier-protected state): touch shared memory first
+// so that the clock is read after the barrier has really been passed
+#define NSX_PH(c, k, t0) NSX_SINGLE { long long t1__ = NSX_CLOCK() + (*(volatile int32_t*)&(c).phase & 0); (c).ph[k] += t1__ - (t0); (t0) = t1__; }
 
 #define NSX_PATH_CAP 512  // cycle entries per side kept in shared memory (longer cycles spill to HBM)
+#define NSX_LOG_CAP 64    // shift-log capacity (lazy preorder positions)
 
 // Scratch of the pivot CTA (shared memory on the device).
 struct NsxPivotScratch {
@@ -152,7 +157,14 @@ struct NsxPivotScratch {
     int32_t art_delta;
     int32_t rounds;
     int32_t pending;
+    int32_t p_pos;             // preorder position of the new parent p (tree update)
     int32_t jkey;              // scan walk: min over common ancestors of (size << 16 | node)
+    // Lazy preorder positions (trees that live in HBM).  Moving the cut subtree shifts every entry
+    // between its old and new place; instead of rewriting the position of each shifted node, the
+    // shift is logged as "positions in [a, b) move by d".  A node stores (stamp << 24 | position):
+    // its position is current after replaying log entries stamp .. log_len-1.
+    int32_t log_len;
+    int32_t log_a[NSX_LOG_CAP], log_b[NSX_LOG_CAP], log_d[NSX_LOG_CAP];
     double theta;
     int32_t path_h[NSX_PATH_CAP];
     int32_t path_t[NSX_PATH_CAP];
@@ -173,6 +185,15 @@ NSX_FN bool nsx_isinf(double x) { return x == NSX_INF; }
 NSX_FN int32_t nsx_tail(const NsxDev& d, int64_t a) { return a < d.m ? d.tail[a] : d.atail[a - d.m]; }
 NSX_FN int32_t nsx_head(const NsxDev& d, int64_t a) { return a < d.m ? d.head[a] : d.ahead[a - d.m]; }
 NSX_FN double nsx_upper(const NsxDev& d, int64_t a) { return a < d.m ? d.upper[a] : d.aupper[a - d.m]; }
+
+// current preorder position from a stored (stamp << 24 | position) word; a no-op in eager mode
+NSX_FN int32_t nsx_pos(const NsxPivotScratch& s, int32_t raw) {
+    int32_t p = raw & 0xffffff;
+#pragma unroll 4
+    for (int32_t k = (int32_t)((uint32_t)raw >> 24); k < s.log_len; ++k)
+        if (p >= s.log_a[k] && p < s.log_b[k]) p += s.log_d[k];
+    return p;
+}
 
 NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
     uint8_t b = 0;
@@ -213,8 +234,8 @@ struct NsxPotScratch {
 // round trips and no CTA-wide barrier.  The parent precedes the child in preorder, hence sits in
 // the same or an earlier warp and the rounds terminate.
 #define NSX_POT_EMPTY 0x7ff8dead0badc0deLL
-NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
-                                     NsxPotScratch& s, int64_t* rounds_out) {
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv, int32_t phase, int64_t lo,
+                                     int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
     int32_t rounds = 0;
     volatile long long* vbits = reinterpret_cast<volatile long long*>(s.val);
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
@@ -232,11 +253,13 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
             cst = nsx_arc_cost(d, phase, r.pred2 >> 1);
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
-            const int32_t ppos = d.node[r.parent].pos;
+            const int32_t ppos = nsx_pos(pv, d.node[r.parent].pos);
             if (ppos >= c0) { par = (int32_t)(ppos - c0); done = false; vbits[j] = NSX_POT_EMPTY; }
             else { val = NSX_ADD(d.pi[r.parent], cst); vbits[j] = __double_as_longlong(val); }  // x - c == x + (-c) exactly
         }
         NSX_SYNC();
+        // (explicit reconvergence before every warp collective: a collective reached by a diverged
+        // warp takes a slow multi-step path)
         while (!__all_sync(0xffffffffu, done)) {
             if (!done) {
                 const long long pb = vbits[par];
@@ -247,6 +270,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
                 }
             }
             ++rounds;
+            __syncwarp();
         }
         if (active) {
             d.pi[v] = val;
@@ -267,8 +291,8 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
 // A chunk is finished level by level: a waiting node of depth L has its parent at depth L-1, which
 // is either outside the chunk (final), or final from the chunk set-up, or was computed in the
 // previous level step.  One barrier per tree level present in the chunk.
-NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo, int64_t hi,
-                                     NsxPotScratch& s, int64_t* rounds_out) {
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv, int32_t phase, int64_t lo,
+                                     int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
     NSX_SINGLE { s.rounds = 0; }
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
         int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
@@ -284,7 +308,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
             s.cst[j] = cst;
-            int32_t ppos = d.node[r.parent].pos;
+            int32_t ppos = nsx_pos(pv, d.node[r.parent].pos);
             if (ppos >= c0) {
                 int32_t dep = d.depth[v];
                 s.par_local[j] = (int32_t)(ppos - c0);
@@ -319,6 +343,18 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, int64_t lo,
 }
 
 #endif
+
+// Rewrite every stored position from the preorder array and empty the shift log.
+NSX_FN void nsx_compact_positions(const NsxDev& d, NsxPivotScratch& s) {
+    if (!d.lazy_pos) return;
+    NSX_SYNC();
+    if (s.log_len > 0) {
+        NSX_PAR_FOR(x, 0, d.n) { d.node[d.order[x]].pos = (int32_t)x; }
+    }
+    NSX_SYNC();
+    NSX_SINGLE { s.log_len = 0; }
+    NSX_SYNC();
+}
 
 // ------------------------------------------------------------------------------------------
 // Cycle walk: tree paths from both ends of the entering arc up to their join, found with the
@@ -433,6 +469,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                 if (k < NSX_PATH_CAP) { list_n[NSX_PATH_CAP + k] = (int32_t)w; list_s[NSX_PATH_CAP + k] = rec.size; }
             }
         }
+        __syncwarp();
         jk = __reduce_min_sync(0xffffffffu, jk);
         if ((threadIdx.x & 31) == 0 && jk != 0x7fffffff) NSX_ATOMIC_MIN_I32(&s.jkey, jk);
         NSX_SYNC();
@@ -455,6 +492,31 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                           threadIdx.x == 0 ? d.gpath_h : d.gpath_t, &len, &join);
             if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
         }
+    } else if (d.lazy_pos) {
+        // Depth-synchronised climb (no positions needed): lane 0 holds the head-side node, lane 1
+        // the tail-side node; the deeper one climbs, both climb when level, until they meet.
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            int32_t du = d.depth[h], dv = d.depth[t];
+            int32_t me = lane == 0 ? h : t;
+            int32_t len = 0;
+            for (;;) {
+                __syncwarp();
+                const int32_t u = __shfl_sync(0xffffffffu, me, 0), v = __shfl_sync(0xffffffffu, me, 1);
+                if (u == v) break;
+                const bool climb_u = du >= dv, climb_v = dv >= du;
+                if ((lane == 0 && climb_u) || (lane == 1 && climb_v)) {
+                    if (len < NSX_PATH_CAP) (lane == 0 ? s.path_h : s.path_t)[len] = me;
+                    else (lane == 0 ? d.gpath_h : d.gpath_t)[len] = me;
+                    ++len;
+                    me = d.node[me].parent;
+                }
+                du -= climb_u ? 1 : 0;
+                dv -= climb_v ? 1 : 0;
+            }
+            if (lane == 0) { s.nh = len; s.join = me; }
+            if (lane == 1) s.nt = len;
+        }
     } else if (threadIdx.x < 2) {
         int32_t from = threadIdx.x == 0 ? h : t;
         int32_t opos = d.node[threadIdx.x == 0 ? t : h].pos;
@@ -464,7 +526,15 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
     }
 #else
-    {
+    if (d.lazy_pos) {
+        int32_t u = h, v = t, du = d.depth[h], dv = d.depth[t], nh_ = 0, nt_ = 0;
+        while (u != v) {
+            const bool climb_u = du >= dv, climb_v = dv >= du;
+            if (climb_u) { if (nh_ < NSX_PATH_CAP) s.path_h[nh_] = u; else d.gpath_h[nh_] = u; ++nh_; u = d.node[u].parent; --du; }
+            if (climb_v) { if (nt_ < NSX_PATH_CAP) s.path_t[nt_] = v; else d.gpath_t[nt_] = v; ++nt_; v = d.node[v].parent; --dv; }
+        }
+        s.nh = nh_; s.nt = nt_; s.join = u;
+    } else {
         int32_t len, join;
         nsx_walk_side(d, h, d.node[t].pos, s.path_h, d.gpath_h, &len, &join);
         s.nh = len; s.join = join;
@@ -525,6 +595,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     if (threadIdx.x < 32) {
         NsxRatio rr; nsx_ratio_init(rr);
         for (int32_t k = threadIdx.x; k < ncyc; k += 32) nsx_ratio_add(rr, res[k], arc2[k] >> 1, k);
+        __syncwarp();
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             NsxRatio o;
@@ -610,7 +681,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t r = spath[kk];
     const NsxNode rec_r = d.node[r];
     const NsxNode rec_p = d.node[p];
-    const int32_t a0 = rec_r.pos, sz = rec_r.size, P = rec_p.pos;
+    const int32_t sz = rec_r.size;
     const int32_t depth_q_new = d.depth[p] + 1;
     // stem snapshot (old pos / size / depth / pred2): shared scratch reusing res[] / arc2[], or the
     // global spill arrays when the cycle did not fit (garc2: 2n+1 ints, gres: 2n+1 doubles)
@@ -619,9 +690,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     int32_t* st_depth = spill ? (int32_t*)d.gres : ((int32_t*)s.res) + 2 * NSX_PATH_CAP;
     int32_t* st_pred2 = spill ? ((int32_t*)d.gres) + d.n : s.arc2;
     NSX_SYNC();  // everyone has read arc2/res for the flow update before they are reused
-    NSX_PAR_FOR(i, 0, kk + 1) {
+    NSX_PAR_FOR(i, 0, kk + 2) {
+        if (i == kk + 1) { s.p_pos = nsx_pos(s, rec_p.pos); continue; }  // position of the new parent
         NsxNode x = d.node[spath[i]];
-        st_pos[i] = x.pos; st_size[i] = x.size; st_pred2[i] = x.pred2;
+        st_pos[i] = nsx_pos(s, x.pos); st_size[i] = x.size; st_pred2[i] = x.pred2;
         st_depth[i] = d.depth[spath[i]];
     }
     // subtree-size bookkeeping of the untouched ancestors on both sides of the cycle
@@ -633,6 +705,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     // The block S = [a0, a0+sz) of the preorder array is re-rooted at q and moved under p: either
     // right behind p or to the end of p's old subtree, whichever shifts fewer entries (both are
     // valid preorders).  `ins` is the insertion point in old coordinates.
+    const int32_t a0 = st_pos[kk], P = s.p_pos;  // r = s_k is the root of the cut subtree
     const int64_t S0 = a0, S1 = (int64_t)a0 + sz;
     const int64_t insA = (int64_t)P + 1, insB = (int64_t)P + rec_p.size;
     const int64_t dA = insA <= S0 ? S0 - insA : insA - S1;
@@ -642,13 +715,17 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     if (ins <= S0) { lo = ins; hi = S1; s_base = ins; xshift = sz; }        // [ins, S0) moves right
     else           { lo = S0; hi = ins; s_base = ins - sz; xshift = -(int64_t)sz; }  // [S1, ins) moves left
     const int32_t k_stem = kk;
+    // Lazy mode: only the nodes of S get their position written (stamped with the log length after
+    // this pivot's entry); the other entries of the window are a plain coalesced move of `order`.
+    const int32_t stamp = d.lazy_pos ? ((s.log_len + 1) << 24) : 0;
+    const int64_t w_lo = d.lazy_pos ? S0 : lo, w_hi = d.lazy_pos ? S1 : hi;
     {
         // four entries per thread and step: the loads of all four are issued before any store
         const int64_t T = NSX_NTHREADS;
-        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+        for (int64_t x0 = w_lo + NSX_TID; x0 < w_hi; x0 += 4 * T) {
             int32_t v[4], dv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.order[x] : -1; }
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < w_hi ? d.order[x] : -1; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int64_t x = x0 + u * T;
@@ -678,7 +755,37 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                     fx = x + xshift;
                 }
                 d.tmp[fx] = v[u];
-                d.node[v[u]].pos = (int32_t)fx;
+                d.node[v[u]].pos = (int32_t)fx | stamp;
+            }
+        }
+        if (d.lazy_pos) {
+            // the entries between the old and the new place of S, [ins, S0) or [S1, ins), shift by
+            // +-sz IN PLACE: blocks of 16 entries per thread are read into registers, then written,
+            // starting from the end the block moves towards (a later block never reads what an
+            // earlier one wrote).  S itself was copied to `tmp` above and is written back below.
+            const int64_t m_lo = ins <= S0 ? ins : S1, m_hi = ins <= S0 ? S0 : ins;
+            NSX_SINGLE {
+                const int32_t k = s.log_len;
+                s.log_a[k] = (int32_t)m_lo; s.log_b[k] = (int32_t)m_hi; s.log_d[k] = (int32_t)xshift;
+            }
+            const int64_t B = 16 * T;
+            const int64_t nblk = (m_hi - m_lo + B - 1) / B;
+            for (int64_t b = 0; b < nblk; ++b) {
+                // right shift: blocks from the high end down; left shift: from the low end up
+                const int64_t b_lo = xshift > 0 ? m_hi - (b + 1) * B : m_lo + b * B;
+                int32_t v[16];
+                NSX_SYNC();  // S has been read (first block) / the previous block has been written
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int64_t x = b_lo + u * T + NSX_TID;
+                    v[u] = (x >= m_lo && x < m_hi) ? d.order[x] : -1;
+                }
+                NSX_SYNC();
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int64_t x = b_lo + u * T + NSX_TID;
+                    if (x >= m_lo && x < m_hi) d.order[x + xshift] = v[u];
+                }
             }
         }
     }
@@ -686,12 +793,13 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_PH(c, 6, tph);
     {
         const int64_t T = NSX_NTHREADS;
-        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+        const int64_t c_lo = d.lazy_pos ? s_base : lo, c_hi = d.lazy_pos ? s_base + sz : hi;
+        for (int64_t x0 = c_lo + NSX_TID; x0 < c_hi; x0 += 4 * T) {
             int32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.tmp[x] : -1; }
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < c_hi ? d.tmp[x] : -1; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < hi) d.order[x] = v[u]; }
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < c_hi) d.order[x] = v[u]; }
         }
     }
     // stem: reverse parent pointers, new subtree sizes
@@ -708,6 +816,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
     }
     NSX_SINGLE {
+        if (d.lazy_pos) s.log_len++;
         d.state[e] |= NSX_ARC_IN_TREE;
         d.state[leave] &= (uint8_t)~NSX_ARC_IN_TREE;
         c.tree_updates++;
@@ -716,10 +825,11 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         c.sum_window += hi - lo;
     }
     NSX_SYNC();
+    if (d.lazy_pos && s.log_len >= d.log_cap) nsx_compact_positions(d, s);
     NSX_PH(c, 7, tph);
 
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
-    nsx_recompute_potentials(d, c.phase, s_base, s_base + sz, ps, &c.sum_rounds);
+    nsx_recompute_potentials(d, s, c.phase, s_base, s_base + sz, ps, &c.sum_rounds);
     NSX_PH(c, 8, tph);
 
     // ---- 7. reset cadence (simplex.py:1373-1425) -------------------------------------------
@@ -1032,7 +1142,9 @@ NSX_FN void nsx_drv_phase_end(NsxCtl& c, NsxDrv& v, NsxAction& act) {
 template <class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
-    nsx_recompute_potentials(d, 1, 1, d.n, ps, (int64_t*)0);  // Phase-1 costs on the initial star
+    NSX_SINGLE { s.log_len = 0; }
+    NSX_SYNC();
+    nsx_recompute_potentials(d, s, 1, 1, d.n, ps, (int64_t*)0);  // Phase-1 costs on the initial star
     NSX_SINGLE {
         L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
         L.drv.budget = c.maxit;
@@ -1059,7 +1171,10 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         } else if (kind == NSX_ACT_PHASE_END) {
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
-            if (!L.drv.final_check) nsx_recompute_potentials(d, 2, 1, d.n, ps, (int64_t*)0);
+            if (!L.drv.final_check) {
+                nsx_compact_positions(d, s);
+                nsx_recompute_potentials(d, s, 2, 1, d.n, ps, (int64_t*)0);
+            }
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }
         } else {  // NSX_ACT_EXIT

@@ -108,6 +108,7 @@ __device__ __forceinline__ unsigned long long nsx_globaltimer() {
 // Candidate reductions (warp shuffle, then one shared-memory hop)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void nsx_warp_reduce(NsxCand& k) {
+    __syncwarp();  // a shuffle reached by a diverged warp takes a slow path
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         NsxCand o;
@@ -118,6 +119,7 @@ __device__ __forceinline__ void nsx_warp_reduce(NsxCand& k) {
     }
 }
 __device__ __forceinline__ void nsx_warp_reduce(NsxDevexCand& k) {
+    __syncwarp();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         NsxDevexCand o;
@@ -284,6 +286,7 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
         dl.depth = depth_s; dl.order = order_s; dl.tmp = tmp_s;
     }
     dl.scan_walk = d.n <= 32767 ? 1 : 0;
+    dl.lazy_pos = 0;  // shared-memory trees keep eager positions (cheap scatter, needed by the scan walk)
     NSX_SYNC();
     return dl;
 }
@@ -685,9 +688,11 @@ __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
 // Measurement aid (nsx_sweep_probe): `count` sweeps of the initial state through exactly the
 // command / arrival protocol of a solve, no pivots.
 template <class Sweep>
-__device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPotScratch& ps,
-                                               Sweep& sweep, int32_t count) {
-    nsx_recompute_potentials(d, 1, 1, d.n, ps, (int64_t*)0);
+__device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
+                                               NsxPotScratch& ps, Sweep& sweep, int32_t count) {
+    if (threadIdx.x == 0) pv.log_len = 0;
+    NSX_SYNC();
+    nsx_recompute_potentials(d, pv, 1, 1, d.n, ps, (int64_t*)0);
     for (int32_t k = 0; k < count; ++k) {
         NSX_SYNC();
         if (threadIdx.x == 0) {
@@ -731,7 +736,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
         GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull};
-        if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.pot, sweep, a.probe_sweeps);
+        if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
         if (threadIdx.x == 0) {
@@ -1109,6 +1114,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
     d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0;
+    d.lazy_pos = (n < (1 << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0;
+    d.log_cap = nsx_env_int("NSX_LOG_CAP", 32);
+    if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.dzc = arena.at<NsxCand>(o_dzc); ka.dxc = arena.at<NsxDevexCand>(o_dxc);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
@@ -1281,6 +1289,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0;
+        d.lazy_pos = (n < (1u << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0; d.log_cap = 32;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);
         items[i].mpad = nsx_pad_tiles((int64_t)m);

@@ -84,3 +84,15 @@ def test_emulated_core_iteration_limits():
     for limit in (1, 7, full.phase1_iterations, full.phase1_iterations + 1, full.iterations, full.iterations + 5):
         opts = engine_options(cp, 0, max_iterations=limit)
         assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+
+
+@pytest.mark.parametrize("log_cap", [1, 3, 64])
+@pytest.mark.parametrize("family,make,pricing", CASES[:6] + CASES[-2:])
+def test_emulated_core_lazy_positions(family, make, pricing, log_cap, monkeypatch):
+    """Lazy preorder positions (shift log + depth-synchronised cycle walk), the variant the engine
+    uses for trees that live in HBM, gives the same pivots as the oracle for every log capacity."""
+    monkeypatch.setenv("NSX_EMU_LAZY", "1")
+    monkeypatch.setenv("NSX_EMU_LOG_CAP", str(log_cap))
+    cp = make().canonical()
+    opts = engine_options(cp, pricing)
+    assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))

@@ -131,6 +131,18 @@ def test_sweep_probe_prices_every_arc():
     assert r.status == 0 and r.arcs_priced == 10 * cp.n_arcs and r.stats["sweeps"] == 10
 
 
+@pytest.mark.parametrize("lazy,log_cap", [(0, 64), (1, 1), (1, 5), (1, 64)])
+def test_engine_lazy_preorder_positions(lazy, log_cap, monkeypatch):
+    """Trees that live in HBM: eager vs lazy (shift-log) preorder positions give identical pivots."""
+    monkeypatch.setenv("NSX_LAZY", str(lazy))
+    monkeypatch.setenv("NSX_LOG_CAP", str(log_cap))
+    monkeypatch.setenv("NSX_RESIDENT", "0")  # keep the tree out of shared memory
+    cp = gen.netgen_like(4096, 32768, n_sources=16, n_sinks=16, seed=31).canonical()
+    for pricing in (0, 1):
+        opts = engine_options(cp, pricing)
+        assert_same_solution(_capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts, threads=4))
+
+
 def test_engine_without_shared_memory_potentials(monkeypatch):
     monkeypatch.setenv("NSX_STAGE_PI", "0")
     cp = gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15).canonical()
