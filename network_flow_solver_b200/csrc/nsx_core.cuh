@@ -106,6 +106,8 @@ struct NsxDev {
     double penalty;
     double tol;
     int32_t scan_walk;  // node records are in shared memory: find the cycle by a parallel ancestor scan
+    uint16_t* par16;    // optional shared-memory mirror of the parent pointers (parent - 1), for the cycle walk
+    uint32_t* root_bits;  // bit v set: the parent of v is the root (the one value parent - 1 cannot encode)
     int32_t lazy_pos;   // preorder positions are updated lazily through the shift log (large trees in HBM)
     int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
 };
@@ -185,6 +187,22 @@ NSX_FN bool nsx_isinf(double x) { return x == NSX_INF; }
 NSX_FN int32_t nsx_tail(const NsxDev& d, int64_t a) { return a < d.m ? d.tail[a] : d.atail[a - d.m]; }
 NSX_FN int32_t nsx_head(const NsxDev& d, int64_t a) { return a < d.m ? d.head[a] : d.ahead[a - d.m]; }
 NSX_FN double nsx_upper(const NsxDev& d, int64_t a) { return a < d.m ? d.upper[a] : d.aupper[a - d.m]; }
+
+NSX_FN int32_t nsx_parent(const NsxDev& d, int32_t v) {
+    if (d.par16) return ((d.root_bits[v >> 5] >> (v & 31)) & 1u) ? 0 : (int32_t)d.par16[v] + 1;
+    return d.node[v].parent;
+}
+NSX_FN void nsx_set_parent_mirror(const NsxDev& d, int32_t v, int32_t parent) {
+    // (called by one thread per node; root_bits words are shared between nodes => atomic bit ops)
+    if (!d.par16) return;
+#if NSX_ON_DEVICE
+    if (parent == 0) atomicOr(&d.root_bits[v >> 5], 1u << (v & 31));
+    else { atomicAnd(&d.root_bits[v >> 5], ~(1u << (v & 31))); d.par16[v] = (uint16_t)(parent - 1); }
+#else
+    if (parent == 0) d.root_bits[v >> 5] |= 1u << (v & 31);
+    else { d.root_bits[v >> 5] &= ~(1u << (v & 31)); d.par16[v] = (uint16_t)(parent - 1); }
+#endif
+}
 
 // current preorder position from a stored (stamp << 24 | position) word; a no-op in eager mode
 NSX_FN int32_t nsx_pos(const NsxPivotScratch& s, int32_t raw) {
@@ -509,7 +527,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                     if (len < NSX_PATH_CAP) (lane == 0 ? s.path_h : s.path_t)[len] = me;
                     else (lane == 0 ? d.gpath_h : d.gpath_t)[len] = me;
                     ++len;
-                    me = d.node[me].parent;
+                    me = nsx_parent(d, me);
                 }
                 du -= climb_u ? 1 : 0;
                 dv -= climb_v ? 1 : 0;
@@ -530,8 +548,8 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         int32_t u = h, v = t, du = d.depth[h], dv = d.depth[t], nh_ = 0, nt_ = 0;
         while (u != v) {
             const bool climb_u = du >= dv, climb_v = dv >= du;
-            if (climb_u) { if (nh_ < NSX_PATH_CAP) s.path_h[nh_] = u; else d.gpath_h[nh_] = u; ++nh_; u = d.node[u].parent; --du; }
-            if (climb_v) { if (nt_ < NSX_PATH_CAP) s.path_t[nt_] = v; else d.gpath_t[nt_] = v; ++nt_; v = d.node[v].parent; --dv; }
+            if (climb_u) { if (nh_ < NSX_PATH_CAP) s.path_h[nh_] = u; else d.gpath_h[nh_] = u; ++nh_; u = nsx_parent(d, u); --du; }
+            if (climb_v) { if (nt_ < NSX_PATH_CAP) s.path_t[nt_] = v; else d.gpath_t[nt_] = v; ++nt_; v = nsx_parent(d, v); --dv; }
         }
         s.nh = nh_; s.nt = nt_; s.join = u;
     } else {
@@ -805,6 +823,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     // stem: reverse parent pointers, new subtree sizes
     NSX_PAR_FOR(i, 0, k_stem + 1) {
         int32_t v = spath[i];
+        nsx_set_parent_mirror(d, v, i == 0 ? p : spath[i - 1]);
         if (i == 0) {
             d.node[v].parent = p;
             d.node[v].pred2 = e * 2 + (d.tail[e] == p ? 0 : 1);

@@ -208,6 +208,7 @@ struct NsxSmemPlan {
     int32_t stage_pi;   // potentials are copied into shared memory before each sweep (TMA bulk copy)
     uint32_t ring_off;  // byte offset of the tile ring inside the dynamic part
     int32_t stages;     // ring depth (0: this CTA never sweeps)
+    int32_t par16;      // pivot CTA keeps a uint16 mirror of the parent pointers (+ root bitmap) in shared memory
 };
 
 static inline __host__ __device__ size_t nsx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -219,7 +220,7 @@ static inline __host__ __device__ size_t nsx_resident_bytes(int mode, size_t n) 
 // Plan for a CTA that pivots (and, when `sweeps`, also prices: single-CTA and batch modes).
 static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t limit, uint32_t stage_bytes,
                                                              bool sweeps, int want_mode, int want_stage) {
-    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0;
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0;
     const size_t ring_min = sweeps ? 2 * (size_t)stage_bytes : 0;
     for (int mode = want_mode; mode >= NSX_RES_NODES; --mode) {
         if (nsx_resident_bytes(mode, n) + ring_min <= limit) { p.mode = mode; break; }
@@ -227,6 +228,11 @@ static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t li
     size_t used = nsx_resident_bytes(p.mode, n);
     if (p.mode == NSX_RES_NONE && sweeps && want_stage && nsx_align16(8 * n) + ring_min <= limit) {
         p.stage_pi = 1; used = nsx_align16(8 * n);
+    }
+    // trees that stay in HBM: the parent pointers alone (2 B / node + 1 bit) make the cycle walk a
+    // chain of shared-memory loads instead of L2 round trips
+    if (p.mode == NSX_RES_NONE && !sweeps && n <= 65537 && nsx_align16(2 * n) + nsx_align16(n / 8 + 8) <= limit) {
+        p.par16 = 1; used = nsx_align16(2 * n) + nsx_align16(n / 8 + 8);
     }
     p.ring_off = (uint32_t)used;
     if (sweeps) {
@@ -237,7 +243,7 @@ static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t li
 }
 // Plan for a sweep-only worker CTA.
 static inline __host__ __device__ NsxSmemPlan nsx_plan_worker(size_t n, size_t limit, uint32_t stage_bytes, int want_stage) {
-    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0;
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0;
     size_t used = 0;
     if (want_stage && nsx_align16(8 * n) + 3 * (size_t)stage_bytes <= limit) { p.stage_pi = 1; used = nsx_align16(8 * n); }
     p.ring_off = (uint32_t)used;
@@ -272,6 +278,16 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
     NsxDev dl = d;
     double* pis = reinterpret_cast<double*>(dyn);
     *pis_out = pis;
+    if (plan.mode == NSX_RES_NONE && plan.par16) {
+        uint16_t* par = reinterpret_cast<uint16_t*>(dyn);
+        uint32_t* bits = reinterpret_cast<uint32_t*>(dyn + nsx_align16(2 * (size_t)d.n));
+        for (int32_t w = threadIdx.x; w < (d.n + 31) / 32; w += blockDim.x) bits[w] = 0u;
+        NSX_SYNC();
+        dl.par16 = par; dl.root_bits = bits;
+        for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) nsx_set_parent_mirror(dl, v, d.node[v].parent);
+        NSX_SYNC();
+        return dl;
+    }
     if (plan.mode == NSX_RES_NONE) return dl;
     size_t off = nsx_align16((size_t)d.n * 8);
     NsxNode* node_s = reinterpret_cast<NsxNode*>(dyn + off);
@@ -1113,7 +1129,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
-    d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0;
+    d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
     d.lazy_pos = (n < (1 << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0;
     d.log_cap = nsx_env_int("NSX_LOG_CAP", 32);
     if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
@@ -1145,6 +1161,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     const size_t limit = info.smem_optin - fixed;
     const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
     ka.plan = nsx_plan_pivot((size_t)n, limit, st.stage_bytes, grid == 1, want_mode, want_stage);
+    if (!d.lazy_pos || !nsx_env_int("NSX_PAR16", 1)) { if (ka.plan.par16) { ka.plan.par16 = 0; ka.plan.ring_off = 0; } }
     ka.wplan = nsx_plan_worker((size_t)n, limit, st.stage_bytes, want_stage);
     int max_stages = nsx_env_int("NSX_STAGES", NSX_MAX_STAGES);
     if (max_stages < 2) max_stages = 2;
@@ -1288,7 +1305,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.order = arena.at<int32_t>(o.order); d.tmp = arena.at<int32_t>(o.tmp);
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
-        d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0;
+        d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
         d.lazy_pos = (n < (1u << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0; d.log_cap = 32;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);
