@@ -120,6 +120,7 @@ typedef struct nsx_result {
     double pricing_ms;            /* accumulated device clock in pricing sweeps (max over CTAs' leader) */
     double pivot_ms;              /* accumulated device clock in ratio test + tree/potential update */
     double sync_ms;               /* accumulated device clock in grid-wide handshakes */
+    double exchange_ms;           /* accumulated device clock in the cross-GPU candidate exchange (sharded solves) */
     int64_t sum_cycle_len;        /* pivot statistics for DESIGN.md / profiles */
     int64_t sum_subtree;
     int64_t max_subtree;
@@ -145,6 +146,30 @@ int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* option
  * arcs_priced and pricing_ms describe the sweeps; flows / potentials are the initial ones. */
 int nsx_sweep_probe(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
                     nsx_result* result);
+
+/*
+ * Arc-sharded pricing over several GPUs of one node (one process per GPU).  Every rank passes the SAME full
+ * instance; a pricing sweep is split over the sweep CTAs of all ranks, the per-rank candidates are exchanged
+ * through peer-mapped mailboxes over NVLink (one 64-byte record per rank and sweep) and every rank applies the
+ * identical pivot, so all ranks return identical results.  No reference counterpart (the reference is single
+ * process); the pricing rule, tie-break and results are those of nsx_solve.
+ *   mailboxes[r] = mailbox of rank r as a device pointer valid on THIS rank's GPU: the rank's own mailbox from
+ *   nsx_mailbox_create, the others from nsx_mailbox_open on the 64-byte handles exchanged by the host layer.
+ *   Every rank must nsx_mailbox_reset its own mailbox and pass a host barrier before each sharded call.
+ */
+typedef struct nsx_shard {
+    int32_t rank, world;      /* world <= 8 */
+    void* const* mailboxes;   /* [world] */
+} nsx_shard;
+int nsx_solve_sharded(const nsx_problem* problem, const nsx_options* options, nsx_result* result,
+                      const nsx_shard* shard);
+int nsx_sweep_probe_sharded(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
+                            nsx_result* result, const nsx_shard* shard);
+int64_t nsx_mailbox_bytes(void);
+int nsx_mailbox_create(int32_t device, void** mailbox, unsigned char handle[64]);
+int nsx_mailbox_open(int32_t device, const unsigned char handle[64], void** mailbox);
+int nsx_mailbox_reset(int32_t device, void* mailbox);
+int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local);
 
 /* Solve `count` independent instances on one GPU, one CTA per instance (batched config).
  * problems[i] / results[i] as in nsx_solve; options are shared. */

@@ -66,6 +66,10 @@ class NsxOptions(C.Structure):
     ]
 
 
+class NsxShard(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mailboxes", C.POINTER(C.c_void_p))]
+
+
 class NsxResult(C.Structure):
     _fields_ = [
         ("flow", _p_f64),
@@ -96,6 +100,7 @@ class NsxResult(C.Structure):
         ("pricing_ms", C.c_double),
         ("pivot_ms", C.c_double),
         ("sync_ms", C.c_double),
+        ("exchange_ms", C.c_double),
         ("sum_cycle_len", C.c_int64),
         ("sum_subtree", C.c_int64),
         ("max_subtree", C.c_int64),
@@ -233,6 +238,7 @@ class CallFrame:
                 "pricing_ms": float(r.pricing_ms),
                 "pivot_ms": float(r.pivot_ms),
                 "sync_ms": float(r.sync_ms),
+                "exchange_ms": float(r.exchange_ms),
             },
             stats={
                 "grid": int(r.grid_ctas),
@@ -286,6 +292,19 @@ def load_library():
         lib.nsx_sweep_probe.argtypes = [
             C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.c_int32, C.POINTER(NsxResult)]
         lib.nsx_sweep_probe.restype = C.c_int
+        lib.nsx_solve_sharded.argtypes = [
+            C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult), C.POINTER(NsxShard)]
+        lib.nsx_solve_sharded.restype = C.c_int
+        lib.nsx_sweep_probe_sharded.argtypes = [
+            C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.c_int32, C.POINTER(NsxResult), C.POINTER(NsxShard)]
+        lib.nsx_sweep_probe_sharded.restype = C.c_int
+        lib.nsx_mailbox_bytes.restype = C.c_int64
+        lib.nsx_mailbox_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.c_char_p]
+        lib.nsx_mailbox_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.nsx_mailbox_reset.argtypes = [C.c_int32, C.c_void_p]
+        lib.nsx_mailbox_close.argtypes = [C.c_int32, C.c_void_p, C.c_int32]
+        for name in ("nsx_mailbox_create", "nsx_mailbox_open", "nsx_mailbox_reset", "nsx_mailbox_close"):
+            getattr(lib, name).restype = C.c_int
         lib.nsx_solve_batch.argtypes = [
             C.c_int64,
             C.POINTER(NsxProblem),
@@ -339,6 +358,47 @@ def sweep_probe(cp: CanonicalProblem, opts: EngineOptions, device_arrays, sweeps
         C.byref(frame.problem), C.byref(frame.options), int(sweeps), C.byref(frame.result)
     )
     _check(rc, "nsx_sweep_probe")
+    return frame.harvest()
+
+
+def mailbox_create(device: int) -> tuple[int, bytes]:
+    """Allocate this rank's mailbox; returns (device pointer, 64-byte IPC handle)."""
+    lib = load_library()
+    ptr = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    _check(lib.nsx_mailbox_create(int(device), C.byref(ptr), handle), "nsx_mailbox_create")
+    return int(ptr.value), bytes(handle.raw)
+
+
+def mailbox_open(device: int, handle: bytes) -> int:
+    lib = load_library()
+    ptr = C.c_void_p()
+    _check(lib.nsx_mailbox_open(int(device), C.create_string_buffer(handle, 64), C.byref(ptr)), "nsx_mailbox_open")
+    return int(ptr.value)
+
+
+def mailbox_reset(device: int, ptr: int) -> None:
+    _check(load_library().nsx_mailbox_reset(int(device), C.c_void_p(ptr)), "nsx_mailbox_reset")
+
+
+def mailbox_close(device: int, ptr: int, is_local: bool) -> None:
+    _check(load_library().nsx_mailbox_close(int(device), C.c_void_p(ptr), int(is_local)), "nsx_mailbox_close")
+
+
+def solve_sharded(cp: CanonicalProblem, opts: EngineOptions, rank: int, world: int, mailboxes: list[int],
+                  out=None, probe_sweeps: int = 0, device_arrays=None) -> RawSolution:
+    """This rank's part of an arc-sharded solve (nsx_solve_sharded); every rank gets the full result."""
+    lib = load_library()
+    frame = CallFrame(cp, opts, out=out, device_arrays=device_arrays)
+    boxes = (C.c_void_p * world)(*[C.c_void_p(p) for p in mailboxes])
+    shard = NsxShard(int(rank), int(world), C.cast(boxes, C.POINTER(C.c_void_p)))
+    if probe_sweeps > 0:
+        rc = lib.nsx_sweep_probe_sharded(C.byref(frame.problem), C.byref(frame.options), int(probe_sweeps),
+                                         C.byref(frame.result), C.byref(shard))
+    else:
+        rc = lib.nsx_solve_sharded(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result),
+                                   C.byref(shard))
+    _check(rc, "nsx_solve_sharded")
     return frame.harvest()
 
 

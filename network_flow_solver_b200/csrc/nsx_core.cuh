@@ -138,7 +138,7 @@ struct NsxCtl {
     int64_t trace_len, trace_cap;
     int64_t unbounded_arc;
     double unbounded_rc;
-    int64_t clk_pricing, clk_pivot, clk_sync;
+    int64_t clk_pricing, clk_pivot, clk_sync, clk_xchg;
     int64_t ph[12];       // SM-clock cycles per pivot phase (thread 0): walk, residuals, ratio, flow,
                           // bookkeeping, snapshot+sizes, window, copy+stem, potentials, cadence, driver
 };

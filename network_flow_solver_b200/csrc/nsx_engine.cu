@@ -580,6 +580,55 @@ struct NsxSweepCtx {       // what a CTA needs to run sweeps
     int stages;
 };
 
+// ------------------------------------------------------------------------------------------
+// Arc-sharded pricing across GPUs (one process per GPU).  Every GPU holds the full tree and runs
+// the identical pivot; a sweep is split over the sweepers of ALL GPUs (tile t belongs to sweeper
+// t mod (world * W)), so each GPU streams 1/world of the arcs.  After its local merge a pivot CTA
+// stores its candidate straight into every peer's mailbox over NVLink (payload, then a
+// system-scope release of the sequence word) and polls its own mailbox for the peers' candidates;
+// all GPUs then merge the same `world` records with the same rule and pick the same entering arc.
+// ------------------------------------------------------------------------------------------
+#define NSX_MAX_WORLD 8
+struct NsxMailSlot {        // 64 bytes
+    int4 payload[2];        // NsxCand (16 B) or NsxDevexCand (32 B)
+    unsigned long long seq; // exchange number the payload belongs to (written last, release.sys)
+    unsigned long long pad[3];
+};
+struct NsxMailbox { NsxMailSlot slot[2][NSX_MAX_WORLD]; };  // [exchange parity][sender rank]
+struct NsxShard {
+    int32_t rank, world;
+    NsxMailbox* box[NSX_MAX_WORLD];  // box[r]: mailbox of rank r as mapped into this GPU's address space
+};
+
+__device__ __forceinline__ void nsx_st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long nsx_ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Thread 0 of the pivot CTA: publish `mine` to all peers, collect theirs.  `recs[r]` receives the
+// payload of rank r (own included).
+__device__ __forceinline__ void nsx_exchange(const NsxShard& shd, unsigned long long xseq, const int4* mine,
+                                             int nvec, int4 (*recs)[2]) {
+    const int par = (int)(xseq & 1ull);
+    for (int r = 0; r < shd.world; ++r) {
+        if (r == shd.rank) { recs[r][0] = mine[0]; recs[r][1] = nvec > 1 ? mine[1] : make_int4(0, 0, 0, 0); continue; }
+        NsxMailSlot* dst = &shd.box[r]->slot[par][shd.rank];
+        dst->payload[0] = mine[0];
+        if (nvec > 1) dst->payload[1] = mine[1];
+        nsx_st_release_sys_u64(&dst->seq, xseq);
+    }
+    for (int r = 0; r < shd.world; ++r) {
+        if (r == shd.rank) continue;
+        const NsxMailSlot* src = &shd.box[shd.rank]->slot[par][r];
+        while (nsx_ld_acquire_sys_u64(&src->seq) != xseq) { }
+        recs[r][0] = __ldcg(&src->payload[0]);
+        recs[r][1] = nvec > 1 ? __ldcg(&src->payload[1]) : make_int4(0, 0, 0, 0);
+    }
+}
+
 // Sweep functor of CTA 0.
 struct GridSweep {
     const NsxDev& d;      // global view (state bytes, weights, global potentials)
@@ -593,6 +642,28 @@ struct GridSweep {
     int32_t seq;
     unsigned long long target;
     unsigned long long t_price, t_sync;
+    const NsxShard& shd;
+    unsigned long long xseq, t_xchg;
+
+    // candidates of the other GPUs (thread 0 holds the local best in `k`)
+    __device__ void exchange(NsxCand& k) {
+        union { NsxCand c; int4 v[2]; } mine; mine.v[1] = make_int4(0, 0, 0, 0); mine.c = k;
+        int4 recs[NSX_MAX_WORLD][2];
+        const unsigned long long t1 = nsx_globaltimer();
+        nsx_exchange(shd, ++xseq, mine.v, 1, recs);
+        t_xchg += nsx_globaltimer() - t1;
+        nsx_cand_init(k);
+        for (int r = 0; r < shd.world; ++r) { union { NsxCand c; int4 v; } o; o.v = recs[r][0]; nsx_cand_merge(k, o.c); }
+    }
+    __device__ void exchange(NsxDevexCand& k) {
+        union { NsxDevexCand c; int4 v[2]; } mine; mine.c = k;
+        int4 recs[NSX_MAX_WORLD][2];
+        const unsigned long long t1 = nsx_globaltimer();
+        nsx_exchange(shd, ++xseq, mine.v, 2, recs);
+        t_xchg += nsx_globaltimer() - t1;
+        nsx_devex_init(k);
+        for (int r = 0; r < shd.world; ++r) { union { NsxDevexCand c; int4 v[2]; } o; o.v[0] = recs[r][0]; o.v[1] = recs[r][1]; nsx_devex_merge(k, o.c); }
+    }
 
     __device__ void publish(const NsxCmd& cmd) {
         if (threadIdx.x == 0) {
@@ -614,8 +685,9 @@ struct GridSweep {
         if (gridDim.x == 1) {  // alone: this CTA prices everything itself
             NsxCand dz; NsxDevexCand dx;
             if (threadIdx.x == 0) __threadfence();
-            nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
+            nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, shd.rank, shd.world, sh, dz, dx);
             if (threadIdx.x == 0) {
+                if (shd.world > 1) { if (devex) exchange(dx); else exchange(dz); }
                 if (devex) out_dx = dx; else out_dz = dz;
                 t_price += nsx_globaltimer() - t0;
             }
@@ -642,7 +714,7 @@ struct GridSweep {
                 nsx_devex_merge(k, tmp.c);
             }
             nsx_block_reduce(k, sh.dx_buf);
-            if (threadIdx.x == 0) out_dx = k;
+            if (threadIdx.x == 0) { if (shd.world > 1) exchange(k); out_dx = k; }
         } else {
             NsxCand k; nsx_cand_init(k);
             for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
@@ -651,7 +723,7 @@ struct GridSweep {
                 nsx_cand_merge(k, tmp.c);
             }
             nsx_block_reduce(k, sh.dz_buf);
-            if (threadIdx.x == 0) out_dz = k;
+            if (threadIdx.x == 0) { if (shd.world > 1) exchange(k); out_dz = k; }
         }
         if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
@@ -681,6 +753,7 @@ struct NsxKernelArgs {
     NsxSmemPlan plan;    // CTA 0
     NsxSmemPlan wplan;   // sweep workers
     int32_t probe_sweeps;  // > 0: measurement aid, run this many sweeps of the initial state and stop
+    NsxShard shard;        // world == 1: single GPU
 };
 
 __device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
@@ -751,7 +824,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull};
+        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
         if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -759,6 +832,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
             unsigned long long total = nsx_globaltimer() - t_begin;
             sh.ctl.clk_pricing = (int64_t)sweep.t_price;
             sh.ctl.clk_sync = (int64_t)sweep.t_sync;
+            sh.ctl.clk_xchg = (int64_t)sweep.t_xchg;
             sh.ctl.clk_pivot = (int64_t)(total - sweep.t_price);
         }
         NSX_SYNC();
@@ -787,7 +861,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
         nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
-                      (int)blockIdx.x - 1, (int)gridDim.x - 1, sh, dz, dx);
+                      a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
         if (threadIdx.x == 0) {
             NSX_TL(a.grid, 4);
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
@@ -1005,6 +1079,7 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
     res->pricing_ms = (double)c.clk_pricing * 1e-6;
     res->pivot_ms = (double)c.clk_pivot * 1e-6;
     res->sync_ms = (double)c.clk_sync * 1e-6;
+    res->exchange_ms = (double)c.clk_xchg * 1e-6;
     for (int i = 0; i < 12; ++i) res->phase_cycles[i] = c.ph[i];
 }
 
@@ -1044,7 +1119,7 @@ static void nsx_choose_layout(int32_t n, unsigned int cost_flags, bool devex, Ns
 
 // Common implementation; `resident` = arc arrays are device pointers; probe_sweeps > 0 = sweep probe.
 static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_result* res, bool resident,
-                          int32_t probe_sweeps) {
+                          int32_t probe_sweeps, const nsx_shard* shard = nullptr) {
     Arena arena, inputs;
     int rc = nsx_validate(pb, opt, res);
     if (rc) return rc;
@@ -1137,6 +1212,16 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     ka.dzc = arena.at<NsxCand>(o_dzc); ka.dxc = arena.at<NsxDevexCand>(o_dxc);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
     ka.probe_sweeps = probe_sweeps;
+    memset(&ka.shard, 0, sizeof ka.shard);
+    ka.shard.rank = 0; ka.shard.world = 1;
+    if (shard) {
+        if (shard->world < 1 || shard->world > NSX_MAX_WORLD || shard->rank < 0 || shard->rank >= shard->world || !shard->mailboxes) {
+            arena.release(); inputs.release();
+            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad shard description");
+        }
+        ka.shard.rank = shard->rank; ka.shard.world = shard->world;
+        for (int r = 0; r < shard->world; ++r) ka.shard.box[r] = reinterpret_cast<NsxMailbox*>(shard->mailboxes[r]);
+    }
 
     NsxCtl hctl;
     nsx_fill_ctl(hctl, opt, want_trace);
@@ -1231,6 +1316,52 @@ extern "C" int nsx_sweep_probe(const nsx_problem* problem_dev, const nsx_options
                                nsx_result* result) {
     if (sweeps < 1) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "sweeps must be positive");
     return nsx_solve_impl(problem_dev, options, result, true, sweeps);
+}
+
+extern "C" int nsx_solve_sharded(const nsx_problem* problem, const nsx_options* options, nsx_result* result,
+                                 const nsx_shard* shard) {
+    if (!shard) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null shard");
+    return nsx_solve_impl(problem, options, result, false, 0, shard);
+}
+extern "C" int nsx_sweep_probe_sharded(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
+                                       nsx_result* result, const nsx_shard* shard) {
+    if (!shard || sweeps < 1) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad argument");
+    return nsx_solve_impl(problem_dev, options, result, true, sweeps, shard);
+}
+extern "C" int64_t nsx_mailbox_bytes(void) { return (int64_t)sizeof(NsxMailbox); }
+extern "C" int nsx_mailbox_create(int32_t device, void** mailbox, unsigned char handle[64]) {
+    if (!mailbox || !handle) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(mailbox, sizeof(NsxMailbox));
+    if (e == cudaSuccess) e = cudaMemset(*mailbox, 0, sizeof(NsxMailbox));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *mailbox);
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_create: ") + cudaGetErrorString(e));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" int nsx_mailbox_open(int32_t device, const unsigned char handle[64], void** mailbox) {
+    if (!mailbox || !handle) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(mailbox, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_open: ") + cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int nsx_mailbox_reset(int32_t device, void* mailbox) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMemset(mailbox, 0, sizeof(NsxMailbox));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_reset: ") + cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = is_local ? cudaFree(mailbox) : cudaIpcCloseMemHandle(mailbox);
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_close: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const nsx_options* opt, nsx_result* results) {
