@@ -144,6 +144,9 @@ def main() -> int:
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU-baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N>1: independent replicas (weak scaling) or ONE instance with arc-sharded pricing (strong)")
+    ap.add_argument("--max-pivots", type=int, default=0, help="bound the solve to this many pivots (0 = to optimality)")
     ap.add_argument("--probe-sweeps", type=int, default=200)
     args = ap.parse_args()
 
@@ -162,7 +165,9 @@ def main() -> int:
         "description": wl.description,
         "pricing": "devex" if wl.pricing == 1 else ("row_scan" if "transport" in wl.name else "dantzig"),
         "perturbation_eps": wl.eps_base,
-        "parallelism": f"replicas x{world}" if not batch_mode else f"batch round-robin x{world}",
+        "parallelism": (f"batch round-robin x{world}" if batch_mode else
+                        f"arc-sharded pricing x{world} (NVLink candidate exchange)" if args.mode == "sharded" else f"replicas x{world}"),
+        "max_pivots": args.max_pivots or None,
         "l2_policy": "256 MB memset (> 126 MB L2) between timed steps; within a step the arc store is re-streamed once per pivot",
     }
 
@@ -239,9 +244,11 @@ def main() -> int:
         stats = {}
         cp0 = cps[0]
     else:
-        cp0 = wl.canonical(rank)
+        sharded = args.mode == "sharded"
+        cp0 = wl.canonical(0 if sharded else rank)
         m = cp0.n_arcs
-        opts = wl.engine_options(cp0, device=device)
+        okw = {"max_iterations": args.max_pivots} if args.max_pivots > 0 else {}
+        opts = wl.engine_options(cp0, device=device, **okw)
         # pinned host copies (e2e path) and resident device copies (kernel-only path)
         keep, host = [], {}
         for name in ("tail", "head", "pert_cost", "upper"):
@@ -256,13 +263,28 @@ def main() -> int:
                  "state": torch.empty(ma, dtype=torch.uint8).pin_memory()}
         out = {k: v.numpy() for k, v in out_t.items()}
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")  # > 126 MB L2
+        ring = None
+        if sharded:
+            from network_flow_solver_b200.sharded import MailboxRing, solve_canonical_sharded
+            ring = MailboxRing(device, dist)
+
+        def solve_dev():   # arc arrays resident in HBM
+            if sharded:
+                return solve_canonical_sharded(cp0, opts, ring, out=out)  # (host-buffer entry; device-timed part is solve_ms)
+            return _capi.solve_resident(cp0, opts, ptrs, out=out)
+
+        def solve_host():  # pinned host arrays in, pinned host results out
+            if sharded:
+                return solve_canonical_sharded(cp0, opts, ring, out=out)
+            return _capi.solve_canonical(cp0, opts, out=out)
+
         for _ in range(args.warmup):
-            last = _capi.solve_resident(cp0, opts, ptrs, out=out)
+            last = solve_dev()
         barrier(); sampler.start()
         dev_ms = 0.0; pivots = 0; arcs = 0; pricing_ms = pivot_ms = sync_ms = 0.0
         for _ in range(args.steps):
             flush.zero_(); torch.cuda.synchronize()
-            last = _capi.solve_resident(cp0, opts, ptrs, out=out)
+            last = solve_dev()
             dev_ms += last.timing["solve_ms"]; pivots += last.iterations; arcs += last.arcs_priced
             pricing_ms += last.timing["pricing_ms"]; pivot_ms += last.timing["pivot_ms"]; sync_ms += last.timing["sync_ms"]
         barrier()
@@ -272,13 +294,13 @@ def main() -> int:
         for _ in range(args.steps):
             flush.zero_(); torch.cuda.synchronize()
             t0 = time.perf_counter()
-            r = _capi.solve_canonical(cp0, opts, out=out)   # pinned host arrays in, pinned host results out
+            r = solve_host()
             e2e_ms += 1e3 * (time.perf_counter() - t0)       # wall clock of the C-ABI call: alloc + H2D + solve + D2H
             e2e_dev_ms += r.timing["h2d_ms"] + r.timing["solve_ms"] + r.timing["d2h_ms"]
         barrier(); clocks = sampler.stop()
         # the sweep kernel alone: K sweeps of the initial state through the real command / arrival protocol
         probe = {}
-        if rank == 0 and not args.no_probe:
+        if rank == 0 and not args.no_probe and not sharded:
             for label, env in (("engine_layout", None), ("wide_layout", "wide")):
                 old = os.environ.get("NSX_LAYOUT")
                 if env: os.environ["NSX_LAYOUT"] = env
@@ -314,6 +336,8 @@ def main() -> int:
                 ["walk", "residuals", "ratio", "flow", "bookkeeping", "snapshot", "window", "copy_stem",
                  "potentials", "cadence"], last.stats["phase_cycles"])},
             "e2e_device_events_ms_per_step": e2e_dev_ms / args.steps,
+            "exchange_ms_per_step": last.timing.get("exchange_ms", 0.0),
+            "exchange_us_per_sweep": 1e3 * last.timing.get("exchange_ms", 0.0) / max(last.stats["sweeps"], 1),
             "sweep_probe": probe,
         }
 
@@ -325,9 +349,12 @@ def main() -> int:
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = (float(x) for x in t_dev.tolist())
     pivots_all, arcs_all = (float(x) for x in work.tolist())
+    if args.mode == "sharded" and not batch_mode:
+        pivots_all /= world  # every rank applies the same pivots: one solve, counted once
     value = pivots_all / (dev_ms_max * 1e-3)
     e2e_value = pivots_all / (e2e_ms_max * 1e-3)
-    achieved = (arcs / args.steps) * bpa / (dev_ms / args.steps * 1e-3) / 1e9  # this rank's kernel
+    my_arcs = arcs / world if (args.mode == "sharded" and not batch_mode) else arcs  # arcs THIS rank streamed
+    achieved = (my_arcs / args.steps) * bpa / (dev_ms / args.steps * 1e-3) / 1e9  # this rank's kernel
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -339,6 +366,8 @@ def main() -> int:
         cpu = {"value": s["pivots_per_s"], "unit": "pivots/s", "cores": threads, "kind": "port",
                "sample": f"first {s['pivots']} pivots of the same instance ({s['seconds']:.1f} s)"}
 
+    if not batch_mode and ring is not None:
+        ring.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -354,7 +383,8 @@ def main() -> int:
     line = {
         "metric": "pivots_per_second", "value": value, "unit": "pivots/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong" if (args.mode == "sharded" and not batch_mode) else "weak",
+        "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "pivots/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},

@@ -75,6 +75,24 @@ WORKLOADS = {
     "transport_1024": Workload(
         "transport_1024", "dense transportation 1024x1024 (1M arcs), row-scan pricing, eps=0",
         _capi.PRICING_DANTZIG, 0.0, _transport(1024)),
+    # config 5 - the single largest instance (arc-sharded pricing across GPUs); eps = 0 as for config 3
+    "netgen_2e20_devex": Workload(
+        "netgen_2e20_devex", "NETGEN-style 2^20 nodes / 2^26 arcs, Devex block pricing (block = M/16), eps=0",
+        _capi.PRICING_DEVEX, 0.0,
+        lambda off: gen.netgen_like(1 << 20, 1 << 26, n_sources=4096, n_sinks=4096, seed=2026 + off)),
+    "netgen_2e20_dantzig": Workload(
+        "netgen_2e20_dantzig", "NETGEN-style 2^20 nodes / 2^26 arcs, Dantzig full sweeps, eps=0",
+        _capi.PRICING_DANTZIG, 0.0,
+        lambda off: gen.netgen_like(1 << 20, 1 << 26, n_sources=4096, n_sinks=4096, seed=2026 + off)),
+    # quarter-scale stand-ins of config 5 (same family and ratio m/n = 64)
+    "netgen_2e18_devex": Workload(
+        "netgen_2e18_devex", "NETGEN-style 2^18 nodes / 2^24 arcs, Devex block pricing, eps=0",
+        _capi.PRICING_DEVEX, 0.0,
+        lambda off: gen.netgen_like(1 << 18, 1 << 24, n_sources=1024, n_sinks=1024, seed=2026 + off)),
+    "netgen_2e18_dantzig": Workload(
+        "netgen_2e18_dantzig", "NETGEN-style 2^18 nodes / 2^24 arcs, Dantzig full sweeps, eps=0",
+        _capi.PRICING_DANTZIG, 0.0,
+        lambda off: gen.netgen_like(1 << 18, 1 << 24, n_sources=1024, n_sinks=1024, seed=2026 + off)),
     # config 4 - one instance of the batch (the batch itself is built by bench.py)
     "goto_64": Workload(
         "goto_64", "GOTO-style grid-on-torus 64x64 (4096 nodes / ~32.7K arcs), Dantzig",
