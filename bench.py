@@ -203,6 +203,11 @@ def main() -> int:
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
+    # NCCL / torch print banners on stdout; the contract is ONE JSON line there, so everything
+    # before the final print goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     dist = None
@@ -398,6 +403,8 @@ def main() -> int:
         "cpu_baseline": cpu,
         "detail": stats,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line))
     return 0
 
