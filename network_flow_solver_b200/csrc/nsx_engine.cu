@@ -54,6 +54,9 @@ __device__ __forceinline__ unsigned long long nsx_ld_acquire_u64(const unsigned 
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void nsx_red_release_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void nsx_st_release(int32_t* p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -362,14 +365,13 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
     uint32_t any = 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        sb[u] = sb[u] & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD) & ((sb[u] & NSX_ARC_IN_TREE) - 1u);
+        sb[u] = sb[u] & ((sb[u] & NSX_ARC_IN_TREE) ? 0u : (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD));
         any |= sb[u];
     }
     if (!any) return;
     // node ids are stored zero-based from node 1 (uint16 layout) - `pi1` points at pi[1]
     int32_t tl[4], hd[4];
     double c[4];
-    const int bias = st.node_kind == NSX_NODE_U16 ? 1 : 0;
     if (st.node_kind == NSX_NODE_U16) {
         const uint16_t* pt = reinterpret_cast<const uint16_t*>(sp);
         const uint16_t* ph = reinterpret_cast<const uint16_t*>(sp + st.off_head);
@@ -395,7 +397,7 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_CONSUMERS + tid];
     }
     const double tol = d.tol;
-    const double* pi1 = (PISMEM ? pis : d.pi) + bias;
+    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
     // all four reduced costs first (independent dependency chains), decisions after
     double rc[4];
     const double i0 = (double)(tile_base + tid);
@@ -417,14 +419,14 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         // bits): it only filters - the exact rule runs in nsx_dantzig_improving on the few arcs that
         // reach it, so a stale gate costs time, never correctness.
         const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(&sh.gate_bits);
-        const unsigned long long sign = 0x8000000000000000ull;
         uint32_t hit = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned long long b = (unsigned long long)__double_as_longlong(rc[u]);
-            const uint32_t f = (b >= g) ? NSX_ARC_CAN_FWD : 0u;
-            const uint32_t r = ((b ^ sign) >= g) ? NSX_ARC_CAN_BWD : 0u;
-            hit |= sb[u] & (f | r);
+        for (int u = 0; u < 4; ++u)
+            hit |= ((unsigned long long)__double_as_longlong(rc[u]) >= g) ? (sb[u] & NSX_ARC_CAN_FWD) : 0u;
+        if (any & NSX_ARC_CAN_BWD) {  // arcs with flow to push back are rare
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                hit |= (((unsigned long long)__double_as_longlong(rc[u]) ^ 0x8000000000000000ull) >= g) ? (sb[u] & NSX_ARC_CAN_BWD) : 0u;
         }
         if (hit) {
             const int32_t before = dz.arc2;
@@ -672,7 +674,8 @@ struct GridSweep {
             int4* dst = reinterpret_cast<int4*>(&g->cmd);
             dst[0] = tmp.v[0]; dst[1] = tmp.v[1]; dst[2] = tmp.v[2];
             g->t_pub = nsx_globaltimer();
-            __threadfence();
+            // release is cumulative: it orders the command words above and every pivot write the other
+            // threads of this CTA made before the preceding barrier
             nsx_st_release(&g->seq, ++seq);
         }
     }
@@ -699,7 +702,6 @@ struct GridSweep {
             unsigned long long t1 = nsx_globaltimer();
             target += gridDim.x - 1;
             while (nsx_ld_acquire_u64(&g->arrived) < target) { }
-            __threadfence();
             t_sync += nsx_globaltimer() - t1;
             g->tl[6] += nsx_globaltimer() - g->t_pub;
         }
@@ -849,7 +851,6 @@ nsx_resident_kernel(const NsxKernelArgs a) {
             int32_t s;
             while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(20); }
             seen = s;
-            __threadfence();
             NSX_TL(a.grid, 0);
             union { NsxCmd c; int4 v[3]; } tmp;
             const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
@@ -865,8 +866,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         if (threadIdx.x == 0) {
             NSX_TL(a.grid, 4);
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
-            __threadfence();
-            atomicAdd(&a.grid->arrived, 1ull);
+            nsx_red_release_add(&a.grid->arrived, 1ull);  // the candidate above is ordered before the count
             NSX_TL(a.grid, 5);
         }
     }
