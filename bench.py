@@ -246,7 +246,11 @@ def main() -> int:
         h2d = sum(cp.n_arcs * 24 + cp.n_nodes * 8 for cp in cps)
         d2h = sum((cp.n_arcs + cp.n_nodes) * 9 + cp.n_nodes * 8 for cp in cps)
         launches = 1
-        stats = {}
+        from collections import Counter
+        stats = {"instances_this_rank": len(cps), "status_counts": dict(Counter(int(o.status) for o in outs)),
+                 "pivots_per_instance_mean": pivots / args.steps / max(len(cps), 1),
+                 "grid_ctas": outs[0].stats.get("grid"), "bytes_per_arc": outs[0].stats["bytes_per_arc"],
+                 "resident_mode": outs[0].stats["resident_mode"], "ring_stages": outs[0].stats["ring_stages"]}
         cp0 = cps[0]
     else:
         sharded = args.mode == "sharded"
@@ -371,7 +375,7 @@ def main() -> int:
         cpu = {"value": s["pivots_per_s"], "unit": "pivots/s", "cores": threads, "kind": "port",
                "sample": f"first {s['pivots']} pivots of the same instance ({s['seconds']:.1f} s)"}
 
-    if not batch_mode and ring is not None:
+    if not batch_mode and ring is not None:  # (ring only exists on the single-instance path)
         ring.close()
     if dist is not None:
         dist.barrier()
@@ -397,7 +401,7 @@ def main() -> int:
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "nsx_resident_kernel (whole resident pivot loop: sweeps + pivots)",
+                     "kernel": ("nsx_batch_kernel" if batch_mode else "nsx_resident_kernel") + " (whole resident pivot loop: sweeps + pivots)",
                      "bytes_per_arc": bpa, "arcs_priced_per_launch": arcs / args.steps,
                      "algorithmic_bytes_per_launch": arcs / args.steps * bpa},
         "cpu_baseline": cpu,

@@ -225,8 +225,12 @@ static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t li
                                                              bool sweeps, int want_mode, int want_stage) {
     NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0;
     const size_t ring_min = sweeps ? 2 * (size_t)stage_bytes : 0;
-    for (int mode = want_mode; mode >= NSX_RES_NODES; --mode) {
-        if (nsx_resident_bytes(mode, n) + ring_min <= limit) { p.mode = mode; break; }
+    // a CTA that also sweeps wants a ring of >= 4 stages more than it wants depth / preorder on-chip
+    for (int want_ring = sweeps ? 4 : 0; p.mode == NSX_RES_NONE && want_ring >= (sweeps ? 2 : 0); want_ring -= 2) {
+        for (int mode = want_mode; mode >= NSX_RES_NODES; --mode) {
+            if (nsx_resident_bytes(mode, n) + (size_t)want_ring * stage_bytes <= limit) { p.mode = mode; break; }
+        }
+        if (!sweeps) break;
     }
     size_t used = nsx_resident_bytes(p.mode, n);
     if (p.mode == NSX_RES_NONE && sweeps && want_stage && nsx_align16(8 * n) + ring_min <= limit) {
