@@ -113,7 +113,8 @@ typedef struct nsx_result {
     int32_t ring_stages;          /* depth of the shared-memory tile ring of a sweeping CTA */
     int32_t resident_mode;        /* node state held in the pivot CTA's shared memory: 0 none, 1 records +
                                      potentials, 2 everything */
-    int32_t reserved;
+    int32_t store_layout;         /* encoding of the pricing store: node ids (0 int32, 1 uint16) | cost (0 float64,
+                                     1 int32, 2 int16) << 8 */
     /* device-side timing (milliseconds unless stated) */
     double solve_ms;              /* CUDA-event time of the resident pivot loop */
     double h2d_ms, d2h_ms;        /* host<->device copies (host-buffer entry points only) */

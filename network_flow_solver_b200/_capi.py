@@ -93,7 +93,7 @@ class NsxResult(C.Structure):
         ("bytes_per_arc", C.c_int32),
         ("ring_stages", C.c_int32),
         ("resident_mode", C.c_int32),
-        ("reserved", C.c_int32),
+        ("store_layout", C.c_int32),
         ("solve_ms", C.c_double),
         ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double),
@@ -245,6 +245,8 @@ class CallFrame:
                 "bytes_per_arc": int(r.bytes_per_arc),
                 "ring_stages": int(r.ring_stages),
                 "resident_mode": int(r.resident_mode),
+                "node_kind": int(r.store_layout) & 0xff,
+                "cost_kind": (int(r.store_layout) >> 8) & 0xff,
                 "sweeps": int(r.sweeps),
                 "sum_cycle_len": int(r.sum_cycle_len),
                 "sum_subtree": int(r.sum_subtree),

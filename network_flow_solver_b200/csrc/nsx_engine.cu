@@ -1301,6 +1301,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     res->grid_ctas = grid;
     res->bytes_per_arc = (int32_t)(2 * nsx_node_bytes(st.node_kind) + nsx_cost_bytes(st.cost_kind) + 1);
     res->ring_stages = grid == 1 ? ka.plan.stages : ka.wplan.stages;
+    res->store_layout = st.node_kind | (st.cost_kind << 8);
     res->resident_mode = ka.plan.mode;
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream);
@@ -1502,7 +1503,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         nsx_result& r = results[i];
         nsx_harvest(ctls[i], &r);
         r.h2d_ms = h2d; r.solve_ms = solve; r.d2h_ms = d2h; r.grid_ctas = (int32_t)grid;
-        r.bytes_per_arc = (int32_t)(2 * nsx_node_bytes(layout.node_kind) + 9); r.ring_stages = plan.stages; r.resident_mode = plan.mode;
+        r.bytes_per_arc = (int32_t)(2 * nsx_node_bytes(layout.node_kind) + 9); r.ring_stages = plan.stages; r.resident_mode = plan.mode; r.store_layout = layout.node_kind | (layout.cost_kind << 8);
         if (items[i].trace) {
             int64_t cnt = ctls[i].trace_len < opt->trace_capacity ? ctls[i].trace_len : opt->trace_capacity;
             if (cnt > 0) NSX_CUDA(cudaMemcpy(r.entering_trace, items[i].trace, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
