@@ -34,6 +34,13 @@
 // Grid-wide command / arrival handshake
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long nsx_globaltimer();
+// One candidate slot per sweep worker: payload, then the command sequence number it answers
+// (release store).  The pivot CTA polls one slot per thread - no shared arrival counter.
+struct alignas(64) NsxSlot {
+    int4 v[2];      // NsxCand (16 B) or NsxDevexCand (32 B)
+    int32_t seq;
+    int32_t pad[7];
+};
 struct NsxGridCtl {
     int32_t seq;  // command sequence number, release-published by CTA 0
     int32_t pad;
@@ -639,8 +646,7 @@ __device__ __forceinline__ void nsx_exchange(const NsxShard& shd, unsigned long 
 struct GridSweep {
     const NsxDev& d;      // global view (state bytes, weights, global potentials)
     NsxGridCtl* g;
-    NsxCand* dzc;
-    NsxDevexCand* dxc;
+    NsxSlot* slots;
     NsxCtaShared& sh;
     NsxSweepCtx cx;
     uint32_t& stage_count;
@@ -680,8 +686,9 @@ struct GridSweep {
             g->t_pub = nsx_globaltimer();
             // release is cumulative: it orders the command words above and every pivot write the other
             // threads of this CTA made before the preceding barrier
-            nsx_st_release(&g->seq, ++seq);
+            nsx_st_release(&g->seq, seq + 1);
         }
+        ++seq;  // every thread keeps its own copy of the sequence number (the slot polls compare against it)
     }
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
         unsigned long long t0 = 0;
@@ -702,34 +709,32 @@ struct GridSweep {
             return;
         }
         publish(cmd);
-        if (threadIdx.x == 0) {
-            unsigned long long t1 = nsx_globaltimer();
-            target += gridDim.x - 1;
-            while (nsx_ld_acquire_u64(&g->arrived) < target) { }
-            t_sync += nsx_globaltimer() - t1;
-            g->tl[6] += nsx_globaltimer() - g->t_pub;
+        unsigned long long t1 = 0;
+        if (threadIdx.x == 0) t1 = nsx_globaltimer();
+        // every worker's candidate: thread b polls slot b until it carries this command's number
+        NsxDevexCand kx; nsx_devex_init(kx);
+        NsxCand kz; nsx_cand_init(kz);
+        for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            const NsxSlot* sl = slots + b;
+            while (nsx_ld_acquire(&sl->seq) != seq) { }
+            if (devex) {
+                union { NsxDevexCand c; int4 v[2]; } tmp;
+                tmp.v[0] = __ldcg(&sl->v[0]); tmp.v[1] = __ldcg(&sl->v[1]);
+                nsx_devex_merge(kx, tmp.c);
+            } else {
+                union { NsxCand c; int4 v; } tmp;
+                tmp.v = __ldcg(&sl->v[0]);
+                nsx_cand_merge(kz, tmp.c);
+            }
         }
         NSX_SYNC();
-        // merge the candidates of the other CTAs (one per thread), then reduce across the block
+        if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; g->tl[6] += nsx_globaltimer() - g->t_pub; }
         if (devex) {
-            NsxDevexCand k; nsx_devex_init(k);
-            for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-                const int4* src = (const int4*)(dxc + b);
-                union { NsxDevexCand c; int4 v[2]; } tmp;
-                tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1);
-                nsx_devex_merge(k, tmp.c);
-            }
-            nsx_block_reduce(k, sh.dx_buf);
-            if (threadIdx.x == 0) { if (shd.world > 1) exchange(k); out_dx = k; }
+            nsx_block_reduce(kx, sh.dx_buf);
+            if (threadIdx.x == 0) { if (shd.world > 1) exchange(kx); out_dx = kx; }
         } else {
-            NsxCand k; nsx_cand_init(k);
-            for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-                union { NsxCand c; int4 v; } tmp;
-                tmp.v = __ldcg((const int4*)(dzc + b));
-                nsx_cand_merge(k, tmp.c);
-            }
-            nsx_block_reduce(k, sh.dz_buf);
-            if (threadIdx.x == 0) { if (shd.world > 1) exchange(k); out_dz = k; }
+            nsx_block_reduce(kz, sh.dz_buf);
+            if (threadIdx.x == 0) { if (shd.world > 1) exchange(kz); out_dz = kz; }
         }
         if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
@@ -753,8 +758,7 @@ struct NsxKernelArgs {
     NsxStore st;
     NsxCtl* ctl;
     NsxGridCtl* grid;
-    NsxCand* dzc;
-    NsxDevexCand* dxc;
+    NsxSlot* slots;
     int32_t* trace;
     NsxSmemPlan plan;    // CTA 0
     NsxSmemPlan wplan;   // sweep workers
@@ -830,7 +834,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.dzc, a.dxc, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
+        GridSweep sweep{d, a.grid, a.slots, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
         if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -869,8 +873,15 @@ nsx_resident_kernel(const NsxKernelArgs a) {
                       a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
         if (threadIdx.x == 0) {
             NSX_TL(a.grid, 4);
-            if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) a.dxc[blockIdx.x] = dx; else a.dzc[blockIdx.x] = dz;
-            nsx_red_release_add(&a.grid->arrived, 1ull);  // the candidate above is ordered before the count
+            NsxSlot* sl = a.slots + blockIdx.x;
+            if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) {
+                union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx;
+                sl->v[0] = tmp.v[0]; sl->v[1] = tmp.v[1];
+            } else {
+                union { NsxCand c; int4 v; } tmp; tmp.c = dz;
+                sl->v[0] = tmp.v;
+            }
+            nsx_st_release(&sl->seq, seen);  // the payload above is ordered before the sequence number
             NSX_TL(a.grid, 5);
         }
     }
@@ -1196,7 +1207,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_gph = arena.plan((size_t)n * 4), o_gpt = arena.plan((size_t)n * 4);
     size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
     size_t o_ctl = arena.plan(sizeof(NsxCtl)), o_grid = arena.plan(sizeof(NsxGridCtl));
-    size_t o_dzc = arena.plan(sizeof(NsxCand) * 1024), o_dxc = arena.plan(sizeof(NsxDevexCand) * 1024);
+    size_t o_slots = arena.plan(sizeof(NsxSlot) * 1024);
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     NSX_CUDA(arena.commit());
 
@@ -1213,7 +1224,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.log_cap = nsx_env_int("NSX_LOG_CAP", 32);
     if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
-    ka.dzc = arena.at<NsxCand>(o_dzc); ka.dxc = arena.at<NsxDevexCand>(o_dxc);
+    ka.slots = arena.at<NsxSlot>(o_slots);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
     ka.probe_sweeps = probe_sweeps;
     memset(&ka.shard, 0, sizeof ka.shard);
@@ -1231,6 +1242,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     nsx_fill_ctl(hctl, opt, want_trace);
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
+    NSX_CUDA(cudaMemsetAsync(ka.slots, 0, sizeof(NsxSlot) * 1024, stream));
     NSX_CUDA(cudaMemsetAsync(d.state, 0, state_len, stream));
     if (devex) NSX_CUDA(cudaMemsetAsync(d.wgt, 0, (size_t)mpad * 4, stream));
     nsx_pack_kernel<<<util_blocks, 256, 0, stream>>>(d.tail, d.head, d.pert, m, mpad, st);
