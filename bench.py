@@ -401,7 +401,7 @@ def main() -> int:
     line = {
         "metric": "pivots_per_second", "value": value, "unit": "pivots/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-        "higher_is_better": True, "scaling": "strong" if (args.mode == "sharded" and not batch_mode) else "weak",
+        "higher_is_better": True, "scaling": "strong" if (args.mode == "sharded" or batch_mode) else "weak",  # fixed total work: one sharded instance / one batch
         "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "pivots/s", "h2d_bytes_per_step": int(h2d),
