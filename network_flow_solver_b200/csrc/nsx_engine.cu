@@ -356,69 +356,79 @@ enum { NSX_MODE_DANTZIG = 0, NSX_MODE_DEVEX = 1, NSX_MODE_DANTZIG_ZERO = 2, NSX_
 // gathers are free of shared-memory bank conflicts.  `gate` caches the key a Dantzig candidate
 // has to reach (-tol while there is none): a single compare rejects almost every arc.
 // PISMEM: potentials are gathered from shared memory (`pis`), else from L2.
-template <int MODE, bool PHASE1, bool PISMEM>
+// Q landed tiles are priced together (Q = 2 in the steady state): 4Q independent dependency chains
+// per thread hide the latency of the potential gathers and of the float64 pipe.
+template <int MODE, bool PHASE1, bool PISMEM, int Q>
 __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
-                                               const double* pis, const unsigned char* sp, int32_t tile_base,
-                                               int32_t lo, int32_t hi, NsxCand& dz, NsxDevexCand& dx,
-                                               NsxCtaShared& sh) {
+                                               const double* pis, const unsigned char* const (&spq)[Q],
+                                               const int32_t (&tbq)[Q], int32_t lo, int32_t hi, NsxCand& dz,
+                                               NsxDevexCand& dx, NsxCtaShared& sh) {
     const int tid = threadIdx.x;
-    uint32_t sb[4];
+    constexpr int NA = 4 * Q;  // arcs per thread
+#define SPU(u) (spq[(u) >> 2])
+#define OFFU(u) (((u) & 3) * NSX_CONSUMERS + tid)
+#define IDXU(u) (tbq[(u) >> 2] + ((u) & 3) * NSX_CONSUMERS + tid)
+    uint32_t sb[NA];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sb[u] = sp[st.off_state + u * NSX_CONSUMERS + tid];
-    if (tile_base < lo || tile_base + NSX_TILE > hi) {  // ragged first / last tile of the range
+    for (int u = 0; u < NA; ++u) sb[u] = SPU(u)[st.off_state + OFFU(u)];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int32_t i = tile_base + u * NSX_CONSUMERS + tid;
-            if (i < lo || i >= hi) sb[u] = 0;
+    for (int q = 0; q < Q; ++q) {
+        if (tbq[q] < lo || tbq[q] + NSX_TILE > hi) {  // ragged first / last tile of the range
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const int32_t i = tbq[q] + uu * NSX_CONSUMERS + tid;
+                if (i < lo || i >= hi) sb[4 * q + uu] = 0;
+            }
         }
     }
     // eligibility bits: residual forward / backward and not in the tree
     uint32_t any = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < NA; ++u) {
         sb[u] = sb[u] & ((sb[u] & NSX_ARC_IN_TREE) ? 0u : (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD));
         any |= sb[u];
     }
     if (!any) return;
     // node ids are stored zero-based from node 1 (uint16 layout) - `pi1` points at pi[1]
-    int32_t tl[4], hd[4];
-    double c[4];
+    int32_t tl[NA], hd[NA];
+    double c[NA];
     if (st.node_kind == NSX_NODE_U16) {
-        const uint16_t* pt = reinterpret_cast<const uint16_t*>(sp);
-        const uint16_t* ph = reinterpret_cast<const uint16_t*>(sp + st.off_head);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_CONSUMERS + tid]; hd[u] = ph[u * NSX_CONSUMERS + tid]; }
+        for (int u = 0; u < NA; ++u) {
+            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)];
+            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)];
+        }
     } else {
-        const int32_t* pt = reinterpret_cast<const int32_t*>(sp);
-        const int32_t* ph = reinterpret_cast<const int32_t*>(sp + st.off_head);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { tl[u] = pt[u * NSX_CONSUMERS + tid]; hd[u] = ph[u * NSX_CONSUMERS + tid]; }
+        for (int u = 0; u < NA; ++u) {
+            tl[u] = reinterpret_cast<const int32_t*>(SPU(u))[OFFU(u)];
+            hd[u] = reinterpret_cast<const int32_t*>(SPU(u) + st.off_head)[OFFU(u)];
+        }
     }
     if (st.cost_kind == NSX_COST_F64) {
-        const double* pc = reinterpret_cast<const double*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = pc[u * NSX_CONSUMERS + tid];
+        for (int u = 0; u < NA; ++u) c[u] = reinterpret_cast<const double*>(SPU(u) + st.off_cost)[OFFU(u)];
     } else if (st.cost_kind == NSX_COST_I32) {
-        const int32_t* pc = reinterpret_cast<const int32_t*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (double)pc[u * NSX_CONSUMERS + tid];
+        for (int u = 0; u < NA; ++u) c[u] = (double)reinterpret_cast<const int32_t*>(SPU(u) + st.off_cost)[OFFU(u)];
     } else {
-        const int16_t* pc = reinterpret_cast<const int16_t*>(sp + st.off_cost);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (double)(int32_t)pc[u * NSX_CONSUMERS + tid];
+        for (int u = 0; u < NA; ++u) c[u] = (double)(int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)];
     }
     const double tol = d.tol;
     const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
     // all four reduced costs first (independent dependency chains), decisions after
-    double rc[4];
-    const double i0 = (double)(tile_base + tid);
+    double rc[NA];
+    double i0[Q];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int q = 0; q < Q; ++q) i0[q] = (double)(tbq[q] + tid);
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
         double cost = c[u];
         // Phase-1 tree cost  pert - 1 - 1e-6*idx  (simplex.py:1162-1168); Devex prices with the
         // perturbed Phase-2 cost in both phases.  idx as a double:
         // i0 + u*T is exact
-        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, NSX_ADD(i0, (double)(u * NSX_CONSUMERS))));
+        if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, NSX_ADD(i0[u >> 2], (double)((u & 3) * NSX_CONSUMERS))));
         const double pt = PISMEM ? pi1[tl[u]] : __ldcg(pi1 + tl[u]);
         const double ph = PISMEM ? pi1[hd[u]] : __ldcg(pi1 + hd[u]);
         rc[u] = NSX_SUB(NSX_ADD(cost, pt), ph);
@@ -432,39 +442,40 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(&sh.gate_bits);
         uint32_t hit = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < NA; ++u)
             hit |= ((unsigned long long)__double_as_longlong(rc[u]) >= g) ? (sb[u] & NSX_ARC_CAN_FWD) : 0u;
         if (any & NSX_ARC_CAN_BWD) {  // arcs with flow to push back are rare
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < NA; ++u)
                 hit |= (((unsigned long long)__double_as_longlong(rc[u]) ^ 0x8000000000000000ull) >= g) ? (sb[u] & NSX_ARC_CAN_BWD) : 0u;
         }
         if (hit) {
             const int32_t before = dz.arc2;
             const double kbefore = dz.key;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nsx_dantzig_improving(dz, tile_base + u * NSX_CONSUMERS + tid, sb[u], rc[u], tol);
+            for (int u = 0; u < NA; ++u) nsx_dantzig_improving(dz, IDXU(u), sb[u], rc[u], tol);
             if (dz.arc2 >= 0 && (before < 0 || dz.key < kbefore))
                 atomicMax(&sh.gate_bits, (unsigned long long)__double_as_longlong(dz.key));
         }
     } else if (MODE == NSX_MODE_DANTZIG_ZERO) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NA; ++u) {
             if (sb[u] && fabs(rc[u]) <= tol) {  // simplex_pricing.py:132-135
-                const int32_t cand = (tile_base + u * NSX_CONSUMERS + tid) * 2 + ((sb[u] & NSX_ARC_CAN_FWD) ? 0 : 1);
+                const int32_t cand = (IDXU(u)) * 2 + ((sb[u] & NSX_ARC_CAN_FWD) ? 0 : 1);
                 if (cand < dz.zero2) dz.zero2 = cand;
             }
         }
     } else {
-        uint32_t wv[4] = {1u, 1u, 1u, 1u};
-        if (MODE == NSX_MODE_DEVEX) {
-            const uint32_t* pw = reinterpret_cast<const uint32_t*>(sp + st.off_wgt);
+        uint32_t wv[NA];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) wv[u] = pw[u * NSX_CONSUMERS + tid];
+        for (int u = 0; u < NA; ++u) wv[u] = 1u;
+        if (MODE == NSX_MODE_DEVEX) {
+#pragma unroll
+            for (int u = 0; u < NA; ++u) wv[u] = reinterpret_cast<const uint32_t*>(SPU(u) + st.off_wgt)[OFFU(u)];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int32_t i = tile_base + u * NSX_CONSUMERS + tid;
+        for (int u = 0; u < NA; ++u) {
+            const int32_t i = IDXU(u);
             const uint32_t s = sb[u];
             if (i == cmd.excluded) continue;
             const bool fv = (s & NSX_ARC_CAN_FWD) && rc[u] < -tol;
@@ -485,6 +496,9 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
         }
     }
 }
+#undef SPU
+#undef OFFU
+#undef IDXU
 
 // Sweep of [cmd.lo, cmd.hi) by sweeper `worker` of `nworkers`: tiles worker, worker + nworkers, ...
 // of the range, ascending or (cmd.reverse) descending.  `pos` is the ring position of this CTA
@@ -527,9 +541,28 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         int32_t tile = first;
         const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
         uint32_t s = stage, par = parity;
-        for (int32_t j = 0; j < my_n; ++j) {
+        int32_t j = 0;
+        if (stages >= 4) {
+            for (; j + 1 < my_n; j += 2) {  // two tiles per step
+                uint32_t s2 = s + 1, par2 = par;
+                if (s2 == (uint32_t)stages) { s2 = 0; par2 ^= 1u; }
+                nsx_mbar_wait(&sh.full[s], par);
+                nsx_mbar_wait(&sh.full[s2], par2);
+                const unsigned char* const sp[2] = {ring + s * st.stage_bytes, ring + s2 * st.stage_bytes};
+                const int32_t tb[2] = {tile * NSX_TILE, (tile + step) * NSX_TILE};
+                nsx_price_tile<MODE, PHASE1, PISMEM, 2>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
+                __syncwarp();
+                if (lane == 0) { nsx_mbar_arrive(&sh.empty[s]); nsx_mbar_arrive(&sh.empty[s2]); }
+                tile += 2 * step;
+                s = s2 + 1; par = par2;
+                if (s == (uint32_t)stages) { s = 0; par ^= 1u; }
+            }
+        }
+        for (; j < my_n; ++j) {
             nsx_mbar_wait(&sh.full[s], par);
-            nsx_price_tile<MODE, PHASE1, PISMEM>(d, st, cmd, pis, ring + s * st.stage_bytes, tile * NSX_TILE, lo, hi, dz, dx, sh);
+            const unsigned char* const sp[1] = {ring + s * st.stage_bytes};
+            const int32_t tb[1] = {tile * NSX_TILE};
+            nsx_price_tile<MODE, PHASE1, PISMEM, 1>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
             __syncwarp();
             if (lane == 0) nsx_mbar_arrive(&sh.empty[s]);
             tile += step;
