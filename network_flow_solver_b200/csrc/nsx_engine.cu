@@ -1079,6 +1079,21 @@ struct Arena {
     cudaError_t commit() { return cudaMalloc((void**)&base, size ? size : 256); }
     template <class T> T* at(size_t off) { return reinterpret_cast<T*>(base + off); }
     void release() { if (base) { cudaFree(base); base = nullptr; } }
+    ~Arena() { release(); }
+};
+// Stream + timing events of one call; destroyed on every exit path.
+struct CallResources {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaError_t create() {
+        cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ev[i]);
+        return e;
+    }
+    ~CallResources() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
 
 static int nsx_validate(const nsx_problem* p, const nsx_options* o, const nsx_result* r) {
@@ -1185,10 +1200,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     const bool devex = opt->pricing == NSX_PRICING_DEVEX;
     const bool want_trace = res->entering_trace && opt->trace_capacity > 0;
 
-    cudaStream_t stream;
-    NSX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    cudaEvent_t ev[4];
-    for (auto& e : ev) NSX_CUDA(cudaEventCreate(&e));
+    CallResources rs;
+    NSX_CUDA(rs.create());
+    cudaStream_t stream = rs.stream;
+    cudaEvent_t* ev = rs.ev;
 
     // ---- inputs: canonical arrays in HBM (uploaded, or the caller's resident copies) ----
     size_t i_tail = 0, i_head = 0, i_pert = 0, i_upper = 0;
@@ -1348,8 +1363,6 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     res->ring_stages = grid == 1 ? ka.plan.stages : ka.wplan.stages;
     res->store_layout = st.node_kind | (st.cost_kind << 8);
     res->resident_mode = ka.plan.mode;
-    for (auto& e : ev) cudaEventDestroy(e);
-    cudaStreamDestroy(stream);
     arena.release();
     inputs.release();
     if (hctl.status < 0) return nsx_fail(NSX_ERR_INTERNAL, "resident kernel ended without a status");
@@ -1462,10 +1475,10 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     size_t o_next = arena.plan(8);
     NSX_CUDA(arena.commit());
 
-    cudaStream_t stream;
-    NSX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    cudaEvent_t ev[4];
-    for (auto& e : ev) NSX_CUDA(cudaEventCreate(&e));
+    CallResources rs;
+    NSX_CUDA(rs.create());
+    cudaStream_t stream = rs.stream;
+    cudaEvent_t* ev = rs.ev;
     std::vector<NsxBatchItem> items(count);
     std::vector<NsxCtl> ctls(count);
     NSX_CUDA(cudaEventRecord(ev[0], stream));
@@ -1555,8 +1568,6 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         }
         if (ctls[i].status < 0) bad++;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
-    cudaStreamDestroy(stream);
     arena.release();
     if (bad) return nsx_fail(NSX_ERR_INTERNAL, "batch kernel left instances without a status");
     return 0;
