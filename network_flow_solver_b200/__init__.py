@@ -25,6 +25,7 @@ from .exceptions import (
     SolverConfigurationError,
     UnboundedProblemError,
 )
+from .dimacs import load_dimacs_canonical, parse_dimacs_file, parse_dimacs_string
 from .io import load_problem, save_result
 from .solver import solve_min_cost_flow
 
@@ -48,7 +49,10 @@ __all__ = [
     "SolverOptions",
     "UnboundedProblemError",
     "build_problem",
+    "load_dimacs_canonical",
     "load_problem",
+    "parse_dimacs_file",
+    "parse_dimacs_string",
     "save_result",
     "solve_min_cost_flow",
     "__version__",
