@@ -7,7 +7,7 @@ reference in the build container:
 (the reference's parser imports `src.network_solver`, so the working directory must be a copy of the
 reference root).  For every case the DIMACS text, what the reference's parser made of it (nodes, arcs)
 and - where the instance is inside the accelerated scope - a recorded reference solve are stored in
-tests/golden/dimacs.json.gz.  Cases: the reference's three hand-made `.min` fixtures
+tests/golden/dimacs/dimacs.json.gz.  Cases: the reference's three hand-made `.min` fixtures
 (benchmarks/problems/generated, known optima 111 / 95 / 11: benchmarks/metadata/known_solutions.json:29-55)
 and generated files whose ids reach three digits (lexicographic id order matters), with lower bounds,
 uncapacitated arcs in all three spellings and the 4-field arc variant.
@@ -86,7 +86,7 @@ def main() -> None:
         except RefInvalid as exc:
             errors.append({"text": text, "error": str(exc)})
     raw = json.dumps({"cases": out, "errors": errors}, separators=(",", ":")).encode()
-    path = REPO / "tests" / "golden" / "dimacs.json.gz"
+    path = REPO / "tests" / "golden" / "dimacs" / "dimacs.json.gz"
     with gzip.GzipFile(path, "wb", mtime=0) as fh:
         fh.write(raw)
     print(f"wrote {path} ({path.stat().st_size / 1024:.1f} KiB)")

@@ -18,7 +18,7 @@ from network_flow_solver_b200.exceptions import InvalidProblemError
 from network_flow_solver_b200.solver import prepare
 from oracle import oracle
 
-DOC = json.loads(gzip.open(Path(__file__).resolve().parent / "golden" / "dimacs.json.gz", "rb").read().decode())
+DOC = json.loads(gzip.open(Path(__file__).resolve().parent / "golden" / "dimacs" / "dimacs.json.gz", "rb").read().decode())
 CASES = {c["name"]: c for c in DOC["cases"]}
 
 
