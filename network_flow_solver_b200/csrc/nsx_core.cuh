@@ -245,13 +245,17 @@ struct NsxPotScratch {
 };
 
 #if NSX_ON_DEVICE
-// Device version: one preorder entry per thread.  An entry whose parent lies inside the chunk polls
-// the parent's slot in shared memory until it holds a value (slots start as a NaN bit pattern that
-// no potential can take; 8-byte shared-memory stores are single transactions, so no flag or fence
-// is needed).  Warps retry in rounds of their own: a chain of k tree levels costs k shared-memory
-// round trips and no CTA-wide barrier.  The parent precedes the child in preorder, hence sits in
-// the same or an earlier warp and the rounds terminate.
+// Device version: one preorder entry per thread.  The value of an entry is the left-to-right fold of
+// the signed costs along its path from the nearest ancestor whose value is already known - the same
+// additions, in the same order, as the reference's top-down walk.  Each thread climbs up to NSX_HOP
+// ancestors inside the chunk (parent index + signed cost per entry live in shared memory), keeping
+// the costs in registers, until it meets an entry that already holds a value (slots start as a NaN
+// bit pattern that no potential can take; 8-byte shared-memory stores are single transactions);
+// then it folds back down and publishes its own value.  If NSX_HOP hops were not enough it polls
+// the ancestor it stopped at.  k tree levels therefore cost about k / NSX_HOP dependent waits
+// instead of k, and no CTA-wide barrier.  Parents precede children in preorder, so waits terminate.
 #define NSX_POT_EMPTY 0x7ff8dead0badc0deLL
+#define NSX_HOP 8
 NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv, int32_t phase, int64_t lo,
                                      int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
     int32_t rounds = 0;
@@ -263,33 +267,60 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
         const int64_t x = c0 + j;
         const bool active = j < NSX_CHUNK && x < c1;
         bool done = true;
-        int32_t v = 0, par = 0;
-        double cst = 0.0, val = 0.0;
+        int32_t v = 0;
+        double val = 0.0;
         if (active) {
             v = d.order[x];
             const NsxNode r = d.node[v];
-            cst = nsx_arc_cost(d, phase, r.pred2 >> 1);
+            double cst = nsx_arc_cost(d, phase, r.pred2 >> 1);
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
             const int32_t ppos = nsx_pos(pv, d.node[r.parent].pos);
-            if (ppos >= c0) { par = (int32_t)(ppos - c0); done = false; vbits[j] = NSX_POT_EMPTY; }
-            else { val = NSX_ADD(d.pi[r.parent], cst); vbits[j] = __double_as_longlong(val); }  // x - c == x + (-c) exactly
+            s.cst[j] = cst;
+            if (ppos >= c0) { s.par_local[j] = (int32_t)(ppos - c0); done = false; vbits[j] = NSX_POT_EMPTY; }
+            else { s.par_local[j] = -1; val = NSX_ADD(d.pi[r.parent], cst); vbits[j] = __double_as_longlong(val); }  // x - c == x + (-c) exactly
         }
         NSX_SYNC();
-        // (explicit reconvergence before every warp collective: a collective reached by a diverged
-        // warp takes a slow multi-step path)
-        while (!__all_sync(0xffffffffu, done)) {
-            if (!done) {
-                const long long pb = vbits[par];
-                if (pb != NSX_POT_EMPTY) {
-                    val = NSX_ADD(__longlong_as_double(pb), cst);
+        // climb: c[0] = own cost, c[h] = cost of the h-th ancestor; `a` = first entry not yet folded in
+        double c[NSX_HOP];
+        int32_t len = 0, a = 0;
+        long long base = 0;
+        bool pending = !done;
+        if (pending) {
+            len = 1; a = s.par_local[j];
+            c[0] = s.cst[j];
+            base = vbits[a];
+#pragma unroll
+            for (int h = 1; h < NSX_HOP; ++h) {
+                if (base == NSX_POT_EMPTY) {
+                    c[h] = s.cst[a];
+                    a = s.par_local[a];  // >= 0: an entry without a value has its parent inside the chunk
+                    base = vbits[a];
+                    len = h + 1;
+                } else {
+                    c[h] = 0.0;
+                }
+            }
+        }
+        // fold + publish inside a warp-uniform loop (a lane may be waiting for another lane of its own
+        // warp: the publishing store must not sit behind a reconvergence point the waiter never reaches)
+        __syncwarp();
+        while (__any_sync(0xffffffffu, pending)) {
+            if (pending) {
+                if (base == NSX_POT_EMPTY) base = vbits[a];  // deeper than NSX_HOP: wait for that ancestor
+                if (base != NSX_POT_EMPTY) {
+                    val = __longlong_as_double(base);
+#pragma unroll
+                    for (int h = NSX_HOP - 1; h >= 0; --h)
+                        if (h < len) val = NSX_ADD(val, c[h]);
                     vbits[j] = __double_as_longlong(val);
-                    done = true;
+                    pending = false;
                 }
             }
             ++rounds;
             __syncwarp();
         }
+        __syncwarp();
         if (active) {
             d.pi[v] = val;
             if (d.pi_mirror) d.pi_mirror[v] = val;
@@ -297,7 +328,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
     }
     NSX_SYNC();
     if (rounds_out) {
-        // statistics only: rounds of the slowest warp, summed over chunks
+        // statistics only: polls of the slowest warp, summed over chunks
         NSX_SINGLE { s.rounds = 0; }
         NSX_SYNC();
         if ((NSX_TID & 31) == 0) NSX_ATOMIC_MAX_I32(&s.rounds, rounds);
