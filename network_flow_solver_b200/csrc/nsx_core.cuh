@@ -166,6 +166,7 @@ struct NsxPivotScratch {
     // shift is logged as "positions in [a, b) move by d".  A node stores (stamp << 24 | position):
     // its position is current after replaying log entries stamp .. log_len-1.
     int32_t log_len;
+    int32_t pos_mask;          // 0xffffff with lazy positions (stamp in the top byte), all ones otherwise
     int32_t log_a[NSX_LOG_CAP], log_b[NSX_LOG_CAP], log_d[NSX_LOG_CAP];
     double theta;
     int32_t path_h[NSX_PATH_CAP];
@@ -206,7 +207,7 @@ NSX_FN void nsx_set_parent_mirror(const NsxDev& d, int32_t v, int32_t parent) {
 
 // current preorder position from a stored (stamp << 24 | position) word; a no-op in eager mode
 NSX_FN int32_t nsx_pos(const NsxPivotScratch& s, int32_t raw) {
-    int32_t p = raw & 0xffffff;
+    int32_t p = raw & s.pos_mask;
 #pragma unroll 4
     for (int32_t k = (int32_t)((uint32_t)raw >> 24); k < s.log_len; ++k)
         if (p >= s.log_a[k] && p < s.log_b[k]) p += s.log_d[k];
@@ -1192,7 +1193,7 @@ NSX_FN void nsx_drv_phase_end(NsxCtl& c, NsxDrv& v, NsxAction& act) {
 template <class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
-    NSX_SINGLE { s.log_len = 0; }
+    NSX_SINGLE { s.log_len = 0; s.pos_mask = d.lazy_pos ? 0xffffff : 0x7fffffff; }
     NSX_SYNC();
     nsx_recompute_potentials(d, s, 1, 1, d.n, ps, (int64_t*)0);  // Phase-1 costs on the initial star
     NSX_SINGLE {

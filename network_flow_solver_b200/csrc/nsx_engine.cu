@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -822,7 +823,7 @@ __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
 template <class Sweep>
 __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
                                                NsxPotScratch& ps, Sweep& sweep, int32_t count) {
-    if (threadIdx.x == 0) pv.log_len = 0;
+    if (threadIdx.x == 0) { pv.log_len = 0; pv.pos_mask = d.lazy_pos ? 0xffffff : 0x7fffffff; }
     NSX_SYNC();
     nsx_recompute_potentials(d, pv, 1, 1, d.n, ps, (int64_t*)0);
     for (int32_t k = 0; k < count; ++k) {
@@ -1147,14 +1148,19 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
 }
 
 struct DeviceInfo { int sms = 0; int coop = 0; size_t smem_optin = 0; bool ok = false; };
+// cudaGetDeviceProperties costs milliseconds: query each device once per process
 static int nsx_device_info(int dev, DeviceInfo& info) {
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) return nsx_fail(NSX_ERR_NO_DEVICE, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
-    info.sms = prop.multiProcessorCount;
-    info.coop = prop.cooperativeLaunch;
-    info.smem_optin = prop.sharedMemPerBlockOptin;
-    info.ok = true;
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && cache[dev].ok) { info = cache[dev]; return 0; }
+    int sms = 0, coop = 0, smem = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_NO_DEVICE, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
+    info.sms = sms; info.coop = coop; info.smem_optin = (size_t)smem; info.ok = true;
+    if (dev >= 0 && dev < 64) cache[dev] = info;
     return 0;
 }
 
