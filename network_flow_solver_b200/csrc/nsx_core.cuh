@@ -494,16 +494,18 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     if (d.scan_walk && c.avg_cycle > 40 * 16) {
         // (long cycles expected: recent average, in 1/16 arcs, above 40)
         // Every node tests in parallel whether it is an ancestor of h / of t (preorder interval
-        // test).  Ancestors of exactly one endpoint are the cycle: they are collected per side,
-        // then ordered by subtree size (strictly increasing from the endpoint towards the join), so
-        // no depth lookup and no dependent load chain is involved.  The join is the common
-        // ancestor of smallest size.
-        int32_t* list_n = s.arc2;                          // [2 * CAP] nodes, head side then tail side
-        int32_t* list_s = reinterpret_cast<int32_t*>(s.res);  // [2 * CAP] their subtree sizes
-        NSX_SINGLE { s.jkey = 0x7fffffff; s.nh = 0; s.nt = 0; }
+        // test).  Ancestors of exactly one endpoint are the cycle; the slot of such a node in its
+        // side's path is its depth distance to the endpoint.  Hits are remembered in registers and
+        // their depths are fetched after the scan, all at once (depth[] may live in L2), so the scan
+        // itself has no dependent load and no atomics.  The join is the common ancestor of smallest
+        // size (warp-reduced, one shared-memory atomic per warp).
+        NSX_SINGLE { s.jkey = 0x7fffffff; }
         const int32_t ph = d.node[h].pos, pt = d.node[t].pos;
+        const int32_t dh = d.depth[h], dt = d.depth[t];
         NSX_SYNC();
         int32_t jk = 0x7fffffff;
+        int32_t hit_w[2] = {-1, -1};
+        bool hit_h[2] = {false, false};
         NSX_PAR_FOR(w, 0, d.n) {
             const NsxNode rec = d.node[w];
             const bool in_h = rec.pos <= ph && ph < rec.pos + rec.size;
@@ -511,36 +513,34 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             if (in_h && in_t) {
                 const int32_t key = (rec.size << 16) | (int32_t)w;
                 jk = key < jk ? key : jk;
-            } else if (in_h) {
-                const int32_t k = NSX_ATOMIC_ADD_I32(&s.nh, 1);
-                if (k < NSX_PATH_CAP) { list_n[k] = (int32_t)w; list_s[k] = rec.size; }
-            } else if (in_t) {
-                const int32_t k = NSX_ATOMIC_ADD_I32(&s.nt, 1);
-                if (k < NSX_PATH_CAP) { list_n[NSX_PATH_CAP + k] = (int32_t)w; list_s[NSX_PATH_CAP + k] = rec.size; }
+            } else if (in_h || in_t) {
+                if (hit_w[0] < 0) { hit_w[0] = (int32_t)w; hit_h[0] = in_h; }
+                else if (hit_w[1] < 0) { hit_w[1] = (int32_t)w; hit_h[1] = in_h; }
+                else {  // a third hit in one thread (rare): place it right away
+                    const int32_t k = (in_h ? dh : dt) - d.depth[w];
+                    int32_t* sp = in_h ? s.path_h : s.path_t;
+                    int32_t* gp = in_h ? d.gpath_h : d.gpath_t;
+                    if (k < NSX_PATH_CAP) sp[k] = (int32_t)w; else gp[k] = (int32_t)w;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (hit_w[i] >= 0) {
+                const int32_t k = (hit_h[i] ? dh : dt) - d.depth[hit_w[i]];
+                int32_t* sp = hit_h[i] ? s.path_h : s.path_t;
+                int32_t* gp = hit_h[i] ? d.gpath_h : d.gpath_t;
+                if (k < NSX_PATH_CAP) sp[k] = hit_w[i]; else gp[k] = hit_w[i];
             }
         }
         __syncwarp();
         jk = __reduce_min_sync(0xffffffffu, jk);
         if ((threadIdx.x & 31) == 0 && jk != 0x7fffffff) NSX_ATOMIC_MIN_I32(&s.jkey, jk);
         NSX_SYNC();
-        const int32_t cnt_h = s.nh, cnt_t = s.nt;
-        if (cnt_h <= NSX_PATH_CAP && cnt_t <= NSX_PATH_CAP) {
-            NSX_PAR_FOR(idx, 0, cnt_h + cnt_t) {
-                const bool hs = idx < cnt_h;
-                const int32_t base = hs ? 0 : NSX_PATH_CAP, cnt = hs ? cnt_h : cnt_t;
-                const int32_t me = hs ? (int32_t)idx : (int32_t)idx - cnt_h;
-                const int32_t my_size = list_s[base + me];
-                int32_t k = 0;
-                for (int32_t o = 0; o < cnt; ++o) k += list_s[base + o] < my_size;
-                (hs ? s.path_h : s.path_t)[k] = list_n[base + me];
-            }
-            NSX_SINGLE { s.join = s.jkey & 0xffff; }
-        } else if (threadIdx.x < 2) {  // a side longer than the shared-memory lists: serial walk
-            int32_t from = threadIdx.x == 0 ? h : t;
-            int32_t len, join;
-            nsx_walk_side(d, from, threadIdx.x == 0 ? pt : ph, threadIdx.x == 0 ? s.path_h : s.path_t,
-                          threadIdx.x == 0 ? d.gpath_h : d.gpath_t, &len, &join);
-            if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
+        NSX_SINGLE {
+            const int32_t join = s.jkey & 0xffff;
+            const int32_t dj = d.depth[join];
+            s.join = join; s.nh = dh - dj; s.nt = dt - dj;
         }
     } else if (d.lazy_pos) {
         // Depth-synchronised climb (no positions needed): lane 0 holds the head-side node, lane 1
