@@ -19,6 +19,7 @@ from .exceptions import DeviceEngineError
 
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
+PRICING_CANDIDATE_LIST = 2  # oracle only so far; the engine rejects it
 
 STATUS_OPTIMAL = 0
 STATUS_INFEASIBLE = 1

@@ -112,6 +112,9 @@ struct NsxDev {
     int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
 };
 
+#define NSX_CL_SIZE 100    // candidate-list length (simplex.py:232)
+#define NSX_CL_REFRESH 10  // major iterations between full refreshes (simplex.py:233)
+#define NSX_CL_MINOR 3     // candidate scans per major iteration (simplex_pricing.py:400)
 // Solver scalars; lives in global memory, written by the pivot CTA only.
 struct NsxCtl {
     int32_t phase;        // 1 or 2
@@ -128,6 +131,9 @@ struct NsxCtl {
     int32_t row_scan_first;
     int64_t tuner_total, tuner_deg, tuner_last;
     int64_t art_with_flow;
+    // candidate-list pricing (simplex_pricing.py:375-542): arcs of the list, refresh / minor-iteration counters
+    int32_t cl_count, cl_since, cl_minor;
+    int32_t cl_list[NSX_CL_SIZE];
     uint32_t wepoch;      // current Devex weight epoch (8 bits used)
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     // statistics
@@ -888,6 +894,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (c.ftc >= c.ft_limit) {
             c.ftc = 0;
             c.pb = 0;
+            c.cl_count = 0; c.cl_since = 0; c.cl_minor = 0;  // pricing_strategy.reset(), simplex.py:1771-1776
             c.resets++;
             c.wepoch = (c.wepoch + 1) & 0xffu;
             if (c.wepoch == 0) c.need_wfill = 1;  // epoch tags wrapped: refill physically
@@ -898,6 +905,43 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_SYNC();
     NSX_PH(c, 9, tph);
     return 0;
+}
+
+// Candidate scan (CandidateListPricing._scan_candidates, simplex_pricing.py:460-505): the <= 100 listed arcs are
+// evaluated in parallel, then one thread folds the results in list order exactly like the reference's loop
+// (improving arcs: smallest key, first in list order on ties; zero-reduced-cost arcs only while nothing is chosen).
+NSX_FN void nsx_cl_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotScratch& s, int allow_zero) {
+    const double tol = d.tol;
+    NSX_SYNC();
+    NSX_PAR_FOR(k, 0, c.cl_count) {
+        const int32_t i = c.cl_list[k];
+        const uint8_t st = d.state[i];
+        int32_t code = 0;
+        double key = 0.0;
+        if (!(st & NSX_ARC_IN_TREE)) {
+            const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
+            if ((st & NSX_ARC_CAN_FWD) && rc < -tol) { code = 1; key = rc; }
+            else if ((st & NSX_ARC_CAN_BWD) && rc > tol) { code = 2; key = -rc; }
+            else if (fabs(rc) <= tol) code = (st & NSX_ARC_CAN_FWD) ? 3 : ((st & NSX_ARC_CAN_BWD) ? 4 : 0);
+        }
+        s.arc2[k] = code;
+        s.res[k] = key;
+    }
+    NSX_SYNC();
+    NSX_SINGLE {
+        int32_t best = -1;
+        double best_rc = 0.0;
+        for (int32_t k = 0; k < c.cl_count; ++k) {
+            const int32_t code = s.arc2[k], i = c.cl_list[k];
+            if (code == 1 || code == 2) {
+                if (best < 0 || s.res[k] < best_rc) { best = i * 2 + (code == 2 ? 1 : 0); best_rc = s.res[k]; }
+            } else if (allow_zero && best < 0 && (code == 3 || code == 4)) {
+                best = i * 2 + (code == 4 ? 1 : 0);
+            }
+        }
+        *out_arc2 = best;
+    }
+    NSX_SYNC();
 }
 
 // Block-size adaptation after each pivot (simplex_adaptive.py:98-151). Single thread.
@@ -1035,9 +1079,15 @@ NSX_FN void nsx_init_node(const NsxDev& d, int32_t v, double supply) {
 // ------------------------------------------------------------------------------------------
 // *_ZERO commands look for zero-reduced-cost candidates only (Phase 1, after the improving sweep of
 // the same range found nothing): the hot sweeps then carry no zero bookkeeping.
-enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2, NSX_CMD_DANTZIG_ZERO = 3, NSX_CMD_DEVEX_ZERO = 4 };
-enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_ZERO = 4, NSX_ST_DEVEX_ZERO = 5 };
-enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4 };
+// NSX_CMD_TOPK refreshes the candidate list: the NSX_CL_SIZE improving arcs of largest |rc| (ties: larger index).
+enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2, NSX_CMD_DANTZIG_ZERO = 3, NSX_CMD_DEVEX_ZERO = 4,
+       NSX_CMD_TOPK = 5 };
+enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_ZERO = 4, NSX_ST_DEVEX_ZERO = 5,
+       // candidate list (CandidateListPricing.select_entering_arc, simplex_pricing.py:418-458): quick scan of the
+       // list, scan after the (optional) periodic refresh, forced refresh, scan after the forced refresh
+       NSX_ST_CL_QUICK = 6, NSX_ST_CL_REFRESH = 7, NSX_ST_CL_MAIN = 8, NSX_ST_CL_FORCED = 9, NSX_ST_CL_LAST = 10 };
+enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4,
+       NSX_ACT_CL_SCAN = 5 };  // CL_SCAN: the pivot CTA evaluates the <= 100 listed arcs itself, no sweep
 
 struct NsxCmd {       // what every CTA does next
     int32_t kind;
@@ -1061,6 +1111,7 @@ struct NsxLoopShared {
     NsxDevexCand dx;
     NsxDrv drv;
     int32_t rc;
+    int32_t cl_arc2;  // result of the last candidate scan (arc*2 + (dir<0)), -1 none
 };
 
 NSX_FN void nsx_drv_devex_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
@@ -1077,6 +1128,27 @@ NSX_FN void nsx_drv_devex_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd) {
     v.blocks_left = v.bc;
     nsx_drv_devex_cmd(c, m, cmd);
 }
+// ---- candidate list (CandidateListPricing.select_entering_arc, simplex_pricing.py:418-458) ----
+NSX_FN void nsx_drv_cl_refresh_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
+    cmd.kind = NSX_CMD_TOPK; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
+    cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+}
+// "time for a refresh" (:434-441): count a major iteration, refresh when due, then scan
+NSX_FN void nsx_drv_cl_major(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    c.cl_since++;
+    c.cl_minor = 0;
+    if (c.cl_since >= NSX_CL_REFRESH || c.cl_count == 0) {
+        v.stage = NSX_ST_CL_REFRESH; act.kind = NSX_ACT_SWEEP;
+        nsx_drv_cl_refresh_cmd(c, m, cmd);
+    } else {
+        v.stage = NSX_ST_CL_MAIN; act.kind = NSX_ACT_CL_SCAN;
+    }
+}
+NSX_FN void nsx_drv_cl_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    if (c.cl_count > 0 && c.cl_minor < NSX_CL_MINOR) { v.stage = NSX_ST_CL_QUICK; act.kind = NSX_ACT_CL_SCAN; return; }
+    nsx_drv_cl_major(c, v, m, cmd, act);
+}
+
 // top of an iteration: first sweep command, or phase end when the budget is used up
 NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
     if (!v.final_check && c.it >= v.budget) { act.kind = NSX_ACT_PHASE_END; return; }
@@ -1085,6 +1157,8 @@ NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxActio
         v.stage = c.row_scan_first ? NSX_ST_ROWSCAN : NSX_ST_DANTZIG;
         cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
         cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+    } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
+        nsx_drv_cl_begin(c, v, m, cmd, act);
     } else {
         nsx_drv_devex_begin(c, v, m, cmd);
     }
@@ -1114,13 +1188,41 @@ NSX_FN void nsx_drv_devex_next(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, Nsx
     act.kind = NSX_ACT_SWEEP;
     nsx_drv_devex_cmd(c, m, cmd);
 }
+// result of a candidate scan (NSX_ACT_CL_SCAN)
+NSX_FN void nsx_drv_on_scan(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
+    if (v.stage == NSX_ST_CL_QUICK) {
+        if (arc2 >= 0) { c.cl_minor++; nsx_drv_choose(c, v, act, arc2, 0, trace); return; }
+        nsx_drv_cl_major(c, v, m, cmd, act);
+    } else if (v.stage == NSX_ST_CL_MAIN) {
+        if (arc2 >= 0) { nsx_drv_choose(c, v, act, arc2, 0, trace); return; }
+        if (c.cl_since > 0) {  // "if still no improving arc, force full refresh" (:448-452)
+            v.stage = NSX_ST_CL_FORCED; act.kind = NSX_ACT_SWEEP;
+            nsx_drv_cl_refresh_cmd(c, m, cmd);
+            return;
+        }
+        nsx_drv_none(c, v, act);
+    } else {  // NSX_ST_CL_LAST
+        if (arc2 >= 0) { nsx_drv_choose(c, v, act, arc2, 0, trace); return; }
+        nsx_drv_none(c, v, act);
+    }
+}
 NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
                               const NsxDevexCand& dx, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
     const int allow_zero = (c.phase == 1) && !v.final_check;
     c.arcs_priced += cmd.hi - cmd.lo;
     c.sweeps++;
+    if (v.stage == NSX_ST_CL_REFRESH || v.stage == NSX_ST_CL_FORCED) {  // the list has just been refreshed
+        c.cl_since = 0;
+        v.stage = v.stage == NSX_ST_CL_REFRESH ? NSX_ST_CL_MAIN : NSX_ST_CL_LAST;
+        act.kind = NSX_ACT_CL_SCAN;
+        return;
+    }
     if (v.stage == NSX_ST_ROWSCAN || v.stage == NSX_ST_DANTZIG) {
         if (dz.arc2 >= 0) { nsx_drv_choose(c, v, act, dz.arc2, 0, trace); return; }
+        if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_CANDIDATE_LIST) {
+            nsx_drv_cl_begin(c, v, m, cmd, act);  // fall through to the configured strategy (simplex.py:1066-1075)
+            return;
+        }
         if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_DEVEX) {
             act.kind = NSX_ACT_SWEEP;  // fall through to the configured strategy (simplex.py:1066-1075)
             nsx_drv_devex_begin(c, v, m, cmd);
@@ -1207,8 +1309,11 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         const int32_t kind = L.act.kind;
         NSX_SYNC();
         if (kind == NSX_ACT_SWEEP) {
-            sweep.run(L.cmd, L.dz, L.dx);
+            sweep.run(L.cmd, L.dz, L.dx, c);
             NSX_SINGLE { nsx_drv_on_result(c, L.drv, d.m, L.dz, L.dx, L.cmd, L.act, trace); }
+        } else if (kind == NSX_ACT_CL_SCAN) {
+            nsx_cl_scan(d, c, &L.cl_arc2, s, (c.phase == 1) && !L.drv.final_check);
+            NSX_SINGLE { nsx_drv_on_scan(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }
         } else if (kind == NSX_ACT_PIVOT) {
             int32_t rc = nsx_pivot(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
             if (c.need_wfill) {  // Devex epoch tags wrapped: physically reset the weights

@@ -279,6 +279,11 @@ struct NsxCtaShared {
     NsxDevexCand dx_buf[32];
     unsigned long long gate_bits;               // Dantzig sweep: raw bits of the best (most negative) key any
                                                 // thread of this CTA has found so far in the current sweep
+    // candidate-list refresh (NSX_CMD_TOPK): entries in the top-k buffer and the (merit bits, arc) an arc has to
+    // exceed to enter it; the buffer itself aliases piv.res (keys) and piv.arc2 (arcs), idle during sweeps
+    int32_t tk_cnt;
+    int32_t tk_thr_idx;
+    unsigned long long tk_thr_key;
     NsxGridCtl* tl_grid;                        // handshake timeline sink (worker CTAs of the grid kernel), or null
     unsigned long long mbar;                    // completion barrier of the potentials bulk copy
     unsigned long long full[NSX_MAX_STAGES];    // tile landed in the stage (TMA complete_tx)
@@ -349,7 +354,7 @@ __device__ __forceinline__ void nsx_dantzig_improving(NsxCand& k, int32_t i, uin
     }
 }
 
-enum { NSX_MODE_DANTZIG = 0, NSX_MODE_DEVEX = 1, NSX_MODE_DANTZIG_ZERO = 2, NSX_MODE_DEVEX_ZERO = 3 };
+enum { NSX_MODE_DANTZIG = 0, NSX_MODE_DEVEX = 1, NSX_MODE_DANTZIG_ZERO = 2, NSX_MODE_DEVEX_ZERO = 3, NSX_MODE_TOPK = 4 };
 
 // One landed tile.  Thread t prices arcs t, t + T, t + 2T, t + 3T of the tile (T = block size):
 // consecutive lanes take consecutive arcs, so the column reads from the stage and - on instances
@@ -501,6 +506,131 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
 #undef OFFU
 #undef IDXU
 
+// ------------------------------------------------------------------------------------------
+// Candidate-list refresh (CandidateListPricing._refresh_candidate_list, simplex_pricing.py:507-536): the
+// NSX_CL_SIZE improving arcs of largest merit |rc|, ties to the LARGER arc index (Python sorts (merit, idx)
+// tuples in descending order).  Each CTA keeps a buffer of NSX_TK_CAP (merit bits, arc) pairs in shared memory;
+// an arc is appended when it beats the current threshold (the 100th best seen so far by this CTA); when fewer
+// than one sub-step's worth of slots is left the buffer is bitonic-sorted, cut to 100 and the threshold raised.
+// The per-CTA lists go to HBM and the pivot CTA merges them with the same routine.
+// ------------------------------------------------------------------------------------------
+#define NSX_TK_CAP 1024
+struct NsxTopkOut {  // one per CTA, in HBM
+    int32_t count;
+    int32_t pad[3];
+    unsigned long long key[NSX_CL_SIZE];
+    int32_t idx[NSX_CL_SIZE];
+};
+struct NsxBarConsumers { __device__ __forceinline__ void operator()() const { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NSX_CONSUMERS) : "memory"); } };
+struct NsxBarAll { __device__ __forceinline__ void operator()() const { NSX_SYNC(); } };
+// Barrier that also ORs a predicate over the participants.  Used for "is the buffer nearly full?": every thread
+// reads the count after its own append, so the thread that appended last contributes the exact count and the
+// OR is the same, exact answer for everybody - one barrier instead of two.
+__device__ __forceinline__ bool nsx_bar_or_consumers(bool pred) {
+    uint32_t out;
+    __syncwarp();
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.u32 q, %1, 0;\nbar.red.or.pred p, 1, %2, q;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(out) : "r"((uint32_t)pred), "n"(NSX_CONSUMERS) : "memory");
+    return out != 0;
+}
+
+__device__ __forceinline__ bool nsx_tk_less(unsigned long long ka, int32_t ia, unsigned long long kb, int32_t ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+__device__ __forceinline__ void nsx_tk_reset(NsxCtaShared& sh, double tol) {
+    sh.tk_cnt = 0;
+    sh.tk_thr_key = (unsigned long long)__double_as_longlong(tol);  // merit must exceed the tolerance
+    sh.tk_thr_idx = 0x7fffffff;
+}
+// Sort the buffer in descending (merit, arc) order, keep the best NSX_CL_SIZE, raise the threshold.
+// Called by P threads (t = 0..P-1) that all passed a barrier after the last append.
+template <class Bar>
+__device__ __forceinline__ void nsx_tk_compact(NsxCtaShared& sh, int t, int P, Bar bar) {
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(sh.piv.res);
+    int32_t* idx = sh.piv.arc2;
+    const int32_t cnt = sh.tk_cnt;
+    for (int i = t; i < NSX_TK_CAP; i += P) if (i >= cnt) { key[i] = 0ull; idx[i] = -1; }
+    bar();
+    for (int k = 2; k <= NSX_TK_CAP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < NSX_TK_CAP; i += P) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long ka = key[i], kb = key[l];
+                    const int32_t ia = idx[i], ib = idx[l];
+                    const bool desc = (i & k) == 0;  // descending run
+                    const bool swap = desc ? nsx_tk_less(ka, ia, kb, ib) : nsx_tk_less(kb, ib, ka, ia);
+                    if (swap) { key[i] = kb; idx[i] = ib; key[l] = ka; idx[l] = ia; }
+                }
+            }
+            bar();
+        }
+    }
+    if (t == 0) {
+        const int32_t keep = cnt < NSX_CL_SIZE ? cnt : NSX_CL_SIZE;
+        sh.tk_cnt = keep;
+        if (keep == NSX_CL_SIZE) { sh.tk_thr_key = key[NSX_CL_SIZE - 1]; sh.tk_thr_idx = idx[NSX_CL_SIZE - 1]; }
+    }
+    bar();
+}
+// Append this thread's candidate (if it beats the threshold); every lane of the warp must call it.
+__device__ __forceinline__ void nsx_tk_append(NsxCtaShared& sh, bool has, unsigned long long k, int32_t i) {
+    const bool pass = has && nsx_tk_less(sh.tk_thr_key, sh.tk_thr_idx, k, i);
+    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+    if (mask) {
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        int32_t base = 0;
+        if (lane == leader) base = atomicAdd(&sh.tk_cnt, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (pass) {
+            const int32_t pos = base + __popc(mask & ((1u << lane) - 1u));
+            reinterpret_cast<unsigned long long*>(sh.piv.res)[pos] = k;
+            sh.piv.arc2[pos] = i;
+        }
+    }
+}
+// One landed tile in candidate-refresh mode: four sub-steps of one arc per consumer thread.
+template <bool PHASE1, bool PISMEM>
+__device__ __forceinline__ void nsx_topk_tile(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd, const double* pis,
+                                              const unsigned char* sp, int32_t tile_base, NsxCtaShared& sh) {
+    const int tid = threadIdx.x;
+    const double tol = d.tol;
+    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
+    NsxBarConsumers bar;
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+        const int off = u * NSX_CONSUMERS + tid;
+        const int32_t i = tile_base + off;
+        uint32_t sbits = sp[st.off_state + off];
+        if ((int64_t)i < cmd.lo || (int64_t)i >= cmd.hi || (sbits & NSX_ARC_IN_TREE)) sbits = 0;
+        bool has = false;
+        unsigned long long key = 0ull;
+        if (sbits & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD)) {
+            int32_t tl, hd;
+            double cost;
+            if (st.node_kind == NSX_NODE_U16) {
+                tl = reinterpret_cast<const uint16_t*>(sp)[off]; hd = reinterpret_cast<const uint16_t*>(sp + st.off_head)[off];
+            } else {
+                tl = reinterpret_cast<const int32_t*>(sp)[off]; hd = reinterpret_cast<const int32_t*>(sp + st.off_head)[off];
+            }
+            if (st.cost_kind == NSX_COST_F64) cost = reinterpret_cast<const double*>(sp + st.off_cost)[off];
+            else if (st.cost_kind == NSX_COST_I32) cost = (double)reinterpret_cast<const int32_t*>(sp + st.off_cost)[off];
+            else cost = (double)(int32_t)reinterpret_cast<const int16_t*>(sp + st.off_cost)[off];
+            if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, (double)i));
+            const double pt = PISMEM ? pi1[tl] : __ldcg(pi1 + tl);
+            const double ph = PISMEM ? pi1[hd] : __ldcg(pi1 + hd);
+            const double rc = NSX_SUB(NSX_ADD(cost, pt), ph);
+            if (((sbits & NSX_ARC_CAN_FWD) && rc < -tol) || ((sbits & NSX_ARC_CAN_BWD) && rc > tol)) {
+                const double merit = fabs(rc);
+                if (merit > tol) { has = true; key = (unsigned long long)__double_as_longlong(merit); }
+            }
+        }
+        // (also orders the appends of the previous sub-step before this one's)
+        if (nsx_bar_or_consumers(sh.tk_cnt > NSX_TK_CAP - NSX_CONSUMERS)) nsx_tk_compact(sh, tid, NSX_CONSUMERS, bar);
+        nsx_tk_append(sh, has, key, i);
+    }
+}
+
 // Sweep of [cmd.lo, cmd.hi) by sweeper `worker` of `nworkers`: tiles worker, worker + nworkers, ...
 // of the range, ascending or (cmd.reverse) descending.  `pos` is the ring position of this CTA
 // (register copy, identical in all threads): bits 0-15 = stage of the next tile, bit 16 = mbarrier
@@ -543,7 +673,20 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
         uint32_t s = stage, par = parity;
         int32_t j = 0;
-        if (stages >= 4) {
+        if (MODE == NSX_MODE_TOPK) {
+            for (; j < my_n; ++j) {
+                nsx_mbar_wait(&sh.full[s], par);
+                nsx_topk_tile<PHASE1, PISMEM>(d, st, cmd, pis, ring + s * st.stage_bytes, tile * NSX_TILE, sh);
+                __syncwarp();
+                if (lane == 0) nsx_mbar_arrive(&sh.empty[s]);
+                tile += step;
+                if (++s == (uint32_t)stages) { s = 0; par ^= 1u; }
+            }
+            NsxBarConsumers bar;
+            bar();
+            nsx_tk_compact(sh, (int)threadIdx.x, NSX_CONSUMERS, bar);  // sorted list of this CTA
+        }
+        if (MODE != NSX_MODE_TOPK && stages >= 4) {
             for (; j + 1 < my_n; j += 2) {  // two tiles per step
                 uint32_t s2 = s + 1, par2 = par;
                 if (s2 == (uint32_t)stages) { s2 = 0; par2 ^= 1u; }
@@ -596,9 +739,16 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
     nsx_cand_init(dz);
     nsx_devex_init(dx);
     // first candidate must satisfy rc < -tol: start the gate at the largest double below -tol
-    if (threadIdx.x == 0) sh.gate_bits = (unsigned long long)__double_as_longlong(-d.tol) + 1ull;
+    if (threadIdx.x == 0) { sh.gate_bits = (unsigned long long)__double_as_longlong(-d.tol) + 1ull; nsx_tk_reset(sh, d.tol); }
     NSX_SYNC();  // the command is visible; reduction buffers / staged potentials are free again
     if (sh.tl_grid) NSX_TL(sh.tl_grid, 1);
+    if (cmd.kind == NSX_CMD_TOPK) {
+        // (tk_cnt / threshold were reset by thread 0 before the barrier above)
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_TOPK, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_TOPK, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        NSX_SYNC();  // the sorted top list of this CTA is in piv.res / piv.arc2, its length in tk_cnt
+        return;
+    }
     if (cmd.kind == NSX_CMD_DANTZIG) {
         if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
         else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
@@ -676,11 +826,21 @@ __device__ __forceinline__ void nsx_exchange(const NsxShard& shd, unsigned long 
     }
 }
 
+// The sorted top list of this CTA (piv.res / piv.arc2, tk_cnt entries) becomes the candidate list.
+__device__ __forceinline__ void nsx_tk_publish_list(NsxCtaShared& sh, NsxCtl& c) {
+    NSX_SYNC();
+    const int32_t cnt = sh.tk_cnt;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) c.cl_list[k] = sh.piv.arc2[k];
+    if (threadIdx.x == 0) c.cl_count = cnt;
+    NSX_SYNC();
+}
+
 // Sweep functor of CTA 0.
 struct GridSweep {
     const NsxDev& d;      // global view (state bytes, weights, global potentials)
     NsxGridCtl* g;
     NsxSlot* slots;
+    NsxTopkOut* topk;
     NsxCtaShared& sh;
     NsxSweepCtx cx;
     uint32_t& stage_count;
@@ -724,7 +884,28 @@ struct GridSweep {
         }
         ++seq;  // every thread keeps its own copy of the sequence number (the slot polls compare against it)
     }
-    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
+    // candidate-list refresh: merge the sorted per-CTA lists of the workers (HBM) into the final list
+    __device__ void merge_topk(NsxCtl& c) {
+        if (threadIdx.x == 0) nsx_tk_reset(sh, d.tol);
+        NsxBarAll bar;
+        const int P = (int)blockDim.x, t = (int)threadIdx.x;
+        for (int b0 = 1; b0 < (int)gridDim.x; b0 += 4) {  // four lists (<= 400 entries) per step
+            __syncwarp();
+            if (__syncthreads_or(sh.tk_cnt > NSX_TK_CAP - 4 * NSX_CL_SIZE)) nsx_tk_compact(sh, t, P, bar);
+            bool has = false; unsigned long long k = 0ull; int32_t i = -1;
+            if (t < 4 * NSX_CL_SIZE) {
+                const int b = b0 + t / NSX_CL_SIZE, e = t % NSX_CL_SIZE;
+                if (b < (int)gridDim.x && e < __ldcg(&topk[b].count)) {
+                    has = true; k = __ldcg(&topk[b].key[e]); i = __ldcg(&topk[b].idx[e]);
+                }
+            }
+            nsx_tk_append(sh, has, k, i);
+        }
+        bar();
+        nsx_tk_compact(sh, t, P, bar);
+        nsx_tk_publish_list(sh, c);
+    }
+    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
@@ -734,6 +915,11 @@ struct GridSweep {
             NsxCand dz; NsxDevexCand dx;
             if (threadIdx.x == 0) __threadfence();
             nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, shd.rank, shd.world, sh, dz, dx);
+            if (cmd.kind == NSX_CMD_TOPK) {
+                nsx_tk_publish_list(sh, c);
+                if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
+                return;
+            }
             if (threadIdx.x == 0) {
                 if (shd.world > 1) { if (devex) exchange(dx); else exchange(dz); }
                 if (devex) out_dx = dx; else out_dz = dz;
@@ -763,6 +949,11 @@ struct GridSweep {
         }
         NSX_SYNC();
         if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; g->tl[6] += nsx_globaltimer() - g->t_pub; }
+        if (cmd.kind == NSX_CMD_TOPK) {
+            merge_topk(c);
+            if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
+            return;
+        }
         if (devex) {
             nsx_block_reduce(kx, sh.dx_buf);
             if (threadIdx.x == 0) { if (shd.world > 1) exchange(kx); out_dx = kx; }
@@ -793,6 +984,7 @@ struct NsxKernelArgs {
     NsxCtl* ctl;
     NsxGridCtl* grid;
     NsxSlot* slots;
+    NsxTopkOut* topk;
     int32_t* trace;
     NsxSmemPlan plan;    // CTA 0
     NsxSmemPlan wplan;   // sweep workers
@@ -841,7 +1033,7 @@ __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLo
             c.sweeps++;
         }
         NSX_SYNC();
-        sweep.run(L.cmd, L.dz, L.dx);
+        sweep.run(L.cmd, L.dz, L.dx, c);
     }
     NSX_SYNC();
     if (threadIdx.x == 0) { c.status = NSX_STATUS_OPTIMAL; c.total = 0; }
@@ -868,7 +1060,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.slots, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
+        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
         if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -905,6 +1097,17 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         NsxCand dz; NsxDevexCand dx;
         nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
                       a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
+        if (cmd.kind == NSX_CMD_TOPK) {  // this CTA's sorted list -> HBM (the slot release below orders it)
+            NsxTopkOut* out = a.topk + blockIdx.x;
+            const int32_t cnt = sh.tk_cnt;
+            for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+                out->key[k] = reinterpret_cast<unsigned long long*>(sh.piv.res)[k];
+                out->idx[k] = sh.piv.arc2[k];
+            }
+            if (threadIdx.x == 0) out->count = cnt;
+            __threadfence();
+            NSX_SYNC();
+        }
         if (threadIdx.x == 0) {
             NSX_TL(a.grid, 4);
             NsxSlot* sl = a.slots + blockIdx.x;
@@ -996,12 +1199,13 @@ struct LocalSweep {
     NsxSweepCtx cx;
     uint32_t& stage_count;
     uint32_t& q0;
-    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx) {
+    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
         NSX_SYNC();
         if (threadIdx.x == 0) __threadfence();  // this CTA's own state / potential writes reach L2 before the bulk reads
         nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
+        if (cmd.kind == NSX_CMD_TOPK) { nsx_tk_publish_list(sh, c); return; }
         if (threadIdx.x == 0) {
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) out_dx = dx; else out_dz = dz;
         }
@@ -1104,7 +1308,7 @@ static int nsx_validate(const nsx_problem* p, const nsx_options* o, const nsx_re
     if (p->n_arcs > 0 && (!p->tail || !p->head || !p->pert_cost || !p->upper))
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null arc array");
     if (!p->supply) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null supply");
-    if (o->pricing != NSX_PRICING_DANTZIG && o->pricing != NSX_PRICING_DEVEX)
+    if (o->pricing != NSX_PRICING_DANTZIG && o->pricing != NSX_PRICING_DEVEX && o->pricing != NSX_PRICING_CANDIDATE_LIST)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown pricing rule");
     if (o->max_iterations < 0 || !(o->tolerance > 0) || o->ft_update_limit <= 0)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad option value");
@@ -1262,6 +1466,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
     size_t o_ctl = arena.plan(sizeof(NsxCtl)), o_grid = arena.plan(sizeof(NsxGridCtl));
     size_t o_slots = arena.plan(sizeof(NsxSlot) * 1024);
+    size_t o_topk = arena.plan(sizeof(NsxTopkOut) * 160);
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     NSX_CUDA(arena.commit());
 
@@ -1279,6 +1484,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.slots = arena.at<NsxSlot>(o_slots);
+    ka.topk = arena.at<NsxTopkOut>(o_topk);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
     ka.probe_sweeps = probe_sweeps;
     memset(&ka.shard, 0, sizeof ka.shard);

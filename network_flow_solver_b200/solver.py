@@ -55,6 +55,7 @@ def resolve_plan(
     trace_capacity: int = 0,
     device: int = 0,
     flags: int = 0,
+    allow_unaccelerated: bool = False,
 ) -> ResolvedPlan:
     """Mirror of the decisions taken in NetworkSimplex.__init__ / solve().
 
@@ -80,6 +81,9 @@ def resolve_plan(
                 "only the vectorised block search is on the accelerated path."
             )
         pricing = _capi.PRICING_DEVEX
+    elif strategy in ("candidate_list", "adaptive") and allow_unaccelerated:
+        # test-oracle only: "adaptive" never leaves its candidate-list stage in practice (see oracle/nsx_oracle.c)
+        pricing = _capi.PRICING_CANDIDATE_LIST
     else:
         raise SolverConfigurationError(
             f"pricing_strategy='{strategy}' is not on the accelerated path yet (SURVEY.md "
@@ -205,6 +209,7 @@ def prepare(
     device: int = 0,
     flags: int = 0,
     eps_base: float = PERTURB_EPS_BASE,
+    allow_unaccelerated: bool = False,
 ) -> tuple[CanonicalProblem, ResolvedPlan, SolverOptions]:
     """Host-side half of the call: options + canonical arrays, no device work."""
     options = options if options is not None else SolverOptions()
@@ -227,6 +232,7 @@ def prepare(
         trace_capacity=trace_capacity,
         device=device,
         flags=flags,
+        allow_unaccelerated=allow_unaccelerated,
     )
     return cp, plan, options
 

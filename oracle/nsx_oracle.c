@@ -74,6 +74,9 @@ typedef struct {
     int64_t art_with_flow;
     int phase;
     int nthreads;
+    /* candidate-list pricing state (simplex_pricing.py:375-542) */
+    int32_t cl_list[128];
+    int32_t cl_count, cl_since_refresh, cl_minor;
 } oracle_t;
 
 /* --- arc accessors over real + artificial ranges --- */
@@ -330,6 +333,111 @@ static int devex_select(ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir, in
     return 0;
 }
 
+/* ---------------- candidate-list pricing (SolverOptions.pricing_strategy "candidate_list"; also what
+ * "adaptive" - the reference's default - amounts to: AdaptivePricing (simplex_pricing.py:545-639) only
+ * leaves the candidate list after 5 CONSECUTIVE searches that return None, and a search that returns
+ * None ends the phase (simplex.py:1113-1116), so the counter never gets past 2) ---------------- */
+#define CL_SIZE 100   /* simplex.py:232 */
+#define CL_REFRESH 10 /* simplex.py:233 */
+#define CL_MINOR 3    /* simplex_pricing.py:400 */
+
+/* _scan_candidates (simplex_pricing.py:460-505): Dantzig rule over the list, list order, strict < */
+static int cl_scan(const ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir) {
+    const oracle_t* o = &c->o;
+    const double tol = o->tol;
+    int32_t best = -1, bdir = 0;
+    double best_rc = 0.0;
+    for (int32_t k = 0; k < o->cl_count; ++k) {
+        int32_t i = o->cl_list[k];
+        if (o->intree[i]) continue;
+        double rc = rc_of(c, i, o->tcost[i]);
+        double fr = fwd_res(c, i), br = o->flow[i];
+        if (fr > tol && rc < -tol) {
+            if (best < 0 || rc < best_rc) { best = i; bdir = 1; best_rc = rc; }
+        } else if (br > tol && rc > tol) {
+            if (best < 0 || -rc < best_rc) { best = i; bdir = -1; best_rc = -rc; }
+        } else if (allow_zero && fr > tol && fabs(rc) <= tol && best < 0) {
+            best = i; bdir = 1;
+        } else if (allow_zero && br > tol && fabs(rc) <= tol && best < 0) {
+            best = i; bdir = -1;
+        }
+    }
+    if (best < 0) return 0;
+    *arc = best; *dir = bdir;
+    return 1;
+}
+
+/* _refresh_candidate_list (simplex_pricing.py:507-536): the CL_SIZE arcs of largest |rc| among the improving
+ * ones; Python sorts the (merit, idx) tuples in descending order, so ties go to the LARGER index. */
+static void cl_refresh(ctx_t* c, int64_t* priced) {
+    oracle_t* o = &c->o;
+    const double tol = o->tol;
+    double hm[CL_SIZE]; int32_t hi[CL_SIZE]; /* min-heap on (merit, idx) */
+    int32_t cnt = 0;
+    *priced += o->m;
+    for (int64_t i = 0; i < o->m; ++i) {
+        if (o->intree[i]) continue;
+        double rc = rc_of(c, i, o->tcost[i]);
+        double fr = fwd_res(c, i), br = o->flow[i];
+        double merit = 0.0;
+        if ((fr > tol && rc < -tol) || (br > tol && rc > tol)) merit = fabs(rc);
+        if (!(merit > tol)) continue;
+#define CL_LESS(m1, i1, m2, i2) ((m1) < (m2) || ((m1) == (m2) && (i1) < (i2)))
+        if (cnt < CL_SIZE) {
+            int32_t k = cnt++;
+            hm[k] = merit; hi[k] = (int32_t)i;
+            while (k > 0) { /* sift up */
+                int32_t p = (k - 1) / 2;
+                if (!CL_LESS(hm[k], hi[k], hm[p], hi[p])) break;
+                double tm = hm[k]; hm[k] = hm[p]; hm[p] = tm;
+                int32_t ti = hi[k]; hi[k] = hi[p]; hi[p] = ti;
+                k = p;
+            }
+        } else if (CL_LESS(hm[0], hi[0], merit, (int32_t)i)) {
+            hm[0] = merit; hi[0] = (int32_t)i;
+            int32_t k = 0;
+            for (;;) { /* sift down */
+                int32_t l = 2 * k + 1, r = l + 1, sm = k;
+                if (l < cnt && CL_LESS(hm[l], hi[l], hm[sm], hi[sm])) sm = l;
+                if (r < cnt && CL_LESS(hm[r], hi[r], hm[sm], hi[sm])) sm = r;
+                if (sm == k) break;
+                double tm = hm[k]; hm[k] = hm[sm]; hm[sm] = tm;
+                int32_t ti = hi[k]; hi[k] = hi[sm]; hi[sm] = ti;
+                k = sm;
+            }
+        }
+    }
+    /* descending (merit, idx): selection sort of <= 100 entries */
+    for (int32_t a = 0; a < cnt; ++a) {
+        int32_t mx = a;
+        for (int32_t b = a + 1; b < cnt; ++b)
+            if (CL_LESS(hm[mx], hi[mx], hm[b], hi[b])) mx = b;
+        double tm = hm[a]; hm[a] = hm[mx]; hm[mx] = tm;
+        int32_t ti = hi[a]; hi[a] = hi[mx]; hi[mx] = ti;
+        o->cl_list[a] = hi[a];
+    }
+    o->cl_count = cnt;
+#undef CL_LESS
+}
+
+/* CandidateListPricing.select_entering_arc (simplex_pricing.py:418-458) */
+static int cl_select(ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir, int64_t* priced) {
+    oracle_t* o = &c->o;
+    if (o->cl_count > 0 && o->cl_minor < CL_MINOR) {
+        if (cl_scan(c, allow_zero, arc, dir)) { o->cl_minor++; return 1; }
+    }
+    o->cl_since_refresh++;
+    o->cl_minor = 0;
+    if (o->cl_since_refresh >= CL_REFRESH || o->cl_count == 0) { cl_refresh(c, priced); o->cl_since_refresh = 0; }
+    if (cl_scan(c, allow_zero, arc, dir)) return 1;
+    if (o->cl_since_refresh > 0) {
+        cl_refresh(c, priced);
+        o->cl_since_refresh = 0;
+        return cl_scan(c, allow_zero, arc, dir);
+    }
+    return 0;
+}
+
 /* ---------------- pivot ---------------- */
 
 typedef struct {
@@ -436,6 +544,7 @@ static int pivot(ctx_t* c, int32_t e, int32_t dir, int want_weight, ostats_t* st
         o->ftc = 0;
         for (int64_t i = 0; i < o->m; ++i) o->weight[i] = 1.0;
         o->pb = 0;
+        o->cl_count = 0; o->cl_since_refresh = 0; o->cl_minor = 0; /* pricing_strategy.reset(), simplex.py:1771-1776 */
         st->resets++;
     } else o->ftc++;
     return 0;
@@ -461,6 +570,7 @@ static int find_entering(ctx_t* c, const nsx_options* opt, int allow_zero, int32
         if (dantzig_select(c, 0, arc, dir)) return 1;
     }
     if (opt->pricing == NSX_PRICING_DANTZIG) { *priced += o->m; return dantzig_select(c, allow_zero, arc, dir); }
+    if (opt->pricing == NSX_PRICING_CANDIDATE_LIST) return cl_select(c, allow_zero, arc, dir, priced);
     return devex_select(c, allow_zero, arc, dir, want_weight, priced);
 }
 

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../network_flow_solver_b200/csrc/nsx_core.cuh"
@@ -17,9 +19,25 @@ namespace {
 struct SerialSweep {
     const NsxDev& d;
     SerialSweep(const NsxDev& dev) : d(dev) {}
-    void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx) {
+    void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         nsx_cand_init(dz);
         nsx_devex_init(dx);
+        if (cmd.kind == NSX_CMD_TOPK) {  // candidate-list refresh (simplex_pricing.py:507-536)
+            std::vector<std::pair<double, int32_t>> cands;
+            for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
+                const uint8_t st = d.state[i];
+                if (st & NSX_ARC_IN_TREE) continue;
+                double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
+                double merit = 0.0;
+                if (((st & NSX_ARC_CAN_FWD) && rc < -d.tol) || ((st & NSX_ARC_CAN_BWD) && rc > d.tol)) merit = fabs(rc);
+                if (merit > d.tol) cands.push_back({merit, (int32_t)i});
+            }
+            std::sort(cands.begin(), cands.end(), [](const std::pair<double, int32_t>& a, const std::pair<double, int32_t>& b) {
+                return a.first > b.first || (a.first == b.first && a.second > b.second); });
+            c.cl_count = (int32_t)(cands.size() < NSX_CL_SIZE ? cands.size() : NSX_CL_SIZE);
+            for (int32_t k = 0; k < c.cl_count; ++k) c.cl_list[k] = cands[k].second;
+            return;
+        }
         if (cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO) {
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
                 double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);

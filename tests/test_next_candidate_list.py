@@ -1,0 +1,91 @@
+"""Next scope row: the reference's DEFAULT pricing - "adaptive", which in practice is its
+candidate-list rule (top-100 arcs by |rc|, refreshed every 10 major iterations, 3 minor iterations per candidate
+scan, reset with the Devex cadence).  The oracle restates it and is pinned here to runs recorded from the unmodified
+reference (tests/golden/make_candidate_golden.py).  The CUDA engine does not implement this rule yet: the drop-in
+rejects the option instead of running something else."""
+
+import gzip
+import json
+from pathlib import Path
+
+import pytest
+
+from helpers import assert_matches_reference, rebuild_problem
+from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, _capi
+from network_flow_solver_b200.solver import prepare
+from oracle import oracle
+
+DOC = json.loads(gzip.open(Path(__file__).resolve().parent / "golden" / "next" / "candidate_list.json.gz", "rb").read().decode())
+RUNS = [(c["name"], i) for c in DOC["cases"] for i in range(len(c["runs"]))]
+CASES = {c["name"]: c for c in DOC["cases"]}
+
+
+@pytest.mark.parametrize("name,i", RUNS)
+def test_oracle_reproduces_reference_candidate_list_runs(name, i):
+    case, run = CASES[name], CASES[name]["runs"][i]
+    problem = rebuild_problem(case["problem"])
+    options = SolverOptions(**run["options"])
+    cp, plan, options = prepare(problem, options, run.get("max_iterations"), trace_capacity=1 << 16,
+                                allow_unaccelerated=True)
+    want = {"CandidateListPricing": _capi.PRICING_CANDIDATE_LIST, "AdaptivePricing": _capi.PRICING_CANDIDATE_LIST,
+            "DantzigPricing": _capi.PRICING_DANTZIG}[run["strategy"]]
+    assert plan.engine.pricing == want
+    assert_matches_reference(run, cp, oracle.solve_canonical(cp, plan.engine), options)
+
+
+@pytest.mark.parametrize("name,i", RUNS)
+def test_emulated_device_core_reproduces_reference_candidate_list_runs(name, i):
+    """The device driver / candidate scan / reset cadence (nsx_core.cuh compiled for the host, serial refresh)."""
+    from emu import emu
+
+    case, run = CASES[name], CASES[name]["runs"][i]
+    problem = rebuild_problem(case["problem"])
+    cp, plan, options = prepare(problem, SolverOptions(**run["options"]), run.get("max_iterations"),
+                                trace_capacity=1 << 16, allow_unaccelerated=True)
+    assert_matches_reference(run, cp, emu.solve_canonical(cp, plan.engine), options)
+
+
+def test_adaptive_and_candidate_list_coincide_in_the_reference():
+    for case in DOC["cases"]:
+        by = {r["strategy"]: r for r in case["runs"] if r.get("max_iterations") is None}
+        if "AdaptivePricing" in by and "CandidateListPricing" in by:
+            assert by["AdaptivePricing"]["trace"] == by["CandidateListPricing"]["trace"], case["name"]
+
+
+def test_dropin_still_rejects_the_rule_it_does_not_accelerate():
+    problem = rebuild_problem(DOC["cases"][0]["problem"])
+    with pytest.raises(SolverConfigurationError):
+        prepare(problem, SolverOptions(auto_scale=False))  # reference defaults = adaptive
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,i", RUNS)
+def test_engine_reproduces_reference_candidate_list_runs(name, i):
+    """CUDA engine (single-CTA path: these instances are small) against the recorded reference runs."""
+    case, run = CASES[name], CASES[name]["runs"][i]
+    problem = rebuild_problem(case["problem"])
+    cp, plan, options = prepare(problem, SolverOptions(**run["options"]), run.get("max_iterations"),
+                                trace_capacity=1 << 16, allow_unaccelerated=True)
+    assert_matches_reference(run, cp, _capi.solve_canonical(cp, plan.engine), options)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", [0, 5])
+def test_engine_candidate_list_multi_cta_matches_oracle(grid, monkeypatch):
+    """Grid-wide top-100 refresh (per-CTA buffers, bitonic compaction, merge in the pivot CTA) against the oracle."""
+    import numpy as np
+    from network_flow_solver_b200 import generators as gen
+    from network_flow_solver_b200.canonical import initial_block_size
+
+    if grid:
+        monkeypatch.setenv("NSX_GRID", str(grid))
+    cp = gen.netgen_like(1 << 13, 1 << 17, n_sources=32, n_sinks=32, cost_max=50, seed=77).canonical()
+    m = cp.n_arcs
+    opts = _capi.EngineOptions(pricing=_capi.PRICING_CANDIDATE_LIST, row_scan_first=False, block_size=initial_block_size(m),
+                               auto_block=True, ft_update_limit=64, max_iterations=max(100, 20 * (m + cp.n_nodes - 1)),
+                               tolerance=1e-6, trace_capacity=1 << 20)
+    a, b = _capi.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts, threads=4)
+    assert (a.status, a.iterations) == (b.status, b.iterations)
+    np.testing.assert_array_equal(a.trace, b.trace)
+    np.testing.assert_array_equal(a.flow, b.flow)
+    np.testing.assert_array_equal(a.potential, b.potential)
