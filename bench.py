@@ -169,7 +169,7 @@ def main() -> int:
     config = {
         "workload": args.workload,
         "description": wl.description,
-        "pricing": "devex" if wl.pricing == 1 else ("row_scan" if "transport" in wl.name else "dantzig"),
+        "pricing": ("row_scan" if "transport" in wl.name else {0: "dantzig", 1: "devex", 2: "candidate_list"}[wl.pricing]),
         "perturbation_eps": wl.eps_base,
         "parallelism": (f"batch round-robin x{world}" if batch_mode else
                         f"arc-sharded pricing x{world} (NVLink candidate exchange)" if args.mode == "sharded" else f"replicas x{world}"),

@@ -31,9 +31,8 @@ extern "C" {
 #define NSX_PRICING_DANTZIG 0 /* DantzigPricing.select_entering_arc, simplex_pricing.py:97-137 */
 #define NSX_PRICING_DEVEX 1   /* DevexPricing._select_entering_arc_vectorized, simplex_pricing.py:310-357 + simplex.py:528-617 */
 #define NSX_PRICING_CANDIDATE_LIST 2 /* CandidateListPricing (simplex_pricing.py:375-542), which is also what the
-                                        reference's default "adaptive" strategy runs in practice.  NEXT ROW:
-                                        restated and pinned in the test oracle; nsx_solve rejects it until the device
-                                        top-k refresh sweep exists */
+                                        reference's default "adaptive" strategy (simplex_pricing.py:545-639) runs in
+                                        practice: candidate scan in the pivot CTA, top-100 refresh as a grid-wide sweep */
 
 /* solver outcome (FlowResult.status, data.py:269-322; UnboundedProblemError, simplex.py:1231-1246) */
 #define NSX_STATUS_OPTIMAL 0

@@ -19,7 +19,7 @@ from .exceptions import DeviceEngineError
 
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
-PRICING_CANDIDATE_LIST = 2  # oracle only so far; the engine rejects it
+PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
 
 STATUS_OPTIMAL = 0
 STATUS_INFEASIBLE = 1

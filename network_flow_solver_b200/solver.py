@@ -81,13 +81,14 @@ def resolve_plan(
                 "only the vectorised block search is on the accelerated path."
             )
         pricing = _capi.PRICING_DEVEX
-    elif strategy in ("candidate_list", "adaptive") and allow_unaccelerated:
-        # test-oracle only: "adaptive" never leaves its candidate-list stage in practice (see oracle/nsx_oracle.c)
+    elif strategy in ("candidate_list", "adaptive"):
+        # "adaptive" (the reference's default) only leaves its candidate-list stage after 5 consecutive searches
+        # that return None, and a search that returns None ends the phase: it IS the candidate-list rule
+        # (simplex_pricing.py:545-639; tests/test_next_candidate_list.py pins this against the reference)
         pricing = _capi.PRICING_CANDIDATE_LIST
     else:
         raise SolverConfigurationError(
-            f"pricing_strategy='{strategy}' is not on the accelerated path yet (SURVEY.md "
-            f"section 8f: candidate_list / adaptive are 'next' rows). Pass 'dantzig' or 'devex'."
+            f"Unknown pricing strategy '{strategy}'. Valid options: 'devex', 'dantzig', 'candidate_list', 'adaptive'."
         )
     if cp.network_type == NET_TRANSPORTATION:
         row_scan = True

@@ -65,6 +65,10 @@ WORKLOADS = {
         "netgen_2e16_devex", "NETGEN-style 2^16 nodes / 2^20 arcs, Devex (auto block)",
         _capi.PRICING_DEVEX, PERTURB_EPS_BASE,
         lambda off: gen.netgen_like(1 << 16, 1 << 20, n_sources=256, n_sinks=256, seed=1601 + off)),
+    "netgen_2e16_candidate": Workload(
+        "netgen_2e16_candidate", "NETGEN-style 2^16 nodes / 2^20 arcs, candidate-list pricing (the reference's default)",
+        _capi.PRICING_CANDIDATE_LIST, PERTURB_EPS_BASE,
+        lambda off: gen.netgen_like(1 << 16, 1 << 20, n_sources=256, n_sinks=256, seed=1601 + off)),
     # config 3 - the pricing-bandwidth-bound case
     "transport_4096": Workload(
         "transport_4096", "dense transportation 4096x4096 (16.7M arcs), row-scan pricing, eps=0",

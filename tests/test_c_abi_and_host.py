@@ -91,8 +91,7 @@ def test_option_resolution_matches_the_reference_rules():
     assert plan2.strategy == "dantzig"                                                               # simplex.py:358-374
 
 
-@pytest.mark.parametrize("kwargs", [dict(pricing_strategy="adaptive"), dict(pricing_strategy="candidate_list"),
-                                    dict(pricing_strategy="devex", use_vectorized_pricing=False)])
+@pytest.mark.parametrize("kwargs", [dict(pricing_strategy="devex", use_vectorized_pricing=False)])
 def test_paths_outside_the_accelerated_scope_fail_loudly(kwargs):
     with pytest.raises(SolverConfigurationError):
         prepare(small_problem(), SolverOptions(explicit_pricing_strategy=True, auto_scale=False, **kwargs))

@@ -1,8 +1,8 @@
-"""Next scope row: the reference's DEFAULT pricing - "adaptive", which in practice is its
+"""Scope row SURVEY.md section 8f-2: the reference's DEFAULT pricing - "adaptive", which in practice is its
 candidate-list rule (top-100 arcs by |rc|, refreshed every 10 major iterations, 3 minor iterations per candidate
 scan, reset with the Devex cadence).  The oracle restates it and is pinned here to runs recorded from the unmodified
-reference (tests/golden/make_candidate_golden.py).  The CUDA engine does not implement this rule yet: the drop-in
-rejects the option instead of running something else."""
+reference (tests/golden/make_candidate_golden.py); the device driver is checked through the host emulation and the
+CUDA engine (candidate scan in the pivot CTA, grid-wide top-100 refresh sweep) through the C ABI."""
 
 import gzip
 import json
@@ -11,7 +11,7 @@ from pathlib import Path
 import pytest
 
 from helpers import assert_matches_reference, rebuild_problem
-from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, _capi
+from network_flow_solver_b200 import SolverOptions, _capi
 from network_flow_solver_b200.solver import prepare
 from oracle import oracle
 
@@ -52,10 +52,23 @@ def test_adaptive_and_candidate_list_coincide_in_the_reference():
             assert by["AdaptivePricing"]["trace"] == by["CandidateListPricing"]["trace"], case["name"]
 
 
-def test_dropin_still_rejects_the_rule_it_does_not_accelerate():
+def test_default_options_resolve_to_the_candidate_list_rule():
     problem = rebuild_problem(DOC["cases"][0]["problem"])
-    with pytest.raises(SolverConfigurationError):
-        prepare(problem, SolverOptions(auto_scale=False))  # reference defaults = adaptive
+    _, plan, _ = prepare(problem, SolverOptions(auto_scale=False))  # reference defaults = adaptive
+    assert plan.engine.pricing == _capi.PRICING_CANDIDATE_LIST
+    with pytest.raises(Exception):
+        SolverOptions(pricing_strategy="steepest_edge")
+
+
+@pytest.mark.gpu
+def test_public_api_with_default_options_matches_the_reference():
+    from network_flow_solver_b200 import solve_min_cost_flow
+
+    for case in DOC["cases"]:
+        run = next(r for r in case["runs"] if r["options"] == {"auto_scale": False})
+        result = solve_min_cost_flow(rebuild_problem(case["problem"]), SolverOptions(auto_scale=False))
+        assert (result.status, result.iterations, result.objective) == (run["status"], run["iterations"], run["objective"])
+        assert result.flows == {(a, b): v for a, b, v in run["flows"]}
 
 
 @pytest.mark.gpu
