@@ -44,6 +44,7 @@ class ResolvedPlan:
 
     strategy: str
     engine: _capi.EngineOptions
+    scaling: object = None  # scaling.ScalingFactors when the instance was rescaled before the solve
 
 
 def resolve_plan(
@@ -128,22 +129,25 @@ def _np_round12(x: float) -> float:
     return float(round(np.float64(x), 12))
 
 
-def objective_value(cp: CanonicalProblem, raw: _capi.RawSolution) -> float:
+def objective_value(cp: CanonicalProblem, raw: _capi.RawSolution, divisor: float | None = None) -> float:
     """Sum over real arcs in index order of (flow+shift)*original cost, rounded like the
-    reference (simplex.py:1703-1714,1759)."""
+    reference (simplex.py:1703-1714,1759); `divisor` = cost_scale * supply_scale when the instance was
+    rescaled (the division happens before the rounding, simplex.py:1753-1759)."""
     m = cp.n_arcs
     if m == 0:
         return 0.0
     values = raw.flow[:m] + cp.shift
     total = float(np.cumsum(values * cp.orig_cost)[-1])  # cumsum folds left to right
+    if divisor is not None:
+        total = total / divisor
     touched = bool(np.any(raw.state[:m] & _capi.ARC_TOUCHED))
     return _np_round12(total) if touched else float(round(total, 12))
 
 
 def finish(
-    cp: CanonicalProblem, raw: _capi.RawSolution, options: SolverOptions
+    cp: CanonicalProblem, raw: _capi.RawSolution, options: SolverOptions, scaling=None
 ) -> FlowResult:
-    """Raw engine arrays -> FlowResult (simplex.py:1600-1624,1703-1765)."""
+    """Raw engine arrays -> FlowResult (simplex.py:1600-1624,1703-1765); `scaling` = factors applied by prepare()."""
     if raw.status == _capi.STATUS_UNBOUNDED:
         key = cp.arc_keys[raw.unbounded_arc] if cp.arc_keys is not None else None
         raise UnboundedProblemError(
@@ -191,8 +195,12 @@ def finish(
             tree_arcs={cp.arc_keys[i] for i in in_tree},
             arc_flows={cp.arc_keys[i]: float(raw.flow[i]) for i in in_tree},
         )
+    divisor = None
+    if scaling is not None and scaling.enabled:  # simplex.py:1753-1756: flows after their rounding, objective before
+        flows = {k: v / scaling.supply_scale for k, v in flows.items()}
+        divisor = scaling.cost_scale * scaling.supply_scale
     return FlowResult(
-        objective=objective_value(cp, raw),
+        objective=objective_value(cp, raw, divisor),
         flows=flows,
         status=status,
         iterations=raw.iterations,
@@ -214,15 +222,13 @@ def prepare(
 ) -> tuple[CanonicalProblem, ResolvedPlan, SolverOptions]:
     """Host-side half of the call: options + canonical arrays, no device work."""
     options = options if options is not None else SolverOptions()
-    if options.auto_scale:
-        from .scaling import should_scale_problem
+    factors = None
+    if options.auto_scale:  # simplex.py:103-114
+        from .scaling import compute_scaling_factors, scale_problem, should_scale_problem
 
         if should_scale_problem(problem):
-            raise SolverConfigurationError(
-                "auto_scale=True would rescale this problem (value ranges differ by more than "
-                "1e6, scaling.py:37-95); automatic scaling is a host pre/post step outside the "
-                "accelerated path - pass SolverOptions(auto_scale=False)."
-            )
+            factors = compute_scaling_factors(problem)
+            problem = scale_problem(problem, factors)
     cp = canonicalize(problem, options.tolerance, eps_base)
     goto = is_likely_goto(problem, cp.n_arcs, options.tolerance)
     plan = resolve_plan(
@@ -235,6 +241,7 @@ def prepare(
         flags=flags,
         allow_unaccelerated=allow_unaccelerated,
     )
+    plan.scaling = factors
     return cp, plan, options
 
 
@@ -261,7 +268,7 @@ def solve_min_cost_flow(
         )
     cp, plan, options = prepare(problem, options, max_iterations, device=device)
     raw = _capi.solve_canonical(cp, plan.engine)
-    result = finish(cp, raw, options)
+    result = finish(cp, raw, options, plan.scaling)
     if raw.status in (_capi.STATUS_OPTIMAL, _capi.STATUS_ITERATION_LIMIT):
         rate = (raw.degenerate_pivots / raw.iterations * 100) if raw.iterations > 0 else 0.0
         # the reference prints this line unconditionally (simplex.py:1672-1674)
