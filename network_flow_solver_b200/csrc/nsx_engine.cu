@@ -1494,6 +1494,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
             arena.release(); inputs.release();
             return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad shard description");
         }
+        if (shard->world > 1 && opt->pricing == NSX_PRICING_CANDIDATE_LIST) {
+            arena.release(); inputs.release();
+            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "candidate-list pricing is not available in arc-sharded solves yet (the refresh sweep merges per-GPU lists only)");
+        }
         ka.shard.rank = shard->rank; ka.shard.world = shard->world;
         for (int r = 0; r < shard->world; ++r) ka.shard.box[r] = reinterpret_cast<NsxMailbox*>(shard->mailboxes[r]);
     }
