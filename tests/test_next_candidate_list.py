@@ -104,3 +104,21 @@ def test_engine_candidate_list_multi_cta_matches_oracle(grid, monkeypatch):
     np.testing.assert_array_equal(a.trace, b.trace)
     np.testing.assert_array_equal(a.flow, b.flow)
     np.testing.assert_array_equal(a.potential, b.potential)
+
+
+@pytest.mark.gpu
+def test_batch_kernel_with_candidate_list_matches_oracle():
+    import numpy as np
+    from network_flow_solver_b200 import generators as gen
+    from network_flow_solver_b200.canonical import initial_block_size
+
+    cps = [gen.netgen_like(256, 2048, n_sources=4, n_sinks=4, seed=300 + k).canonical() for k in range(6)]
+    m = cps[0].n_arcs
+    opts = _capi.EngineOptions(pricing=_capi.PRICING_CANDIDATE_LIST, row_scan_first=False, block_size=initial_block_size(m),
+                               auto_block=True, ft_update_limit=64, max_iterations=10**7, tolerance=1e-6,
+                               trace_capacity=1 << 16)
+    for cp, got in zip(cps, _capi.solve_batch_canonical(cps, opts)):
+        want = oracle.solve_canonical(cp, opts)
+        assert (got.status, got.iterations) == (want.status, want.iterations)
+        np.testing.assert_array_equal(got.trace, want.trace)
+        np.testing.assert_array_equal(got.flow, want.flow)
