@@ -27,6 +27,7 @@ from .exceptions import (
 )
 from .dimacs import load_dimacs_canonical, parse_dimacs_file, parse_dimacs_string
 from .io import load_problem, save_result
+from .preprocessing import PreprocessingResult, preprocess_and_solve, preprocess_problem, translate_result
 from .solver import solve_min_cost_flow
 
 __version__ = "0.1.0"
@@ -43,6 +44,7 @@ __all__ = [
     "NetworkSolverError",
     "Node",
     "NumericalInstabilityError",
+    "PreprocessingResult",
     "ProgressCallback",
     "ProgressInfo",
     "SolverConfigurationError",
@@ -53,7 +55,10 @@ __all__ = [
     "load_problem",
     "parse_dimacs_file",
     "parse_dimacs_string",
+    "preprocess_and_solve",
+    "preprocess_problem",
     "save_result",
     "solve_min_cost_flow",
+    "translate_result",
     "__version__",
 ]
