@@ -55,6 +55,10 @@ extern "C" {
 #define NSX_ARC_IN_TREE 1u
 #define NSX_ARC_CAN_FWD 2u  /* upper - flow > tol */
 #define NSX_ARC_CAN_BWD 4u  /* flow > tol */
+#define NSX_ARC_STALE 16u  /* warm start only: the arc was put into the initial tree and has not been on a pivot
+                               cycle since; the reference's ratio test still sees its cold-start flow there
+                               (forward/backward_residuals are refreshed per cycle arc only, simplex.py:1276-1283, and
+                               never after _apply_warm_start_basis) and the engine reproduces that */
 #define NSX_ARC_TOUCHED 8u  /* flow was written by a pivot with theta > 0 (drives NumPy-vs-Python rounding
                                of the result, simplex.py:1703-1721) */
 
@@ -174,6 +178,22 @@ int nsx_mailbox_create(int32_t device, void** mailbox, unsigned char handle[64])
 int nsx_mailbox_open(int32_t device, const unsigned char handle[64], void** mailbox);
 int nsx_mailbox_reset(int32_t device, void* mailbox);
 int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local);
+
+/*
+ * Warm start (NetworkSimplex._apply_warm_start_basis / _recompute_tree_flows, simplex.py:740-1021; phase choice
+ * simplex.py:1494-1530).  The host layer turns the reference's Basis(tree_arcs, arc_flows) into the initial state
+ * below - which arcs (real and artificial) form the spanning tree, every arc's flow, and whether Phase 1 is
+ * skipped - and the engine starts its resident pivot loop from that tree instead of the all-artificial star.
+ * in_tree must mark exactly n_nodes - 1 arcs that span all nodes (artificial arc M + v - 1 joins node v and the
+ * root); anything else is NSX_ERR_INVALID_ARGUMENT.  Host buffers, nsx_solve's conventions otherwise.
+ */
+typedef struct nsx_warm_start {
+    const uint8_t* in_tree; /* [M + n_nodes - 1] 1 = arc belongs to the initial tree */
+    const double* flow;     /* [M + n_nodes - 1] initial flows (0 on arcs outside the tree) */
+    int32_t start_phase;    /* 1 = Phase 1 first; 2 = no artificial arc in the tree, Phase 1 skipped */
+} nsx_warm_start;
+int nsx_solve_warm(const nsx_problem* problem, const nsx_options* options, const nsx_warm_start* warm,
+                   nsx_result* result);
 
 /* Solve `count` independent instances on one GPU, one CTA per instance (batched config).
  * problems[i] / results[i] as in nsx_solve; options are shared. */

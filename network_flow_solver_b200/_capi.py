@@ -71,6 +71,17 @@ class NsxShard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mailboxes", C.POINTER(C.c_void_p))]
 
 
+class NsxWarmStart(C.Structure):
+    """nsx_warm_start (include/nsx_b200.h): initial spanning tree + flows built by warm_start.apply_basis."""
+
+    _fields_ = [("in_tree", C.POINTER(C.c_uint8)), ("flow", C.POINTER(C.c_double)), ("start_phase", C.c_int32)]
+
+    @classmethod
+    def of(cls, warm) -> "NsxWarmStart":
+        """`warm` = warm_start.WarmStart; the arrays must stay alive for the duration of the call."""
+        return cls(_ptr(warm.in_tree, _p_u8), _ptr(warm.flow, _p_f64), int(warm.start_phase))
+
+
 class NsxResult(C.Structure):
     _fields_ = [
         ("flow", _p_f64),
@@ -292,6 +303,9 @@ def load_library():
             fn = getattr(lib, name)
             fn.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult)]
             fn.restype = C.c_int
+        lib.nsx_solve_warm.argtypes = [
+            C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxWarmStart), C.POINTER(NsxResult)]
+        lib.nsx_solve_warm.restype = C.c_int
         lib.nsx_sweep_probe.argtypes = [
             C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.c_int32, C.POINTER(NsxResult)]
         lib.nsx_sweep_probe.restype = C.c_int
@@ -332,10 +346,16 @@ def _check(rc: int, what: str) -> None:
         raise DeviceEngineError(f"{what} failed with code {rc}: {last_error()}")
 
 
-def solve_canonical(cp: CanonicalProblem, opts: EngineOptions, out=None) -> RawSolution:
-    """One instance, host buffers in, host buffers out (nsx_solve). Releases the GIL."""
+def solve_canonical(cp: CanonicalProblem, opts: EngineOptions, out=None, warm=None) -> RawSolution:
+    """One instance, host buffers in, host buffers out (nsx_solve; nsx_solve_warm when `warm`, a
+    warm_start.WarmStart, gives the initial tree). Releases the GIL."""
     lib = load_library()
     frame = CallFrame(cp, opts, out=out)
+    if warm is not None:
+        w = NsxWarmStart.of(warm)
+        rc = lib.nsx_solve_warm(C.byref(frame.problem), C.byref(frame.options), C.byref(w), C.byref(frame.result))
+        _check(rc, "nsx_solve_warm")
+        return frame.harvest()
     rc = lib.nsx_solve(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result))
     _check(rc, "nsx_solve")
     return frame.harvest()

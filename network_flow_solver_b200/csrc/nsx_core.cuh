@@ -136,6 +136,7 @@ struct NsxCtl {
     int32_t cl_list[NSX_CL_SIZE];
     uint32_t wepoch;      // current Devex weight epoch (8 bits used)
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
+    int32_t warm;         // started from a caller-supplied tree (nsx_solve_warm): NSX_ARC_STALE bits may be set
     // statistics
     int64_t degenerate, tree_updates, resets, arcs_priced, sweeps;
     int64_t avg_cycle;    // running mean of the cycle length * 16 (chooses the cycle-walk variant)
@@ -629,6 +630,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             sign = dir;
         }
         double f = d.flow[a];
+        if (c.warm && (d.state[a] & NSX_ARC_STALE)) {  // the reference's residual mirrors still hold the cold-start flow
+            double up0 = nsx_upper(d, a);               // (see NSX_ARC_STALE): 0 on a real arc, |supply| on an artificial one
+            f = (a < d.m || nsx_isinf(up0)) ? 0.0 : up0;
+        }
         double r;
         if (sign == 1) {
             double up = nsx_upper(d, a);
@@ -686,15 +691,17 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t leave = s.leave_arc;
     const int32_t leave_k = s.leave_k;
 
-    // ---- 4. flow update (simplex.py:1255-1283); nothing changes when theta == 0 -----------
-    if (theta > 0.0) {
+    // ---- 4. flow update (simplex.py:1255-1283); nothing changes when theta == 0 - except after a warm start,
+    // where the pass also drops the NSX_ARC_STALE marks of the cycle arcs (their residual mirrors get refreshed)
+    if (theta > 0.0 || c.warm) {
         NSX_PAR_FOR(k, 0, ncyc) {
             int32_t a = arc2[k] >> 1;
             int32_t sign = (arc2[k] & 1) ? -1 : 1;
             double old = d.flow[a];
             double up = nsx_upper(d, a);
             double f = sign > 0 ? NSX_ADD(old, theta) : NSX_SUB(old, theta);
-            uint8_t st = (uint8_t)(d.state[a] | NSX_ARC_TOUCHED);
+            uint8_t st = d.state[a];
+            if (theta > 0.0) st |= NSX_ARC_TOUCHED;
             if (f < NSX_SUB(0.0, tol)) { f = 0.0; st &= (uint8_t)~NSX_ARC_TOUCHED; }
             if (!nsx_isinf(up) && f > NSX_ADD(up, tol)) { f = up; st &= (uint8_t)~NSX_ARC_TOUCHED; }
             d.flow[a] = f;
@@ -1071,6 +1078,28 @@ NSX_FN void nsx_init_node(const NsxDev& d, int32_t v, double supply) {
     d.node[v] = r; d.depth[v] = 1; d.order[v] = v;
 }
 
+// Warm start (nsx_solve_warm): arc a of [0, ma) from the caller's tree flags and flows.  Artificial arcs keep the
+// geometry of the cold start (direction / capacity by the sign of the supply, simplex.py:645-698); node records, depth and
+// the preorder array are laid out on the host (csrc/nsx_warm.h) and copied in.  Returns 1 for an artificial arc with flow.
+NSX_FN int nsx_init_arc_warm(const NsxDev& d, int64_t a, const double* supply, const uint8_t* in_tree) {
+    const uint8_t tree = in_tree[a] ? (uint8_t)(NSX_ARC_IN_TREE | NSX_ARC_STALE) : (uint8_t)0;
+    const double f = d.flow[a];
+    if (a < d.m) {
+        d.state[a] = (uint8_t)(tree | nsx_bounds_bits(f, d.upper[a], d.tol));
+        if (d.wgt) d.wgt[a] = 1u;
+        return 0;
+    }
+    const int32_t v = (int32_t)(a - d.m) + 1;
+    const double sp = supply[v];
+    double up; int32_t tl, hd;
+    if (fabs(sp) <= d.tol) { tl = 0; hd = v; up = NSX_INF; }
+    else if (sp > 0) { tl = v; hd = 0; up = sp; }
+    else { tl = 0; hd = v; up = -sp; }
+    d.atail[v - 1] = tl; d.ahead[v - 1] = hd; d.aupper[v - 1] = up;
+    d.state[a] = (uint8_t)(tree | nsx_bounds_bits(f, up, d.tol));
+    return f > d.tol ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Driver state machine (single thread of the pivot CTA).  Restates the control flow of
 // NetworkSimplex.solve / _run_simplex_iterations / _find_entering_arc
@@ -1297,7 +1326,8 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
     NSX_SINGLE { s.log_len = 0; s.pos_mask = d.lazy_pos ? 0xffffff : 0x7fffffff; }
     NSX_SYNC();
-    nsx_recompute_potentials(d, s, 1, 1, d.n, ps, (int64_t*)0);  // Phase-1 costs on the initial star
+    // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
+    nsx_recompute_potentials(d, s, c.phase, 1, d.n, ps, (int64_t*)0);
     NSX_SINGLE {
         L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
         L.drv.budget = c.maxit;

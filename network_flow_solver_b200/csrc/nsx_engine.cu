@@ -28,6 +28,7 @@
 #define NSX_THREADS 512
 #endif
 #include "nsx_core.cuh"
+#include "nsx_warm.h"
 
 #define NSX_PI_SMEM_MAX_NODES 12288  // node potentials staged in shared memory up to this many nodes
 
@@ -1137,6 +1138,16 @@ extern "C" __global__ void nsx_init_kernel(const NsxDev d, const double* supply,
     if (art) atomicAdd((unsigned long long*)&ctl->art_with_flow, art);
 }
 
+// Warm start: arc state from the caller's tree flags; flows, node records, depth and the preorder array were copied in.
+extern "C" __global__ void nsx_init_warm_kernel(const NsxDev d, const double* supply, const uint8_t* in_tree, NsxCtl* ctl) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long art = 0;
+    for (int64_t a = g; a < d.ma; a += T) art += (unsigned long long)nsx_init_arc_warm(d, a, supply, in_tree);
+    if (g == 0) d.pi[0] = 0.0;
+    if (art) atomicAdd((unsigned long long*)&ctl->art_with_flow, art);
+}
+
 // Which compact cost encodings are exact for this instance: bit 0 set = some cost is not an
 // int32-valued integer, bit 1 set = some cost is not an int16-valued integer.
 extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, int64_t m, unsigned int* flags) {
@@ -1392,10 +1403,25 @@ static void nsx_choose_layout(int32_t n, unsigned int cost_flags, bool devex, Ns
 
 // Common implementation; `resident` = arc arrays are device pointers; probe_sweeps > 0 = sweep probe.
 static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_result* res, bool resident,
-                          int32_t probe_sweeps, const nsx_shard* shard = nullptr) {
+                          int32_t probe_sweeps, const nsx_shard* shard = nullptr, const nsx_warm_start* warm = nullptr) {
     Arena arena, inputs;
     int rc = nsx_validate(pb, opt, res);
     if (rc) return rc;
+    // warm start: lay the caller's tree out as preorder array + node records on the host (csrc/nsx_warm.h)
+    std::vector<NsxNode> w_node;
+    std::vector<int32_t> w_depth, w_order;
+    if (warm) {
+        if (resident || shard || probe_sweeps) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "warm start is a host-buffer, single-GPU entry point");
+        if (!warm->in_tree || !warm->flow || (warm->start_phase != 1 && warm->start_phase != 2))
+            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad warm start description");
+        int bad = nsx_warm_layout(pb->n_nodes, pb->n_arcs, pb->tail, pb->head, pb->supply, opt->tolerance, warm->in_tree,
+                                  w_node, w_depth, w_order);
+        if (bad) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, bad == -1 ? "warm start: in_tree must mark exactly n_nodes - 1 arcs"
+                                                                     : "warm start: the marked arcs do not span all nodes");
+        if (warm->start_phase == 2)
+            for (int64_t a = pb->n_arcs; a < pb->n_arcs + pb->n_nodes - 1; ++a)
+                if (warm->in_tree[a]) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "warm start: Phase 1 can only be skipped when no artificial arc is in the tree");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return nsx_fail(NSX_ERR_NO_DEVICE, "no CUDA device visible (the engine has no CPU fallback)");
@@ -1422,6 +1448,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         i_pert = inputs.plan((size_t)(m + 4) * 8); i_upper = inputs.plan((size_t)(m + 4) * 8);
     }
     size_t i_supply = inputs.plan((size_t)n * 8), i_flags = inputs.plan(16);
+    size_t i_wtree = warm ? inputs.plan((size_t)ma + 16) : 0;
     NSX_CUDA(inputs.commit());
     NsxKernelArgs ka;
     NsxDev& d = ka.d;
@@ -1504,6 +1531,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
 
     NsxCtl hctl;
     nsx_fill_ctl(hctl, opt, want_trace);
+    if (warm) { hctl.warm = 1; hctl.phase = warm->start_phase; }
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
     NSX_CUDA(cudaMemsetAsync(ka.slots, 0, sizeof(NsxSlot) * 1024, stream));
@@ -1548,7 +1576,17 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         int ib = (int)((m + n + 1023) / 1024);
         if (ib < 1) ib = 1;
         if (ib > info.sms * 8) ib = info.sms * 8;
-        nsx_init_kernel<<<ib, 1024, 0, stream>>>(d, d_supply, ka.ctl);
+        if (warm) {
+            uint8_t* d_wtree = inputs.at<uint8_t>(i_wtree);
+            NSX_CUDA(cudaMemcpyAsync(d_wtree, warm->in_tree, (size_t)ma, cudaMemcpyHostToDevice, stream));
+            NSX_CUDA(cudaMemcpyAsync(d.flow, warm->flow, (size_t)ma * 8, cudaMemcpyHostToDevice, stream));
+            NSX_CUDA(cudaMemcpyAsync(d.node, w_node.data(), (size_t)n * sizeof(NsxNode), cudaMemcpyHostToDevice, stream));
+            NSX_CUDA(cudaMemcpyAsync(d.depth, w_depth.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+            NSX_CUDA(cudaMemcpyAsync(d.order, w_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+            nsx_init_warm_kernel<<<ib, 1024, 0, stream>>>(d, d_supply, d_wtree, ka.ctl);
+        } else {
+            nsx_init_kernel<<<ib, 1024, 0, stream>>>(d, d_supply, ka.ctl);
+        }
         NSX_CUDA(cudaGetLastError());
     }
     void* kargs[] = {(void*)&ka};
@@ -1587,6 +1625,11 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
 
 extern "C" int nsx_solve(const nsx_problem* problem, const nsx_options* options, nsx_result* result) {
     return nsx_solve_impl(problem, options, result, false, 0);
+}
+extern "C" int nsx_solve_warm(const nsx_problem* problem, const nsx_options* options, const nsx_warm_start* warm,
+                              nsx_result* result) {
+    if (!warm) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null warm start");
+    return nsx_solve_impl(problem, options, result, false, 0, nullptr, warm);
 }
 extern "C" int nsx_solve_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result) {
     return nsx_solve_impl(problem_dev, options, result, true, 0);

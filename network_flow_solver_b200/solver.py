@@ -257,17 +257,21 @@ def solve_min_cost_flow(
 ) -> FlowResult:
     """Solve a minimum-cost flow problem on the GPU; drop-in for the reference call
     (solver.py:13-104).  Raises DeviceEngineError when the CUDA engine is unavailable."""
-    if warm_start_basis is not None:
-        raise SolverConfigurationError(
-            "warm_start_basis is not on the accelerated path yet (SURVEY.md section 8f row 3)."
-        )
     if progress_callback is not None:
         _log.info(
             "progress_callback is not invoked: the pivot loop is device-resident with no host "
             "round-trip per pivot"
         )
     cp, plan, options = prepare(problem, options, max_iterations, device=device)
-    raw = _capi.solve_canonical(cp, plan.engine)
+    warm = None
+    if warm_start_basis is not None:  # simplex.py:1494-1530; None = basis rejected, cold start
+        from .warm_start import apply_basis
+
+        _log.info("Attempting to apply warm-start basis")
+        warm = apply_basis(cp, warm_start_basis, options.tolerance)
+        if warm is None:
+            _log.info("Warm-start failed, performing cold start")
+    raw = _capi.solve_canonical(cp, plan.engine, warm=warm)
     result = finish(cp, raw, options, plan.scaling)
     if raw.status in (_capi.STATUS_OPTIMAL, _capi.STATUS_ITERATION_LIMIT):
         rate = (raw.degenerate_pivots / raw.iterations * 100) if raw.iterations > 0 else 0.0

@@ -51,6 +51,7 @@ typedef struct {
     double* flow;   /* [ma] */
     uint8_t* intree;
     uint8_t* touched;
+    uint8_t* stale; /* warm start only: the reference's residual mirrors still hold the cold-start flow of this arc */
     double* weight; /* [m] Devex weights as seen by pricing */
     /* nodes */
     int32_t* parent;
@@ -188,6 +189,46 @@ static void init_tree(ctx_t* c, const double* supply) {
         o->pdir[v] = (c->atail[v - 1] == 0) ? 1 : -1;
         link_child(o, 0, v);
     }
+}
+
+/* Warm start (simplex.py:740-1021): the caller supplies which arcs form the tree and every arc's flow; parent
+ * pointers come from a walk from the root over the tree arcs (TreeBasis.rebuild, basis.py:82-125). Returns 0, or
+ * -1 when the marked arcs do not span all nodes. Artificial arcs keep the geometry init_tree gave them. */
+static int init_tree_warm(ctx_t* c, const double* supply, const nsx_warm_start* w) {
+    oracle_t* o = &c->o;
+    init_tree(c, supply);
+    int64_t marked = 0;
+    for (int64_t a = 0; a < o->ma; ++a) { o->intree[a] = w->in_tree[a] ? 1 : 0; o->flow[a] = w->flow[a]; marked += o->intree[a]; }
+    if (marked != o->n - 1) return -1;
+    o->stale = malloc((size_t)o->ma + 1);
+    memcpy(o->stale, o->intree, (size_t)o->ma);
+    o->art_with_flow = 0;
+    for (int64_t a = o->m; a < o->ma; ++a) if (o->flow[a] > o->tol) o->art_with_flow++;
+    /* adjacency of the tree arcs (CSR) */
+    int64_t* start = calloc((size_t)o->n + 1, sizeof(int64_t));
+    int64_t* adj = malloc(sizeof(int64_t) * 2 * (size_t)(o->n > 1 ? o->n - 1 : 1));
+    for (int64_t a = 0; a < o->ma; ++a) if (o->intree[a]) { start[TAIL(c, a) + 1]++; start[HEAD(c, a) + 1]++; }
+    for (int32_t v = 0; v < o->n; ++v) start[v + 1] += start[v];
+    int64_t* fill = malloc(sizeof(int64_t) * (size_t)o->n);
+    for (int32_t v = 0; v < o->n; ++v) fill[v] = start[v];
+    for (int64_t a = 0; a < o->ma; ++a) if (o->intree[a]) { adj[fill[TAIL(c, a)]++] = a; adj[fill[HEAD(c, a)]++] = a; }
+    for (int32_t v = 0; v < o->n; ++v) { o->fchild[v] = o->nsib[v] = o->psib[v] = -1; o->parent[v] = -1; }
+    o->parent[0] = 0; o->pred[0] = -1; o->pdir[0] = 0;
+    int64_t sp = 0, seen = 1;
+    o->stack[sp++] = 0;
+    while (sp) {
+        int32_t u = o->stack[--sp];
+        for (int64_t k = start[u]; k < start[u + 1]; ++k) {
+            int64_t a = adj[k];
+            int32_t v = TAIL(c, a) == u ? HEAD(c, a) : TAIL(c, a);
+            if (v == u || o->parent[v] >= 0) continue;
+            o->parent[v] = u; o->pred[v] = (int32_t)a; o->pdir[v] = TAIL(c, a) == u ? 1 : -1;
+            link_child(o, u, v);
+            o->stack[sp++] = v; ++seen;
+        }
+    }
+    free(start); free(adj); free(fill);
+    return seen == o->n ? 0 : -1;
 }
 
 /* ---------------- pricing ---------------- */
@@ -468,9 +509,16 @@ static int pivot(ctx_t* c, int32_t e, int32_t dir, int want_weight, ostats_t* st
         if (k < nh) { int32_t x = o->path_h[k]; a = o->pred[x]; sign = o->pdir[x] < 0 ? 1 : -1; side = 1; pos = k; }
         else if (k < nh + nt) { pos = nt - 1 - (k - nh); int32_t x = o->path_t[pos]; a = o->pred[x]; sign = o->pdir[x] > 0 ? 1 : -1; side = 2; }
         else { a = e; sign = dir; side = 0; pos = -1; }
-        double r;
-        if (sign == 1) { double up = UPPER(c, a); r = isinf(up) ? INFINITY : up - o->flow[a]; }
-        else r = o->flow[a];
+        double r, fl = o->flow[a];
+        if (o->stale && o->stale[a]) { /* forward/backward_residuals are only refreshed for arcs of a pivot cycle
+                                          (simplex.py:1276-1283) and never after a warm start (simplex.py:728 is the only
+                                          full sync): the ratio test still sees the cold-start flow - 0 on a real arc,
+                                          |supply| on the artificial arc of a supply / demand node */
+            double up0 = UPPER(c, a);
+            fl = (a < o->m || isinf(up0)) ? 0.0 : up0;
+        }
+        if (sign == 1) { double up = UPPER(c, a); r = isinf(up) ? INFINITY : up - fl; }
+        else r = fl;
         if (r < theta - tol) { theta = r; leave = a; best = r; leave_side = side; leave_pos = pos; }
         else if (fabs(r - theta) <= tol) {
             if (r > best + tol || (fabs(r - best) <= tol && a < leave)) { leave = a; best = r; leave_side = side; leave_pos = pos; }
@@ -495,6 +543,7 @@ static int pivot(ctx_t* c, int32_t e, int32_t dir, int want_weight, ostats_t* st
         if (f < 0.0 - tol) { f = 0.0; o->touched[a] = 0; }
         if (!isinf(up) && f > up + tol) { f = up; o->touched[a] = 0; }
         o->flow[a] = f;
+        if (o->stale) o->stale[a] = 0;
         if (art) { int has = f > tol; if (had && !has) o->art_with_flow--; else if (!had && has) o->art_with_flow++; }
     }
     /* Devex weight := tree-path length, set by pricing before the pivot (simplex_pricing.py:350-352;
@@ -574,7 +623,11 @@ static int find_entering(ctx_t* c, const nsx_options* opt, int allow_zero, int32
     return devex_select(c, allow_zero, arc, dir, want_weight, priced);
 }
 
+int nsx_oracle_solve_warm(const nsx_problem* pb, const nsx_options* opt, const nsx_warm_start* warm, nsx_result* res, int nthreads);
 int nsx_oracle_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* res, int nthreads) {
+    return nsx_oracle_solve_warm(pb, opt, NULL, res, nthreads);
+}
+int nsx_oracle_solve_warm(const nsx_problem* pb, const nsx_options* opt, const nsx_warm_start* warm, nsx_result* res, int nthreads) {
     ctx_t cx; memset(&cx, 0, sizeof cx);
     oracle_t* o = &cx.o;
     o->n = pb->n_nodes; o->m = pb->n_arcs; o->ma = o->m + o->n - 1;
@@ -594,17 +647,24 @@ int nsx_oracle_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* 
     o->ftc = 0; o->ft_limit = opt->ft_update_limit; o->auto_block = opt->auto_block;
     o->tuner_total = o->tuner_deg = o->tuner_last = 0;
 
-    init_tree(&cx, pb->supply);
+    int bad_warm = 0;
+    if (warm) bad_warm = init_tree_warm(&cx, pb->supply, warm); else init_tree(&cx, pb->supply);
     ostats_t st; memset(&st, 0, sizeof st);
     int64_t total = 0, priced = 0, trace_len = 0;
     int status = NSX_STATUS_OPTIMAL;
     int64_t maxit = opt->max_iterations;
+    int64_t it = 0;
+    int32_t arc = -1, dir = 0; int ww = 0;
+    if (bad_warm) { status = -1; goto done; }
+    if (warm && warm->start_phase == 2) { /* simplex.py:1504-1513: no artificial arc in the tree, Phase 1 skipped */
+        res->phase1_iterations = 0;
+        res->artificial_with_flow = o->art_with_flow;
+        goto phase2;
+    }
 
     /* Phase 1 (simplex.py:1541-1554) */
     apply_phase_costs(&cx, 1);
     recompute_all(&cx);
-    int64_t it = 0;
-    int32_t arc = -1, dir = 0; int ww = 0;
     while (it < maxit) {
         if (!find_entering(&cx, opt, 1, &arc, &dir, &ww, &priced)) break;
         if (res->entering_trace && trace_len < opt->trace_capacity) res->entering_trace[trace_len] = arc * 2 + (dir < 0);
@@ -623,6 +683,7 @@ int nsx_oracle_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* 
         goto done;
     }
     /* Phase 2 (simplex.py:1626-1644) */
+phase2:
     {
         int64_t remaining = maxit - total; if (remaining < 0) remaining = 0;
         apply_phase_costs(&cx, 2);
@@ -663,11 +724,11 @@ done:
                                       (o->flow[i] > o->tol ? NSX_ARC_CAN_BWD : 0) | (o->touched[i] ? NSX_ARC_TOUCHED : 0));
         }
     }
-    free(o->tcost); free(o->flow); free(o->intree); free(o->touched); free(o->weight);
+    free(o->tcost); free(o->flow); free(o->intree); free(o->touched); free(o->weight); free(o->stale);
     free(o->parent); free(o->pred); free(o->pdir); free(o->depth); free(o->pi);
     free(o->fchild); free(o->nsib); free(o->psib); free(o->stack); free(o->path_h); free(o->path_t);
     free(cx.atail); free(cx.ahead); free(cx.aupper);
-    return 0;
+    return bad_warm ? -1 : 0;
 }
 
 int nsx_oracle_max_threads(void) {

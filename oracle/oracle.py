@@ -17,6 +17,7 @@ from network_flow_solver_b200._capi import (
     NsxOptions,
     NsxProblem,
     NsxResult,
+    NsxWarmStart,
     RawSolution,
 )
 from network_flow_solver_b200.canonical import CanonicalProblem
@@ -44,6 +45,10 @@ def _load():
             C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult), C.c_int,
         ]
         lib.nsx_oracle_solve.restype = C.c_int
+        lib.nsx_oracle_solve_warm.argtypes = [
+            C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxWarmStart), C.POINTER(NsxResult), C.c_int,
+        ]
+        lib.nsx_oracle_solve_warm.restype = C.c_int
         lib.nsx_oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -53,11 +58,18 @@ def max_threads() -> int:
     return int(_load().nsx_oracle_max_threads())
 
 
-def solve_canonical(cp: CanonicalProblem, opts: EngineOptions, threads: int = 1) -> RawSolution:
+def solve_canonical(cp: CanonicalProblem, opts: EngineOptions, threads: int = 1, warm=None) -> RawSolution:
     """Run the restatement on one canonical problem; `threads` parallelises the pricing sweep only
-    (order-preserving reduction, result independent of the thread count)."""
+    (order-preserving reduction, result independent of the thread count); `warm` = warm_start.WarmStart."""
     lib = _load()
     frame = CallFrame(cp, opts)
+    if warm is not None:
+        w = NsxWarmStart.of(warm)
+        rc = lib.nsx_oracle_solve_warm(C.byref(frame.problem), C.byref(frame.options), C.byref(w),
+                                       C.byref(frame.result), int(threads))
+        if rc != 0:
+            raise RuntimeError(f"nsx_oracle_solve_warm returned {rc}")
+        return frame.harvest()
     rc = lib.nsx_oracle_solve(C.byref(frame.problem), C.byref(frame.options),
                               C.byref(frame.result), int(threads))
     if rc != 0:

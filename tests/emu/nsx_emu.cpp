@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../network_flow_solver_b200/csrc/nsx_core.cuh"
+#include "../../network_flow_solver_b200/csrc/nsx_warm.h"
 
 namespace {
 
@@ -56,7 +57,7 @@ struct SerialSweep {
 
 }  // namespace
 
-extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* res) {
+static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, const nsx_warm_start* warm, nsx_result* res) {
     const int32_t n = pb->n_nodes;
     const int64_t m = pb->n_arcs, ma = m + n - 1;
     std::vector<int32_t> atail(n), ahead(n), depth(n), order(n), tmp(n), gph(n), gpt(n), garc2(2 * (size_t)n + 1);
@@ -85,11 +86,21 @@ extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_
     c.trace_cap = res->entering_trace ? opt->trace_capacity : 0;
     c.unbounded_arc = -1;
 
-    for (int64_t i = 0; i < m; ++i) nsx_init_real_arc(d, i);
     int64_t art = 0;
-    for (int32_t v = 0; v < n; ++v) {
-        nsx_init_node(d, v, pb->supply[v]);
-        if (v > 0 && flow[m + v - 1] > d.tol) art++;
+    if (warm) {  // same steps as nsx_solve_warm: host layout, copies, element-wise arc init
+        int bad = nsx_warm_layout(n, m, pb->tail, pb->head, pb->supply, d.tol, warm->in_tree, node, depth, order);
+        if (bad) return bad;
+        memcpy(flow.data(), warm->flow, (size_t)ma * 8);
+        for (int64_t a = 0; a < ma; ++a) art += nsx_init_arc_warm(d, a, pb->supply, warm->in_tree);
+        pi[0] = 0.0;
+        c.warm = 1;
+        c.phase = warm->start_phase == 2 ? 2 : 1;
+    } else {
+        for (int64_t i = 0; i < m; ++i) nsx_init_real_arc(d, i);
+        for (int32_t v = 0; v < n; ++v) {
+            nsx_init_node(d, v, pb->supply[v]);
+            if (v > 0 && flow[m + v - 1] > d.tol) art++;
+        }
     }
     c.art_with_flow = art;
 
@@ -119,6 +130,13 @@ extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_
     if (res->potential) memcpy(res->potential, pi.data(), (size_t)n * 8);
     if (res->state) memcpy(res->state, state.data(), ma);
     return 0;
+}
+
+extern "C" int nsx_emu_solve(const nsx_problem* pb, const nsx_options* opt, nsx_result* res) {
+    return nsx_emu_solve_impl(pb, opt, nullptr, res);
+}
+extern "C" int nsx_emu_solve_warm(const nsx_problem* pb, const nsx_options* opt, const nsx_warm_start* warm, nsx_result* res) {
+    return nsx_emu_solve_impl(pb, opt, warm, res);
 }
 
 // Consistency check of the preorder representation (used by tests after a solve is not possible
