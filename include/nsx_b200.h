@@ -34,6 +34,17 @@ extern "C" {
                                         reference's default "adaptive" strategy (simplex_pricing.py:545-639) runs in
                                         practice: candidate scan in the pivot CTA, top-100 refresh as a grid-wide sweep */
 
+/* structure-specific entering rules tried before `pricing` on every iteration; when one finds nothing the configured
+ * rule runs (NetworkSimplex._find_entering_arc, simplex.py:1058-1075; select_pivot_strategy,
+ * specialized_pivots.py:452-527).  Values of nsx_options.row_scan_first. */
+#define NSX_SPECIAL_NONE 0
+#define NSX_SPECIAL_ROW_SCAN 1      /* transportation: Dantzig-rule row scan, specialized_pivots.py:80-120 */
+#define NSX_SPECIAL_ASSIGNMENT 2    /* forward arcs only, a candidate replaces the incumbent when its reduced cost is
+                                       lower by MORE than the tolerance (sequential scan), specialized_pivots.py:179-209 */
+#define NSX_SPECIAL_MAX_FLOW 3      /* largest residual * |reduced cost|, first arc on ties, specialized_pivots.py:294-343 */
+#define NSX_SPECIAL_SHORTEST_PATH 4 /* the assignment scan restricted to forward arcs whose tail is reachable from the
+                                       source (nsx_options.node_mask) plus backward arcs, specialized_pivots.py:368-424 */
+
 /* solver outcome (FlowResult.status, data.py:269-322; UnboundedProblemError, simplex.py:1231-1246) */
 #define NSX_STATUS_OPTIMAL 0
 #define NSX_STATUS_INFEASIBLE 1          /* artificial flow left after Phase 1, simplex.py:1600-1624 */
@@ -81,8 +92,9 @@ typedef struct nsx_problem {
 
 typedef struct nsx_options {
     int32_t pricing;          /* NSX_PRICING_* */
-    int32_t row_scan_first;   /* 1: transportation row-scan rule tried first (specialized_pivots.py:80-120,
-                                 simplex.py:1060-1064); falls through to `pricing` when it finds nothing */
+    int32_t row_scan_first;   /* NSX_SPECIAL_*: 1 = transportation row-scan rule tried first (specialized_pivots.py:80-120,
+                                 simplex.py:1060-1064), 2..4 the other structure rules; all fall through to `pricing`
+                                 when they find nothing */
     int64_t block_size;       /* initial Devex block size (simplex_adaptive.py:70-96 when auto) */
     int32_t auto_block;       /* 1: x1.5 / x0.75 adaptation every 50 pivots (simplex_adaptive.py:98-151) */
     int32_t ft_update_limit;  /* Devex weights and pricing block reset on every (limit+1)-th tree change
@@ -92,6 +104,9 @@ typedef struct nsx_options {
     int64_t trace_capacity;   /* entries available in result->entering_trace (0 = no trace) */
     int32_t device;           /* CUDA device ordinal */
     uint32_t flags;           /* NSX_FLAG_* */
+    const uint8_t* node_mask; /* [n_nodes] host buffer, NSX_SPECIAL_SHORTEST_PATH only: 1 = node reachable from the
+                                 source over the real arcs (the nodes that carry a distance label in
+                                 ShortestPathPivotStrategy, specialized_pivots.py:426-450); NULL otherwise */
 } nsx_options;
 
 typedef struct nsx_result {

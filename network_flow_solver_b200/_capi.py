@@ -20,6 +20,8 @@ from .exceptions import DeviceEngineError
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
 PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
+# EngineOptions.row_scan_first: structure-specific rule tried before the configured one (NSX_SPECIAL_*)
+SPECIAL_NONE, SPECIAL_ROW_SCAN, SPECIAL_ASSIGNMENT, SPECIAL_MAX_FLOW, SPECIAL_SHORTEST_PATH = 0, 1, 2, 3, 4
 
 STATUS_OPTIMAL = 0
 STATUS_INFEASIBLE = 1
@@ -64,6 +66,7 @@ class NsxOptions(C.Structure):
         ("trace_capacity", C.c_int64),
         ("device", C.c_int32),
         ("flags", C.c_uint32),
+        ("node_mask", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -137,11 +140,16 @@ class EngineOptions:
     trace_capacity: int = 0
     device: int = 0
     flags: int = 0
+    node_mask: object = None  # uint8[n_nodes], SPECIAL_SHORTEST_PATH only (kept alive by this record)
 
     def to_c(self) -> NsxOptions:
+        mask = None
+        if self.node_mask is not None:
+            self.node_mask = np.ascontiguousarray(self.node_mask, dtype=np.uint8)
+            mask = _ptr(self.node_mask, _p_u8)
         return NsxOptions(
             int(self.pricing),
-            int(bool(self.row_scan_first)),
+            int(self.row_scan_first),  # SPECIAL_*: False/True = none / transportation row scan
             int(self.block_size),
             int(bool(self.auto_block)),
             int(self.ft_update_limit),
@@ -150,6 +158,7 @@ class EngineOptions:
             int(self.trace_capacity),
             int(self.device),
             int(self.flags),
+            mask,
         )
 
 

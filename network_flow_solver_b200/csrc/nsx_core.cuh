@@ -108,6 +108,7 @@ struct NsxDev {
     int32_t scan_walk;  // node records are in shared memory: find the cycle by a parallel ancestor scan
     uint16_t* par16;    // optional shared-memory mirror of the parent pointers (parent - 1), for the cycle walk
     uint32_t* root_bits;  // bit v set: the parent of v is the root (the one value parent - 1 cannot encode)
+    const uint8_t* node_mask;  // [n] NSX_SPECIAL_SHORTEST_PATH: node reachable from the source (HBM), else null
     int32_t lazy_pos;   // preorder positions are updated lazily through the shift log (large trees in HBM)
     int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
 };
@@ -172,6 +173,7 @@ struct NsxPivotScratch {
     // between its old and new place; instead of rewriting the position of each shifted node, the
     // shift is logged as "positions in [a, b) move by d".  A node stores (stamp << 24 | position):
     // its position is current after replaying log entries stamp .. log_len-1.
+    int32_t sp_any;            // structure-rule scan: some arc of the current chunk qualifies
     int32_t log_len;
     int32_t pos_mask;          // 0xffffff with lazy positions (stamp in the top byte), all ones otherwise
     int32_t log_a[NSX_LOG_CAP], log_b[NSX_LOG_CAP], log_d[NSX_LOG_CAP];
@@ -951,6 +953,71 @@ NSX_FN void nsx_cl_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotS
     NSX_SYNC();
 }
 
+// Structure-specific entering rules (specialized_pivots.py:150-450; c.row_scan_first = NSX_SPECIAL_ASSIGNMENT /
+// MAX_FLOW / SHORTEST_PATH).  The assignment and shortest-path rules are SEQUENTIAL scans - a later arc replaces the
+// incumbent only if its reduced cost is lower by more than the tolerance - so the result depends on the scan order and
+// is not a reduction.  The pivot CTA walks the arcs in chunks of NSX_SP_CHUNK: all threads evaluate one chunk in
+// parallel (reduced cost, eligibility, key), one thread folds the chunk in index order exactly like the reference's
+// loop, and chunks without any qualifying arc (the common case after the first pivots) skip the fold.
+//   assignment    (:179-209)  forward arcs:  rc < best - tol                      -> best = rc
+//   shortest path (:368-424)  forward arcs with a labelled tail (node_mask): same; backward arcs: -rc < best - tol
+//   max flow      (:294-343)  merit = residual * |rc| in either direction, strictly larger wins (first arc on ties)
+// Returns arc*2 + (dir<0) or -1 in *out_arc2; -1 sends the driver on to the configured strategy (simplex.py:1066-1075).
+#define NSX_SP_CHUNK 1024
+NSX_FN void nsx_special_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotScratch& s) {
+    const double tol = d.tol;
+    const int32_t rule = c.row_scan_first;
+    int32_t best = -1;        // thread 0 carries the incumbent across chunks
+    double best_key = rule == NSX_SPECIAL_MAX_FLOW ? -NSX_INF : 0.0;
+    NSX_SYNC();
+    NSX_SINGLE { s.sp_any = 0; }
+    NSX_SYNC();
+    for (int64_t base = 0; base < d.m; base += NSX_SP_CHUNK) {
+        const int64_t cnt = d.m - base < NSX_SP_CHUNK ? d.m - base : NSX_SP_CHUNK;
+        NSX_PAR_FOR(k, 0, cnt) {
+            const int64_t i = base + k;
+            const uint8_t st = d.state[i];
+            int32_t code = 0;
+            double key = 0.0;
+            if (!(st & NSX_ARC_IN_TREE)) {
+                const int32_t tl = d.tail[i];
+                const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[tl]), d.pi[d.head[i]]);
+                if ((st & NSX_ARC_CAN_FWD) && rc < -tol) {
+                    if (rule == NSX_SPECIAL_MAX_FLOW) {
+                        const double up = d.upper[i];
+                        const double fr = nsx_isinf(up) ? NSX_INF : NSX_SUB(up, d.flow[i]);
+                        code = 1; key = NSX_MUL(fr, fabs(rc));
+                    } else if (rule == NSX_SPECIAL_ASSIGNMENT || d.node_mask[tl]) {
+                        code = 1; key = rc;
+                    }
+                } else if ((st & NSX_ARC_CAN_BWD) && rc > tol) {
+                    if (rule == NSX_SPECIAL_MAX_FLOW) { code = 2; key = NSX_MUL(d.flow[i], fabs(rc)); }
+                    else if (rule == NSX_SPECIAL_SHORTEST_PATH) { code = 2; key = -rc; }
+                }
+            }
+            s.arc2[k] = code;
+            s.res[k] = key;
+            if (code) s.sp_any = 1;
+        }
+        NSX_SYNC();
+        NSX_SINGLE {
+            if (s.sp_any) {
+                s.sp_any = 0;
+                for (int64_t k = 0; k < cnt; ++k) {
+                    const int32_t code = s.arc2[k];
+                    if (!code) continue;
+                    const double key = s.res[k];
+                    const bool take = rule == NSX_SPECIAL_MAX_FLOW ? key > best_key : key < NSX_SUB(best_key, tol);
+                    if (take) { best_key = key; best = (int32_t)(base + k) * 2 + (code == 2 ? 1 : 0); }
+                }
+            }
+        }
+        NSX_SYNC();
+    }
+    NSX_SINGLE { *out_arc2 = best; c.arcs_priced += d.m; }
+    NSX_SYNC();
+}
+
 // Block-size adaptation after each pivot (simplex_adaptive.py:98-151). Single thread.
 NSX_FN void nsx_adapt_block(NsxCtl& c, int64_t m, int64_t iteration) {
     if (!c.auto_block) return;
@@ -1114,9 +1181,11 @@ enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2, NSX_CMD_DANTZIG
 enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_ZERO = 4, NSX_ST_DEVEX_ZERO = 5,
        // candidate list (CandidateListPricing.select_entering_arc, simplex_pricing.py:418-458): quick scan of the
        // list, scan after the (optional) periodic refresh, forced refresh, scan after the forced refresh
-       NSX_ST_CL_QUICK = 6, NSX_ST_CL_REFRESH = 7, NSX_ST_CL_MAIN = 8, NSX_ST_CL_FORCED = 9, NSX_ST_CL_LAST = 10 };
+       NSX_ST_CL_QUICK = 6, NSX_ST_CL_REFRESH = 7, NSX_ST_CL_MAIN = 8, NSX_ST_CL_FORCED = 9, NSX_ST_CL_LAST = 10,
+       NSX_ST_SPECIAL = 11 };  // structure-specific rule (assignment / max flow / shortest path) before the configured one
 enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4,
-       NSX_ACT_CL_SCAN = 5 };  // CL_SCAN: the pivot CTA evaluates the <= 100 listed arcs itself, no sweep
+       NSX_ACT_CL_SCAN = 5,    // CL_SCAN: the pivot CTA evaluates the <= 100 listed arcs itself, no sweep
+       NSX_ACT_SPECIAL_SCAN = 6 };  // the pivot CTA runs nsx_special_scan over all arcs
 
 struct NsxCmd {       // what every CTA does next
     int32_t kind;
@@ -1181,6 +1250,7 @@ NSX_FN void nsx_drv_cl_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAc
 // top of an iteration: first sweep command, or phase end when the budget is used up
 NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
     if (!v.final_check && c.it >= v.budget) { act.kind = NSX_ACT_PHASE_END; return; }
+    if (c.row_scan_first >= NSX_SPECIAL_ASSIGNMENT) { v.stage = NSX_ST_SPECIAL; act.kind = NSX_ACT_SPECIAL_SCAN; return; }
     act.kind = NSX_ACT_SWEEP;
     if (c.row_scan_first || c.pricing == NSX_PRICING_DANTZIG) {
         v.stage = c.row_scan_first ? NSX_ST_ROWSCAN : NSX_ST_DANTZIG;
@@ -1233,6 +1303,20 @@ NSX_FN void nsx_drv_on_scan(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, NsxCm
     } else {  // NSX_ST_CL_LAST
         if (arc2 >= 0) { nsx_drv_choose(c, v, act, arc2, 0, trace); return; }
         nsx_drv_none(c, v, act);
+    }
+}
+// after nsx_special_scan: pivot on its arc, or hand over to the configured strategy (simplex.py:1061-1075)
+NSX_FN void nsx_drv_on_special(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
+    if (arc2 >= 0) { nsx_drv_choose(c, v, act, arc2, 0, trace); return; }
+    act.kind = NSX_ACT_SWEEP;
+    if (c.pricing == NSX_PRICING_DANTZIG) {
+        v.stage = NSX_ST_DANTZIG;
+        cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
+        cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+    } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
+        nsx_drv_cl_begin(c, v, m, cmd, act);
+    } else {
+        nsx_drv_devex_begin(c, v, m, cmd);
     }
 }
 NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
@@ -1344,6 +1428,9 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         } else if (kind == NSX_ACT_CL_SCAN) {
             nsx_cl_scan(d, c, &L.cl_arc2, s, (c.phase == 1) && !L.drv.final_check);
             NSX_SINGLE { nsx_drv_on_scan(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }
+        } else if (kind == NSX_ACT_SPECIAL_SCAN) {
+            nsx_special_scan(d, c, &L.cl_arc2, s);
+            NSX_SINGLE { nsx_drv_on_special(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }
         } else if (kind == NSX_ACT_PIVOT) {
             int32_t rc = nsx_pivot(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
             if (c.need_wfill) {  // Devex epoch tags wrapped: physically reset the weights

@@ -1323,6 +1323,10 @@ static int nsx_validate(const nsx_problem* p, const nsx_options* o, const nsx_re
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown pricing rule");
     if (o->max_iterations < 0 || !(o->tolerance > 0) || o->ft_update_limit <= 0)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad option value");
+    if (o->row_scan_first < NSX_SPECIAL_NONE || o->row_scan_first > NSX_SPECIAL_SHORTEST_PATH)
+        return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown structure-specific rule (nsx_options.row_scan_first)");
+    if (o->row_scan_first == NSX_SPECIAL_SHORTEST_PATH && !o->node_mask)
+        return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "the shortest-path rule needs nsx_options.node_mask");
     return 0;
 }
 
@@ -1449,6 +1453,8 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     }
     size_t i_supply = inputs.plan((size_t)n * 8), i_flags = inputs.plan(16);
     size_t i_wtree = warm ? inputs.plan((size_t)ma + 16) : 0;
+    const bool want_mask = opt->row_scan_first == NSX_SPECIAL_SHORTEST_PATH;
+    size_t i_mask = want_mask ? inputs.plan((size_t)n + 16) : 0;
     NSX_CUDA(inputs.commit());
     NsxKernelArgs ka;
     NsxDev& d = ka.d;
@@ -1470,6 +1476,12 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     unsigned int* d_flags = inputs.at<unsigned int>(i_flags);
     NSX_CUDA(cudaMemcpyAsync(d_supply, pb->supply, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(d_flags, 0, 16, stream));
+    d.node_mask = nullptr;
+    if (want_mask) {
+        uint8_t* d_mask = inputs.at<uint8_t>(i_mask);
+        NSX_CUDA(cudaMemcpyAsync(d_mask, opt->node_mask, (size_t)n, cudaMemcpyHostToDevice, stream));
+        d.node_mask = d_mask;
+    }
     const int util_blocks = info.sms * 8;
     if (m > 0) {
         nsx_classify_costs_kernel<<<util_blocks, 256, 0, stream>>>(d.pert, m, d_flags);
@@ -1520,6 +1532,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         if (shard->world < 1 || shard->world > NSX_MAX_WORLD || shard->rank < 0 || shard->rank >= shard->world || !shard->mailboxes) {
             arena.release(); inputs.release();
             return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad shard description");
+        }
+        if (shard->world > 1 && opt->row_scan_first >= NSX_SPECIAL_ASSIGNMENT) {
+            arena.release(); inputs.release();
+            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "structure-specific pivot rules run inside one pivot CTA and are not available in arc-sharded solves");
         }
         if (shard->world > 1 && opt->pricing == NSX_PRICING_CANDIDATE_LIST) {
             arena.release(); inputs.release();
@@ -1690,6 +1706,8 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     Arena arena, inputs;
     if (count < 0 || (count > 0 && (!problems || !results)) || !opt) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
     if (count == 0) return 0;
+    if (opt->row_scan_first == NSX_SPECIAL_SHORTEST_PATH)
+        return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "the shortest-path rule needs a per-instance node mask; batches share one option record");
     for (int64_t i = 0; i < count; ++i) {
         int rc = nsx_validate(&problems[i], opt, &results[i]);
         if (rc) return rc;
@@ -1759,6 +1777,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
+        d.node_mask = nullptr;
         d.lazy_pos = (n < (1u << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0; d.log_cap = 32;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);

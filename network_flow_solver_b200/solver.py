@@ -17,7 +17,10 @@ import numpy as np
 
 from . import _capi
 from .canonical import (
+    NET_ASSIGNMENT,
     NET_GENERAL,
+    NET_MAX_FLOW,
+    NET_SHORTEST_PATH,
     NET_TRANSPORTATION,
     PERTURB_EPS_BASE,
     CanonicalProblem,
@@ -45,6 +48,59 @@ class ResolvedPlan:
     strategy: str
     engine: _capi.EngineOptions
     scaling: object = None  # scaling.ScalingFactors when the instance was rescaled before the solve
+
+
+def reachable_from(n_nodes: int, tail: np.ndarray, head: np.ndarray, source: int) -> np.ndarray:
+    """uint8[n_nodes]: 1 for every node reachable from `source` along tail -> head (frontier-at-a-time BFS)."""
+    order = np.argsort(tail, kind="stable")
+    heads = np.asarray(head)[order]
+    start = np.searchsorted(np.asarray(tail)[order], np.arange(n_nodes + 1))
+    mask = np.zeros(n_nodes, dtype=np.uint8)
+    mask[source] = 1
+    frontier = np.asarray([source], dtype=np.int64)
+    while frontier.size:
+        lo, cnt = start[frontier], start[frontier + 1] - start[frontier]
+        total = int(cnt.sum())
+        if total == 0:
+            break
+        offs = np.arange(total) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        nxt = heads[np.repeat(lo, cnt) + offs]
+        nxt = np.unique(nxt[mask[nxt] == 0])
+        mask[nxt] = 1
+        frontier = nxt.astype(np.int64)
+    return mask
+
+
+def special_rule(cp: CanonicalProblem, tol: float) -> tuple[int, np.ndarray | None]:
+    """Mirror of select_pivot_strategy (specialized_pivots.py:452-527): which structure-specific entering rule runs before
+    the configured one, and the node mask the shortest-path rule needs.  Supplies are the shifted ones (node_supply after
+    _build_arcs), the tolerance is the solver's."""
+    kind = cp.network_type
+    supply = np.asarray(cp.supply, dtype=np.float64)
+    if kind == NET_GENERAL:
+        return _capi.SPECIAL_NONE, None
+    if kind == NET_TRANSPORTATION:
+        return _capi.SPECIAL_ROW_SCAN, None
+    if kind == NET_ASSIGNMENT:
+        return _capi.SPECIAL_ASSIGNMENT, None
+    if kind == NET_MAX_FLOW:  # first supply node, then first demand node, in index order (:487-499)
+        src = np.flatnonzero(supply[1:] > tol)
+        snk = np.flatnonzero(supply[1:] < -tol)
+        return (_capi.SPECIAL_MAX_FLOW if src.size and snk.size else _capi.SPECIAL_NONE), None
+    if kind == NET_SHORTEST_PATH:  # first node with supply +1, then first OTHER node with supply -1 (:501-516)
+        src = np.flatnonzero(np.abs(supply[1:] - 1.0) <= tol)
+        if src.size:
+            s = int(src[0]) + 1
+            snk = [v for v in (np.flatnonzero(np.abs(supply[1:] + 1.0) <= tol) + 1).tolist() if v != s]
+            if snk:
+                return _capi.SPECIAL_SHORTEST_PATH, reachable_from(cp.n_nodes, cp.tail, cp.head, s)
+        return _capi.SPECIAL_NONE, None
+    raise SolverConfigurationError(
+        f"detected network type '{kind}': the reference's rule for it (BipartiteMatchingPivotStrategy, "
+        f"specialized_pivots.py:212-273) walks Python sets of node indices built from sets of node-id strings, so the arc "
+        f"it picks depends on PYTHONHASHSEED; there is no sequence to reproduce and it is not on the accelerated path "
+        f"(SURVEY.md section 8f row 4)."
+    )
 
 
 def resolve_plan(
@@ -91,16 +147,7 @@ def resolve_plan(
         raise SolverConfigurationError(
             f"Unknown pricing strategy '{strategy}'. Valid options: 'devex', 'dantzig', 'candidate_list', 'adaptive'."
         )
-    if cp.network_type == NET_TRANSPORTATION:
-        row_scan = True
-    elif cp.network_type == NET_GENERAL:
-        row_scan = False
-    else:
-        raise SolverConfigurationError(
-            f"detected network type '{cp.network_type}': the reference overrides pricing with a "
-            f"specialised pivot rule here (specialized_pivots.py:150-450) that is outside the "
-            f"accelerated path (SURVEY.md section 2 row 7)."
-        )
+    row_scan, node_mask = special_rule(cp, options.tolerance)
     auto = options.block_size is None or isinstance(options.block_size, str)
     block = initial_block_size(cp.n_arcs) if auto else int(options.block_size)
     if max_iterations is None:
@@ -119,6 +166,7 @@ def resolve_plan(
         trace_capacity=trace_capacity,
         device=device,
         flags=flags,
+        node_mask=node_mask,
     )
     return ResolvedPlan(strategy=strategy, engine=eng)
 

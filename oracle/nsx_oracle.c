@@ -265,6 +265,54 @@ static void dantzig_range(const ctx_t* c, int64_t a, int64_t b, cand_t* best, ca
     }
 }
 
+/* Structure-specific entering rules (specialized_pivots.py). All scan the real arcs in index order with the tree cost
+ * of the current phase and return 0 when nothing qualifies (the configured strategy then runs, simplex.py:1066-1075). */
+/* AssignmentPivotStrategy.find_entering_arc_min_cost (specialized_pivots.py:179-209): forward direction only; a later
+ * arc replaces the incumbent only when it is better by more than the tolerance. */
+static int assignment_select(const ctx_t* c, int32_t* arc, int32_t* dir) {
+    const oracle_t* o = &c->o;
+    const double tol = o->tol;
+    double best_rc = 0.0; int found = 0;
+    for (int64_t i = 0; i < o->m; ++i) {
+        if (o->intree[i]) continue;
+        double rc = rc_of(c, i, o->tcost[i]);
+        if (fwd_res(c, i) > tol && rc < best_rc - tol) { best_rc = rc; *arc = (int32_t)i; *dir = 1; found = 1; }
+    }
+    return found;
+}
+/* MaxFlowPivotStrategy.find_entering_arc (specialized_pivots.py:294-343): merit = residual * |rc|, strictly larger wins. */
+static int maxflow_select(const ctx_t* c, int32_t* arc, int32_t* dir) {
+    const oracle_t* o = &c->o;
+    const double tol = o->tol;
+    double best = -INFINITY; int found = 0;
+    for (int64_t i = 0; i < o->m; ++i) {
+        if (o->intree[i]) continue;
+        double rc = rc_of(c, i, o->tcost[i]);
+        double fr = fwd_res(c, i), br = o->flow[i];
+        if (fr > tol && rc < -tol) { double merit = fr * fabs(rc); if (merit > best) { best = merit; *arc = (int32_t)i; *dir = 1; found = 1; } }
+        if (br > tol && rc > tol) { double merit = br * fabs(rc); if (merit > best) { best = merit; *arc = (int32_t)i; *dir = -1; found = 1; } }
+    }
+    return found;
+}
+/* ShortestPathPivotStrategy.find_entering_arc (specialized_pivots.py:368-424). The distance labels only ever decide
+ * "does the tail have a label"; labels are seeded by a BFS from the source over all real arcs (:426-450) and a head gets
+ * one when its tail has one, so the labelled set is the set reachable from the source for the whole solve: mask[]. */
+static int shortest_path_select(const ctx_t* c, const uint8_t* mask, int32_t* arc, int32_t* dir) {
+    const oracle_t* o = &c->o;
+    const double tol = o->tol;
+    double best_rc = 0.0; int found = 0;
+    for (int64_t i = 0; i < o->m; ++i) {
+        if (o->intree[i]) continue;
+        double rc = rc_of(c, i, o->tcost[i]);
+        double fr = fwd_res(c, i), br = o->flow[i];
+        if (fr > tol && rc < -tol) {
+            if (mask[o->tail_r[i]] && rc < best_rc - tol) { best_rc = rc; *arc = (int32_t)i; *dir = 1; found = 1; }
+        }
+        if (br > tol && rc > tol && -rc < best_rc - tol) { best_rc = -rc; *arc = (int32_t)i; *dir = -1; found = 1; }
+    }
+    return found;
+}
+
 static int dantzig_select(const ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir) {
     const oracle_t* o = &c->o;
     int T = o->nthreads > 1 && o->m >= 65536 ? o->nthreads : 1;
@@ -616,7 +664,12 @@ static int find_entering(ctx_t* c, const nsx_options* opt, int allow_zero, int32
     *want_weight = 0;
     if (opt->row_scan_first) { /* simplex.py:1060-1064 */
         *priced += o->m;
-        if (dantzig_select(c, 0, arc, dir)) return 1;
+        int hit;
+        if (opt->row_scan_first == NSX_SPECIAL_ASSIGNMENT) hit = assignment_select(c, arc, dir);
+        else if (opt->row_scan_first == NSX_SPECIAL_MAX_FLOW) hit = maxflow_select(c, arc, dir);
+        else if (opt->row_scan_first == NSX_SPECIAL_SHORTEST_PATH) hit = opt->node_mask ? shortest_path_select(c, opt->node_mask, arc, dir) : 0;
+        else hit = dantzig_select(c, 0, arc, dir);
+        if (hit) return 1;
     }
     if (opt->pricing == NSX_PRICING_DANTZIG) { *priced += o->m; return dantzig_select(c, allow_zero, arc, dir); }
     if (opt->pricing == NSX_PRICING_CANDIDATE_LIST) return cl_select(c, allow_zero, arc, dir, priced);

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from helpers import assert_matches_reference
-from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, _capi
+from network_flow_solver_b200 import SolverOptions, _capi
 from network_flow_solver_b200.canonical import canonicalize
 from network_flow_solver_b200.dimacs import (lexicographic_ranks, load_dimacs_canonical, parse_dimacs_file,
                                              parse_dimacs_string, write_dimacs)
@@ -78,17 +78,15 @@ def solvable_runs():
     return out
 
 
+STRUCTURE_RULES = ("assignment", "max_flow", "shortest_path")  # the reference runs a structure-specific rule there
+
+
 def run_case(name, i, solve):
     case, run = CASES[name], CASES[name]["runs"][i]
     problem = parse_dimacs_string(case["text"])
     options = SolverOptions(**run["options"])
-    if run["network_type"] == "assignment":
-        # the reference switches to its assignment pivot rule here (specialized_pivots.py:150-250): outside the
-        # accelerated scope, and the drop-in says so instead of running a different rule
-        with pytest.raises(SolverConfigurationError):
-            prepare(problem, options)
-        return
     cp, plan, options = prepare(problem, options, trace_capacity=1 << 16)
+    assert (plan.engine.row_scan_first >= _capi.SPECIAL_ASSIGNMENT) == (run["network_type"] in STRUCTURE_RULES)
     assert_matches_reference(run, cp, solve(cp, plan.engine), options)
 
 
@@ -97,9 +95,24 @@ def test_oracle_reproduces_reference_on_dimacs_instances(name, i):
     run_case(name, i, lambda cp, eng: oracle.solve_canonical(cp, eng))
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("name,i", solvable_runs())
+def test_emulated_device_core_reproduces_reference_on_dimacs_instances(name, i):
+    from emu import emu
+
+    run_case(name, i, lambda cp, eng: emu.solve_canonical(cp, eng))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,i", [r for r in solvable_runs() if CASES[r[0]]["runs"][r[1]]["network_type"] not in STRUCTURE_RULES])
 def test_engine_reproduces_reference_on_dimacs_instances(name, i):
+    run_case(name, i, lambda cp, eng: _capi.solve_canonical(cp, eng))
+
+
+@pytest.mark.gpu
+@pytest.mark.gpu_unverified
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("name,i", [r for r in solvable_runs() if CASES[r[0]]["runs"][r[1]]["network_type"] in STRUCTURE_RULES])
+def test_engine_reproduces_reference_on_dimacs_instances_with_structure_rules(name, i):
     run_case(name, i, lambda cp, eng: _capi.solve_canonical(cp, eng))
 
 

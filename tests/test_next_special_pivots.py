@@ -1,0 +1,93 @@
+"""Scope row SURVEY.md section 8f-4 (third part): the structure-specific entering rules the reference switches on by
+itself when it recognises an assignment, max-flow or shortest-path instance (specializations.py:187-288,
+specialized_pivots.py:150-450, wiring simplex.py:259-261,1058-1075).  Vectors recorded from the unmodified reference
+(tests/golden/make_special_golden.py), including its own failure modes on these classes (zero-cost max-flow instances end
+"infeasible" / at the iteration limit because the artificial penalty max|c|*(N+2) is 0).  CPU: oracle and the emulated
+device core; GPU: the CUDA engine."""
+
+import gzip
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from emu import emu
+from helpers import assert_matches_reference, rebuild_problem
+from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, _capi, build_problem, solve_min_cost_flow
+from network_flow_solver_b200.solver import prepare, reachable_from
+from oracle import oracle
+
+DOC = json.loads(gzip.open(Path(__file__).resolve().parent / "golden" / "next" / "special_pivots.json.gz", "rb").read().decode())
+CASES = {c["name"]: c for c in DOC["cases"]}
+RUNS = [(c["name"], i) for c in DOC["cases"] for i in range(len(c["runs"]))]
+RULE = {"assignment": _capi.SPECIAL_ASSIGNMENT, "max_flow": _capi.SPECIAL_MAX_FLOW, "shortest_path": _capi.SPECIAL_SHORTEST_PATH}
+
+
+def setup(name, i):
+    case, run = CASES[name], CASES[name]["runs"][i]
+    cp, plan, options = prepare(rebuild_problem(case["problem"]), SolverOptions(**run["options"]), run.get("max_iterations"),
+                                trace_capacity=1 << 16)
+    return run, cp, plan, options
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_structure_detection_and_rule_choice(name):
+    run, cp, plan, options = setup(name, 0)
+    kind = name.rsplit("_", 10)[0]
+    kind = "assignment" if name.startswith("assignment") else "max_flow" if name.startswith("max_flow") else "shortest_path"
+    assert cp.network_type == kind == run.get("network_type", kind)
+    assert plan.engine.row_scan_first == RULE[kind]
+    assert (plan.engine.node_mask is not None) == (kind == "shortest_path")
+    if kind == "shortest_path":  # some nodes are cut off from the source on purpose: the mask is not all-ones
+        assert 0 < int(plan.engine.node_mask[1:].sum()) < cp.n_nodes - 1
+
+
+def test_reachability_mask():
+    tail, head = np.array([1, 2, 2, 4, 5]), np.array([2, 3, 1, 2, 5])
+    assert reachable_from(6, tail, head, 1).tolist() == [0, 1, 1, 1, 0, 0]
+    assert reachable_from(6, tail, head, 4).tolist() == [0, 1, 1, 1, 1, 0]
+    assert reachable_from(6, tail, head, 3).tolist() == [0, 0, 0, 1, 0, 0]
+
+
+def test_bipartite_matching_rule_is_refused_loudly():
+    nodes = [{"id": "a", "supply": 1.0}, {"id": "b", "supply": 1.0}, {"id": "x", "supply": -1.0}, {"id": "y", "supply": 0.0},
+             {"id": "z", "supply": -1.0}]
+    arcs = [{"tail": "a", "head": "x", "capacity": 1.0, "cost": 1.0}, {"tail": "b", "head": "y", "capacity": 1.0, "cost": 1.0},
+            {"tail": "y", "head": "z", "capacity": 1.0, "cost": 1.0}, {"tail": "x", "head": "b", "capacity": 1.0, "cost": 2.0}]
+    problem = build_problem(nodes, arcs, directed=True, tolerance=1e-6)
+    with pytest.raises(SolverConfigurationError, match="PYTHONHASHSEED"):
+        prepare(problem, SolverOptions())
+
+
+@pytest.mark.parametrize("name,i", RUNS)
+def test_oracle_matches_reference(name, i):
+    run, cp, plan, options = setup(name, i)
+    assert_matches_reference(run, cp, oracle.solve_canonical(cp, plan.engine), options)
+
+
+@pytest.mark.parametrize("name,i", RUNS)
+def test_emulated_device_core_matches_reference(name, i):
+    run, cp, plan, options = setup(name, i)
+    assert_matches_reference(run, cp, emu.solve_canonical(cp, plan.engine), options)
+
+
+@pytest.mark.gpu
+@pytest.mark.gpu_unverified
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("name,i", RUNS)
+def test_engine_matches_reference(name, i):
+    run, cp, plan, options = setup(name, i)
+    assert_matches_reference(run, cp, _capi.solve_canonical(cp, plan.engine), options)
+
+
+@pytest.mark.gpu
+@pytest.mark.gpu_unverified
+@pytest.mark.timeout(300, method="thread")
+def test_public_api_picks_the_rule_by_itself(capsys):
+    for name in ("assignment_16", "max_flow_48_unit_cost", "shortest_path_96"):
+        case = CASES[name]
+        run = case["runs"][3]  # default options apart from auto_scale
+        result = solve_min_cost_flow(rebuild_problem(case["problem"]), SolverOptions(**run["options"]))
+        assert (result.status, result.iterations, result.objective) == (run["status"], run["iterations"], run["objective"])
+        assert result.flows == {(a, b): v for a, b, v in run["flows"]}
