@@ -34,6 +34,12 @@ extern "C" {
                                         reference's default "adaptive" strategy (simplex_pricing.py:545-639) runs in
                                         practice: candidate scan in the pivot CTA, top-100 refresh as a grid-wide sweep */
 
+#define NSX_PRICING_DEVEX_LOOP 3 /* DevexPricing.select_entering_arc with use_vectorized_pricing=False (simplex_pricing.py:
+                                    205-269): same blocks, weights and reset cadence as NSX_PRICING_DEVEX, but a sequential
+                                    scan - tree cost of the current phase, a later arc wins only when its merit is larger by
+                                    more than the tolerance, first zero-reduced-cost arc of the block, the block pointer
+                                    advances after a zero pick, no exclusion of the last degenerate arc */
+
 /* structure-specific entering rules tried before `pricing` on every iteration; when one finds nothing the configured
  * rule runs (NetworkSimplex._find_entering_arc, simplex.py:1058-1075; select_pivot_strategy,
  * specialized_pivots.py:452-527).  Values of nsx_options.row_scan_first. */

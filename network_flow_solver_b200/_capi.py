@@ -20,6 +20,7 @@ from .exceptions import DeviceEngineError
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
 PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
+PRICING_DEVEX_LOOP = 3  # use_vectorized_pricing=False: the sequential Devex block scan (simplex_pricing.py:205-269)
 # EngineOptions.row_scan_first: structure-specific rule tried before the configured one (NSX_SPECIAL_*)
 SPECIAL_NONE, SPECIAL_ROW_SCAN, SPECIAL_ASSIGNMENT, SPECIAL_MAX_FLOW, SPECIAL_SHORTEST_PATH = 0, 1, 2, 3, 4
 

@@ -1018,6 +1018,65 @@ NSX_FN void nsx_special_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxP
     NSX_SYNC();
 }
 
+// Loop-based Devex block scan (DevexPricing.select_entering_arc with use_vectorized_pricing=False,
+// simplex_pricing.py:205-269) over [lo, hi): like nsx_special_scan a sequential rule - a later arc replaces the
+// incumbent only when its merit rc^2/w is larger by MORE than the tolerance (_is_better_candidate, :294-308, in ascending
+// index order) - evaluated chunk-parallel and folded in order by one thread.  Differences from the vectorised search
+// (nsx_price_devex): tree cost of the current phase instead of the perturbed Phase-2 cost, forward tested before
+// backward per arc, the FIRST zero-reduced-cost arc of the block whatever its direction, no excluded arc.
+// *out_arc2 = improving pick, *out_zero2 = first zero candidate (both arc*2 + (dir<0), -1 none).
+NSX_FN void nsx_devex_loop_scan(const NsxDev& d, NsxCtl& c, int64_t lo, int64_t hi, int allow_zero,
+                                int32_t* out_arc2, int32_t* out_zero2, NsxPivotScratch& s) {
+    const double tol = d.tol;
+    int32_t best = -1, zero = -1;
+    double best_merit = -NSX_INF;
+    NSX_SYNC();
+    NSX_SINGLE { s.sp_any = 0; }
+    NSX_SYNC();
+    for (int64_t base = lo; base < hi; base += NSX_SP_CHUNK) {
+        const int64_t cnt = hi - base < NSX_SP_CHUNK ? hi - base : NSX_SP_CHUNK;
+        NSX_PAR_FOR(k, 0, cnt) {
+            const int64_t i = base + k;
+            const uint8_t st = d.state[i];
+            int32_t code = 0;
+            double key = 0.0;
+            if (!(st & NSX_ARC_IN_TREE)) {
+                const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
+                const bool fv = (st & NSX_ARC_CAN_FWD) && rc < -tol;
+                const bool bv = !fv && (st & NSX_ARC_CAN_BWD) && rc > tol;
+                if (fv || bv) {
+                    const uint32_t wraw = d.wgt[i];
+                    const double w = (wraw >> 24) == c.wepoch ? (double)(wraw & 0xffffffu) : 1.0;
+                    code = fv ? 1 : 2;
+                    key = NSX_DIV(NSX_MUL(rc, rc), w);
+                } else if (allow_zero && fabs(rc) <= tol) {
+                    code = (st & NSX_ARC_CAN_FWD) ? 3 : ((st & NSX_ARC_CAN_BWD) ? 4 : 0);
+                }
+            }
+            s.arc2[k] = code;
+            s.res[k] = key;
+            if (code) s.sp_any = 1;
+        }
+        NSX_SYNC();
+        NSX_SINGLE {
+            if (s.sp_any) {
+                s.sp_any = 0;
+                for (int64_t k = 0; k < cnt; ++k) {
+                    const int32_t code = s.arc2[k];
+                    if (code == 1 || code == 2) {
+                        if (s.res[k] > NSX_ADD(best_merit, tol)) { best_merit = s.res[k]; best = (int32_t)(base + k) * 2 + (code == 2 ? 1 : 0); }
+                    } else if (code && zero < 0) {
+                        zero = (int32_t)(base + k) * 2 + (code == 4 ? 1 : 0);
+                    }
+                }
+            }
+        }
+        NSX_SYNC();
+    }
+    NSX_SINGLE { *out_arc2 = best; *out_zero2 = zero; c.arcs_priced += hi - lo; }
+    NSX_SYNC();
+}
+
 // Block-size adaptation after each pivot (simplex_adaptive.py:98-151). Single thread.
 NSX_FN void nsx_adapt_block(NsxCtl& c, int64_t m, int64_t iteration) {
     if (!c.auto_block) return;
@@ -1182,10 +1241,12 @@ enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_
        // candidate list (CandidateListPricing.select_entering_arc, simplex_pricing.py:418-458): quick scan of the
        // list, scan after the (optional) periodic refresh, forced refresh, scan after the forced refresh
        NSX_ST_CL_QUICK = 6, NSX_ST_CL_REFRESH = 7, NSX_ST_CL_MAIN = 8, NSX_ST_CL_FORCED = 9, NSX_ST_CL_LAST = 10,
-       NSX_ST_SPECIAL = 11 };  // structure-specific rule (assignment / max flow / shortest path) before the configured one
+       NSX_ST_SPECIAL = 11,    // structure-specific rule (assignment / max flow / shortest path) before the configured one
+       NSX_ST_DEVEX_LOOP = 12 };  // loop-based Devex: one block scanned by the pivot CTA per step
 enum { NSX_ACT_SWEEP = 0, NSX_ACT_PIVOT = 1, NSX_ACT_PHASE_END = 2, NSX_ACT_EXIT = 3, NSX_ACT_RECOMPUTE = 4,
        NSX_ACT_CL_SCAN = 5,    // CL_SCAN: the pivot CTA evaluates the <= 100 listed arcs itself, no sweep
-       NSX_ACT_SPECIAL_SCAN = 6 };  // the pivot CTA runs nsx_special_scan over all arcs
+       NSX_ACT_SPECIAL_SCAN = 6,    // the pivot CTA runs nsx_special_scan over all arcs
+       NSX_ACT_BLOCK_SCAN = 7 };    // the pivot CTA runs nsx_devex_loop_scan over the block [cmd.lo, cmd.hi)
 
 struct NsxCmd {       // what every CTA does next
     int32_t kind;
@@ -1210,6 +1271,7 @@ struct NsxLoopShared {
     NsxDrv drv;
     int32_t rc;
     int32_t cl_arc2;  // result of the last candidate scan (arc*2 + (dir<0)), -1 none
+    int32_t zero2;    // loop-based Devex: first zero-reduced-cost candidate of the scanned block, -1 none
 };
 
 NSX_FN void nsx_drv_devex_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
@@ -1247,6 +1309,21 @@ NSX_FN void nsx_drv_cl_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAc
     nsx_drv_cl_major(c, v, m, cmd, act);
 }
 
+// ---- loop-based Devex (simplex_pricing.py:205-269): the block loop of select_entering_arc, one block per step ----
+NSX_FN void nsx_drv_devex_loop_block(NsxCtl& c, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    int64_t st = c.pb * c.bs;
+    if (st >= m) { c.pb = 0; st = 0; }
+    cmd.lo = st; cmd.hi = st + c.bs < m ? st + c.bs : m; cmd.phase = c.phase;
+    act.kind = NSX_ACT_BLOCK_SCAN;
+}
+NSX_FN void nsx_drv_devex_loop_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
+    v.stage = NSX_ST_DEVEX_LOOP;
+    v.bc = (m + c.bs - 1) / c.bs;
+    if (v.bc < 1) v.bc = 1;
+    v.blocks_left = v.bc;
+    nsx_drv_devex_loop_block(c, m, cmd, act);
+}
+
 // top of an iteration: first sweep command, or phase end when the budget is used up
 NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
     if (!v.final_check && c.it >= v.budget) { act.kind = NSX_ACT_PHASE_END; return; }
@@ -1258,6 +1335,8 @@ NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxActio
         cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
     } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
         nsx_drv_cl_begin(c, v, m, cmd, act);
+    } else if (c.pricing == NSX_PRICING_DEVEX_LOOP) {
+        nsx_drv_devex_loop_begin(c, v, m, cmd, act);
     } else {
         nsx_drv_devex_begin(c, v, m, cmd);
     }
@@ -1315,9 +1394,21 @@ NSX_FN void nsx_drv_on_special(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, Ns
         cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
     } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
         nsx_drv_cl_begin(c, v, m, cmd, act);
+    } else if (c.pricing == NSX_PRICING_DEVEX_LOOP) {
+        nsx_drv_devex_loop_begin(c, v, m, cmd, act);
     } else {
         nsx_drv_devex_begin(c, v, m, cmd);
     }
+}
+// after nsx_devex_loop_scan of one block (simplex_pricing.py:256-266)
+NSX_FN void nsx_drv_on_block(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, int32_t zero2, NsxCmd& cmd, NsxAction& act,
+                             int32_t* trace) {
+    if (arc2 >= 0) { nsx_drv_choose(c, v, act, arc2, 1, trace); return; }  // weight updated for the selected arc only
+    c.pb = (c.pb + 1) % v.bc;
+    if (zero2 >= 0) { nsx_drv_choose(c, v, act, zero2, 0, trace); return; }
+    v.blocks_left--;
+    if (v.blocks_left == 0) { nsx_drv_none(c, v, act); return; }
+    nsx_drv_devex_loop_block(c, m, cmd, act);
 }
 NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
                               const NsxDevexCand& dx, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
@@ -1334,6 +1425,10 @@ NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz
         if (dz.arc2 >= 0) { nsx_drv_choose(c, v, act, dz.arc2, 0, trace); return; }
         if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_CANDIDATE_LIST) {
             nsx_drv_cl_begin(c, v, m, cmd, act);  // fall through to the configured strategy (simplex.py:1066-1075)
+            return;
+        }
+        if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_DEVEX_LOOP) {
+            nsx_drv_devex_loop_begin(c, v, m, cmd, act);  // fall through to the configured strategy (simplex.py:1066-1075)
             return;
         }
         if (v.stage == NSX_ST_ROWSCAN && c.pricing == NSX_PRICING_DEVEX) {
@@ -1428,6 +1523,9 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         } else if (kind == NSX_ACT_CL_SCAN) {
             nsx_cl_scan(d, c, &L.cl_arc2, s, (c.phase == 1) && !L.drv.final_check);
             NSX_SINGLE { nsx_drv_on_scan(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }
+        } else if (kind == NSX_ACT_BLOCK_SCAN) {
+            nsx_devex_loop_scan(d, c, L.cmd.lo, L.cmd.hi, (c.phase == 1) && !L.drv.final_check, &L.cl_arc2, &L.zero2, s);
+            NSX_SINGLE { nsx_drv_on_block(c, L.drv, d.m, L.cl_arc2, L.zero2, L.cmd, L.act, trace); }
         } else if (kind == NSX_ACT_SPECIAL_SCAN) {
             nsx_special_scan(d, c, &L.cl_arc2, s);
             NSX_SINGLE { nsx_drv_on_special(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }

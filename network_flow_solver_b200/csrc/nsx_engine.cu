@@ -1319,7 +1319,8 @@ static int nsx_validate(const nsx_problem* p, const nsx_options* o, const nsx_re
     if (p->n_arcs > 0 && (!p->tail || !p->head || !p->pert_cost || !p->upper))
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null arc array");
     if (!p->supply) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null supply");
-    if (o->pricing != NSX_PRICING_DANTZIG && o->pricing != NSX_PRICING_DEVEX && o->pricing != NSX_PRICING_CANDIDATE_LIST)
+    if (o->pricing != NSX_PRICING_DANTZIG && o->pricing != NSX_PRICING_DEVEX && o->pricing != NSX_PRICING_CANDIDATE_LIST &&
+        o->pricing != NSX_PRICING_DEVEX_LOOP)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown pricing rule");
     if (o->max_iterations < 0 || !(o->tolerance > 0) || o->ft_update_limit <= 0)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad option value");
@@ -1437,7 +1438,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
 
     const int32_t n = pb->n_nodes;
     const int64_t m = pb->n_arcs, ma = m + n - 1, mpad = nsx_pad_tiles(m);
-    const bool devex = opt->pricing == NSX_PRICING_DEVEX;
+    const bool devex = opt->pricing == NSX_PRICING_DEVEX || opt->pricing == NSX_PRICING_DEVEX_LOOP;
     const bool want_trace = res->entering_trace && opt->trace_capacity > 0;
 
     CallResources rs;
@@ -1533,9 +1534,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
             arena.release(); inputs.release();
             return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad shard description");
         }
-        if (shard->world > 1 && opt->row_scan_first >= NSX_SPECIAL_ASSIGNMENT) {
+        if (shard->world > 1 && (opt->row_scan_first >= NSX_SPECIAL_ASSIGNMENT || opt->pricing == NSX_PRICING_DEVEX_LOOP)) {
             arena.release(); inputs.release();
-            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "structure-specific pivot rules run inside one pivot CTA and are not available in arc-sharded solves");
+            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "rules that scan inside the pivot CTA (structure-specific rules, loop-based Devex) are not available in arc-sharded solves");
         }
         if (shard->world > 1 && opt->pricing == NSX_PRICING_CANDIDATE_LIST) {
             arena.release(); inputs.release();
@@ -1720,7 +1721,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     DeviceInfo info;
     int rc = nsx_device_info(opt->device, info);
     if (rc) return rc;
-    const bool devex = opt->pricing == NSX_PRICING_DEVEX;
+    const bool devex = opt->pricing == NSX_PRICING_DEVEX || opt->pricing == NSX_PRICING_DEVEX_LOOP;
 
     // batch instances keep float64 costs; node ids are narrowed when every instance allows it.
     // Each CTA packs the store of its instance itself before the first sweep.

@@ -131,13 +131,8 @@ def resolve_plan(
     if strategy == "dantzig":
         pricing = _capi.PRICING_DANTZIG
     elif strategy == "devex":
-        if not options.use_vectorized_pricing:
-            raise SolverConfigurationError(
-                "use_vectorized_pricing=False selects the reference's loop-based Devex rule "
-                "(simplex_pricing.py:205-269), which the device engine does not implement; "
-                "only the vectorised block search is on the accelerated path."
-            )
-        pricing = _capi.PRICING_DEVEX
+        # use_vectorized_pricing=False selects the reference's loop-based block scan (simplex_pricing.py:205-269)
+        pricing = _capi.PRICING_DEVEX if options.use_vectorized_pricing else _capi.PRICING_DEVEX_LOOP
     elif strategy in ("candidate_list", "adaptive"):
         # "adaptive" (the reference's default) only leaves its candidate-list stage after 5 consecutive searches
         # that return None, and a search that returns None ends the phase: it IS the candidate-list rule

@@ -422,6 +422,46 @@ static int devex_select(ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir, in
     return 0;
 }
 
+/* Loop-based Devex (DevexPricing.select_entering_arc, use_vectorized_pricing=False; simplex_pricing.py:205-269).
+ * _is_better_candidate (:294-308) reduces to "merit > best + tol" because the scan runs in ascending index order. */
+static int devex_loop_select(ctx_t* c, int allow_zero, int32_t* arc, int32_t* dir, int* want_weight, int64_t* priced) {
+    oracle_t* o = &c->o;
+    const double tol = o->tol;
+    int64_t m = o->m;
+    int64_t bc = (m + o->bs - 1) / o->bs;
+    if (bc < 1) bc = 1;
+    for (int64_t k = 0; k < bc; ++k) {
+        int64_t st = o->pb * o->bs;
+        if (st >= m) { o->pb = 0; st = 0; }
+        int64_t en = st + o->bs < m ? st + o->bs : m;
+        *priced += en - st;
+        double best_merit = -INFINITY;
+        int32_t best = -1, bdir = 0, zero = -1, zdir = 0;
+        for (int64_t i = st; i < en; ++i) {
+            if (o->intree[i]) continue;
+            double rc = rc_of(c, i, o->tcost[i]);
+            double fr = fwd_res(c, i), br = o->flow[i];
+            int d = 0;
+            if (fr > tol && rc < -tol) d = 1;
+            else if (br > tol && rc > tol) d = -1;
+            if (d) {
+                double w = o->weight[i] > 1e-12 ? o->weight[i] : 1e-12;
+                double merit = (rc * rc) / w;
+                if (merit > best_merit + tol) { best_merit = merit; best = (int32_t)i; bdir = d; }
+                continue;
+            }
+            if (allow_zero && zero < 0 && fabs(rc) <= tol) {
+                if (fr > tol) { zero = (int32_t)i; zdir = 1; }
+                else if (br > tol) { zero = (int32_t)i; zdir = -1; }
+            }
+        }
+        if (best >= 0) { *arc = best; *dir = bdir; *want_weight = 1; return 1; }
+        o->pb = (o->pb + 1) % bc;
+        if (zero >= 0) { *arc = zero; *dir = zdir; *want_weight = 0; return 1; }
+    }
+    return 0;
+}
+
 /* ---------------- candidate-list pricing (SolverOptions.pricing_strategy "candidate_list"; also what
  * "adaptive" - the reference's default - amounts to: AdaptivePricing (simplex_pricing.py:545-639) only
  * leaves the candidate list after 5 CONSECUTIVE searches that return None, and a search that returns
@@ -673,6 +713,7 @@ static int find_entering(ctx_t* c, const nsx_options* opt, int allow_zero, int32
     }
     if (opt->pricing == NSX_PRICING_DANTZIG) { *priced += o->m; return dantzig_select(c, allow_zero, arc, dir); }
     if (opt->pricing == NSX_PRICING_CANDIDATE_LIST) return cl_select(c, allow_zero, arc, dir, priced);
+    if (opt->pricing == NSX_PRICING_DEVEX_LOOP) return devex_loop_select(c, allow_zero, arc, dir, want_weight, priced);
     return devex_select(c, allow_zero, arc, dir, want_weight, priced);
 }
 

@@ -96,6 +96,10 @@ def main():
     case("shortest_path_64_ties", shortest_path(64, 300, 10, unreachable=8, cost_max=3))
     case("shortest_path_96", shortest_path(96, 500, 11, unreachable=10, cost_max=40))
     case("shortest_path_20_sink_cut_off", shortest_path(20, 60, 8, sink_in_core=False))
+    # more than 1024 arcs: the device scan walks these in several chunks
+    case("assignment_40", assignment(40, 12), variants=(DZ, DX, AD))
+    case("max_flow_200_unit_cost", max_flow(200, 1400, 13, 25, 1.0), variants=(DZ, AD))
+    case("shortest_path_300", shortest_path(300, 1500, 14, unreachable=20, cost_max=60), variants=(DZ, DX, AD))
     path = REPO / "tests" / "golden" / "next" / "special_pivots.json.gz"
     with gzip.GzipFile(path, "wb", mtime=0) as fh:
         fh.write(json.dumps({"cases": cases}, separators=(",", ":")).encode())

@@ -91,10 +91,17 @@ def test_option_resolution_matches_the_reference_rules():
     assert plan2.strategy == "dantzig"                                                               # simplex.py:358-374
 
 
-@pytest.mark.parametrize("kwargs", [dict(pricing_strategy="devex", use_vectorized_pricing=False)])
-def test_paths_outside_the_accelerated_scope_fail_loudly(kwargs):
+def test_paths_outside_the_accelerated_scope_fail_loudly():
+    options = SolverOptions(explicit_pricing_strategy=True, auto_scale=False)
+    object.__setattr__(options, "pricing_strategy", "steepest")  # past the constructor's own check (data.py:163)
     with pytest.raises(SolverConfigurationError):
-        prepare(small_problem(), SolverOptions(explicit_pricing_strategy=True, auto_scale=False, **kwargs))
+        prepare(small_problem(), options)
+
+
+def test_loop_based_devex_has_its_own_engine_rule():
+    _, plan, _ = prepare(small_problem(), SolverOptions(pricing_strategy="devex", explicit_pricing_strategy=True, auto_scale=False,
+                                                         use_vectorized_pricing=False))
+    assert plan.engine.pricing == _capi.PRICING_DEVEX_LOOP
 
 
 def test_unbalanced_problem_is_rejected_like_the_reference():
