@@ -77,10 +77,7 @@ def apply_basis(cp: CanonicalProblem, basis: Basis, tolerance: float) -> WarmSta
         _log.warning("Warm-start basis is empty. Falling back to cold start.")
         return None
     if cp.arc_keys is None:
-        raise ValueError("a warm-start basis is keyed by (tail id, head id); the problem has no arc keys")
-    n, m = cp.n_nodes, cp.n_arcs
-    ma = m + n - 1
-    tol = tolerance
+        raise ValueError("a Basis is keyed by (tail id, head id) and this problem has no arc keys: use apply_tree_arcs")
     index_of = {key: i for i, key in enumerate(cp.arc_keys)}  # parallel arcs: the last one wins (simplex.py:766-769)
     chosen: list[int] = []
     for key in basis.tree_arcs:
@@ -89,13 +86,26 @@ def apply_basis(cp: CanonicalProblem, basis: Basis, tolerance: float) -> WarmSta
             _log.warning(f"Warm-start basis contains arc {key} not in current problem. Falling back to cold start.")
             return None
         chosen.append(i)
+    flows = {i: basis.arc_flows[cp.arc_keys[i]] for i in chosen if cp.arc_keys[i] in basis.arc_flows}
+    return apply_tree_arcs(cp, chosen, flows, tolerance)
+
+
+def apply_tree_arcs(cp: CanonicalProblem, chosen, flows, tolerance: float) -> WarmStart | None:
+    """Array-native form of `apply_basis`: `chosen` = indices of the real arcs of the previous tree (canonical arc order),
+    `flows` = {arc index: previous flow} for the ones whose flow is known (it is only validated, simplex.py:785-803; the
+    tree flows are recomputed from conservation).  For instances built without NetworkProblem objects
+    (INTEGRATION.md section 5): `np.flatnonzero(raw.state[:M] & ARC_IN_TREE)` of the previous RawSolution."""
+    chosen = [int(i) for i in chosen]
+    n, m = cp.n_nodes, cp.n_arcs
+    ma = m + n - 1
+    tol = tolerance
     upper = cp.upper
     flow = np.zeros(ma, dtype=np.float64)
     in_tree = np.zeros(ma, dtype=np.uint8)
     for i in chosen:
-        key = cp.arc_keys[i]
-        if key in basis.arc_flows:
-            f = basis.arc_flows[key]
+        if i in flows:
+            f = flows[i]
+            key = cp.arc_keys[i] if cp.arc_keys is not None else i
             if f < 0.0 - tol:  # internal lower bounds are 0 after the shift (simplex.py:416-428)
                 _log.warning(f"Warm-start basis has flow {f:.2f} below lower bound 0.00 on arc {key}. Falling back to cold start.")
                 return None

@@ -815,7 +815,8 @@ done:
             double up = i < m ? o->upper_r[i] : cx.aupper[i - m];
             double fr = isinf(up) ? INFINITY : up - o->flow[i];
             res->state[i] = (uint8_t)((o->intree[i] ? NSX_ARC_IN_TREE : 0) | (fr > o->tol ? NSX_ARC_CAN_FWD : 0) |
-                                      (o->flow[i] > o->tol ? NSX_ARC_CAN_BWD : 0) | (o->touched[i] ? NSX_ARC_TOUCHED : 0));
+                                      (o->flow[i] > o->tol ? NSX_ARC_CAN_BWD : 0) | (o->touched[i] ? NSX_ARC_TOUCHED : 0) |
+                                      (o->stale && o->stale[i] ? NSX_ARC_STALE : 0));
         }
     }
     free(o->tcost); free(o->flow); free(o->intree); free(o->touched); free(o->weight); free(o->stale);
