@@ -56,7 +56,15 @@ def solve_with(names, supply, arcs, strategy, solve):
     # assignment / max-flow / shortest-path structure: the reference switches to its structure-specific rule, which has
     # its own hazards (zero-cost instances end "infeasible"); those rules are pinned in test_next_special_pivots.py
     assume(plan.engine.row_scan_first < _capi.SPECIAL_ASSIGNMENT)
-    return finish(cp, solve(cp, plan.engine), options)
+    result = finish(cp, solve(cp, plan.engine), options)
+    if result.status != "optimal":
+        # the reference's own Phase 1 can end "infeasible" on feasible instances with tiny costs (its artificial penalty
+        # max|c|*(N+2) is then too small): the drop-in must reproduce that outcome - the pinned oracle
+        # says the same - and the optimality properties below do not apply to such a run
+        from oracle import oracle
+
+        assert finish(cp, oracle.solve_canonical(cp, plan.engine), options).status == result.status
+    return result
 
 
 def check_instance(names, supply, arcs, solve):
@@ -76,7 +84,8 @@ def check_instance(names, supply, arcs, solve):
     caps = {(a, b): cap for a, b, cap, _ in arcs}
     costs = {(a, b): cost for a, b, _, cost in arcs}
     for r in results:
-        assert r.status == "optimal"
+        if r.status != "optimal":
+            continue
         assert r.objective == optimum                                                    # independent exact optimum
         assert abs(sum(f * costs[k] for k, f in r.flows.items()) - r.objective) < 1e-9
         balance = {v: 0.0 for v in names}
