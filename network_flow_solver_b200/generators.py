@@ -17,7 +17,10 @@ from dataclasses import dataclass
 import numpy as np
 
 from .canonical import (
+    NET_ASSIGNMENT,
     NET_GENERAL,
+    NET_MAX_FLOW,
+    NET_SHORTEST_PATH,
     NET_TRANSPORTATION,
     PERTURB_EPS_BASE,
     CanonicalProblem,
@@ -236,3 +239,40 @@ def gridgen_like(
     supply[picks[:n_sources]] = supply_each
     supply[picks[n_sources:]] = -total / n_sinks
     return ArcArrays(n, tail, head, cost, cap, supply, NET_GENERAL, "gridgen_like", seed)
+
+
+def assignment(n: int, *, cost_max: int = 200, seed: int = 0) -> ArcArrays:
+    """Dense n x n assignment instance: unit supplies / demands, unit capacities, integer costs U[1, cost_max].  The
+    reference recognises the structure (specializations.py:214-245) and runs its assignment pivot rule first."""
+    rng = np.random.default_rng(seed)
+    tail = np.repeat(np.arange(n, dtype=np.int64), n)
+    head = n + np.tile(np.arange(n, dtype=np.int64), n)
+    supply = np.concatenate([np.ones(n), -np.ones(n)])
+    cost = rng.integers(1, cost_max + 1, size=n * n).astype(np.float64)
+    return ArcArrays(2 * n, tail, head, cost, np.ones(n * n), supply, NET_ASSIGNMENT, "assignment", seed)
+
+
+def shortest_path(n_nodes: int, n_arcs: int, *, cost_max: int = 500, cut_fraction: int = 8, seed: int = 0) -> ArcArrays:
+    """One unit from a source to a sink over an uncapacitated NETGEN-style graph (ring skeleton + random arcs).  The last
+    1/cut_fraction of the nodes keep their arcs into the rest but lose every arc coming from it, so they are not
+    reachable from the source - the part of the graph the reference's shortest-path rule never prices forward
+    (specialized_pivots.py:396-399).  Source and sink are placed in the reachable part."""
+    a = netgen_like(n_nodes, n_arcs, n_sources=1, n_sinks=1, supply_each=1, cost_max=cost_max, seed=seed)
+    first_cut = n_nodes - n_nodes // cut_fraction
+    keep = ~((a.head >= first_cut) & (a.tail < first_cut))
+    supply = np.zeros(n_nodes, dtype=np.float64)
+    rng = np.random.default_rng(seed + 7)
+    src, dst = rng.choice(first_cut, size=2, replace=False)
+    supply[src], supply[dst] = 1.0, -1.0
+    m = int(keep.sum())
+    return ArcArrays(n_nodes, a.tail[keep], a.head[keep], a.cost[keep], np.full(m, np.inf), supply, NET_SHORTEST_PATH,
+                     "shortest_path", seed)
+
+
+def max_flow(n_nodes: int, n_arcs: int, *, flow: int = 40, seed: int = 0) -> ArcArrays:
+    """`flow` units from one source to one sink, every arc at cost 1 (the uniform-cost form the reference classifies as
+    max flow, specializations.py:268-286), capacities U[1, flow] on the random arcs and `flow` on the ring skeleton."""
+    a = netgen_like(n_nodes, n_arcs, n_sources=1, n_sinks=1, supply_each=flow, cost_max=1, cap_max=flow, seed=seed)
+    a.network_type = NET_MAX_FLOW
+    a.family = "max_flow"
+    return a

@@ -14,7 +14,7 @@ from dataclasses import dataclass
 
 from . import _capi
 from . import generators as gen
-from .canonical import NET_TRANSPORTATION, PERTURB_EPS_BASE, CanonicalProblem, initial_block_size
+from .canonical import PERTURB_EPS_BASE, CanonicalProblem, initial_block_size
 
 
 @dataclass
@@ -32,10 +32,14 @@ class Workload:
         return self.arrays(seed_offset).canonical(eps_base=self.eps_base)
 
     def engine_options(self, cp: CanonicalProblem, **overrides) -> _capi.EngineOptions:
+        from .solver import special_rule  # which structure-specific rule the reference would run first, + its node mask
+
         m = cp.n_arcs
+        rule, mask = special_rule(cp, 1e-6)
         opts = dict(
             pricing=self.pricing,
-            row_scan_first=cp.network_type == NET_TRANSPORTATION,
+            row_scan_first=rule,
+            node_mask=mask,
             block_size=initial_block_size(m),
             auto_block=True,
             ft_update_limit=64,
@@ -97,6 +101,23 @@ WORKLOADS = {
         "netgen_2e18_dantzig", "NETGEN-style 2^18 nodes / 2^24 arcs, Dantzig full sweeps, eps=0",
         _capi.PRICING_DANTZIG, 0.0,
         lambda off: gen.netgen_like(1 << 18, 1 << 24, n_sources=1024, n_sinks=1024, seed=2026 + off)),
+    # instances on which the reference switches to a structure-specific pivot rule
+    "assignment_1024": Workload(
+        "assignment_1024", "dense assignment 1024x1024 (1M arcs), assignment rule first, then Dantzig; eps=0",
+        _capi.PRICING_DANTZIG, 0.0, lambda off: gen.assignment(1024, cost_max=1000, seed=512 + off)),
+    "assignment_256": Workload(
+        "assignment_256", "dense assignment 256x256 (65.5K arcs), assignment rule first, then Dantzig",
+        _capi.PRICING_DANTZIG, PERTURB_EPS_BASE, lambda off: gen.assignment(256, cost_max=1000, seed=256 + off)),
+    "shortest_path_2e16": Workload(
+        "shortest_path_2e16", "one unit over a NETGEN-style graph 2^16 nodes / ~2^20 arcs, shortest-path rule first, then Dantzig",
+        _capi.PRICING_DANTZIG, PERTURB_EPS_BASE, lambda off: gen.shortest_path(1 << 16, 1 << 20, seed=1701 + off)),
+    "max_flow_2e14": Workload(
+        "max_flow_2e14", "unit-cost max-flow form, 2^14 nodes / 2^18 arcs, max-flow rule first, then Dantzig",
+        _capi.PRICING_DANTZIG, PERTURB_EPS_BASE, lambda off: gen.max_flow(1 << 14, 1 << 18, flow=64, seed=1801 + off)),
+    "netgen_2e16_devex_loop": Workload(
+        "netgen_2e16_devex_loop", "NETGEN-style 2^16 nodes / 2^20 arcs, loop-based Devex (use_vectorized_pricing=False)",
+        _capi.PRICING_DEVEX_LOOP, PERTURB_EPS_BASE,
+        lambda off: gen.netgen_like(1 << 16, 1 << 20, n_sources=256, n_sinks=256, seed=1601 + off)),
     # config 4 - one instance of the batch (the batch itself is built by bench.py)
     "goto_64": Workload(
         "goto_64", "GOTO-style grid-on-torus 64x64 (4096 nodes / ~32.7K arcs), Dantzig",

@@ -10,7 +10,7 @@ import pytest
 from emu import emu
 from network_flow_solver_b200 import _capi
 from network_flow_solver_b200 import generators as gen
-from network_flow_solver_b200.canonical import NET_ASSIGNMENT, NET_MAX_FLOW, NET_SHORTEST_PATH, initial_block_size
+from network_flow_solver_b200.canonical import initial_block_size
 from network_flow_solver_b200.solver import special_rule
 from network_flow_solver_b200.warm_start import apply_tree_arcs
 from oracle import oracle
@@ -26,41 +26,13 @@ def options_for(cp, pricing, **kw):
     return _capi.EngineOptions(**base)
 
 
-def assignment_arrays(n, seed, cost_max=200):
-    rng = np.random.default_rng(seed)
-    tail = np.repeat(np.arange(n), n)
-    head = n + np.tile(np.arange(n), n)
-    supply = np.concatenate([np.ones(n), -np.ones(n)])
-    return gen.ArcArrays(2 * n, tail, head, rng.integers(1, cost_max + 1, size=n * n).astype(np.float64),
-                         np.ones(n * n), supply, NET_ASSIGNMENT, "assignment", seed)
-
-
-def shortest_path_arrays(n, m, seed):
-    a = gen.netgen_like(n, m, n_sources=1, n_sinks=1, supply_each=1, cost_max=500, seed=seed)  # ring skeleton: all reachable
-    a.capacity[:] = np.inf
-    keep = np.ones(a.n_arcs, dtype=bool)
-    cut = np.arange(n - n // 8, n)  # no arc from the rest INTO the last eighth: it is not reachable from the source ...
-    keep &= ~(np.isin(a.head, cut) & ~np.isin(a.tail, cut))
-    src, dst = int(np.flatnonzero(a.supply > 0)[0]), int(np.flatnonzero(a.supply < 0)[0])
-    if src in cut or dst in cut:
-        pytest.skip("endpoints fell into the cut-off part")
-    out = gen.ArcArrays(n, a.tail[keep], a.head[keep], a.cost[keep], a.capacity[keep], a.supply, NET_SHORTEST_PATH, "shortest_path", seed)
-    return out
-
-
-def max_flow_arrays(n, m, seed, flow=40):
-    a = gen.netgen_like(n, m, n_sources=1, n_sinks=1, supply_each=flow, cost_max=1, cap_max=flow, seed=seed)
-    a.network_type = NET_MAX_FLOW  # all costs 1, one source, one sink
-    return a
-
-
 SCANS = [
-    ("assignment_64", lambda: assignment_arrays(64, 1), _capi.PRICING_DANTZIG),
-    ("assignment_64", lambda: assignment_arrays(64, 1), _capi.PRICING_CANDIDATE_LIST),
-    ("assignment_48_ties", lambda: assignment_arrays(48, 2, cost_max=3), _capi.PRICING_DEVEX),
-    ("shortest_path_2048", lambda: shortest_path_arrays(2048, 12000, 3), _capi.PRICING_DANTZIG),
-    ("shortest_path_2048", lambda: shortest_path_arrays(2048, 12000, 3), _capi.PRICING_DEVEX_LOOP),
-    ("max_flow_1024", lambda: max_flow_arrays(1024, 6000, 4), _capi.PRICING_DANTZIG),
+    ("assignment_64", lambda: gen.assignment(64, seed=1), _capi.PRICING_DANTZIG),
+    ("assignment_64", lambda: gen.assignment(64, seed=1), _capi.PRICING_CANDIDATE_LIST),
+    ("assignment_48_ties", lambda: gen.assignment(48, cost_max=3, seed=2), _capi.PRICING_DEVEX),
+    ("shortest_path_2048", lambda: gen.shortest_path(2048, 12000, seed=3), _capi.PRICING_DANTZIG),
+    ("shortest_path_2048", lambda: gen.shortest_path(2048, 12000, seed=3), _capi.PRICING_DEVEX_LOOP),
+    ("max_flow_1024", lambda: gen.max_flow(1024, 6000, seed=4), _capi.PRICING_DANTZIG),
     ("loop_devex_netgen_2048", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), _capi.PRICING_DEVEX_LOOP),
     ("loop_devex_transport", lambda: gen.transportation(64, 96, cost_max=100, supply_each=48, seed=7), _capi.PRICING_DEVEX_LOOP),
 ]

@@ -43,6 +43,17 @@ def test_structure_detection_and_rule_choice(name):
         assert 0 < int(plan.engine.node_mask[1:].sum()) < cp.n_nodes - 1
 
 
+def test_generators_build_what_the_structure_test_recognises():
+    """Array-native instances carry their network type as a declaration (no NetworkProblem objects to analyse): it must be
+    what the structure test (specializations.py:187-288) says about the same instance."""
+    from network_flow_solver_b200 import generators as gen
+    from network_flow_solver_b200.canonical import detect_network_type
+
+    for arrays in (gen.assignment(12, seed=1), gen.shortest_path(96, 400, seed=2), gen.max_flow(64, 300, seed=3),
+                   gen.transportation(8, 12, seed=4), gen.netgen_like(64, 256, n_sources=4, n_sinks=4, seed=5)):
+        assert detect_network_type(gen.to_network_problem(arrays, tolerance=1e-6)) == arrays.network_type, arrays.family
+
+
 def test_reachability_mask():
     tail, head = np.array([1, 2, 2, 4, 5]), np.array([2, 3, 1, 2, 5])
     assert reachable_from(6, tail, head, 1).tolist() == [0, 1, 1, 1, 0, 0]
