@@ -46,6 +46,21 @@
 #define NSX_CLOCK() clock64()
 #define NSX_ATOMIC_MIN_I32(p, v) atomicMin((p), (v))
 #define NSX_ATOMIC_MAX_I32(p, v) atomicMax((p), (v))
+#elif defined(NSX_HOST_MT)
+// Test-only: the CTA emulated by real host threads (tests/emu, NSX_HOST_MT).  NSX_SYNC is a thread barrier, so a barrier
+// that some "thread" skips deadlocks and a missing barrier shows up as a data race (ThreadSanitizer) - the two hazards
+// the serial emulation cannot see.
+extern thread_local int nsx_mt_tid;
+extern int nsx_mt_nthreads;
+void nsx_mt_barrier();
+#define NSX_ON_DEVICE 0
+#define NSX_FN static inline
+#define NSX_PAR_FOR(i, lo, hi) for (int64_t i = (int64_t)(lo) + nsx_mt_tid; i < (int64_t)(hi); i += nsx_mt_nthreads)
+#define NSX_SYNC() nsx_mt_barrier()
+#define NSX_SINGLE if (nsx_mt_tid == 0)
+#define NSX_TID nsx_mt_tid
+#define NSX_NTHREADS nsx_mt_nthreads
+#define NSX_HOST_SERIAL if (nsx_mt_tid == 0)  /* host-only stand-ins for warp-level device code run on one thread */
 #else
 #define NSX_ON_DEVICE 0
 #define NSX_FN static inline
@@ -54,15 +69,32 @@
 #define NSX_SINGLE
 #define NSX_TID 0
 #define NSX_NTHREADS 1
+#define NSX_HOST_SERIAL
+#endif
+// several threads may raise the same flag at once (same value, nobody reads it before the next barrier)
+#if defined(NSX_HOST_MT) && !(defined(__CUDACC__) && !defined(NSX_HOST_EMU))
+#define NSX_RAISE(flag) __atomic_store_n(&(flag), 1, __ATOMIC_RELAXED)
+#else
+#define NSX_RAISE(flag) ((flag) = 1)
+#endif
+#if !NSX_ON_DEVICE
 #define NSX_ADD(a, b) ((a) + (b)) /* compiled with -ffp-contract=off */
 #define NSX_SUB(a, b) ((a) - (b))
 #define NSX_MUL(a, b) ((a) * (b))
 #define NSX_DIV(a, b) ((a) / (b))
 #define NSX_INF INFINITY
-#define NSX_ATOMIC_ADD_I32(p, v) ((*(p) += (v)) - (v))
 #define NSX_CLOCK() 0ll
+#if defined(NSX_HOST_MT)
+#define NSX_ATOMIC_ADD_I32(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+static inline int32_t nsx_mt_min(int32_t* p, int32_t v) { int32_t o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+static inline int32_t nsx_mt_max(int32_t* p, int32_t v) { int32_t o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+#define NSX_ATOMIC_MIN_I32(p, v) nsx_mt_min((p), (v))
+#define NSX_ATOMIC_MAX_I32(p, v) nsx_mt_max((p), (v))
+#else
+#define NSX_ATOMIC_ADD_I32(p, v) ((*(p) += (v)) - (v))
 #define NSX_ATOMIC_MIN_I32(p, v) (*(p) = (v) < *(p) ? (v) : *(p))
 #define NSX_ATOMIC_MAX_I32(p, v) (*(p) = (v) > *(p) ? (v) : *(p))
+#endif
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -585,6 +617,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (threadIdx.x == 0) { s.nh = len; s.join = join; } else { s.nt = len; }
     }
 #else
+    NSX_HOST_SERIAL {
     if (d.lazy_pos) {
         int32_t u = h, v = t, du = d.depth[h], dv = d.depth[t], nh_ = 0, nt_ = 0;
         while (u != v) {
@@ -599,6 +632,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         s.nh = len; s.join = join;
         nsx_walk_side(d, t, d.node[h].pos, s.path_t, d.gpath_t, &len, &join);
         s.nt = len;
+    }
     }
 #endif
     NSX_SYNC();
@@ -671,7 +705,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         if (threadIdx.x == 0) nsx_ratio_finish(rr, res, arc2, ncyc, e, tol, s);
     }
 #else
-    {
+    NSX_HOST_SERIAL {
         NsxRatio lanes[4];
         for (int l = 0; l < 4; ++l) nsx_ratio_init(lanes[l]);
         for (int32_t k = 0; k < ncyc; ++k) nsx_ratio_add(lanes[k & 3], res[k], arc2[k] >> 1, k);
@@ -997,7 +1031,7 @@ NSX_FN void nsx_special_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxP
             }
             s.arc2[k] = code;
             s.res[k] = key;
-            if (code) s.sp_any = 1;
+            if (code) NSX_RAISE(s.sp_any);
         }
         NSX_SYNC();
         NSX_SINGLE {
@@ -1055,7 +1089,7 @@ NSX_FN void nsx_devex_loop_scan(const NsxDev& d, NsxCtl& c, int64_t lo, int64_t 
             }
             s.arc2[k] = code;
             s.res[k] = key;
-            if (code) s.sp_any = 1;
+            if (code) NSX_RAISE(s.sp_any);
         }
         NSX_SYNC();
         NSX_SINGLE {

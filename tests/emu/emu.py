@@ -4,6 +4,7 @@ Test infrastructure only (see nsx_emu.cpp)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -16,7 +17,21 @@ _WARM = _HERE.parents[1] / "network_flow_solver_b200" / "csrc" / "nsx_warm.h"
 _lib = None
 
 
+_FLAGS = ["-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared"]
+
+
+def build_mt(out: Path, sanitize: bool = False) -> Path:
+    """The multi-threaded variant (NSX_HOST_MT): the pivot CTA as real threads (NSX_EMU_THREADS, default 8) with
+    NSX_SYNC as a barrier; `sanitize` adds ThreadSanitizer.  Select it with NSX_EMU_LIB=<path>."""
+    extra = ["-fsanitize=thread", "-O1", "-g"] if sanitize else ["-O2"]
+    subprocess.run(["/usr/bin/g++", *extra, *_FLAGS, "-DNSX_HOST_MT", "-pthread", "-o", str(out), str(_HERE / "nsx_emu.cpp")],
+                   check=True, capture_output=True)
+    return out
+
+
 def build(force: bool = False) -> Path:
+    if os.environ.get("NSX_EMU_LIB"):
+        return Path(os.environ["NSX_EMU_LIB"])
     src = _HERE / "nsx_emu.cpp"
     header = _HERE.parents[1] / "include" / "nsx_b200.h"
     newest = max(src.stat().st_mtime, _CORE.stat().st_mtime, _WARM.stat().st_mtime, header.stat().st_mtime)
@@ -32,8 +47,7 @@ def build(force: bool = False) -> Path:
 def solve_canonical(cp, opts: EngineOptions, warm=None) -> RawSolution:
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(str(_LIB))
+        _lib = C.CDLL(str(build()))
         _lib.nsx_emu_solve.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult)]
         _lib.nsx_emu_solve.restype = C.c_int
         _lib.nsx_emu_solve_warm.argtypes = [C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxWarmStart), C.POINTER(NsxResult)]

@@ -12,6 +12,16 @@
 #include <utility>
 #include <vector>
 
+#ifdef NSX_HOST_MT
+// Multi-threaded variant (libnsx_emu_mt.so): the pivot CTA is NSX_EMU_THREADS real threads, NSX_SYNC a barrier.
+#include <pthread.h>
+#include <thread>
+thread_local int nsx_mt_tid = 0;
+int nsx_mt_nthreads = 1;
+static pthread_barrier_t nsx_mt_bar;
+void nsx_mt_barrier() { pthread_barrier_wait(&nsx_mt_bar); }
+#endif
+
 #include "../../network_flow_solver_b200/csrc/nsx_core.cuh"
 #include "../../network_flow_solver_b200/csrc/nsx_warm.h"
 
@@ -21,6 +31,11 @@ struct SerialSweep {
     const NsxDev& d;
     SerialSweep(const NsxDev& dev) : d(dev) {}
     void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
+        NSX_SYNC();
+        NSX_SINGLE { run_serial(cmd, dz, dx, c); }  // the grid sweep is not what this emulation is about
+        NSX_SYNC();
+    }
+    void run_serial(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         nsx_cand_init(dz);
         nsx_devex_init(dx);
         if (cmd.kind == NSX_CMD_TOPK) {  // candidate-list refresh (simplex_pricing.py:507-536)
@@ -108,7 +123,21 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     NsxPivotScratch* s = new NsxPivotScratch;
     NsxPotScratch* ps = new NsxPotScratch;
     SerialSweep sweep(d);
+#ifdef NSX_HOST_MT
+    {
+        const char* nt = getenv("NSX_EMU_THREADS");
+        nsx_mt_nthreads = nt && *nt ? atoi(nt) : 8;
+        if (nsx_mt_nthreads < 1) nsx_mt_nthreads = 1;
+        pthread_barrier_init(&nsx_mt_bar, nullptr, (unsigned)nsx_mt_nthreads);
+        std::vector<std::thread> team;
+        for (int t = 0; t < nsx_mt_nthreads; ++t)
+            team.emplace_back([&, t] { nsx_mt_tid = t; nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep); });
+        for (auto& th : team) th.join();
+        pthread_barrier_destroy(&nsx_mt_bar);
+    }
+#else
     nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep);
+#endif
     delete L; delete s; delete ps;
 
     res->status = c.status;
