@@ -764,7 +764,7 @@ int nsx_oracle_solve_warm(const nsx_problem* pb, const nsx_options* opt, const n
         if (res->entering_trace && trace_len < opt->trace_capacity) res->entering_trace[trace_len] = arc * 2 + (dir < 0);
         trace_len++;
         int rc = pivot(&cx, arc, dir, ww, &st);
-        if (rc == 3) { status = NSX_STATUS_UNBOUNDED; res->unbounded_arc = arc; goto done; }
+        if (rc == 3) { status = NSX_STATUS_UNBOUNDED; res->unbounded_arc = arc; { double urc = rc_of(&cx, arc, o->tcost[arc]); res->unbounded_rc = dir == 1 ? urc : -urc; } /* simplex.py:1233-1239 */ goto done; }
         it++;
         adapt_block(o, it);
         if (o->art_with_flow == 0) break;
@@ -788,7 +788,7 @@ phase2:
             if (res->entering_trace && trace_len < opt->trace_capacity) res->entering_trace[trace_len] = arc * 2 + (dir < 0);
             trace_len++;
             int rc = pivot(&cx, arc, dir, ww, &st);
-            if (rc == 3) { status = NSX_STATUS_UNBOUNDED; res->unbounded_arc = arc; total += it; goto done; }
+            if (rc == 3) { status = NSX_STATUS_UNBOUNDED; res->unbounded_arc = arc; { double urc = rc_of(&cx, arc, o->tcost[arc]); res->unbounded_rc = dir == 1 ? urc : -urc; } /* simplex.py:1233-1239 */ total += it; goto done; }
             it++;
             adapt_block(o, total + it);
         }
