@@ -73,9 +73,9 @@ void nsx_mt_barrier();
 #endif
 // several threads may raise the same flag at once (same value, nobody reads it before the next barrier)
 #if defined(NSX_HOST_MT) && !(defined(__CUDACC__) && !defined(NSX_HOST_EMU))
-#define NSX_RAISE(flag) __atomic_store_n(&(flag), 1, __ATOMIC_RELAXED)
+#define NSX_RAISE_TO(flag, v) __atomic_store_n(&(flag), (v), __ATOMIC_RELAXED)
 #else
-#define NSX_RAISE(flag) ((flag) = 1)
+#define NSX_RAISE_TO(flag, v) ((flag) = (v))
 #endif
 #if !NSX_ON_DEVICE
 #define NSX_ADD(a, b) ((a) + (b)) /* compiled with -ffp-contract=off */
@@ -205,11 +205,13 @@ struct NsxPivotScratch {
     // between its old and new place; instead of rewriting the position of each shifted node, the
     // shift is logged as "positions in [a, b) move by d".  A node stores (stamp << 24 | position):
     // its position is current after replaying log entries stamp .. log_len-1.
-    int32_t sp_any;            // structure-rule scan: some arc of the current chunk qualifies
+    int32_t sp_any;            // rule scan: number of the last round in which some thread saw an arc that beats the incumbent
+    int32_t sp_best, sp_zero;  // rule scan: incumbent arc*2 + (dir<0) / first zero-reduced-cost candidate, -1 none
     int32_t log_len;
     int32_t pos_mask;          // 0xffffff with lazy positions (stamp in the top byte), all ones otherwise
     int32_t log_a[NSX_LOG_CAP], log_b[NSX_LOG_CAP], log_d[NSX_LOG_CAP];
     double theta;
+    double sp_key;             // rule scan: key of the incumbent
     int32_t path_h[NSX_PATH_CAP];
     int32_t path_t[NSX_PATH_CAP];
     int32_t arc2[2 * NSX_PATH_CAP + 1];  // scan order: arc*2 + (sign<0)
@@ -987,128 +989,129 @@ NSX_FN void nsx_cl_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotS
     NSX_SYNC();
 }
 
-// Structure-specific entering rules (specialized_pivots.py:150-450; c.row_scan_first = NSX_SPECIAL_ASSIGNMENT /
-// MAX_FLOW / SHORTEST_PATH).  The assignment and shortest-path rules are SEQUENTIAL scans - a later arc replaces the
-// incumbent only if its reduced cost is lower by more than the tolerance - so the result depends on the scan order and
-// is not a reduction.  The pivot CTA walks the arcs in chunks of NSX_SP_CHUNK: all threads evaluate one chunk in
-// parallel (reduced cost, eligibility, key), one thread folds the chunk in index order exactly like the reference's
-// loop, and chunks without any qualifying arc (the common case after the first pivots) skip the fold.
+// Sequential entering rules evaluated by the pivot CTA: the structure-specific rules (specialized_pivots.py:150-450;
+// c.row_scan_first = NSX_SPECIAL_ASSIGNMENT / MAX_FLOW / SHORTEST_PATH) and the loop-based Devex block scan
+// (simplex_pricing.py:205-269).  Three of the four are NOT reductions - a later arc replaces the incumbent only if its key
+// beats it by MORE than the tolerance - so the result depends on the scan order:
 //   assignment    (:179-209)  forward arcs:  rc < best - tol                      -> best = rc
 //   shortest path (:368-424)  forward arcs with a labelled tail (node_mask): same; backward arcs: -rc < best - tol
 //   max flow      (:294-343)  merit = residual * |rc| in either direction, strictly larger wins (first arc on ties)
-// Returns arc*2 + (dir<0) or -1 in *out_arc2; -1 sends the driver on to the configured strategy (simplex.py:1066-1075).
+//   loop Devex    (:205-269)  merit = rc^2 / w  > best + tol (_is_better_candidate in ascending index order), tree cost of
+//                             the phase, forward tested before backward, first zero-reduced-cost arc of the block
+// The incumbent only ever moves one way, so an arc that the sequential scan would take also beats the incumbent the
+// round STARTED with.  Each round all threads evaluate NSX_SP_PER_THREAD arcs apiece against that start value (registers
+// only); only if some thread saw such an arc is the round folded in index order - chunk-parallel evaluation into shared
+// memory, one thread replaying the reference's loop.  Rounds without a hit (almost all after the first pivots) cost two
+// barriers and one coalesced read of the arcs.
 #define NSX_SP_CHUNK 1024
-NSX_FN void nsx_special_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotScratch& s) {
-    const double tol = d.tol;
-    const int32_t rule = c.row_scan_first;
-    int32_t best = -1;        // thread 0 carries the incumbent across chunks
-    double best_key = rule == NSX_SPECIAL_MAX_FLOW ? -NSX_INF : 0.0;
-    NSX_SYNC();
-    NSX_SINGLE { s.sp_any = 0; }
-    NSX_SYNC();
-    for (int64_t base = 0; base < d.m; base += NSX_SP_CHUNK) {
-        const int64_t cnt = d.m - base < NSX_SP_CHUNK ? d.m - base : NSX_SP_CHUNK;
-        NSX_PAR_FOR(k, 0, cnt) {
-            const int64_t i = base + k;
-            const uint8_t st = d.state[i];
-            int32_t code = 0;
-            double key = 0.0;
-            if (!(st & NSX_ARC_IN_TREE)) {
-                const int32_t tl = d.tail[i];
-                const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[tl]), d.pi[d.head[i]]);
-                if ((st & NSX_ARC_CAN_FWD) && rc < -tol) {
-                    if (rule == NSX_SPECIAL_MAX_FLOW) {
-                        const double up = d.upper[i];
-                        const double fr = nsx_isinf(up) ? NSX_INF : NSX_SUB(up, d.flow[i]);
-                        code = 1; key = NSX_MUL(fr, fabs(rc));
-                    } else if (rule == NSX_SPECIAL_ASSIGNMENT || d.node_mask[tl]) {
-                        code = 1; key = rc;
-                    }
-                } else if ((st & NSX_ARC_CAN_BWD) && rc > tol) {
-                    if (rule == NSX_SPECIAL_MAX_FLOW) { code = 2; key = NSX_MUL(d.flow[i], fabs(rc)); }
-                    else if (rule == NSX_SPECIAL_SHORTEST_PATH) { code = 2; key = -rc; }
-                }
-            }
-            s.arc2[k] = code;
-            s.res[k] = key;
-            if (code) NSX_RAISE(s.sp_any);
-        }
-        NSX_SYNC();
-        NSX_SINGLE {
-            if (s.sp_any) {
-                s.sp_any = 0;
-                for (int64_t k = 0; k < cnt; ++k) {
-                    const int32_t code = s.arc2[k];
-                    if (!code) continue;
-                    const double key = s.res[k];
-                    const bool take = rule == NSX_SPECIAL_MAX_FLOW ? key > best_key : key < NSX_SUB(best_key, tol);
-                    if (take) { best_key = key; best = (int32_t)(base + k) * 2 + (code == 2 ? 1 : 0); }
-                }
-            }
-        }
-        NSX_SYNC();
-    }
-    NSX_SINGLE { *out_arc2 = best; c.arcs_priced += d.m; }
-    NSX_SYNC();
-}
+#define NSX_SP_PER_THREAD 16
+#define NSX_RULE_DEVEX_LOOP 5  // internal rule id next to NSX_SPECIAL_ASSIGNMENT (2) / MAX_FLOW (3) / SHORTEST_PATH (4)
 
-// Loop-based Devex block scan (DevexPricing.select_entering_arc with use_vectorized_pricing=False,
-// simplex_pricing.py:205-269) over [lo, hi): like nsx_special_scan a sequential rule - a later arc replaces the
-// incumbent only when its merit rc^2/w is larger by MORE than the tolerance (_is_better_candidate, :294-308, in ascending
-// index order) - evaluated chunk-parallel and folded in order by one thread.  Differences from the vectorised search
-// (nsx_price_devex): tree cost of the current phase instead of the perturbed Phase-2 cost, forward tested before
-// backward per arc, the FIRST zero-reduced-cost arc of the block whatever its direction, no excluded arc.
-// *out_arc2 = improving pick, *out_zero2 = first zero candidate (both arc*2 + (dir<0), -1 none).
-NSX_FN void nsx_devex_loop_scan(const NsxDev& d, NsxCtl& c, int64_t lo, int64_t hi, int allow_zero,
-                                int32_t* out_arc2, int32_t* out_zero2, NsxPivotScratch& s) {
+// arc i under `rule`: 0 = not a candidate, 1 / 2 = improving forward / backward with *key, 3 / 4 = zero-reduced-cost
+// forward / backward (loop Devex in Phase 1 only)
+NSX_FN int32_t nsx_rule_eval(const NsxDev& d, const NsxCtl& c, int32_t rule, int allow_zero, int64_t i, double tol, double* key) {
+    const uint8_t st = d.state[i];
+    if (st & NSX_ARC_IN_TREE) return 0;
+    const int32_t tl = d.tail[i];
+    const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[tl]), d.pi[d.head[i]]);
+    const bool fv = (st & NSX_ARC_CAN_FWD) && rc < -tol;
+    const bool bv = !fv && (st & NSX_ARC_CAN_BWD) && rc > tol;
+    if (rule == NSX_RULE_DEVEX_LOOP) {
+        if (fv || bv) {
+            const uint32_t wraw = d.wgt[i];
+            const double w = (wraw >> 24) == c.wepoch ? (double)(wraw & 0xffffffu) : 1.0;
+            *key = NSX_DIV(NSX_MUL(rc, rc), w);
+            return fv ? 1 : 2;
+        }
+        if (allow_zero && fabs(rc) <= tol) return (st & NSX_ARC_CAN_FWD) ? 3 : ((st & NSX_ARC_CAN_BWD) ? 4 : 0);
+        return 0;
+    }
+    if (rule == NSX_SPECIAL_MAX_FLOW) {
+        if (fv) {
+            const double up = d.upper[i];
+            *key = NSX_MUL(nsx_isinf(up) ? NSX_INF : NSX_SUB(up, d.flow[i]), fabs(rc));
+            return 1;
+        }
+        if (bv) { *key = NSX_MUL(d.flow[i], fabs(rc)); return 2; }
+        return 0;
+    }
+    if (fv) {
+        if (rule == NSX_SPECIAL_ASSIGNMENT || d.node_mask[tl]) { *key = rc; return 1; }
+        return 0;
+    }
+    if (bv && rule == NSX_SPECIAL_SHORTEST_PATH) { *key = -rc; return 2; }
+    return 0;
+}
+NSX_FN bool nsx_rule_beats(int32_t rule, double key, double incumbent, double tol) {
+    if (rule == NSX_SPECIAL_MAX_FLOW) return key > incumbent;
+    if (rule == NSX_RULE_DEVEX_LOOP) return key > NSX_ADD(incumbent, tol);
+    return key < NSX_SUB(incumbent, tol);
+}
+// in-order fold of [lo, hi) into the incumbent kept in s.sp_key / s.sp_best / s.sp_zero
+NSX_FN void nsx_rule_fold(const NsxDev& d, const NsxCtl& c, int32_t rule, int64_t lo, int64_t hi, int allow_zero,
+                          NsxPivotScratch& s) {
     const double tol = d.tol;
-    int32_t best = -1, zero = -1;
-    double best_merit = -NSX_INF;
-    NSX_SYNC();
-    NSX_SINGLE { s.sp_any = 0; }
-    NSX_SYNC();
     for (int64_t base = lo; base < hi; base += NSX_SP_CHUNK) {
         const int64_t cnt = hi - base < NSX_SP_CHUNK ? hi - base : NSX_SP_CHUNK;
         NSX_PAR_FOR(k, 0, cnt) {
-            const int64_t i = base + k;
-            const uint8_t st = d.state[i];
-            int32_t code = 0;
             double key = 0.0;
-            if (!(st & NSX_ARC_IN_TREE)) {
-                const double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, c.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
-                const bool fv = (st & NSX_ARC_CAN_FWD) && rc < -tol;
-                const bool bv = !fv && (st & NSX_ARC_CAN_BWD) && rc > tol;
-                if (fv || bv) {
-                    const uint32_t wraw = d.wgt[i];
-                    const double w = (wraw >> 24) == c.wepoch ? (double)(wraw & 0xffffffu) : 1.0;
-                    code = fv ? 1 : 2;
-                    key = NSX_DIV(NSX_MUL(rc, rc), w);
-                } else if (allow_zero && fabs(rc) <= tol) {
-                    code = (st & NSX_ARC_CAN_FWD) ? 3 : ((st & NSX_ARC_CAN_BWD) ? 4 : 0);
-                }
-            }
-            s.arc2[k] = code;
+            s.arc2[k] = nsx_rule_eval(d, c, rule, allow_zero, base + k, tol, &key);
             s.res[k] = key;
-            if (code) NSX_RAISE(s.sp_any);
         }
         NSX_SYNC();
         NSX_SINGLE {
-            if (s.sp_any) {
-                s.sp_any = 0;
-                for (int64_t k = 0; k < cnt; ++k) {
-                    const int32_t code = s.arc2[k];
-                    if (code == 1 || code == 2) {
-                        if (s.res[k] > NSX_ADD(best_merit, tol)) { best_merit = s.res[k]; best = (int32_t)(base + k) * 2 + (code == 2 ? 1 : 0); }
-                    } else if (code && zero < 0) {
-                        zero = (int32_t)(base + k) * 2 + (code == 4 ? 1 : 0);
-                    }
+            double best_key = s.sp_key;
+            int32_t best = s.sp_best, zero = s.sp_zero;
+            for (int64_t k = 0; k < cnt; ++k) {
+                const int32_t code = s.arc2[k];
+                if (code == 1 || code == 2) {
+                    if (nsx_rule_beats(rule, s.res[k], best_key, tol)) { best_key = s.res[k]; best = (int32_t)(base + k) * 2 + (code == 2 ? 1 : 0); }
+                } else if (code && zero < 0) {
+                    zero = (int32_t)(base + k) * 2 + (code == 4 ? 1 : 0);
                 }
             }
+            s.sp_key = best_key; s.sp_best = best; s.sp_zero = zero;
         }
         NSX_SYNC();
     }
-    NSX_SINGLE { *out_arc2 = best; *out_zero2 = zero; c.arcs_priced += hi - lo; }
+}
+// *out_arc2 = the rule's pick over [lo, hi), *out_zero2 = first zero candidate (both arc*2 + (dir<0), -1 none)
+NSX_FN void nsx_rule_scan(const NsxDev& d, NsxCtl& c, int32_t rule, int64_t lo, int64_t hi, int allow_zero,
+                          int32_t* out_arc2, int32_t* out_zero2, NsxPivotScratch& s) {
+    const double tol = d.tol;
+    const bool larger_wins = rule == NSX_SPECIAL_MAX_FLOW || rule == NSX_RULE_DEVEX_LOOP;
     NSX_SYNC();
+    NSX_SINGLE { s.sp_key = larger_wins ? -NSX_INF : 0.0; s.sp_best = -1; s.sp_zero = -1; s.sp_any = 0; }
+    NSX_SYNC();
+    const int64_t span = (int64_t)NSX_NTHREADS * NSX_SP_PER_THREAD;
+    int32_t round = 0;
+    for (int64_t r0 = lo; r0 < hi; r0 += span) {
+        const int64_t r1 = hi - r0 < span ? hi : r0 + span;
+        ++round;
+        const double incumbent = s.sp_key;  // written before the last barrier
+        const bool want_zero = allow_zero && s.sp_zero < 0;
+        bool hit = false;
+        NSX_PAR_FOR(i, r0, r1) {
+            double key = 0.0;
+            const int32_t code = nsx_rule_eval(d, c, rule, allow_zero, i, tol, &key);
+            if (code == 1 || code == 2) { if (nsx_rule_beats(rule, key, incumbent, tol)) hit = true; }
+            else if (code && want_zero) hit = true;
+        }
+        if (hit) NSX_RAISE_TO(s.sp_any, round);  // several threads may store the same round number
+        NSX_SYNC();
+        const bool fold = s.sp_any == round;
+        NSX_SYNC();  // everybody has read the flag before the next round can raise it again
+        if (fold) nsx_rule_fold(d, c, rule, r0, r1, allow_zero, s);
+    }
+    NSX_SINGLE { *out_arc2 = s.sp_best; if (out_zero2) *out_zero2 = s.sp_zero; c.arcs_priced += hi - lo; }
+    NSX_SYNC();
+}
+NSX_FN void nsx_special_scan(const NsxDev& d, NsxCtl& c, int32_t* out_arc2, NsxPivotScratch& s) {
+    nsx_rule_scan(d, c, c.row_scan_first, 0, d.m, 0, out_arc2, (int32_t*)0, s);
+}
+NSX_FN void nsx_devex_loop_scan(const NsxDev& d, NsxCtl& c, int64_t lo, int64_t hi, int allow_zero,
+                                int32_t* out_arc2, int32_t* out_zero2, NsxPivotScratch& s) {
+    nsx_rule_scan(d, c, NSX_RULE_DEVEX_LOOP, lo, hi, allow_zero, out_arc2, out_zero2, s);
 }
 
 // Block-size adaptation after each pivot (simplex_adaptive.py:98-151). Single thread.
