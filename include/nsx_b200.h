@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NSX_ABI_VERSION 1
+#define NSX_ABI_VERSION 2 /* 2: nsx_options.node_mask, NSX_SPECIAL_*, NSX_PRICING_DEVEX_LOOP, nsx_solve_warm, NSX_ARC_STALE */
 
 /* pricing rules: SolverOptions.pricing_strategy (src/network_solver/data.py:459-488) */
 #define NSX_PRICING_DANTZIG 0 /* DantzigPricing.select_entering_arc, simplex_pricing.py:97-137 */

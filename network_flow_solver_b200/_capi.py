@@ -17,6 +17,7 @@ import numpy as np
 from .canonical import CanonicalProblem
 from .exceptions import DeviceEngineError
 
+ABI_VERSION = 2  # NSX_ABI_VERSION of include/nsx_b200.h these declarations mirror
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
 PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
@@ -341,6 +342,13 @@ def load_library():
         lib.nsx_solve_batch.restype = C.c_int
         lib.nsx_last_error.restype = C.c_char_p
         lib.nsx_version.argtypes = [_p_i32, _p_i32]
+        abi = C.c_int32(-1)
+        lib.nsx_version(C.byref(abi), None)
+        if abi.value != ABI_VERSION:  # a stale build would read the structs with another layout
+            raise DeviceEngineError(
+                f"{path} implements ABI version {abi.value}, these bindings need {ABI_VERSION}: rebuild it "
+                f"(python -c 'import __graft_entry__ as g; g.build()')."
+            )
         lib.nsx_device_count.restype = C.c_int
         _lib = lib
         return lib

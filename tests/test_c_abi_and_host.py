@@ -25,13 +25,13 @@ def test_library_exports_every_declared_symbol():
     lib_path = entry.build_engine()
     lib = ctypes.CDLL(str(lib_path))
     symbols = entry.declared_symbols()
-    assert {"nsx_solve", "nsx_solve_resident", "nsx_solve_batch", "nsx_solve_sharded", "nsx_sweep_probe",
+    assert {"nsx_solve", "nsx_solve_warm", "nsx_solve_resident", "nsx_solve_batch", "nsx_solve_sharded", "nsx_sweep_probe",
             "nsx_mailbox_create", "nsx_mailbox_open", "nsx_mailbox_bytes", "nsx_last_error", "nsx_version"} <= set(symbols)
     for name in symbols:
         assert hasattr(lib, name), name
     abi, arch = ctypes.c_int32(), ctypes.c_int32()
     lib.nsx_version(ctypes.byref(abi), ctypes.byref(arch))
-    assert (abi.value, arch.value) == (1, 100)
+    assert (abi.value, arch.value) == (_capi.ABI_VERSION, 100) == (2, 100)
 
 
 def test_ctypes_structs_match_the_header(tmp_path):
