@@ -43,6 +43,7 @@
 #define NSX_DIV(a, b) __ddiv_rn((a), (b))
 #define NSX_INF __longlong_as_double(0x7ff0000000000000LL)
 #define NSX_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#define NSX_ATOMIC_ADD_F64(p, v) atomicAdd((p), (v))
 #define NSX_CLOCK() clock64()
 #define NSX_ATOMIC_MIN_I32(p, v) atomicMin((p), (v))
 #define NSX_ATOMIC_MAX_I32(p, v) atomicMax((p), (v))
@@ -86,12 +87,19 @@ void nsx_mt_barrier();
 #define NSX_CLOCK() 0ll
 #if defined(NSX_HOST_MT)
 #define NSX_ATOMIC_ADD_I32(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+static inline void nsx_mt_addf(double* p, double v) {
+    uint64_t o = __atomic_load_n((uint64_t*)p, __ATOMIC_RELAXED), n;
+    double t;
+    do { memcpy(&t, &o, 8); t += v; memcpy(&n, &t, 8); } while (!__atomic_compare_exchange_n((uint64_t*)p, &o, n, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+#define NSX_ATOMIC_ADD_F64(p, v) nsx_mt_addf((p), (v))
 static inline int32_t nsx_mt_min(int32_t* p, int32_t v) { int32_t o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v < o && !__atomic_compare_exchange_n(p, &o, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 static inline int32_t nsx_mt_max(int32_t* p, int32_t v) { int32_t o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 #define NSX_ATOMIC_MIN_I32(p, v) nsx_mt_min((p), (v))
 #define NSX_ATOMIC_MAX_I32(p, v) nsx_mt_max((p), (v))
 #else
 #define NSX_ATOMIC_ADD_I32(p, v) ((*(p) += (v)) - (v))
+#define NSX_ATOMIC_ADD_F64(p, v) (*(p) += (v))
 #define NSX_ATOMIC_MIN_I32(p, v) (*(p) = (v) < *(p) ? (v) : *(p))
 #define NSX_ATOMIC_MAX_I32(p, v) (*(p) = (v) > *(p) ? (v) : *(p))
 #endif
@@ -141,6 +149,8 @@ struct NsxDev {
     uint16_t* par16;    // optional shared-memory mirror of the parent pointers (parent - 1), for the cycle walk
     uint32_t* root_bits;  // bit v set: the parent of v is the root (the one value parent - 1 cannot encode)
     const uint8_t* node_mask;  // [n] NSX_SPECIAL_SHORTEST_PATH: node reachable from the source (HBM), else null
+    double* imbalance;         // [n] warm starts only (else null): flow that clamping to a bound added at / removed from
+                               // each node - the reference checks conservation after Phase 1 (simplex.py:1575-1598)
     int32_t lazy_pos;   // preorder positions are updated lazily through the shift log (large trees in HBM)
     int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
 };
@@ -170,6 +180,7 @@ struct NsxCtl {
     uint32_t wepoch;      // current Devex weight epoch (8 bits used)
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     int32_t warm;         // started from a caller-supplied tree (nsx_solve_warm): NSX_ARC_STALE bits may be set
+    int32_t unbalanced;   // warm start: some node's balance is off by more than tol after Phase 1 (simplex.py:1575-1598)
     // statistics
     int64_t degenerate, tree_updates, resets, arcs_priced, sweeps;
     int64_t avg_cycle;    // running mean of the cycle length * 16 (chooses the cycle-walk variant)
@@ -740,8 +751,19 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             double f = sign > 0 ? NSX_ADD(old, theta) : NSX_SUB(old, theta);
             uint8_t st = d.state[a];
             if (theta > 0.0) st |= NSX_ARC_TOUCHED;
+            const double pushed = f;
             if (f < NSX_SUB(0.0, tol)) { f = 0.0; st &= (uint8_t)~NSX_ARC_TOUCHED; }
             if (!nsx_isinf(up) && f > NSX_ADD(up, tol)) { f = up; st &= (uint8_t)~NSX_ARC_TOUCHED; }
+            if (d.imbalance && f != pushed) {
+                // A clamp takes flow out of (or puts it into) the arc without a matching change elsewhere. It cannot
+                // happen from a consistent state; after a warm start the stale residuals (NSX_ARC_STALE) make the ratio
+                // test over-push, the reference clamps silently (simplex.py:1263-1266) and only its conservation check
+                // after Phase 1 notices.  Every other flow change is a cycle push, so the node balances are exactly the
+                // sums of these corrections.
+                const double fix = NSX_SUB(f, pushed);
+                NSX_ATOMIC_ADD_F64(&d.imbalance[nsx_tail(d, a)], -fix);
+                NSX_ATOMIC_ADD_F64(&d.imbalance[nsx_head(d, a)], fix);
+            }
             d.flow[a] = f;
             st = (uint8_t)((st & (NSX_ARC_IN_TREE | NSX_ARC_TOUCHED)) | nsx_bounds_bits(f, up, tol));
             d.state[a] = st;
@@ -1517,7 +1539,7 @@ NSX_FN void nsx_drv_phase_end(NsxCtl& c, NsxDrv& v, NsxAction& act) {
         c.total = c.it;
         c.phase1_iterations = c.it;
         c.art_after_p1 = c.art_with_flow;
-        if (c.art_with_flow > 0) {  // simplex.py:1600-1624
+        if (c.art_with_flow > 0 || c.unbalanced) {  // simplex.py:1571-1624
             c.status = c.total >= c.maxit ? NSX_STATUS_ITERATION_LIMIT_P1 : NSX_STATUS_INFEASIBLE;
             act.kind = NSX_ACT_EXIT;
             return;
@@ -1532,6 +1554,15 @@ NSX_FN void nsx_drv_phase_end(NsxCtl& c, NsxDrv& v, NsxAction& act) {
         if (c.total >= c.maxit) { v.final_check = 1; act.kind = NSX_ACT_RECOMPUTE; }
         else { c.status = NSX_STATUS_OPTIMAL; act.kind = NSX_ACT_EXIT; }
     }
+}
+
+// Conservation check after Phase 1 of a warm solve (simplex.py:1575-1598): any node other than the root whose balance is
+// off by more than tol makes the run "infeasible" (see the clamp note in nsx_pivot).
+NSX_FN void nsx_check_conservation(const NsxDev& d, NsxCtl& c) {
+    const double tol = d.tol;
+    NSX_SYNC();
+    NSX_PAR_FOR(v, 1, d.n) { if (fabs(d.imbalance[v]) > tol) NSX_RAISE_TO(c.unbalanced, 1); }
+    NSX_SYNC();
 }
 
 // The resident loop of the pivot CTA.  `Sweep::run(cmd, dz, dx)` prices the arc range of `cmd`
@@ -1577,6 +1608,8 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_after_pivot(c, L.drv, d.m, rc, L.cmd, L.act); }
         } else if (kind == NSX_ACT_PHASE_END) {
+            // (d.imbalance first: without it nobody but thread 0 may touch c.phase here, thread 0 is about to change it)
+            if (d.imbalance && c.phase == 1) nsx_check_conservation(d, c);
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
             if (!L.drv.final_check) {

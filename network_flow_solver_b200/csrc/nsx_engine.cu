@@ -1508,6 +1508,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_slots = arena.plan(sizeof(NsxSlot) * 1024);
     size_t o_topk = arena.plan(sizeof(NsxTopkOut) * 160);
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
+    size_t o_imb = warm ? arena.plan((size_t)n * 8) : 0;
     NSX_CUDA(arena.commit());
 
     st.base = arena.at<unsigned char>(o_store);
@@ -1519,6 +1520,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
     d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
+    d.imbalance = warm ? arena.at<double>(o_imb) : nullptr;
     d.lazy_pos = (n < (1 << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0;
     d.log_cap = nsx_env_int("NSX_LOG_CAP", 32);
     if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
@@ -1594,6 +1596,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         if (ib < 1) ib = 1;
         if (ib > info.sms * 8) ib = info.sms * 8;
         if (warm) {
+            NSX_CUDA(cudaMemsetAsync(d.imbalance, 0, (size_t)n * 8, stream));
             uint8_t* d_wtree = inputs.at<uint8_t>(i_wtree);
             NSX_CUDA(cudaMemcpyAsync(d_wtree, warm->in_tree, (size_t)ma, cudaMemcpyHostToDevice, stream));
             NSX_CUDA(cudaMemcpyAsync(d.flow, warm->flow, (size_t)ma * 8, cudaMemcpyHostToDevice, stream));
@@ -1778,7 +1781,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.gpath_h = arena.at<int32_t>(o.gph); d.gpath_t = arena.at<int32_t>(o.gpt);
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
-        d.node_mask = nullptr;
+        d.node_mask = nullptr; d.imbalance = nullptr;
         d.lazy_pos = (n < (1u << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0; d.log_cap = 32;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);

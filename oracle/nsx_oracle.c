@@ -772,7 +772,17 @@ int nsx_oracle_solve_warm(const nsx_problem* pb, const nsx_options* opt, const n
     total = it;
     res->phase1_iterations = it;
     res->artificial_with_flow = o->art_with_flow;
-    if (o->art_with_flow > 0) {
+    int unbalanced = 0;
+    if (warm) { /* conservation check after Phase 1 (simplex.py:1575-1598), every arc in index order per node. It can only
+                   fail after a warm start: the stale residuals let the ratio test over-push an arc and the flow update
+                   clamps it back to its bound (simplex.py:1263-1266) */
+        double* net = malloc(n * 8);
+        for (size_t v = 0; v < n; ++v) net[v] = pb->supply[v];
+        for (int64_t a = 0; a < o->ma; ++a) { net[TAIL(&cx, a)] -= o->flow[a]; net[HEAD(&cx, a)] += o->flow[a]; }
+        for (size_t v = 1; v < n; ++v) if (fabs(net[v]) > o->tol) unbalanced = 1;
+        free(net);
+    }
+    if (o->art_with_flow > 0 || unbalanced) {
         status = total >= maxit ? NSX_STATUS_ITERATION_LIMIT_P1 : NSX_STATUS_INFEASIBLE;
         goto done;
     }

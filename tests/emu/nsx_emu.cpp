@@ -87,7 +87,7 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     d.flow = flow.data(); d.state = state.data(); d.wgt = wgt.data();
     d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.pi_mirror = nullptr; d.order = order.data();
     d.tmp = tmp.data(); d.gpath_h = gph.data(); d.gpath_t = gpt.data(); d.garc2 = garc2.data();
-    d.node_mask = opt->node_mask; d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
+    d.node_mask = opt->node_mask; d.imbalance = nullptr; d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
     { const char* lz = getenv("NSX_EMU_LAZY"); d.lazy_pos = lz && *lz ? atoi(lz) : 0;
       const char* lc = getenv("NSX_EMU_LOG_CAP"); d.log_cap = lc && *lc ? atoi(lc) : NSX_LOG_CAP;
       if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP; }
@@ -102,6 +102,8 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     c.unbounded_arc = -1;
 
     int64_t art = 0;
+    std::vector<double> imbalance(warm ? (size_t)n : 0, 0.0);
+    if (warm) d.imbalance = imbalance.data();
     if (warm) {  // same steps as nsx_solve_warm: host layout, copies, element-wise arc init
         int bad = nsx_warm_layout(n, m, pb->tail, pb->head, pb->supply, d.tol, warm->in_tree, node, depth, order);
         if (bad) return bad;

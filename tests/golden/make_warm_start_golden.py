@@ -123,6 +123,16 @@ def main():
     case("small_partial_basis", small, small, allv,
          basis_edit=lambda b: RefBasis(tree_arcs={("s", "b")}, arc_flows={("s", "b"): 10.0}))
 
+    # found by scripts/fuzz_warm_start_vs_reference.py: the reference's stale residual mirrors let the first pivot push 7
+    # units through an arc with 5 units of room, the flow update clamps it back and the conservation check after Phase 1
+    # (simplex.py:1575-1598) turns the run into "infeasible" although the edited instance is feasible
+    over = mg.problem_to_spec(mg.ref_build(
+        [{"id": "v0", "supply": 5.0}, {"id": "v1", "supply": 2.0}, {"id": "v2", "supply": -3.0}, {"id": "v3", "supply": -4.0}],
+        [{"tail": a, "head": b, "capacity": c, "cost": w} for a, b, c, w in
+         [("v0", "v1", 7.0, 1.0), ("v2", "v1", 7.0, 0.0), ("v0", "v3", 6.0, 3.0), ("v3", "v1", 6.0, 4.0), ("v0", "v2", 5.0, 1.0),
+          ("v1", "v2", 7.0, 2.0), ("v2", "v3", 7.0, 7.0)]], directed=True, tolerance=1e-6))
+    case("overpush_breaks_conservation", over, edit(over, capacity_mul={3: 4.0 / 6.0}), [DZ, CL, AD])
+
     def fam(arrays, tol=1e-3):
         p = gen.to_network_problem(arrays)
         return mg.problem_to_spec(mg.ref_build([{"id": n.id, "supply": n.supply} for n in p.nodes.values()],

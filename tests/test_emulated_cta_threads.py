@@ -15,7 +15,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
 SELECT = ("emulated and (assignment_6 or shortest_path_20 or max_flow_24 or netgen_64 or transport_32 or small_ or "
-          "uncap_64_costs or transport_16 or candidate)")
+          "uncap_64_costs or overpush or transport_16 or candidate)")
 FILES = ["tests/test_next_special_pivots.py", "tests/test_next_devex_loop.py", "tests/test_next_warm_start.py",
          "tests/test_next_candidate_list.py"]
 

@@ -105,9 +105,14 @@ def test_engine_on_the_reduced_instance_then_translation(name, i):
     assert_final(final_of(case, run, inner), run["final"])
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", ["oracle", pytest.param("engine", marks=pytest.mark.gpu)])
 @pytest.mark.parametrize("name", ["chain_of_three", "decorated_96", "nothing_to_do"])
-def test_preprocess_and_solve_end_to_end(name, capsys):
+def test_preprocess_and_solve_end_to_end(name, backend, capsys, monkeypatch):
+    if backend == "oracle":  # test-only stand-in for the C-ABI call: runs the host half of the public call on CPU
+        from network_flow_solver_b200 import solver as solver_module
+
+        monkeypatch.setattr(solver_module._capi, "solve_canonical",
+                            lambda cp, opts, out=None, warm=None: oracle.solve_canonical(cp, opts, warm=warm))
     case = CASES[name]
     for run in case["runs"]:
         pre, result = preprocess_and_solve(rebuild_problem(case["problem"]), options=SolverOptions(**run["inner"]["options"]))
