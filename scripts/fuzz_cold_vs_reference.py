@@ -12,13 +12,16 @@ os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
 logging.disable(logging.CRITICAL)
 from network_solver import SolverOptions as RefOptions, build_problem as ref_build, solve_min_cost_flow as ref_solve
 from network_solver.exceptions import UnboundedProblemError as RefUnbounded
-from network_solver.preprocessing import preprocess_problem as ref_preprocess
+from network_solver.preprocessing import preprocess_problem as ref_preprocess, preprocess_and_solve as ref_pas
 from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, UnboundedProblemError, build_problem
-from network_flow_solver_b200.preprocessing import preprocess_problem
+from network_flow_solver_b200.preprocessing import preprocess_problem, preprocess_and_solve
+from network_flow_solver_b200 import solver as solver_module
 from network_flow_solver_b200.solver import finish, prepare
 from oracle import oracle
 from emu import emu
 
+# the public call's C-ABI step is served by the oracle here (no GPU in the build container); everything around it is the product's host code
+solver_module._capi.solve_canonical = lambda cp, opts, out=None, warm=None: oracle.solve_canonical(cp, opts, warm=warm)
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 
@@ -83,6 +86,12 @@ seen_kinds = collections.Counter()
 for trial in range(trials):
     nodes, arcs, directed = instance()
     kw, limit = options()
+    if rng.random() < 0.15:  # badly scaled values + the default auto_scale=True (scaling.py)
+        cm, qm = rng.choice([1e-4, 1e-3, 1e3, 1e5]), rng.choice([1.0, 1e3, 1e4])
+        nodes = {k: v * qm for k, v in nodes.items()}
+        arcs = [(a, b, None if c is None else c * qm, w * cm, lo * qm) for a, b, c, w, lo in arcs]
+        kw["auto_scale"] = True
+    via_preprocessing = rng.random() < 0.15  # preprocess_and_solve(): reduce, solve, translate back
     mk = lambda build: build([{"id": k, "supply": v} for k, v in nodes.items()],
                              [{"tail": a, "head": b, "capacity": c, "cost": w, "lower": lo} for a, b, c, w, lo in arcs], directed=directed, tolerance=1e-6)
     try:
@@ -97,6 +106,32 @@ for trial in range(trials):
         bad += 1
         print(f"trial {trial}: preprocess_problem differs\n   nodes {nodes}\n   arcs {arcs} directed {directed}")
     # solve
+    if via_preprocessing:
+        try:
+            with redirect_stdout(io.StringIO()):
+                _, ref = ref_pas(rp, options=RefOptions(**kw), max_iterations=limit)
+            want = (ref.status, ref.iterations, ref.objective, ref.flows, ref.duals)
+        except RefUnbounded as exc:
+            want = ("unbounded", tuple(exc.entering_arc), exc.reduced_cost)
+        except Exception as exc:
+            want = ("error", type(exc).__name__)
+        try:
+            with redirect_stdout(io.StringIO()):
+                _, r = preprocess_and_solve(mp, options=SolverOptions(**kw), max_iterations=limit)  # C-ABI call -> oracle, see below
+            got = (r.status, r.iterations, r.objective, r.flows, r.duals)
+        except UnboundedProblemError as exc:
+            got = ("unbounded", tuple(exc.entering_arc), exc.reduced_cost)
+        except SolverConfigurationError:
+            skipped += 1
+            continue
+        except Exception as exc:
+            got = ("error", type(exc).__name__)
+        compared += 1
+        seen_kinds[("preprocess_and_solve", str(want[0]), 'directed' if directed else 'undirected')] += 1
+        if got != want:
+            bad += 1
+            print(f"trial {trial}: preprocess_and_solve {kw} limit {limit}\n   reference {want[:3]}\n   mine      {got[:3]}\n   nodes {nodes}\n   arcs {arcs} directed {directed}")
+        continue
     try:
         with redirect_stdout(io.StringIO()):
             ref = ref_solve(rp, RefOptions(**kw), max_iterations=limit)
@@ -115,7 +150,7 @@ for trial in range(trials):
     else:
         def outcome(raw):
             try:
-                r = finish(cp, raw, opts)
+                r = finish(cp, raw, opts, plan.scaling)
                 return (r.status, r.iterations, r.objective, r.flows, r.duals)
             except UnboundedProblemError as exc:
                 return ("unbounded", tuple(exc.entering_arc), exc.reduced_cost)
