@@ -4,7 +4,7 @@ negative costs (unbounded exits), assignment / max-flow / shortest-path structur
 strategies, loop-based Devex, fixed block sizes, iteration limits).  The reference solves each instance; this repo's host
 logic + oracle + emulated device core must give the same status, iteration count, objective, flows and duals (or the same
 exception), and preprocess_problem() the same reduced problem and maps.
-    NUMBA_CACHE_DIR=/tmp/numba_cache python scripts/fuzz_cold_vs_reference.py [trials] [seed]"""
+    NUMBA_CACHE_DIR=/tmp/numba_cache [FUZZ_SCALE=4] python scripts/fuzz_cold_vs_reference.py [trials] [seed]"""
 import io, logging, os, random, sys
 from contextlib import redirect_stdout
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); sys.path.insert(0, '/root/reference/src')
@@ -22,17 +22,18 @@ from emu import emu
 
 # the public call's C-ABI step is served by the oracle here (no GPU in the build container); everything around it is the product's host code
 solver_module._capi.solve_canonical = lambda cp, opts, out=None, warm=None: oracle.solve_canonical(cp, opts, warm=warm)
+SCALE = int(os.environ.get('FUZZ_SCALE', '1'))  # node-count multiplier: >1 reaches the 50-pivot block adaptation and the 65-pivot reset cadence
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 
 
 def instance():
     kind = rng.random()
-    n = rng.randint(3, 10)
+    n = rng.randint(3, 10) * SCALE
     ids = [f"v{i}" for i in range(n)]
     directed = True
     if kind < 0.12:  # assignment
-        k = rng.randint(2, 5)
+        k = rng.randint(2, 5) * max(1, SCALE // 2)
         nodes = {f"w{i}": 1.0 for i in range(k)} | {f"j{i}": -1.0 for i in range(k)}
         arcs = [(f"w{i}", f"j{j}", 1.0, float(rng.randint(1, 9)), 0.0) for i in range(k) for j in range(k) if i == j or rng.random() < 0.7]
         return nodes, arcs, True
@@ -51,7 +52,7 @@ def instance():
     order = ids[:]; rng.shuffle(order)
     for a, b in zip(order, order[1:] + order[:1]):  # a ring with room for everything: feasible whatever the supplies
         arcs.append((a, b, total + 1.0, float(rng.randint(1, 9)) if uniform is None else uniform, 0.0)); seen.add((a, b))
-    for _ in range(rng.randint(0, 2 * n)):
+    for _ in range(rng.randint(0, 2 * n) * (2 if SCALE > 1 else 1)):
         a, b = rng.sample(ids, 2)
         if (a, b) in seen or (not directed and (b, a) in seen):
             continue
