@@ -17,12 +17,13 @@ from oracle import oracle
 sys.path.insert(0, 'tests')
 from emu import emu
 
+SCALE = int(os.environ.get('FUZZ_SCALE', '1'))  # node-count multiplier
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 STRATEGIES = ["dantzig", "devex", "candidate_list", "adaptive"]
 bad = applied = rejected = errors = 0
 for trial in range(trials):
-    n = rng.randint(4, 9)
+    n = rng.randint(4, 9) * SCALE
     ids = [f"v{i}" for i in range(n)]
     total = rng.randint(2, 12)
     supply = {v: 0 for v in ids}
@@ -38,7 +39,7 @@ for trial in range(trials):
             seen.add((a, b)); arcs.append([ids[a], ids[b], float(rng.randint(1, total)), float(rng.randint(0, 9))])
     rng.shuffle(arcs)
     edited = [list(x) for x in arcs]
-    for _ in range(rng.randint(1, 4)):
+    for _ in range(rng.randint(1, 4) * SCALE):
         k = rng.randrange(len(edited))
         what = rng.random()
         if what < 0.5: edited[k][3] = float(rng.randint(0, 9))
