@@ -38,6 +38,8 @@ def test_cta_of_real_threads_neither_deadlocks_nor_races(tmp_path, lazy):
     log = tmp_path / "tsan.log"
     proc = run_suite(lib, {"LD_PRELOAD": tsan, "TSAN_OPTIONS": f"report_signal_unsafe=0 exitcode=0 log_path={log}",
                            "NSX_EMU_LAZY": lazy, "NSX_EMU_LOG_CAP": "3"}, tmp_path)
+    if "unexpected memory mapping" in proc.stderr or "unexpected memory mapping" in proc.stdout:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory on this kernel (ASLR layout)")
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]  # a deadlock ends in the timeout above
     assert " passed" in proc.stdout and "failed" not in proc.stdout
     reports = [p.read_text() for p in tmp_path.glob("tsan.log*")]
