@@ -17,5 +17,7 @@ rec = dict(workload=name, status=r.status, iterations=r.iterations, phase1=r.pha
            pi_sha=hashlib.sha256(r.potential.tobytes()).hexdigest(), state_sha=hashlib.sha256(r.state.tobytes()).hexdigest(),
            oracle_seconds=dt, oracle_threads=threads, final_block_size=r.final_block_size)
 print(json.dumps(rec), flush=True)
-import os; os.makedirs("tests/golden/full", exist_ok=True)
-json.dump(rec, open(f"tests/golden/full/{name}.json", "w"), indent=1)
+import os
+out = sys.argv[3] if len(sys.argv) > 3 else "tests/golden/full"  # tests/golden/full_next: workloads of rows not yet run on hardware
+os.makedirs(out, exist_ok=True)
+json.dump(rec, open(f"{out}/{name}.json", "w"), indent=1)
