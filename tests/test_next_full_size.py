@@ -1,7 +1,7 @@
 """Full-size workloads of the rows added after the hardware budget of round 1 (structure-specific rules, loop-based Devex):
 the oracle was run once per workload (scripts/oracle_full.py <name> 8 tests/golden/full_next) and its status, pivot counts,
 objective and the SHA-256 of its entering-arc trace / flows / potentials / arc states are committed.  CPU: the emulated
-device core reproduces the two smaller records; GPU: the CUDA engine must reproduce every record bit for bit and end in a
+device core reproduces the smaller records; GPU: the CUDA engine must reproduce every record bit for bit and end in a
 state that satisfies the optimality conditions."""
 
 import json
@@ -34,7 +34,7 @@ def check(name, solve):
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("name", [n for n in NAMES if n in ("assignment_192", "max_flow_2e12")])
+@pytest.mark.parametrize("name", [n for n in NAMES if n in ("assignment_192", "max_flow_2e12", "netgen_2e13_devex_loop")])
 def test_emulated_device_core_reproduces_the_record(name):
     check(name, emu.solve_canonical)
 
