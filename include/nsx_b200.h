@@ -211,7 +211,10 @@ int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local);
 typedef struct nsx_warm_start {
     const uint8_t* in_tree; /* [M + n_nodes - 1] 1 = arc belongs to the initial tree */
     const double* flow;     /* [M + n_nodes - 1] initial flows (0 on arcs outside the tree) */
-    int32_t start_phase;    /* 1 = Phase 1 first; 2 = no artificial arc in the tree, Phase 1 skipped */
+    int32_t start_phase;    /* 1 = Phase 1 first; 2 = Phase 1 skipped, accepted only when no artificial arc is marked
+                               (simplex.py:1504-1513). A tree that spans the root always contains an artificial arc - only
+                               those touch the root - so 2 is rejected for every valid tree, as the reference's own
+                               skip never triggers; the host layer always passes 1 */
 } nsx_warm_start;
 int nsx_solve_warm(const nsx_problem* problem, const nsx_options* options, const nsx_warm_start* warm,
                    nsx_result* result);
