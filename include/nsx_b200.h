@@ -25,7 +25,9 @@
 extern "C" {
 #endif
 
-#define NSX_ABI_VERSION 2 /* 2: nsx_options.node_mask, NSX_SPECIAL_*, NSX_PRICING_DEVEX_LOOP, nsx_solve_warm, NSX_ARC_STALE */
+#define NSX_ABI_VERSION 3 /* 2: nsx_options.node_mask, NSX_SPECIAL_*, NSX_PRICING_DEVEX_LOOP, nsx_solve_warm, NSX_ARC_STALE
+                             3: nsx_options.spin_timeout_ms, nsx_options.flags reserved (NSX_FLAG_FAST_POTENTIALS removed),
+                                nsx_mailbox_abort, nsx_result.fault */
 
 /* pricing rules: SolverOptions.pricing_strategy (src/network_solver/data.py:459-488) */
 #define NSX_PRICING_DANTZIG 0 /* DantzigPricing.select_entering_arc, simplex_pricing.py:97-137 */
@@ -63,10 +65,6 @@ extern "C" {
 #define NSX_ERR_CUDA (-2)
 #define NSX_ERR_NO_DEVICE (-3)
 #define NSX_ERR_INTERNAL (-4)
-
-/* option flags */
-#define NSX_FLAG_FAST_POTENTIALS 1u /* non-parity mode: subtree potentials shifted by a parallel add of delta
-                                       instead of the exact top-down recompute */
 
 /* per-arc state byte returned in nsx_result.state */
 #define NSX_ARC_IN_TREE 1u
@@ -109,10 +107,14 @@ typedef struct nsx_options {
     double tolerance;         /* SolverOptions.tolerance */
     int64_t trace_capacity;   /* entries available in result->entering_trace (0 = no trace) */
     int32_t device;           /* CUDA device ordinal */
-    uint32_t flags;           /* NSX_FLAG_* */
+    uint32_t flags;           /* reserved, must be 0 (the engine has one arithmetic mode: the reference's float64 operation
+                                 order with the exact top-down potential recompute, SURVEY.md 8/a0 + a8) */
     const uint8_t* node_mask; /* [n_nodes] host buffer, NSX_SPECIAL_SHORTEST_PATH only: 1 = node reachable from the
                                  source over the real arcs (the nodes that carry a distance label in
                                  ShortestPathPivotStrategy, specialized_pivots.py:426-450); NULL otherwise */
+    int32_t spin_timeout_ms;  /* deadline of every device-side wait (a sweep worker's answer, a peer GPU's candidate, the
+                                 next command): when it passes, all CTAs leave the resident kernel and the call returns
+                                 NSX_ERR_INTERNAL instead of hanging the GPU.  0 = default (30 000 ms) */
 } nsx_options;
 
 typedef struct nsx_result {
@@ -161,6 +163,9 @@ typedef struct nsx_result {
     int64_t handshake_ns[8];      /* grid handshake timeline, ns after the command is published, summed over all
                                      sweeps: worker 1 saw the command, entered the sweep, potentials staged,
                                      tiles done, reduced, arrived; pivot CTA saw all arrivals, merged */
+    int32_t fault;                /* 0, or why the resident kernel gave up (the call then returns NSX_ERR_INTERNAL):
+                                     1 a sweep worker did not answer, 2 a peer GPU did not deliver its candidate,
+                                     3 a peer GPU raised its abort word, 4 a worker saw no command, 5 bad node id */
 } nsx_result;
 
 /* Solve one instance on one GPU; all nsx_problem / nsx_result pointers are HOST memory. */
@@ -192,6 +197,11 @@ typedef struct nsx_shard {
 } nsx_shard;
 int nsx_solve_sharded(const nsx_problem* problem, const nsx_options* options, nsx_result* result,
                       const nsx_shard* shard);
+/* Same with tail / head / pert_cost / upper already resident in THIS rank's HBM (device pointers, as in
+ * nsx_solve_resident): the ranks then start their kernels within microseconds of the host barrier instead of after
+ * differently long uploads. */
+int nsx_solve_sharded_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result,
+                               const nsx_shard* shard);
 int nsx_sweep_probe_sharded(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
                             nsx_result* result, const nsx_shard* shard);
 int64_t nsx_mailbox_bytes(void);
@@ -199,6 +209,10 @@ int nsx_mailbox_create(int32_t device, void** mailbox, unsigned char handle[64])
 int nsx_mailbox_open(int32_t device, const unsigned char handle[64], void** mailbox);
 int nsx_mailbox_reset(int32_t device, void* mailbox);
 int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local);
+/* Raise the abort word of a mailbox (own or peer-mapped): the kernel polling that mailbox leaves with fault 3.  The host
+ * layer calls it on every peer when its own rank fails between the barrier and the launch, so the others do not wait out
+ * the full deadline. */
+int nsx_mailbox_abort(int32_t device, void* mailbox);
 
 /*
  * Warm start (NetworkSimplex._apply_warm_start_basis / _recompute_tree_flows, simplex.py:740-1021; phase choice

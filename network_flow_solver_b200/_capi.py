@@ -17,7 +17,7 @@ import numpy as np
 from .canonical import CanonicalProblem
 from .exceptions import DeviceEngineError
 
-ABI_VERSION = 2  # NSX_ABI_VERSION of include/nsx_b200.h these declarations mirror
+ABI_VERSION = 3  # NSX_ABI_VERSION of include/nsx_b200.h these declarations mirror
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
 PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
@@ -30,8 +30,6 @@ STATUS_INFEASIBLE = 1
 STATUS_ITERATION_LIMIT = 2
 STATUS_UNBOUNDED = 3
 STATUS_ITERATION_LIMIT_P1 = 4
-
-FLAG_FAST_POTENTIALS = 1
 
 ARC_IN_TREE = 1
 ARC_CAN_FWD = 2
@@ -69,6 +67,7 @@ class NsxOptions(C.Structure):
         ("device", C.c_int32),
         ("flags", C.c_uint32),
         ("node_mask", C.POINTER(C.c_uint8)),
+        ("spin_timeout_ms", C.c_int32),
     ]
 
 
@@ -125,6 +124,7 @@ class NsxResult(C.Structure):
         ("sum_window", C.c_int64),
         ("phase_cycles", C.c_int64 * 12),
         ("handshake_ns", C.c_int64 * 8),
+        ("fault", C.c_int32),
     ]
 
 
@@ -141,8 +141,9 @@ class EngineOptions:
     tolerance: float = 1e-6
     trace_capacity: int = 0
     device: int = 0
-    flags: int = 0
+    flags: int = 0  # reserved by the C ABI, must stay 0
     node_mask: object = None  # uint8[n_nodes], SPECIAL_SHORTEST_PATH only (kept alive by this record)
+    spin_timeout_ms: int = 0  # deadline of device-side waits, 0 = the library default (30 s)
 
     def to_c(self) -> NsxOptions:
         mask = None
@@ -161,6 +162,7 @@ class EngineOptions:
             int(self.device),
             int(self.flags),
             mask,
+            int(self.spin_timeout_ms),
         )
 
 
@@ -221,6 +223,12 @@ class CallFrame:
         )
         self.options = opts.to_c()
         out = out or {}
+        for key, dtype, size in (("flow", np.float64, ma), ("potential", np.float64, cp.n_nodes), ("state", np.uint8, ma)):
+            buf = out.get(key)
+            if buf is not None and not (isinstance(buf, np.ndarray) and buf.dtype == dtype and buf.ndim == 1
+                                        and buf.shape[0] == size and buf.flags.c_contiguous and buf.flags.writeable):
+                raise ValueError(f"out[{key!r}] must be a writable C-contiguous {np.dtype(dtype).name}[{size}] array "
+                                 f"(the engine writes it through a raw pointer)")
         self.flow = out.get("flow") if out.get("flow") is not None else np.zeros(ma, dtype=np.float64)
         self.potential = (
             out.get("potential") if out.get("potential") is not None else np.zeros(cp.n_nodes, dtype=np.float64)
@@ -323,6 +331,8 @@ def load_library():
         lib.nsx_solve_sharded.argtypes = [
             C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.POINTER(NsxResult), C.POINTER(NsxShard)]
         lib.nsx_solve_sharded.restype = C.c_int
+        lib.nsx_solve_sharded_resident.argtypes = lib.nsx_solve_sharded.argtypes
+        lib.nsx_solve_sharded_resident.restype = C.c_int
         lib.nsx_sweep_probe_sharded.argtypes = [
             C.POINTER(NsxProblem), C.POINTER(NsxOptions), C.c_int32, C.POINTER(NsxResult), C.POINTER(NsxShard)]
         lib.nsx_sweep_probe_sharded.restype = C.c_int
@@ -331,7 +341,8 @@ def load_library():
         lib.nsx_mailbox_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
         lib.nsx_mailbox_reset.argtypes = [C.c_int32, C.c_void_p]
         lib.nsx_mailbox_close.argtypes = [C.c_int32, C.c_void_p, C.c_int32]
-        for name in ("nsx_mailbox_create", "nsx_mailbox_open", "nsx_mailbox_reset", "nsx_mailbox_close"):
+        lib.nsx_mailbox_abort.argtypes = [C.c_int32, C.c_void_p]
+        for name in ("nsx_mailbox_create", "nsx_mailbox_open", "nsx_mailbox_reset", "nsx_mailbox_close", "nsx_mailbox_abort"):
             getattr(lib, name).restype = C.c_int
         lib.nsx_solve_batch.argtypes = [
             C.c_int64,
@@ -422,6 +433,11 @@ def mailbox_reset(device: int, ptr: int) -> None:
     _check(load_library().nsx_mailbox_reset(int(device), C.c_void_p(ptr)), "nsx_mailbox_reset")
 
 
+def mailbox_abort(device: int, ptr: int) -> None:
+    """Raise the abort word of a (local or peer-mapped) mailbox: the kernel polling it leaves with fault 3."""
+    _check(load_library().nsx_mailbox_abort(int(device), C.c_void_p(ptr)), "nsx_mailbox_abort")
+
+
 def mailbox_close(device: int, ptr: int, is_local: bool) -> None:
     _check(load_library().nsx_mailbox_close(int(device), C.c_void_p(ptr), int(is_local)), "nsx_mailbox_close")
 
@@ -436,9 +452,9 @@ def solve_sharded(cp: CanonicalProblem, opts: EngineOptions, rank: int, world: i
     if probe_sweeps > 0:
         rc = lib.nsx_sweep_probe_sharded(C.byref(frame.problem), C.byref(frame.options), int(probe_sweeps),
                                          C.byref(frame.result), C.byref(shard))
-    else:
-        rc = lib.nsx_solve_sharded(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result),
-                                   C.byref(shard))
+    else:  # device_arrays: the arc arrays are already in this rank's HBM
+        fn = lib.nsx_solve_sharded_resident if device_arrays is not None else lib.nsx_solve_sharded
+        rc = fn(C.byref(frame.problem), C.byref(frame.options), C.byref(frame.result), C.byref(shard))
     _check(rc, "nsx_solve_sharded")
     return frame.harvest()
 

@@ -192,6 +192,8 @@ struct NsxCtl {
     int64_t clk_pricing, clk_pivot, clk_sync, clk_xchg;
     int64_t ph[12];       // SM-clock cycles per pivot phase (thread 0): walk, residuals, ratio, flow,
                           // bookkeeping, snapshot+sizes, window, copy+stem, potentials, cadence, driver
+    int32_t fault;        // a device-side wait ran past its deadline or met an abort word (nsx_result.fault); the loop ends
+    int32_t fault_pad;
 };
 // bar.sync blocks lazily (at the next access to barrier-protected state): touch shared memory first
 // so that the clock is read after the barrier has really been passed
@@ -1587,6 +1589,11 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         NSX_SYNC();
         if (kind == NSX_ACT_SWEEP) {
             sweep.run(L.cmd, L.dz, L.dx, c);
+            NSX_SYNC();
+            if (c.fault) {  // (block-uniform: written before the barrier) a worker / peer GPU never answered
+                sweep.finish();
+                break;
+            }
             NSX_SINGLE { nsx_drv_on_result(c, L.drv, d.m, L.dz, L.dx, L.cmd, L.act, trace); }
         } else if (kind == NSX_ACT_CL_SCAN) {
             nsx_cl_scan(d, c, &L.cl_arc2, s, (c.phase == 1) && !L.drv.final_check);

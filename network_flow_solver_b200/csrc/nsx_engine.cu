@@ -45,7 +45,7 @@ struct alignas(64) NsxSlot {
 };
 struct NsxGridCtl {
     int32_t seq;  // command sequence number, release-published by CTA 0
-    int32_t pad;
+    int32_t abort;  // raised by a sweep worker that saw no command before its deadline (fault 4)
     unsigned long long arrived;  // CTAs (other than 0) that delivered their candidate, cumulative
     NsxCmd cmd;
     unsigned long long t_pub;    // globaltimer at the publication of the current command
@@ -285,6 +285,9 @@ struct NsxCtaShared {
     int32_t tk_cnt;
     int32_t tk_thr_idx;
     unsigned long long tk_thr_key;
+    int4 x_mine[2];                             // cross-GPU exchange: this rank's record ...
+    int4 x_recs[8][2];                          // ... and the records of all ranks (filled by threads 0 .. world-1)
+    int32_t x_fault;
     NsxGridCtl* tl_grid;                        // handshake timeline sink (worker CTAs of the grid kernel), or null
     unsigned long long mbar;                    // completion barrier of the potentials bulk copy
     unsigned long long full[NSX_MAX_STAGES];    // tile landed in the stage (TMA complete_tx)
@@ -792,7 +795,12 @@ struct NsxMailSlot {        // 64 bytes
     unsigned long long seq; // exchange number the payload belongs to (written last, release.sys)
     unsigned long long pad[3];
 };
-struct NsxMailbox { NsxMailSlot slot[2][NSX_MAX_WORLD]; };  // [exchange parity][sender rank]
+struct NsxMailbox {
+    NsxMailSlot slot[2][NSX_MAX_WORLD];  // [exchange parity][sender rank]
+    unsigned long long abort;            // raised by a peer (kernel or host) that gave up: leave with fault 3
+    unsigned long long pad[7];
+    NsxTopkOut topk[2][NSX_MAX_WORLD];   // candidate-list refresh: the sender's sorted top list (payload of the slot)
+};
 struct NsxShard {
     int32_t rank, world;
     NsxMailbox* box[NSX_MAX_WORLD];  // box[r]: mailbox of rank r as mapped into this GPU's address space
@@ -806,25 +814,42 @@ __device__ __forceinline__ unsigned long long nsx_ld_acquire_sys_u64(const unsig
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Thread 0 of the pivot CTA: publish `mine` to all peers, collect theirs.  `recs[r]` receives the
-// payload of rank r (own included).
-__device__ __forceinline__ void nsx_exchange(const NsxShard& shd, unsigned long long xseq, const int4* mine,
-                                             int nvec, int4 (*recs)[2]) {
+__device__ __forceinline__ unsigned long long nsx_ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Thread r < world of the pivot CTA handles peer r: it stores `mine` into that peer's mailbox (payload, then a
+// system-scope release of the sequence word) and polls its own mailbox for the record of rank r - every peer in
+// parallel, so the exchange costs one NVLink round trip plus the wait for the slowest rank, not `world` of them.
+// `recs[r]` (shared memory) receives the payload of rank r, own included.  Returns 0, or the fault code when the
+// deadline passed (2) or somebody raised this rank's abort word (3).
+__device__ __forceinline__ int nsx_exchange_peer(const NsxShard& shd, int r, unsigned long long xseq, const int4* mine,
+                                                 int nvec, int4 (*recs)[2], unsigned long long limit_ns) {
     const int par = (int)(xseq & 1ull);
-    for (int r = 0; r < shd.world; ++r) {
-        if (r == shd.rank) { recs[r][0] = mine[0]; recs[r][1] = nvec > 1 ? mine[1] : make_int4(0, 0, 0, 0); continue; }
-        NsxMailSlot* dst = &shd.box[r]->slot[par][shd.rank];
-        dst->payload[0] = mine[0];
-        if (nvec > 1) dst->payload[1] = mine[1];
-        nsx_st_release_sys_u64(&dst->seq, xseq);
+    if (r == shd.rank) { recs[r][0] = mine[0]; recs[r][1] = nvec > 1 ? mine[1] : make_int4(0, 0, 0, 0); return 0; }
+    NsxMailSlot* dst = &shd.box[r]->slot[par][shd.rank];
+    dst->payload[0] = mine[0];
+    if (nvec > 1) dst->payload[1] = mine[1];
+    nsx_st_release_sys_u64(&dst->seq, xseq);
+    const NsxMailbox* own = shd.box[shd.rank];
+    const NsxMailSlot* src = &own->slot[par][r];
+    const unsigned long long t0 = nsx_globaltimer();
+    uint32_t spins = 0;
+    while (nsx_ld_acquire_sys_u64(&src->seq) != xseq) {
+        if ((++spins & 255u) == 0) {
+            if (nsx_ld_relaxed_sys_u64(&own->abort) != 0ull) return 3;
+            if (nsx_globaltimer() - t0 > limit_ns) return 2;
+        }
     }
-    for (int r = 0; r < shd.world; ++r) {
-        if (r == shd.rank) continue;
-        const NsxMailSlot* src = &shd.box[shd.rank]->slot[par][r];
-        while (nsx_ld_acquire_sys_u64(&src->seq) != xseq) { }
-        recs[r][0] = __ldcg(&src->payload[0]);
-        recs[r][1] = nvec > 1 ? __ldcg(&src->payload[1]) : make_int4(0, 0, 0, 0);
-    }
+    recs[r][0] = __ldcg(&src->payload[0]);
+    recs[r][1] = nvec > 1 ? __ldcg(&src->payload[1]) : make_int4(0, 0, 0, 0);
+    return 0;
+}
+// a rank that gives up tells its peers, so they leave at once instead of waiting out their own deadline
+__device__ __forceinline__ void nsx_raise_peer_aborts(const NsxShard& shd) {
+    for (int r = 0; r < shd.world; ++r)
+        if (r != shd.rank && shd.box[r]) nsx_st_release_sys_u64(&shd.box[r]->abort, 1ull);
 }
 
 // The sorted top list of this CTA (piv.res / piv.arc2, tk_cnt entries) becomes the candidate list.
@@ -851,28 +876,39 @@ struct GridSweep {
     unsigned long long t_price, t_sync;
     const NsxShard& shd;
     unsigned long long xseq, t_xchg;
+    unsigned long long spin_ns;  // deadline of every wait in this functor
 
-    // candidates of the other GPUs (thread 0 holds the local best in `k`)
-    __device__ void exchange(NsxCand& k) {
-        union { NsxCand c; int4 v[2]; } mine; mine.v[1] = make_int4(0, 0, 0, 0); mine.c = k;
-        int4 recs[NSX_MAX_WORLD][2];
-        const unsigned long long t1 = nsx_globaltimer();
-        nsx_exchange(shd, ++xseq, mine.v, 1, recs);
-        t_xchg += nsx_globaltimer() - t1;
-        nsx_cand_init(k);
-        for (int r = 0; r < shd.world; ++r) { union { NsxCand c; int4 v; } o; o.v = recs[r][0]; nsx_cand_merge(k, o.c); }
-    }
-    __device__ void exchange(NsxDevexCand& k) {
-        union { NsxDevexCand c; int4 v[2]; } mine; mine.c = k;
-        int4 recs[NSX_MAX_WORLD][2];
-        const unsigned long long t1 = nsx_globaltimer();
-        nsx_exchange(shd, ++xseq, mine.v, 2, recs);
-        t_xchg += nsx_globaltimer() - t1;
-        nsx_devex_init(k);
-        for (int r = 0; r < shd.world; ++r) { union { NsxDevexCand c; int4 v[2]; } o; o.v[0] = recs[r][0]; o.v[1] = recs[r][1]; nsx_devex_merge(k, o.c); }
+    // Candidates of the other GPUs.  Called by ALL threads of the pivot CTA; thread 0 holds the local best in kz / kx
+    // and receives the merged best.  A deadline or a raised abort word ends in c.fault (and tells the peers).
+    __device__ __forceinline__ void exchange_all(bool devex, NsxCand& kz, NsxDevexCand& kx, NsxCtl& c) {
+        ++xseq;  // every thread keeps its own copy of the exchange number
+        if (threadIdx.x == 0) {
+            if (devex) { union { NsxDevexCand c; int4 v[2]; } m; m.c = kx; sh.x_mine[0] = m.v[0]; sh.x_mine[1] = m.v[1]; }
+            else { union { NsxCand c; int4 v; } m; m.c = kz; sh.x_mine[0] = m.v; sh.x_mine[1] = make_int4(0, 0, 0, 0); }
+            sh.x_fault = 0;
+        }
+        NSX_SYNC();
+        unsigned long long t1 = 0;
+        if (threadIdx.x == 0) t1 = nsx_globaltimer();
+        if ((int)threadIdx.x < shd.world) {
+            const int f = nsx_exchange_peer(shd, (int)threadIdx.x, xseq, sh.x_mine, devex ? 2 : 1, sh.x_recs, spin_ns);
+            if (f) atomicMax(&sh.x_fault, f);
+        }
+        NSX_SYNC();
+        if (threadIdx.x == 0) {
+            t_xchg += nsx_globaltimer() - t1;
+            if (sh.x_fault) { c.fault = sh.x_fault; nsx_raise_peer_aborts(shd); }
+            else if (devex) {
+                nsx_devex_init(kx);
+                for (int r = 0; r < shd.world; ++r) { union { NsxDevexCand c; int4 v[2]; } o; o.v[0] = sh.x_recs[r][0]; o.v[1] = sh.x_recs[r][1]; nsx_devex_merge(kx, o.c); }
+            } else {
+                nsx_cand_init(kz);
+                for (int r = 0; r < shd.world; ++r) { union { NsxCand c; int4 v; } o; o.v = sh.x_recs[r][0]; nsx_cand_merge(kz, o.c); }
+            }
+        }
     }
 
-    __device__ void publish(const NsxCmd& cmd) {
+    __device__ __forceinline__ void publish(const NsxCmd& cmd) {
         if (threadIdx.x == 0) {
             union { NsxCmd c; int4 v[3]; } tmp;
             tmp.c = cmd;
@@ -885,8 +921,54 @@ struct GridSweep {
         }
         ++seq;  // every thread keeps its own copy of the sequence number (the slot polls compare against it)
     }
+    // Candidate-list refresh across GPUs.  On entry the sorted top list of THIS rank is in piv.res / piv.arc2 (tk_cnt
+    // entries, all threads past a barrier).  Every rank stores its list into every peer's mailbox (parity-buffered like
+    // the candidate slots), the slot sequence words signal completion, and all ranks merge the same `world` lists with
+    // the same total order (merit, arc) - so they end up with the same candidate list.
+    __device__ __forceinline__ void exchange_topk(NsxCtl& c) {
+        ++xseq;
+        const int par = (int)(xseq & 1ull);
+        const int32_t cnt = sh.tk_cnt;
+        const unsigned long long* key = reinterpret_cast<const unsigned long long*>(sh.piv.res);
+        const int32_t* idx = sh.piv.arc2;
+        for (int r = 0; r < shd.world; ++r) {
+            NsxTopkOut* dst = &shd.box[r]->topk[par][shd.rank];
+            for (int k = threadIdx.x; k < cnt; k += blockDim.x) { dst->key[k] = key[k]; dst->idx[k] = idx[k]; }
+            if (threadIdx.x == 0) dst->count = cnt;
+        }
+        __threadfence_system();  // every storing thread: its list entries are visible system-wide before the barrier
+        if (threadIdx.x == 0) { sh.x_mine[0] = make_int4(cnt, 0, 0, 0); sh.x_mine[1] = make_int4(0, 0, 0, 0); sh.x_fault = 0; }
+        NSX_SYNC();
+        unsigned long long t1 = 0;
+        if (threadIdx.x == 0) t1 = nsx_globaltimer();
+        if ((int)threadIdx.x < shd.world) {
+            const int f = nsx_exchange_peer(shd, (int)threadIdx.x, xseq, sh.x_mine, 1, sh.x_recs, spin_ns);
+            if (f) atomicMax(&sh.x_fault, f);
+        }
+        NSX_SYNC();
+        if (threadIdx.x == 0) {
+            t_xchg += nsx_globaltimer() - t1;
+            if (sh.x_fault) { c.fault = sh.x_fault; nsx_raise_peer_aborts(shd); }
+            nsx_tk_reset(sh, d.tol);
+        }
+        NSX_SYNC();
+        if (c.fault) return;
+        NsxBarAll bar;
+        const NsxMailbox* own = shd.box[shd.rank];
+        for (int r = 0; r < shd.world; ++r) {  // <= 8 lists of <= 100 entries: the buffer (1024) holds them all
+            const NsxTopkOut* src = &own->topk[par][r];
+            const int32_t n = __ldcg(&src->count);
+            for (int k0 = 0; k0 < NSX_CL_SIZE; k0 += (int)blockDim.x) {
+                const int k = k0 + (int)threadIdx.x;
+                const bool has = k < n;
+                nsx_tk_append(sh, has, has ? __ldcg(&src->key[k]) : 0ull, has ? __ldcg(&src->idx[k]) : -1);
+            }
+        }
+        bar();
+        nsx_tk_compact(sh, (int)threadIdx.x, (int)blockDim.x, bar);
+    }
     // candidate-list refresh: merge the sorted per-CTA lists of the workers (HBM) into the final list
-    __device__ void merge_topk(NsxCtl& c) {
+    __device__ __forceinline__ void merge_topk(NsxCtl& c) {
         if (threadIdx.x == 0) nsx_tk_reset(sh, d.tol);
         NsxBarAll bar;
         const int P = (int)blockDim.x, t = (int)threadIdx.x;
@@ -904,9 +986,10 @@ struct GridSweep {
         }
         bar();
         nsx_tk_compact(sh, t, P, bar);
+        if (shd.world > 1) { exchange_topk(c); if (c.fault) return; }
         nsx_tk_publish_list(sh, c);
     }
-    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
+    __device__ __forceinline__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
@@ -917,12 +1000,13 @@ struct GridSweep {
             if (threadIdx.x == 0) __threadfence();
             nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, shd.rank, shd.world, sh, dz, dx);
             if (cmd.kind == NSX_CMD_TOPK) {
+                if (shd.world > 1) { exchange_topk(c); if (c.fault) return; }
                 nsx_tk_publish_list(sh, c);
                 if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
                 return;
             }
+            if (shd.world > 1) exchange_all(devex, dz, dx, c);
             if (threadIdx.x == 0) {
-                if (shd.world > 1) { if (devex) exchange(dx); else exchange(dz); }
                 if (devex) out_dx = dx; else out_dz = dz;
                 t_price += nsx_globaltimer() - t0;
             }
@@ -937,7 +1021,13 @@ struct GridSweep {
         NsxCand kz; nsx_cand_init(kz);
         for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
             const NsxSlot* sl = slots + b;
-            while (nsx_ld_acquire(&sl->seq) != seq) { }
+            uint32_t spins = 0;
+            bool lost = false;
+            const unsigned long long t_wait = nsx_globaltimer();
+            while (nsx_ld_acquire(&sl->seq) != seq) {
+                if ((++spins & 1023u) == 0 && (nsx_ld_acquire(&g->abort) != 0 || nsx_globaltimer() - t_wait > spin_ns)) { lost = true; break; }
+            }
+            if (lost) { c.fault = 1; break; }  // (same value from every thread that gives up)
             if (devex) {
                 union { NsxDevexCand c; int4 v[2]; } tmp;
                 tmp.v[0] = __ldcg(&sl->v[0]); tmp.v[1] = __ldcg(&sl->v[1]);
@@ -949,23 +1039,23 @@ struct GridSweep {
             }
         }
         NSX_SYNC();
+        if (c.fault) {  // a worker never answered (block-uniform after the barrier): tell the peers, the loop ends
+            if (threadIdx.x == 0 && shd.world > 1) nsx_raise_peer_aborts(shd);
+            return;
+        }
         if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; g->tl[6] += nsx_globaltimer() - g->t_pub; }
         if (cmd.kind == NSX_CMD_TOPK) {
             merge_topk(c);
             if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
             return;
         }
-        if (devex) {
-            nsx_block_reduce(kx, sh.dx_buf);
-            if (threadIdx.x == 0) { if (shd.world > 1) exchange(kx); out_dx = kx; }
-        } else {
-            nsx_block_reduce(kz, sh.dz_buf);
-            if (threadIdx.x == 0) { if (shd.world > 1) exchange(kz); out_dz = kz; }
-        }
+        if (devex) nsx_block_reduce(kx, sh.dx_buf); else nsx_block_reduce(kz, sh.dz_buf);
+        if (shd.world > 1) exchange_all(devex, kz, kx, c);
+        if (threadIdx.x == 0) { if (devex) out_dx = kx; else out_dz = kz; }
         if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
     }
-    __device__ void finish() {
+    __device__ __forceinline__ void finish() {
         NsxCmd cmd;
         cmd.kind = NSX_CMD_EXIT; cmd.phase = 0; cmd.lo = cmd.hi = 0; cmd.excluded = -1; cmd.wepoch = 0;
         cmd.reverse = 0; cmd.pad[0] = cmd.pad[1] = cmd.pad[2] = 0;
@@ -991,6 +1081,7 @@ struct NsxKernelArgs {
     NsxSmemPlan wplan;   // sweep workers
     int32_t probe_sweeps;  // > 0: measurement aid, run this many sweeps of the initial state and stop
     NsxShard shard;        // world == 1: single GPU
+    unsigned long long spin_ns;  // deadline of device-side waits (nsx_options.spin_timeout_ms)
 };
 
 __device__ __forceinline__ void nsx_copy_ctl(NsxCtl* dst, const NsxCtl* src) {
@@ -1061,7 +1152,7 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull};
+        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns};
         if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -1084,13 +1175,25 @@ nsx_resident_kernel(const NsxKernelArgs a) {
     for (;;) {
         if (threadIdx.x == 0) {
             int32_t s;
-            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) { __nanosleep(20); }
-            seen = s;
-            NSX_TL(a.grid, 0);
-            union { NsxCmd c; int4 v[3]; } tmp;
-            const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
-            tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1); tmp.v[2] = __ldcg(src + 2);
-            sh.cmd = tmp.c;
+            uint32_t spins = 0;
+            bool lost = false;
+            const unsigned long long t_wait = nsx_globaltimer();
+            // the pivot CTA may itself be waiting for a peer GPU (up to spin_ns) between two commands
+            while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) {
+                __nanosleep(20);
+                if ((++spins & 4095u) == 0 && nsx_globaltimer() - t_wait > 4ull * a.spin_ns) { lost = true; break; }
+            }
+            if (lost) {
+                atomicExch(&a.grid->abort, 4);
+                sh.cmd.kind = NSX_CMD_EXIT;
+            } else {
+                seen = s;
+                NSX_TL(a.grid, 0);
+                union { NsxCmd c; int4 v[3]; } tmp;
+                const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
+                tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1); tmp.v[2] = __ldcg(src + 2);
+                sh.cmd = tmp.c;
+            }
         }
         NSX_SYNC();
         const NsxCmd cmd = sh.cmd;
@@ -1150,7 +1253,9 @@ extern "C" __global__ void nsx_init_warm_kernel(const NsxDev d, const double* su
 
 // Which compact cost encodings are exact for this instance: bit 0 set = some cost is not an
 // int32-valued integer, bit 1 set = some cost is not an int16-valued integer.
-extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, int64_t m, unsigned int* flags) {
+// Bit 2 set = some arc endpoint lies outside 1 .. n-1 (real arcs never touch the root): the call is refused.
+extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, const int32_t* tail, const int32_t* head,
+                                                     int32_t n, int64_t m, unsigned int* flags) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
     unsigned int f = 0;
@@ -1158,6 +1263,8 @@ extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, int64_t
         const double c = pert[i];
         if (!(c == rint(c)) || fabs(c) > 2147483000.0) f |= 3u;
         else if (fabs(c) > 32767.0) f |= 2u;
+        const int32_t tl = tail[i], hd = head[i];
+        if (tl < 1 || tl >= n || hd < 1 || hd >= n) f |= 4u;
     }
     if (f) atomicOr(flags, f);
 }
@@ -1244,10 +1351,20 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
         if (it >= (unsigned long long)count) return;
         const NsxBatchItem& item = items[it];
         const NsxDev& d = item.d;
-        for (int64_t i = threadIdx.x; i < d.m; i += blockDim.x) nsx_init_real_arc(d, i);
+        nsx_copy_ctl(&sh.ctl, item.ctl);
+        NSX_SYNC();
+        for (int64_t i = threadIdx.x; i < d.m; i += blockDim.x) {
+            nsx_init_real_arc(d, i);
+            const int32_t tl = d.tail[i], hd = d.head[i];
+            if (tl < 1 || tl >= d.n || hd < 1 || hd >= d.n) sh.ctl.fault = 5;  // (same value from every thread)
+        }
+        NSX_SYNC();
+        if (sh.ctl.fault) {  // refused: the instance keeps status -1 and the call returns an error
+            nsx_copy_ctl(item.ctl, &sh.ctl);
+            continue;
+        }
         for (int64_t v = threadIdx.x; v < d.n; v += blockDim.x) nsx_init_node(d, (int32_t)v, item.supply[v]);
         nsx_pack_range(d.tail, d.head, d.pert, d.m, item.mpad, item.st, threadIdx.x, blockDim.x);
-        nsx_copy_ctl(&sh.ctl, item.ctl);
         NSX_SYNC();
         if (threadIdx.x == 0) {
             int64_t art = 0;
@@ -1322,8 +1439,9 @@ static int nsx_validate(const nsx_problem* p, const nsx_options* o, const nsx_re
     if (o->pricing != NSX_PRICING_DANTZIG && o->pricing != NSX_PRICING_DEVEX && o->pricing != NSX_PRICING_CANDIDATE_LIST &&
         o->pricing != NSX_PRICING_DEVEX_LOOP)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown pricing rule");
-    if (o->max_iterations < 0 || !(o->tolerance > 0) || o->ft_update_limit <= 0)
+    if (o->max_iterations < 0 || !(o->tolerance > 0) || o->ft_update_limit <= 0 || o->spin_timeout_ms < 0)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad option value");
+    if (o->flags != 0) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "nsx_options.flags is reserved and must be 0");
     if (o->row_scan_first < NSX_SPECIAL_NONE || o->row_scan_first > NSX_SPECIAL_SHORTEST_PATH)
         return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "unknown structure-specific rule (nsx_options.row_scan_first)");
     if (o->row_scan_first == NSX_SPECIAL_SHORTEST_PATH && !o->node_mask)
@@ -1341,7 +1459,28 @@ static void nsx_fill_ctl(NsxCtl& c, const nsx_options* o, bool trace) {
     c.unbounded_arc = -1;
 }
 
+static int nsx_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+static unsigned long long nsx_spin_ns(const nsx_options* o) {
+    long long ms = o->spin_timeout_ms > 0 ? o->spin_timeout_ms : nsx_env_int("NSX_SPIN_TIMEOUT_MS", 30000);
+    if (ms < 1) ms = 1;
+    return (unsigned long long)ms * 1000000ull;
+}
+static const char* nsx_fault_text(int fault) {
+    switch (fault) {
+        case 1: return "a sweep worker CTA did not deliver its candidate before the deadline";
+        case 2: return "a peer GPU did not deliver its candidate before the deadline";
+        case 3: return "a peer GPU (or its host process) raised the abort word";
+        case 4: return "a sweep worker CTA saw no command before the deadline";
+        case 5: return "arc endpoint outside 1 .. n_nodes-1";
+        default: return "resident kernel ended without a status";
+    }
+}
+
 static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
+    res->fault = c.fault;
     res->status = c.status;
     res->iterations = c.total;
     res->phase1_iterations = c.phase1_iterations;
@@ -1384,11 +1523,6 @@ static int nsx_device_info(int dev, DeviceInfo& info) {
     return 0;
 }
 
-static int nsx_env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 static size_t nsx_smem_fixed() { return (sizeof(NsxCtaShared) + 15) & ~(size_t)15; }
 static int64_t nsx_pad_tiles(int64_t m) {
     int64_t t = (m + NSX_TILE - 1) / NSX_TILE;
@@ -1419,6 +1553,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         if (resident || shard || probe_sweeps) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "warm start is a host-buffer, single-GPU entry point");
         if (!warm->in_tree || !warm->flow || (warm->start_phase != 1 && warm->start_phase != 2))
             return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad warm start description");
+        for (int64_t a = 0; a < pb->n_arcs; ++a)  // nsx_warm_layout indexes host arrays with these
+            if (pb->tail[a] < 1 || pb->tail[a] >= pb->n_nodes || pb->head[a] < 1 || pb->head[a] >= pb->n_nodes)
+                return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "arc endpoint outside 1 .. n_nodes-1 (node 0 is the artificial root)");
         int bad = nsx_warm_layout(pb->n_nodes, pb->n_arcs, pb->tail, pb->head, pb->supply, opt->tolerance, warm->in_tree,
                                   w_node, w_depth, w_order);
         if (bad) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, bad == -1 ? "warm start: in_tree must mark exactly n_nodes - 1 arcs"
@@ -1485,14 +1622,18 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     }
     const int util_blocks = info.sms * 8;
     if (m > 0) {
-        nsx_classify_costs_kernel<<<util_blocks, 256, 0, stream>>>(d.pert, m, d_flags);
+        nsx_classify_costs_kernel<<<util_blocks, 256, 0, stream>>>(d.pert, d.tail, d.head, n, m, d_flags);
         NSX_CUDA(cudaGetLastError());
     }
     unsigned int cost_flags = 3u;
     NSX_CUDA(cudaMemcpyAsync(&cost_flags, d_flags, 4, cudaMemcpyDeviceToHost, stream));
     NSX_CUDA(cudaStreamSynchronize(stream));
+    if (m > 0 && (cost_flags & 4u)) {
+        arena.release(); inputs.release();
+        return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "arc endpoint outside 1 .. n_nodes-1 (node 0 is the artificial root)");
+    }
     NsxStore& st = ka.st;
-    nsx_choose_layout(n, cost_flags, devex, st);
+    nsx_choose_layout(n, cost_flags & 3u, devex, st);
 
     // ---- engine-owned device memory ----
     const size_t state_len = (size_t)(ma > mpad ? ma : mpad) + 16;
@@ -1529,20 +1670,13 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     ka.topk = arena.at<NsxTopkOut>(o_topk);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
     ka.probe_sweeps = probe_sweeps;
+    ka.spin_ns = nsx_spin_ns(opt);
     memset(&ka.shard, 0, sizeof ka.shard);
     ka.shard.rank = 0; ka.shard.world = 1;
     if (shard) {
         if (shard->world < 1 || shard->world > NSX_MAX_WORLD || shard->rank < 0 || shard->rank >= shard->world || !shard->mailboxes) {
             arena.release(); inputs.release();
             return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "bad shard description");
-        }
-        if (shard->world > 1 && (opt->row_scan_first >= NSX_SPECIAL_ASSIGNMENT || opt->pricing == NSX_PRICING_DEVEX_LOOP)) {
-            arena.release(); inputs.release();
-            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "rules that scan inside the pivot CTA (structure-specific rules, loop-based Devex) are not available in arc-sharded solves");
-        }
-        if (shard->world > 1 && opt->pricing == NSX_PRICING_CANDIDATE_LIST) {
-            arena.release(); inputs.release();
-            return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "candidate-list pricing is not available in arc-sharded solves yet (the refresh sweep merges per-GPU lists only)");
         }
         ka.shard.rank = shard->rank; ka.shard.world = shard->world;
         for (int r = 0; r < shard->world; ++r) ka.shard.box[r] = reinterpret_cast<NsxMailbox*>(shard->mailboxes[r]);
@@ -1639,7 +1773,8 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     res->resident_mode = ka.plan.mode;
     arena.release();
     inputs.release();
-    if (hctl.status < 0) return nsx_fail(NSX_ERR_INTERNAL, "resident kernel ended without a status");
+    if (hgrid.abort && !res->fault) res->fault = hgrid.abort;
+    if (res->fault || hctl.status < 0) return nsx_fail(NSX_ERR_INTERNAL, std::string("resident kernel gave up: ") + nsx_fault_text(res->fault));
     return 0;
 }
 
@@ -1664,6 +1799,11 @@ extern "C" int nsx_solve_sharded(const nsx_problem* problem, const nsx_options* 
                                  const nsx_shard* shard) {
     if (!shard) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null shard");
     return nsx_solve_impl(problem, options, result, false, 0, shard);
+}
+extern "C" int nsx_solve_sharded_resident(const nsx_problem* problem_dev, const nsx_options* options, nsx_result* result,
+                                          const nsx_shard* shard) {
+    if (!shard) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null shard");
+    return nsx_solve_impl(problem_dev, options, result, true, 0, shard);
 }
 extern "C" int nsx_sweep_probe_sharded(const nsx_problem* problem_dev, const nsx_options* options, int32_t sweeps,
                                        nsx_result* result, const nsx_shard* shard) {
@@ -1697,6 +1837,20 @@ extern "C" int nsx_mailbox_reset(int32_t device, void* mailbox) {
     if (e == cudaSuccess) e = cudaMemset(mailbox, 0, sizeof(NsxMailbox));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_reset: ") + cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int nsx_mailbox_abort(int32_t device, void* mailbox) {
+    if (!mailbox) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
+    const unsigned long long one = 1ull;
+    cudaError_t e = cudaSetDevice(device);
+    // (plain copy on the legacy stream would wait for a running resident kernel: use a private non-blocking stream)
+    cudaStream_t st = nullptr;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(mailbox) + offsetof(NsxMailbox, abort), &one, 8,
+                                              cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (st) cudaStreamDestroy(st);
+    if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_abort: ") + cudaGetErrorString(e));
     return 0;
 }
 extern "C" int nsx_mailbox_close(int32_t device, void* mailbox, int32_t is_local) {
@@ -1838,7 +1992,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     cudaEventElapsedTime(&h2d, ev[0], ev[1]);
     cudaEventElapsedTime(&solve, ev[1], ev[2]);
     cudaEventElapsedTime(&d2h, ev[2], ev[3]);
-    int bad = 0;
+    int bad = 0, bad_ids = 0;
     for (int64_t i = 0; i < count; ++i) {
         nsx_result& r = results[i];
         nsx_harvest(ctls[i], &r);
@@ -1848,9 +2002,10 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
             int64_t cnt = ctls[i].trace_len < opt->trace_capacity ? ctls[i].trace_len : opt->trace_capacity;
             if (cnt > 0) NSX_CUDA(cudaMemcpy(r.entering_trace, items[i].trace, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
         }
-        if (ctls[i].status < 0) bad++;
+        if (ctls[i].status < 0) { bad++; if (ctls[i].fault == 5) bad_ids++; }
     }
     arena.release();
+    if (bad_ids) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "arc endpoint outside 1 .. n_nodes-1 in a batch instance (node 0 is the artificial root)");
     if (bad) return nsx_fail(NSX_ERR_INTERNAL, "batch kernel left instances without a status");
     return 0;
 }

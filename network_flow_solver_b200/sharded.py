@@ -53,6 +53,24 @@ class MailboxRing:
         if self.dist is not None and self.world > 1:
             self.dist.barrier()
 
+    def abort_peers(self):
+        """This rank failed between the barrier and the end of its kernel: raise the abort word in every peer's
+        mailbox so that their resident kernels leave at once (fault 3) instead of waiting out the spin deadline."""
+        for r, p in enumerate(self.pointers):
+            if r != self.rank:
+                try:
+                    self.api.mailbox_abort(self.device, p)
+                except Exception:  # best effort: the peers still have their own deadline
+                    pass
+
+    def agree(self, ok: bool) -> list[bool]:
+        """Every rank learns which ranks completed their part (host collective, after the kernels have ended)."""
+        if self.dist is None or self.world == 1:
+            return [bool(ok)]
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, bool(ok))
+        return [bool(f) for f in flags]
+
     def close(self):
         if self.dist is not None and self.world > 1:
             self.dist.barrier()
@@ -65,8 +83,22 @@ class MailboxRing:
 def solve_canonical_sharded(cp: CanonicalProblem, opts: _capi.EngineOptions, ring: MailboxRing, out=None,
                             probe_sweeps: int = 0, device_arrays=None) -> _capi.RawSolution:
     ring.reset()  # zero this rank's mailbox, then a host barrier: nobody writes before everybody is clean
-    return ring.api.solve_sharded(cp, opts, ring.rank, ring.world, ring.pointers, out=out,
-                                  probe_sweeps=probe_sweeps, device_arrays=device_arrays)
+    error = None
+    sol = None
+    try:
+        sol = ring.api.solve_sharded(cp, opts, ring.rank, ring.world, ring.pointers, out=out,
+                                     probe_sweeps=probe_sweeps, device_arrays=device_arrays)
+    except Exception as exc:  # allocation / launch failure, a spin deadline, a peer's abort word
+        error = exc
+        ring.abort_peers()
+    done = ring.agree(error is None)  # nobody starts the next sharded call before all ranks have left this one
+    if error is not None:
+        raise error
+    if not all(done):
+        from .exceptions import DeviceEngineError
+
+        raise DeviceEngineError(f"arc-sharded solve: ranks {[r for r, ok in enumerate(done) if not ok]} failed their part")
+    return sol
 
 
 def solve_batch_round_robin(cps: list[CanonicalProblem], opts: _capi.EngineOptions, rank: int, world: int,

@@ -95,12 +95,14 @@ def special_rule(cp: CanonicalProblem, tol: float) -> tuple[int, np.ndarray | No
             if snk:
                 return _capi.SPECIAL_SHORTEST_PATH, reachable_from(cp.n_nodes, cp.tail, cp.head, s)
         return _capi.SPECIAL_NONE, None
-    raise SolverConfigurationError(
-        f"detected network type '{kind}': the reference's rule for it (BipartiteMatchingPivotStrategy, "
-        f"specialized_pivots.py:212-273) walks Python sets of node indices built from sets of node-id strings, so the arc "
-        f"it picks depends on PYTHONHASHSEED; there is no sequence to reproduce and it is not on the accelerated path "
-        f"(SURVEY.md section 8f row 4)."
-    )
+    # NET_BIPARTITE_MATCHING: the reference's rule for it (BipartiteMatchingPivotStrategy, specialized_pivots.py:212-273)
+    # walks Python sets of node indices built from sets of node-id strings, so the arc it picks depends on PYTHONHASHSEED -
+    # there is no pivot sequence to reproduce.  The instance is solved with the configured pricing rule instead: same
+    # optimal objective, pivot-for-pivot parity with one particular reference run is not defined for this type.
+    _log.warning(
+        "network type %r: the reference's matching pivot rule is hash-seed dependent; solving with the configured "
+        "pricing rule (optimal objective guaranteed, pivot sequence not comparable)", kind)
+    return _capi.SPECIAL_NONE, None
 
 
 def resolve_plan(
@@ -111,8 +113,6 @@ def resolve_plan(
     goto_like: bool = False,
     trace_capacity: int = 0,
     device: int = 0,
-    flags: int = 0,
-    allow_unaccelerated: bool = False,
 ) -> ResolvedPlan:
     """Mirror of the decisions taken in NetworkSimplex.__init__ / solve().
 
@@ -160,7 +160,6 @@ def resolve_plan(
         tolerance=options.tolerance,
         trace_capacity=trace_capacity,
         device=device,
-        flags=flags,
         node_mask=node_mask,
     )
     return ResolvedPlan(strategy=strategy, engine=eng)
@@ -259,9 +258,7 @@ def prepare(
     *,
     trace_capacity: int = 0,
     device: int = 0,
-    flags: int = 0,
     eps_base: float = PERTURB_EPS_BASE,
-    allow_unaccelerated: bool = False,
 ) -> tuple[CanonicalProblem, ResolvedPlan, SolverOptions]:
     """Host-side half of the call: options + canonical arrays, no device work."""
     options = options if options is not None else SolverOptions()
@@ -281,8 +278,6 @@ def prepare(
         goto_like=goto,
         trace_capacity=trace_capacity,
         device=device,
-        flags=flags,
-        allow_unaccelerated=allow_unaccelerated,
     )
     plan.scaling = factors
     return cp, plan, options

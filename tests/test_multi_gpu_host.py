@@ -34,7 +34,12 @@ class FakeApi:
     def mailbox_close(self, device, ptr, is_local):
         assert (ptr == 1000 + self.rank) == bool(is_local)
 
+    def mailbox_abort(self, device, ptr):
+        self.aborted = getattr(self, "aborted", []) + [ptr]
+
     def solve_sharded(self, cp, opts, rank, world, pointers, out=None, probe_sweeps=0, device_arrays=None):
+        if opts == "rank1 fails" and rank == 1:
+            raise RuntimeError("launch failed on rank 1")
         return ("solved", rank, world, tuple(pointers))
 
     def solve_batch_canonical(self, cps, opts):
@@ -58,8 +63,15 @@ def _worker(rank, world, port, q):
     ring = MailboxRing(0, dist, api=api)
     res = solve_canonical_sharded(None, None, ring)
     batch = solve_batch_round_robin(list(range(7)), None, rank, world, api=api)
+    # a rank that fails raises the peers' abort words; every rank of the call ends with an exception, none hangs
+    try:
+        solve_canonical_sharded(None, "rank1 fails", ring)
+        failed = None
+    except Exception as exc:
+        failed = (type(exc).__name__, getattr(api, "aborted", []))
+    assert failed == (("RuntimeError", [2000]) if rank == 1 else ("DeviceEngineError", [])), failed
     ring.close()
-    q.put((rank, ring.pointers, sorted(api.opened), api.resets, res, sorted(batch)))
+    q.put((rank, ring.pointers, sorted(api.opened), api.resets - 1, res, sorted(batch)))
     dist.destroy_process_group()
 
 

@@ -26,7 +26,7 @@ def test_oracle_reproduces_reference_candidate_list_runs(name, i):
     problem = rebuild_problem(case["problem"])
     options = SolverOptions(**run["options"])
     cp, plan, options = prepare(problem, options, run.get("max_iterations"), trace_capacity=1 << 16,
-                                allow_unaccelerated=True)
+)
     want = {"CandidateListPricing": _capi.PRICING_CANDIDATE_LIST, "AdaptivePricing": _capi.PRICING_CANDIDATE_LIST,
             "DantzigPricing": _capi.PRICING_DANTZIG}[run["strategy"]]
     assert plan.engine.pricing == want
@@ -41,7 +41,7 @@ def test_emulated_device_core_reproduces_reference_candidate_list_runs(name, i):
     case, run = CASES[name], CASES[name]["runs"][i]
     problem = rebuild_problem(case["problem"])
     cp, plan, options = prepare(problem, SolverOptions(**run["options"]), run.get("max_iterations"),
-                                trace_capacity=1 << 16, allow_unaccelerated=True)
+                                trace_capacity=1 << 16)
     assert_matches_reference(run, cp, emu.solve_canonical(cp, plan.engine), options)
 
 
@@ -80,7 +80,7 @@ def test_engine_reproduces_reference_candidate_list_runs(name, i):
     case, run = CASES[name], CASES[name]["runs"][i]
     problem = rebuild_problem(case["problem"])
     cp, plan, options = prepare(problem, SolverOptions(**run["options"]), run.get("max_iterations"),
-                                trace_capacity=1 << 16, allow_unaccelerated=True)
+                                trace_capacity=1 << 16)
     assert_matches_reference(run, cp, _capi.solve_canonical(cp, plan.engine), options)
 
 

@@ -15,7 +15,7 @@ import pytest
 from emu import emu
 from helpers import assert_matches_reference, rebuild_problem
 from network_flow_solver_b200 import SolverConfigurationError, SolverOptions, _capi, build_problem, solve_min_cost_flow
-from network_flow_solver_b200.solver import prepare, reachable_from
+from network_flow_solver_b200.solver import finish, prepare, reachable_from
 from oracle import oracle
 
 DOC = json.loads(gzip.open(Path(__file__).resolve().parent / "golden" / "next" / "special_pivots.json.gz", "rb").read().decode())
@@ -61,14 +61,51 @@ def test_reachability_mask():
     assert reachable_from(6, tail, head, 3).tolist() == [0, 0, 0, 1, 0, 0]
 
 
-def test_bipartite_matching_rule_is_refused_loudly():
+def _matching_typed_instances():
+    """Instances the reference classifies as bipartite_matching (specializations.py:247-266: bipartite, no lower bounds,
+    supplies in {+1, -1, 0}) with the objective the unmodified reference returned for them
+    (status optimal; 3.0 under dantzig / devex / adaptive, 60.0 with default options; recorded 2026-10)."""
     nodes = [{"id": "a", "supply": 1.0}, {"id": "b", "supply": 1.0}, {"id": "x", "supply": -1.0}, {"id": "y", "supply": 0.0},
              {"id": "z", "supply": -1.0}]
     arcs = [{"tail": "a", "head": "x", "capacity": 1.0, "cost": 1.0}, {"tail": "b", "head": "y", "capacity": 1.0, "cost": 1.0},
             {"tail": "y", "head": "z", "capacity": 1.0, "cost": 1.0}, {"tail": "x", "head": "b", "capacity": 1.0, "cost": 2.0}]
-    problem = build_problem(nodes, arcs, directed=True, tolerance=1e-6)
-    with pytest.raises(SolverConfigurationError, match="PYTHONHASHSEED"):
-        prepare(problem, SolverOptions())
+    yield build_problem(nodes, arcs, directed=True, tolerance=1e-6), 3.0
+    # three unit sources and three unit sinks on a 6 x 6 grid (right / down arcs, capacity 3)
+    costs = [5, 6, 9, 1, 8, 4, 1, 3, 2, 6, 8, 4, 7, 9, 2, 4, 1, 4, 7, 5, 3, 7, 3, 2, 3, 8, 3, 3, 1, 1, 4, 4, 3, 3, 5, 6, 4, 9, 4,
+             3, 4, 7, 5, 1, 6, 7, 3, 3, 5, 2, 6, 5, 1, 6, 2, 5, 6, 5, 8, 6]
+    W, k, garcs = 6, 0, []
+    for r in range(W):
+        for c in range(W):
+            if c + 1 < W:
+                garcs.append({"tail": f"n{r}{c}", "head": f"n{r}{c + 1}", "capacity": 3.0, "cost": float(costs[k])}); k += 1
+            if r + 1 < W:
+                garcs.append({"tail": f"n{r}{c}", "head": f"n{r + 1}{c}", "capacity": 3.0, "cost": float(costs[k])}); k += 1
+    supply = {"n00": 1.0, "n02": 1.0, "n20": 1.0, "n55": -1.0, "n53": -1.0, "n35": -1.0}
+    gnodes = [{"id": f"n{r}{c}", "supply": supply.get(f"n{r}{c}", 0.0)} for r in range(W) for c in range(W)]
+    yield build_problem(gnodes, garcs, directed=True, tolerance=1e-6), 60.0
+
+
+def test_matching_typed_instances_fall_through_to_the_configured_rule(caplog):
+    """The reference's matching rule is hash-seed dependent (no sequence to reproduce): the instance is NOT refused, it is
+    solved with the configured pricing rule and must reach the reference's optimal objective."""
+    from network_flow_solver_b200.canonical import NET_BIPARTITE_MATCHING
+
+    for problem, objective in _matching_typed_instances():
+        for strategy in ("dantzig", "devex", "adaptive"):
+            with caplog.at_level("WARNING"):
+                cp, plan, options = prepare(problem, SolverOptions(pricing_strategy=strategy))
+            assert cp.network_type == NET_BIPARTITE_MATCHING and plan.engine.row_scan_first == _capi.SPECIAL_NONE
+            assert "hash-seed dependent" in caplog.text
+            for solve in (oracle.solve_canonical, emu.solve_canonical):
+                result = finish(cp, solve(cp, plan.engine), options)
+                assert result.status == "optimal" and result.objective == objective
+
+
+@pytest.mark.gpu
+def test_matching_typed_instances_on_the_gpu():
+    for problem, objective in _matching_typed_instances():
+        result = solve_min_cost_flow(problem, SolverOptions())
+        assert result.status == "optimal" and result.objective == objective
 
 
 @pytest.mark.parametrize("name,i", RUNS)
