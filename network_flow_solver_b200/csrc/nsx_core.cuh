@@ -20,6 +20,12 @@
 
 #include "../../include/nsx_b200.h"
 
+#if defined(__CUDACC__)
+#define NSX_HD __host__ __device__
+#else
+#define NSX_HD
+#endif
+
 #if defined(__CUDACC__) && !defined(NSX_HOST_EMU)
 #define NSX_ON_DEVICE 1
 #define NSX_FN __device__ __forceinline__
@@ -151,8 +157,9 @@ struct NsxDev {
     const uint8_t* node_mask;  // [n] NSX_SPECIAL_SHORTEST_PATH: node reachable from the source (HBM), else null
     double* imbalance;         // [n] warm starts only (else null): flow that clamping to a bound added at / removed from
                                // each node - the reference checks conservation after Phase 1 (simplex.py:1575-1598)
-    int32_t lazy_pos;   // preorder positions are updated lazily through the shift log (large trees in HBM)
-    int32_t log_cap;    // shift-log entries before positions are rewritten (<= NSX_LOG_CAP)
+    struct NsxBlk* blk; // trees that live in HBM: the preorder array is kept in blocks with slack (see NsxBlk); `order` is
+                        // then the block arena (NSX_BLK_MAX << blk->lg entries) and node.pos a physical index into it
+    int32_t* sidx;      // [n] blocked mode: index of a node inside the sequence nsx_recompute_potentials runs over
 };
 
 #define NSX_CL_SIZE 100    // candidate-list length (simplex.py:232)
@@ -200,7 +207,6 @@ struct NsxCtl {
 #define NSX_PH(c, k, t0) NSX_SINGLE { long long t1__ = NSX_CLOCK() + (*(volatile int32_t*)&(c).phase & 0); (c).ph[k] += t1__ - (t0); (t0) = t1__; }
 
 #define NSX_PATH_CAP 512  // cycle entries per side kept in shared memory (longer cycles spill to HBM)
-#define NSX_LOG_CAP 64    // shift-log capacity (lazy preorder positions)
 
 // Scratch of the pivot CTA (shared memory on the device).
 struct NsxPivotScratch {
@@ -214,15 +220,8 @@ struct NsxPivotScratch {
     int32_t pending;
     int32_t p_pos;             // preorder position of the new parent p (tree update)
     int32_t jkey;              // scan walk: min over common ancestors of (size << 16 | node)
-    // Lazy preorder positions (trees that live in HBM).  Moving the cut subtree shifts every entry
-    // between its old and new place; instead of rewriting the position of each shifted node, the
-    // shift is logged as "positions in [a, b) move by d".  A node stores (stamp << 24 | position):
-    // its position is current after replaying log entries stamp .. log_len-1.
     int32_t sp_any;            // rule scan: number of the last round in which some thread saw an arc that beats the incumbent
     int32_t sp_best, sp_zero;  // rule scan: incumbent arc*2 + (dir<0) / first zero-reduced-cost candidate, -1 none
-    int32_t log_len;
-    int32_t pos_mask;          // 0xffffff with lazy positions (stamp in the top byte), all ones otherwise
-    int32_t log_a[NSX_LOG_CAP], log_b[NSX_LOG_CAP], log_d[NSX_LOG_CAP];
     double theta;
     double sp_key;             // rule scan: key of the incumbent
     int32_t path_h[NSX_PATH_CAP];
@@ -261,13 +260,55 @@ NSX_FN void nsx_set_parent_mirror(const NsxDev& d, int32_t v, int32_t parent) {
 #endif
 }
 
-// current preorder position from a stored (stamp << 24 | position) word; a no-op in eager mode
-NSX_FN int32_t nsx_pos(const NsxPivotScratch& s, int32_t raw) {
-    int32_t p = raw & s.pos_mask;
-#pragma unroll 4
-    for (int32_t k = (int32_t)((uint32_t)raw >> 24); k < s.log_len; ++k)
-        if (p >= s.log_a[k] && p < s.log_b[k]) p += s.log_d[k];
-    return p;
+// ------------------------------------------------------------------------------------------
+// Blocked preorder array (trees that live in HBM / L2: n beyond what the pivot CTA can hold on-chip).
+// A dense preorder array makes re-hanging a subtree S cost a shift of every entry between its old and its new
+// place - ~n/3 entries per pivot, 92 us at n = 2^20 even when S is a single node.  Here the array is cut into
+// NSX_BLK_MAX blocks of CAP = 1 << lg slots that are filled to CAP/2 on average; `dir` lists the blocks in
+// preorder, a node's stored position is PHYSICAL (block * CAP + offset) and its preorder rank is
+// prefix[dirpos[block]] + offset, with `prefix` (entries before each directory slot) recomputed by one scan of the
+// directory per tree update.  Taking S out closes the gap inside at most two blocks and drops the blocks it covered
+// entirely; putting S back behind its new parent shifts the tail of one block or spills into fresh blocks: at most
+// 2 CAP entries move per pivot, plus |S|.  The directory, its inverse, the fill counts, the free list and the prefix
+// sums live in the pivot CTA's shared memory (48 KB).  When the free list runs short the whole array is laid out
+// afresh (O(n), rare).
+// ------------------------------------------------------------------------------------------
+#define NSX_BLK_MAX 4096
+struct NsxBlk {
+    uint16_t dir[NSX_BLK_MAX];      // block ids in preorder, ndir entries
+    uint16_t dirpos[NSX_BLK_MAX];   // block id -> its slot in dir (blocks in use)
+    uint16_t cnt[NSX_BLK_MAX];      // entries in use, by block id
+    uint16_t free_[NSX_BLK_MAX];    // stack of unused block ids, nfree entries
+    int32_t prefix[NSX_BLK_MAX + 1];  // prefix[k] = entries in dir[0 .. k)
+    int32_t wsum[32];               // scan scratch (warp totals)
+    int32_t ndir, nfree, rebuilds;
+    int32_t lg, nb;                 // set before nsx_blk_init: log2 of the block capacity, blocks in the arena (<= NSX_BLK_MAX)
+};
+// smallest power-of-two block capacity for which a half-filled layout of n entries uses at most 5/8 of the blocks
+static inline NSX_HD int32_t nsx_blk_lg(int64_t n) {
+    int32_t lg = 5;
+    while ((n + (1ll << (lg - 1)) - 1) >> (lg - 1) > NSX_BLK_MAX * 5 / 8) ++lg;
+    return lg;
+}
+// preorder rank of a stored position (a no-op for dense arrays)
+NSX_FN int32_t nsx_lpos(const NsxDev& d, int32_t pos) {
+    const NsxBlk* B = d.blk;
+    if (!B) return pos;
+    return B->prefix[B->dirpos[pos >> B->lg]] + (pos & ((1 << B->lg) - 1));
+}
+// directory slot that holds preorder rank x (largest k with prefix[k] <= x)
+NSX_FN int32_t nsx_blk_find(const NsxBlk& B, int32_t x) {
+    int32_t lo = 0, hi = B.ndir - 1;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi + 1) >> 1;
+        if (B.prefix[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// physical index of preorder rank x
+NSX_FN int64_t nsx_blk_phys(const NsxBlk& B, int32_t x) {
+    const int32_t k = nsx_blk_find(B, x);
+    return ((int64_t)B.dir[k] << B.lg) + (x - B.prefix[k]);
 }
 
 NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
@@ -292,6 +333,15 @@ NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
 #define NSX_CHUNK 256
 #endif
 
+// Where the parent of the entry at index x of the sequence `arr[lo .. hi)` sits in that sequence; anything below the
+// current chunk start means "already final".  Dense preorder arrays (sidx == null): the parent's stored position.
+// Blocked mode: the sequence is a flattened copy (d.tmp) and `sidx` maps a node to its index in it; the first entry
+// hangs below a node outside the sequence, and so does every child of the root (whole-tree recompute).
+NSX_FN int32_t nsx_seq_parent(const NsxDev& d, const int32_t* sidx, int64_t x, int64_t lo, int32_t parent) {
+    if (!sidx) return d.node[parent].pos;
+    return (x == lo || parent == 0) ? -1 : sidx[parent];
+}
+
 struct NsxPotScratch {
     double val[NSX_CHUNK];
     double cst[NSX_CHUNK];         // signed cost to add
@@ -313,8 +363,8 @@ struct NsxPotScratch {
 // instead of k, and no CTA-wide barrier.  Parents precede children in preorder, so waits terminate.
 #define NSX_POT_EMPTY 0x7ff8dead0badc0deLL
 #define NSX_HOP 8
-NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv, int32_t phase, int64_t lo,
-                                     int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32_t* arr, const int32_t* sidx,
+                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
     int32_t rounds = 0;
     volatile long long* vbits = reinterpret_cast<volatile long long*>(s.val);
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
@@ -327,12 +377,12 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
         int32_t v = 0;
         double val = 0.0;
         if (active) {
-            v = d.order[x];
+            v = arr[x];
             const NsxNode r = d.node[v];
             double cst = nsx_arc_cost(d, phase, r.pred2 >> 1);
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
-            const int32_t ppos = nsx_pos(pv, d.node[r.parent].pos);
+            const int32_t ppos = nsx_seq_parent(d, sidx, x, lo, r.parent);
             s.cst[j] = cst;
             if (ppos >= c0) { s.par_local[j] = (int32_t)(ppos - c0); done = false; vbits[j] = NSX_POT_EMPTY; }
             else { s.par_local[j] = -1; val = NSX_ADD(d.pi[r.parent], cst); vbits[j] = __double_as_longlong(val); }  // x - c == x + (-c) exactly
@@ -397,8 +447,8 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
 // A chunk is finished level by level: a waiting node of depth L has its parent at depth L-1, which
 // is either outside the chunk (final), or final from the chunk set-up, or was computed in the
 // previous level step.  One barrier per tree level present in the chunk.
-NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv, int32_t phase, int64_t lo,
-                                     int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
+NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32_t* arr, const int32_t* sidx,
+                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
     NSX_SINGLE { s.rounds = 0; }
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
         int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
@@ -407,14 +457,14 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
         NSX_SYNC();
         NSX_PAR_FOR(x, c0, c1) {
             int32_t j = (int32_t)(x - c0);
-            int32_t v = d.order[x];
+            int32_t v = arr[x];
             NsxNode r = d.node[v];
             int32_t a = r.pred2 >> 1;
             double cst = nsx_arc_cost(d, phase, a);
             // pred2 low bit set: arc points child->parent => pi[child] = pi[parent] - cost
             cst = (r.pred2 & 1) ? -cst : cst;
             s.cst[j] = cst;
-            int32_t ppos = nsx_pos(pv, d.node[r.parent].pos);
+            int32_t ppos = nsx_seq_parent(d, sidx, x, lo, r.parent);
             if (ppos >= c0) {
                 int32_t dep = d.depth[v];
                 s.par_local[j] = (int32_t)(ppos - c0);
@@ -439,7 +489,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
         NSX_SINGLE { if (dmax >= dmin) s.rounds += dmax - dmin + 1; }
         NSX_PAR_FOR(x, c0, c1) {
             int32_t j = (int32_t)(x - c0);
-            int32_t v = d.order[x];
+            int32_t v = arr[x];
             d.pi[v] = s.val[j];
             if (d.pi_mirror) d.pi_mirror[v] = s.val[j];
         }
@@ -450,16 +500,217 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, const NsxPivotScratch& pv,
 
 #endif
 
-// Rewrite every stored position from the preorder array and empty the shift log.
-NSX_FN void nsx_compact_positions(const NsxDev& d, NsxPivotScratch& s) {
-    if (!d.lazy_pos) return;
+// ---- blocked preorder array: maintenance (all routines are called by every thread of the pivot CTA) ----
+// prefix[k] = entries in directory slots [0, k)
+NSX_FN void nsx_blk_scan(NsxBlk& B) {
     NSX_SYNC();
-    if (s.log_len > 0) {
-        NSX_PAR_FOR(x, 0, d.n) { d.node[d.order[x]].pos = (int32_t)x; }
+#if NSX_ON_DEVICE
+    const int T = NSX_NTHREADS, tid = NSX_TID, nd = B.ndir;
+    const int per = (nd + T - 1) / T;
+    const int k0 = tid * per < nd ? tid * per : nd, k1 = k0 + per < nd ? k0 + per : nd;
+    int32_t sum = 0;
+    for (int k = k0; k < k1; ++k) sum += B.cnt[B.dir[k]];
+    int32_t incl = sum;
+    __syncwarp();
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31) >= off) incl += o;
+    }
+    if ((tid & 31) == 31) B.wsum[tid >> 5] = incl;
+    NSX_SYNC();
+    if (tid < 32) {
+        const int32_t w = tid < (T >> 5) ? B.wsum[tid] : 0;
+        int32_t wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int32_t o = __shfl_up_sync(0xffffffffu, wi, off);
+            if (tid >= off) wi += o;
+        }
+        B.wsum[tid] = wi - w;  // exclusive
     }
     NSX_SYNC();
-    NSX_SINGLE { s.log_len = 0; }
+    int32_t run = B.wsum[tid >> 5] + incl - sum;
+    for (int k = k0; k < k1; ++k) { B.prefix[k] = run; run += B.cnt[B.dir[k]]; }
+    if (k1 == nd && (k0 < nd || tid == 0)) B.prefix[nd] = run;
+#else
+    NSX_SINGLE {
+        int32_t run = 0;
+        for (int k = 0; k < B.ndir; ++k) { B.prefix[k] = run; run += B.cnt[B.dir[k]]; }
+        B.prefix[B.ndir] = run;
+    }
+#endif
     NSX_SYNC();
+}
+// dst[x - skip] = node of preorder rank x, x in [skip, n); with `sidx` also the inverse map (prefix must be valid)
+NSX_FN void nsx_blk_flatten(const NsxDev& d, const NsxBlk& B, int32_t* dst, int32_t skip, int32_t* sidx) {
+    NSX_PAR_FOR(x, skip, d.n) {
+        const int32_t v = d.order[nsx_blk_phys(B, (int32_t)x)];
+        dst[x - skip] = v;
+        if (sidx) sidx[v] = (int32_t)(x - skip);
+    }
+    NSX_SYNC();
+}
+// Lay the dense preorder sequence tmp[0 .. n) out in half-filled blocks: arena, stored positions, directory, free list.
+NSX_FN void nsx_blk_layout(const NsxDev& d, NsxBlk& B) {
+    const int32_t lg = B.lg, F = 1 << (lg - 1);
+    const int32_t nblk = (d.n + F - 1) / F;
+    NSX_SYNC();
+    NSX_PAR_FOR(x, 0, d.n) {
+        const int32_t v = d.tmp[x];
+        const int32_t dst = (int32_t)(((x / F) << lg) + (x % F));
+        d.order[dst] = v;
+        d.node[v].pos = dst;
+    }
+    NSX_PAR_FOR(k, 0, B.nb) {
+        if (k < nblk) {
+            B.dir[k] = (uint16_t)k; B.dirpos[k] = (uint16_t)k;
+            B.cnt[k] = (uint16_t)(d.n - k * F < F ? d.n - k * F : F);
+        } else {
+            B.free_[k - nblk] = (uint16_t)k; B.cnt[k] = 0;
+        }
+    }
+    NSX_SINGLE { B.ndir = nblk; B.nfree = B.nb - nblk; }
+    NSX_SYNC();
+}
+// first use: `order` still holds the dense preorder array the init kernel (or the warm-start layout) wrote
+NSX_FN void nsx_blk_init(const NsxDev& d, NsxBlk& B) {
+    NSX_SINGLE { B.rebuilds = 0; }
+    NSX_PAR_FOR(x, 0, d.n) { d.tmp[x] = d.order[x]; }
+    NSX_SYNC();
+    nsx_blk_layout(d, B);
+}
+// the free list ran short: flatten and lay out afresh
+NSX_FN void nsx_blk_rebuild(const NsxDev& d, NsxBlk& B) {
+    nsx_blk_scan(B);
+    nsx_blk_flatten(d, B, d.tmp, 0, (int32_t*)0);
+    nsx_blk_layout(d, B);
+    NSX_SINGLE { B.rebuilds++; }
+}
+// order[src .. src + len) moves by `delta` slots (the ranges may overlap; same block): rounds of 4 entries per thread,
+// loaded before any is stored, taken from the end the data moves towards.  Stored positions follow.
+NSX_FN void nsx_blk_move(const NsxDev& d, int64_t src, int32_t len, int32_t delta) {
+    const int64_t T = NSX_NTHREADS, R = 4 * T;
+    const int64_t nr = (len + R - 1) / R;
+    for (int64_t b = 0; b < nr; ++b) {
+        const int64_t b_lo = delta > 0 ? src + len - (b + 1) * R : src + b * R;
+        int32_t v[4];
+        NSX_SYNC();  // the previous round has been written
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t x = b_lo + u * T + NSX_TID;
+            v[u] = (x >= src && x < src + len) ? d.order[x] : -1;
+        }
+        NSX_SYNC();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t x = b_lo + u * T + NSX_TID;
+            if (v[u] >= 0) { d.order[x + delta] = v[u]; d.node[v[u]].pos = (int32_t)(x + delta); }
+        }
+    }
+}
+// directory slots [from, from + count) move by `delta` (same scheme), dirpos follows
+NSX_FN void nsx_blk_dirshift(NsxBlk& B, int32_t from, int32_t count, int32_t delta) {
+    const int32_t T = NSX_NTHREADS, R = 4 * T;
+    const int32_t nr = (count + R - 1) / R;
+    for (int32_t b = 0; b < nr; ++b) {
+        const int32_t b_lo = delta > 0 ? from + count - (b + 1) * R : from + b * R;
+        int32_t v[4];
+        NSX_SYNC();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t k = b_lo + u * T + NSX_TID;
+            v[u] = (k >= from && k < from + count) ? (int32_t)B.dir[k] : -1;
+        }
+        NSX_SYNC();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t k = b_lo + u * T + NSX_TID;
+            if (v[u] >= 0) { B.dir[k + delta] = (uint16_t)v[u]; B.dirpos[v[u]] = (uint16_t)(k + delta); }
+        }
+    }
+}
+// Take the preorder ranks [S0, S0 + sz) out (their nodes have been copied elsewhere).  `prefix` must be valid on
+// entry and is stale afterwards.  Returns the number of entries that moved.
+NSX_FN int32_t nsx_blk_remove(const NsxDev& d, NsxBlk& B, int32_t S0, int32_t sz) {
+    const int32_t lg = B.lg;
+    const int32_t k0 = nsx_blk_find(B, S0), k1 = nsx_blk_find(B, S0 + sz - 1);
+    const int32_t b0 = B.dir[k0], b1 = B.dir[k1];
+    const int32_t o0 = S0 - B.prefix[k0], o1 = S0 + sz - B.prefix[k1];  // first offset taken in b0 / first kept in b1
+    const int32_t c1 = B.cnt[b1], nd = B.ndir, nf = B.nfree;
+    NSX_SYNC();  // every thread holds the values above
+    int32_t newc0, newc1;
+    if (k0 == k1) { nsx_blk_move(d, ((int64_t)b0 << lg) + o1, c1 - o1, -sz); newc0 = newc1 = c1 - sz; }
+    else { nsx_blk_move(d, ((int64_t)b1 << lg) + o1, c1 - o1, -o1); newc0 = o0; newc1 = c1 - o1; }
+    const bool keepA = newc0 > 0, keepB = k1 != k0 && newc1 > 0;
+    const int32_t w = k0 + (keepA ? 1 : 0) + (keepB ? 1 : 0);  // where the directory tail lands
+    const int32_t shift = (k1 + 1) - w;
+    const int32_t mid = k1 > k0 ? k1 - k0 - 1 : 0;
+    NSX_PAR_FOR(k, k0 + 1, k1) { B.free_[nf + (k - k0 - 1)] = B.dir[k]; }  // blocks that S covered entirely
+    NSX_SYNC();
+    NSX_SINGLE {
+        int32_t f = nf + mid, ww = k0;
+        B.cnt[b0] = (uint16_t)newc0;
+        if (k1 != k0) B.cnt[b1] = (uint16_t)newc1;
+        if (keepA) { B.dir[ww] = (uint16_t)b0; B.dirpos[b0] = (uint16_t)ww; ++ww; } else B.free_[f++] = (uint16_t)b0;
+        if (k1 != k0) { if (keepB) { B.dir[ww] = (uint16_t)b1; B.dirpos[b1] = (uint16_t)ww; ++ww; } else B.free_[f++] = (uint16_t)b1; }
+        B.nfree = f;
+        B.ndir = nd - shift;
+    }
+    if (shift > 0) nsx_blk_dirshift(B, k1 + 1, nd - (k1 + 1), -shift);
+    NSX_SYNC();
+    return c1 - o1;
+}
+// Put the sz nodes tmp[0 .. sz) right behind node p in preorder.  Needs nfree >= (sz + CAP) / CAP + 1.
+NSX_FN int32_t nsx_blk_insert(const NsxDev& d, NsxBlk& B, int32_t p, int32_t sz) {
+    const int32_t lg = B.lg, CAP = 1 << lg;
+    const int32_t pp = d.node[p].pos;  // (p may have moved when S was taken out)
+    const int32_t bp = pp >> lg, op = pp & (CAP - 1), kp = B.dirpos[bp], cp = B.cnt[bp];
+    const int32_t t = cp - (op + 1);   // entries behind p in its block
+    const int64_t base = ((int64_t)bp << lg) + op + 1;
+    const int32_t nd = B.ndir, nf = B.nfree;
+    NSX_SYNC();
+    if (cp + sz <= CAP) {
+        nsx_blk_move(d, base, t, sz);
+        NSX_PAR_FOR(j, 0, sz) {
+            const int32_t v = d.tmp[j];
+            d.order[base + j] = v;
+            d.node[v].pos = (int32_t)(base + j);
+        }
+        NSX_SINGLE { B.cnt[bp] = (uint16_t)(cp + sz); }
+    } else {
+        // S and the tail of p's block go to fresh blocks (half filled while the free list allows)
+        const int32_t total = sz + t;
+        int32_t F = CAP >> 1, q = (total + F - 1) / F;
+        if (q > nf) { F = CAP; q = (total + F - 1) / F; }
+        NSX_PAR_FOR(j, 0, total) {
+            const int32_t v = j < sz ? d.tmp[j] : d.order[base + (j - sz)];
+            const int32_t nb = B.free_[nf - 1 - (int32_t)(j / F)];
+            const int64_t dst = ((int64_t)nb << lg) + (j % F);
+            d.order[dst] = v;
+            d.node[v].pos = (int32_t)dst;
+        }
+        nsx_blk_dirshift(B, kp + 1, nd - (kp + 1), q);
+        NSX_PAR_FOR(i, 0, q) {
+            const int32_t nb = B.free_[nf - 1 - (int32_t)i];
+            B.dir[kp + 1 + i] = (uint16_t)nb;
+            B.dirpos[nb] = (uint16_t)(kp + 1 + i);
+            B.cnt[nb] = (uint16_t)(total - (int32_t)i * F < F ? total - (int32_t)i * F : F);
+        }
+        NSX_SINGLE { B.cnt[bp] = (uint16_t)(op + 1); B.ndir = nd + q; B.nfree = nf - q; }
+    }
+    NSX_SYNC();
+    return t;
+}
+// Potentials of the whole tree (start of a phase): dense arrays walk `order`, the blocked array is flattened first.
+NSX_FN void nsx_recompute_all_potentials(const NsxDev& d, int32_t phase, NsxPotScratch& ps) {
+    if (d.blk) {
+        nsx_blk_scan(*d.blk);
+        nsx_blk_flatten(d, *d.blk, d.tmp, 1, d.sidx);
+        nsx_recompute_potentials(d, phase, d.tmp, d.sidx, 0, (int64_t)d.n - 1, ps, (int64_t*)0);
+    } else {
+        nsx_recompute_potentials(d, phase, d.order, (const int32_t*)0, 1, d.n, ps, (int64_t*)0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -598,7 +849,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             const int32_t dj = d.depth[join];
             s.join = join; s.nh = dh - dj; s.nt = dt - dj;
         }
-    } else if (d.lazy_pos) {
+    } else if (d.blk) {
         // Depth-synchronised climb (no positions needed): lane 0 holds the head-side node, lane 1
         // the tail-side node; the deeper one climbs, both climb when level, until they meet.
         if (threadIdx.x < 32) {
@@ -633,7 +884,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     }
 #else
     NSX_HOST_SERIAL {
-    if (d.lazy_pos) {
+    if (d.blk) {
         int32_t u = h, v = t, du = d.depth[h], dv = d.depth[t], nh_ = 0, nt_ = 0;
         while (u != v) {
             const bool climb_u = du >= dv, climb_v = dv >= du;
@@ -808,6 +1059,11 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const NsxNode rec_p = d.node[p];
     const int32_t sz = rec_r.size;
     const int32_t depth_q_new = d.depth[p] + 1;
+    if (d.blk) {
+        // (uniform: every thread reads the same shared-memory words) enough free blocks for the worst case of this update?
+        if (d.blk->nfree < (sz >> d.blk->lg) + 3) nsx_blk_rebuild(d, *d.blk);
+        nsx_blk_scan(*d.blk);  // preorder ranks of stored positions are valid from here until the array is edited
+    }
     // stem snapshot (old pos / size / depth / pred2): shared scratch reusing res[] / arc2[], or the
     // global spill arrays when the cycle did not fit (garc2: 2n+1 ints, gres: 2n+1 doubles)
     int32_t* st_pos = spill ? d.garc2 : (int32_t*)s.res;
@@ -816,9 +1072,9 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     int32_t* st_pred2 = spill ? ((int32_t*)d.gres) + d.n : s.arc2;
     NSX_SYNC();  // everyone has read arc2/res for the flow update before they are reused
     NSX_PAR_FOR(i, 0, kk + 2) {
-        if (i == kk + 1) { s.p_pos = nsx_pos(s, rec_p.pos); continue; }  // position of the new parent
+        if (i == kk + 1) { s.p_pos = nsx_lpos(d, d.node[p].pos); continue; }  // preorder rank of the new parent
         NsxNode x = d.node[spath[i]];
-        st_pos[i] = nsx_pos(s, x.pos); st_size[i] = x.size; st_pred2[i] = x.pred2;
+        st_pos[i] = nsx_lpos(d, x.pos); st_size[i] = x.size; st_pred2[i] = x.pred2;
         st_depth[i] = d.depth[spath[i]];
     }
     // subtree-size bookkeeping of the untouched ancestors on both sides of the cycle
@@ -827,9 +1083,9 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_SYNC();
     NSX_PH(c, 5, tph);
 
-    // The block S = [a0, a0+sz) of the preorder array is re-rooted at q and moved under p: either
-    // right behind p or to the end of p's old subtree, whichever shifts fewer entries (both are
-    // valid preorders).  `ins` is the insertion point in old coordinates.
+    // The block S = [a0, a0+sz) of the preorder sequence is re-rooted at q and moved under p.  Dense array: either
+    // right behind p or to the end of p's old subtree, whichever shifts fewer entries (both are valid preorders);
+    // `ins` is the insertion point in old coordinates.  Blocked array: always right behind p.
     const int32_t a0 = st_pos[kk], P = s.p_pos;  // r = s_k is the root of the cut subtree
     const int64_t S0 = a0, S1 = (int64_t)a0 + sz;
     const int64_t insA = (int64_t)P + 1, insB = (int64_t)P + rec_p.size;
@@ -840,17 +1096,20 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     if (ins <= S0) { lo = ins; hi = S1; s_base = ins; xshift = sz; }        // [ins, S0) moves right
     else           { lo = S0; hi = ins; s_base = ins - sz; xshift = -(int64_t)sz; }  // [S1, ins) moves left
     const int32_t k_stem = kk;
-    // Lazy mode: only the nodes of S get their position written (stamped with the log length after
-    // this pivot's entry); the other entries of the window are a plain coalesced move of `order`.
-    const int32_t stamp = d.lazy_pos ? ((s.log_len + 1) << 24) : 0;
-    const int64_t w_lo = d.lazy_pos ? S0 : lo, w_hi = d.lazy_pos ? S1 : hi;
+    // Blocked mode: only S is permuted (into tmp[0 .. sz), with the inverse map in sidx); the dense array also shifts
+    // the entries between the old and the new place of S in the same pass.
+    const bool blocked = d.blk != nullptr;
+    const int64_t w_lo = blocked ? S0 : lo, w_hi = blocked ? S1 : hi;
     {
         // four entries per thread and step: the loads of all four are issued before any store
         const int64_t T = NSX_NTHREADS;
         for (int64_t x0 = w_lo + NSX_TID; x0 < w_hi; x0 += 4 * T) {
             int32_t v[4], dv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < w_hi ? d.order[x] : -1; }
+            for (int u = 0; u < 4; ++u) {
+                int64_t x = x0 + u * T;
+                v[u] = x < w_hi ? d.order[blocked ? nsx_blk_phys(*d.blk, (int32_t)x) : x] : -1;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 int64_t x = x0 + u * T;
@@ -876,55 +1135,30 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                                (x - ((int64_t)st_pos[i - 1] + st_size[i - 1]));
                     fx = s_base + rel;
                     d.depth[v[u]] = dv[u] - st_depth[i] + depth_q_new + i;
+                    if (blocked) { d.tmp[rel] = v[u]; d.sidx[v[u]] = (int32_t)rel; continue; }
                 } else {
                     fx = x + xshift;
                 }
                 d.tmp[fx] = v[u];
-                d.node[v[u]].pos = (int32_t)fx | stamp;
-            }
-        }
-        if (d.lazy_pos) {
-            // the entries between the old and the new place of S, [ins, S0) or [S1, ins), shift by
-            // +-sz IN PLACE: blocks of 16 entries per thread are read into registers, then written,
-            // starting from the end the block moves towards (a later block never reads what an
-            // earlier one wrote).  S itself was copied to `tmp` above and is written back below.
-            const int64_t m_lo = ins <= S0 ? ins : S1, m_hi = ins <= S0 ? S0 : ins;
-            NSX_SINGLE {
-                const int32_t k = s.log_len;
-                s.log_a[k] = (int32_t)m_lo; s.log_b[k] = (int32_t)m_hi; s.log_d[k] = (int32_t)xshift;
-            }
-            const int64_t B = 16 * T;
-            const int64_t nblk = (m_hi - m_lo + B - 1) / B;
-            for (int64_t b = 0; b < nblk; ++b) {
-                // right shift: blocks from the high end down; left shift: from the low end up
-                const int64_t b_lo = xshift > 0 ? m_hi - (b + 1) * B : m_lo + b * B;
-                int32_t v[16];
-                NSX_SYNC();  // S has been read (first block) / the previous block has been written
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int64_t x = b_lo + u * T + NSX_TID;
-                    v[u] = (x >= m_lo && x < m_hi) ? d.order[x] : -1;
-                }
-                NSX_SYNC();
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int64_t x = b_lo + u * T + NSX_TID;
-                    if (x >= m_lo && x < m_hi) d.order[x + xshift] = v[u];
-                }
+                d.node[v[u]].pos = (int32_t)fx;
             }
         }
     }
     NSX_SYNC();
+    int64_t moved = hi - lo;
+    if (blocked) {
+        moved = sz + nsx_blk_remove(d, *d.blk, (int32_t)S0, sz);
+        moved += nsx_blk_insert(d, *d.blk, p, sz);
+    }
     NSX_PH(c, 6, tph);
-    {
+    if (!blocked) {
         const int64_t T = NSX_NTHREADS;
-        const int64_t c_lo = d.lazy_pos ? s_base : lo, c_hi = d.lazy_pos ? s_base + sz : hi;
-        for (int64_t x0 = c_lo + NSX_TID; x0 < c_hi; x0 += 4 * T) {
+        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
             int32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < c_hi ? d.tmp[x] : -1; }
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.tmp[x] : -1; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < c_hi) d.order[x] = v[u]; }
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < hi) d.order[x] = v[u]; }
         }
     }
     // stem: reverse parent pointers, new subtree sizes
@@ -942,20 +1176,19 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
     }
     NSX_SINGLE {
-        if (d.lazy_pos) s.log_len++;
         d.state[e] |= NSX_ARC_IN_TREE;
         d.state[leave] &= (uint8_t)~NSX_ARC_IN_TREE;
         c.tree_updates++;
         c.sum_subtree += sz;
         if (sz > c.max_subtree) c.max_subtree = sz;
-        c.sum_window += hi - lo;
+        c.sum_window += moved;
     }
     NSX_SYNC();
-    if (d.lazy_pos && s.log_len >= d.log_cap) nsx_compact_positions(d, s);
     NSX_PH(c, 7, tph);
 
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
-    nsx_recompute_potentials(d, s, c.phase, s_base, s_base + sz, ps, &c.sum_rounds);
+    if (blocked) nsx_recompute_potentials(d, c.phase, d.tmp, d.sidx, 0, sz, ps, &c.sum_rounds);
+    else nsx_recompute_potentials(d, c.phase, d.order, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds);
     NSX_PH(c, 8, tph);
 
     // ---- 7. reset cadence (simplex.py:1373-1425) -------------------------------------------
@@ -1573,10 +1806,10 @@ NSX_FN void nsx_check_conservation(const NsxDev& d, NsxCtl& c) {
 template <class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
-    NSX_SINGLE { s.log_len = 0; s.pos_mask = d.lazy_pos ? 0xffffff : 0x7fffffff; }
+    if (d.blk) nsx_blk_init(d, *d.blk);
     NSX_SYNC();
     // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
-    nsx_recompute_potentials(d, s, c.phase, 1, d.n, ps, (int64_t*)0);
+    nsx_recompute_all_potentials(d, c.phase, ps);
     NSX_SINGLE {
         L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
         L.drv.budget = c.maxit;
@@ -1619,10 +1852,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             if (d.imbalance && c.phase == 1) nsx_check_conservation(d, c);
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
-            if (!L.drv.final_check) {
-                nsx_compact_positions(d, s);
-                nsx_recompute_potentials(d, s, 2, 1, d.n, ps, (int64_t*)0);
-            }
+            if (!L.drv.final_check) nsx_recompute_all_potentials(d, 2, ps);
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }
         } else {  // NSX_ACT_EXIT

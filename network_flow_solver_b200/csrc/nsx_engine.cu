@@ -221,6 +221,7 @@ struct NsxSmemPlan {
     uint32_t ring_off;  // byte offset of the tile ring inside the dynamic part
     int32_t stages;     // ring depth (0: this CTA never sweeps)
     int32_t par16;      // pivot CTA keeps a uint16 mirror of the parent pointers (+ root bitmap) in shared memory
+    int32_t blk_off;    // byte offset of the NsxBlk directory (trees in HBM: blocked preorder array), -1 = dense array
 };
 
 static inline __host__ __device__ size_t nsx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -232,8 +233,9 @@ static inline __host__ __device__ size_t nsx_resident_bytes(int mode, size_t n) 
 // Plan for a CTA that pivots (and, when `sweeps`, also prices: single-CTA and batch modes).
 static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t limit, uint32_t stage_bytes,
                                                              bool sweeps, int want_mode, int want_stage) {
-    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0;
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0; p.blk_off = -1;
     const size_t ring_min = sweeps ? 2 * (size_t)stage_bytes : 0;
+    const size_t blk_bytes = nsx_align16(sizeof(NsxBlk));
     // a CTA that also sweeps wants a ring of >= 4 stages more than it wants depth / preorder on-chip
     for (int want_ring = sweeps ? 4 : 0; p.mode == NSX_RES_NONE && want_ring >= (sweeps ? 2 : 0); want_ring -= 2) {
         for (int mode = want_mode; mode >= NSX_RES_NODES; --mode) {
@@ -242,14 +244,16 @@ static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t li
         if (!sweeps) break;
     }
     size_t used = nsx_resident_bytes(p.mode, n);
-    if (p.mode == NSX_RES_NONE && sweeps && want_stage && nsx_align16(8 * n) + ring_min <= limit) {
+    if (p.mode == NSX_RES_NONE && sweeps && want_stage && nsx_align16(8 * n) + blk_bytes + ring_min <= limit) {
         p.stage_pi = 1; used = nsx_align16(8 * n);
     }
     // trees that stay in HBM: the parent pointers alone (2 B / node + 1 bit) make the cycle walk a
     // chain of shared-memory loads instead of L2 round trips
-    if (p.mode == NSX_RES_NONE && !sweeps && n <= 65537 && nsx_align16(2 * n) + nsx_align16(n / 8 + 8) <= limit) {
+    if (p.mode == NSX_RES_NONE && !sweeps && n <= 65537 && nsx_align16(2 * n) + nsx_align16(n / 8 + 8) + blk_bytes <= limit) {
         p.par16 = 1; used = nsx_align16(2 * n) + nsx_align16(n / 8 + 8);
     }
+    // ... and their preorder array is kept in blocks; the directory lives here (nsx_core.cuh, NsxBlk)
+    if (p.mode == NSX_RES_NONE) { p.blk_off = (int32_t)used; used += blk_bytes; }
     p.ring_off = (uint32_t)used;
     if (sweeps) {
         size_t s = (limit - used) / stage_bytes;
@@ -259,7 +263,7 @@ static inline __host__ __device__ NsxSmemPlan nsx_plan_pivot(size_t n, size_t li
 }
 // Plan for a sweep-only worker CTA.
 static inline __host__ __device__ NsxSmemPlan nsx_plan_worker(size_t n, size_t limit, uint32_t stage_bytes, int want_stage) {
-    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0;
+    NsxSmemPlan p; p.mode = NSX_RES_NONE; p.stage_pi = 0; p.ring_off = 0; p.stages = 0; p.par16 = 0; p.blk_off = -1;
     size_t used = 0;
     if (want_stage && nsx_align16(8 * n) + 3 * (size_t)stage_bytes <= limit) { p.stage_pi = 1; used = nsx_align16(8 * n); }
     p.ring_off = (uint32_t)used;
@@ -302,6 +306,8 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
     NsxDev dl = d;
     double* pis = reinterpret_cast<double*>(dyn);
     *pis_out = pis;
+    dl.blk = plan.blk_off >= 0 ? reinterpret_cast<NsxBlk*>(dyn + plan.blk_off) : nullptr;
+    if (dl.blk && threadIdx.x == 0) { dl.blk->lg = nsx_blk_lg(d.n); dl.blk->nb = NSX_BLK_MAX; }  // (barriers follow on every path)
     if (plan.mode == NSX_RES_NONE && plan.par16) {
         uint16_t* par = reinterpret_cast<uint16_t*>(dyn);
         uint32_t* bits = reinterpret_cast<uint32_t*>(dyn + nsx_align16(2 * (size_t)d.n));
@@ -325,8 +331,7 @@ __device__ __forceinline__ NsxDev nsx_make_resident(const NsxDev& d, const NsxSm
         for (int32_t v = threadIdx.x; v < d.n; v += blockDim.x) { depth_s[v] = d.depth[v]; order_s[v] = d.order[v]; }
         dl.depth = depth_s; dl.order = order_s; dl.tmp = tmp_s;
     }
-    dl.scan_walk = d.n <= 32767 ? 1 : 0;
-    dl.lazy_pos = 0;  // shared-memory trees keep eager positions (cheap scatter, needed by the scan walk)
+    dl.scan_walk = d.n <= 32767 ? 1 : 0;  // (shared-memory trees keep a dense preorder array: cheap scatter, needed by the scan walk)
     NSX_SYNC();
     return dl;
 }
@@ -1107,9 +1112,9 @@ __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
 template <class Sweep>
 __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
                                                NsxPotScratch& ps, Sweep& sweep, int32_t count) {
-    if (threadIdx.x == 0) { pv.log_len = 0; pv.pos_mask = d.lazy_pos ? 0xffffff : 0x7fffffff; }
+    if (d.blk) nsx_blk_init(d, *d.blk);
     NSX_SYNC();
-    nsx_recompute_potentials(d, pv, 1, 1, d.n, ps, (int64_t*)0);
+    nsx_recompute_all_potentials(d, 1, ps);
     for (int32_t k = 0; k < count; ++k) {
         NSX_SYNC();
         if (threadIdx.x == 0) {
@@ -1524,6 +1529,11 @@ static int nsx_device_info(int dev, DeviceInfo& info) {
 }
 
 static size_t nsx_smem_fixed() { return (sizeof(NsxCtaShared) + 15) & ~(size_t)15; }
+// entries of the preorder array: the block arena of the blocked layout (which also covers the dense array of n entries)
+static size_t nsx_order_len(size_t n) {
+    const size_t arena = (size_t)NSX_BLK_MAX << nsx_blk_lg((int64_t)n);
+    return arena > n ? arena : n;
+}
 static int64_t nsx_pad_tiles(int64_t m) {
     int64_t t = (m + NSX_TILE - 1) / NSX_TILE;
     return (t < 1 ? 1 : t) * (int64_t)NSX_TILE;
@@ -1642,7 +1652,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_flow = arena.plan((size_t)(ma + 4) * 8), o_state = arena.plan(state_len);
     size_t o_wgt = devex ? arena.plan((size_t)mpad * 4) : 0;
     size_t o_node = arena.plan((size_t)n * sizeof(NsxNode)), o_depth = arena.plan((size_t)n * 4);
-    size_t o_pi = arena.plan((size_t)n * 8 + 16), o_order = arena.plan((size_t)n * 4), o_tmp = arena.plan((size_t)n * 4);
+    const size_t order_len = nsx_order_len((size_t)n);
+    size_t o_pi = arena.plan((size_t)n * 8 + 16), o_order = arena.plan(order_len * 4), o_tmp = arena.plan((size_t)n * 4);
+    size_t o_sidx = arena.plan((size_t)n * 4);
     size_t o_gph = arena.plan((size_t)n * 4), o_gpt = arena.plan((size_t)n * 4);
     size_t o_garc2 = arena.plan(((size_t)2 * n + 1) * 4), o_gres = arena.plan(((size_t)2 * n + 1) * 8);
     size_t o_ctl = arena.plan(sizeof(NsxCtl)), o_grid = arena.plan(sizeof(NsxGridCtl));
@@ -1658,13 +1670,11 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.wgt = devex ? arena.at<uint32_t>(o_wgt) : nullptr;
     d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi); d.pi_mirror = nullptr;
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
+    d.sidx = arena.at<int32_t>(o_sidx); d.blk = nullptr;  // (the pivot CTA points blk at its shared memory)
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
     d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
     d.imbalance = warm ? arena.at<double>(o_imb) : nullptr;
-    d.lazy_pos = (n < (1 << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0;
-    d.log_cap = nsx_env_int("NSX_LOG_CAP", 32);
-    if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP;
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.slots = arena.at<NsxSlot>(o_slots);
     ka.topk = arena.at<NsxTopkOut>(o_topk);
@@ -1707,7 +1717,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     const size_t limit = info.smem_optin - fixed;
     const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
     ka.plan = nsx_plan_pivot((size_t)n, limit, st.stage_bytes, grid == 1, want_mode, want_stage);
-    if (!d.lazy_pos || !nsx_env_int("NSX_PAR16", 1)) { if (ka.plan.par16) { ka.plan.par16 = 0; ka.plan.ring_off = 0; } }
+    if (!nsx_env_int("NSX_PAR16", 1) && ka.plan.par16) {  // (test knob: cycle walk on the node records in L2)
+        ka.plan.par16 = 0; ka.plan.blk_off = 0; ka.plan.ring_off = (uint32_t)nsx_align16(sizeof(NsxBlk));
+    }
     ka.wplan = nsx_plan_worker((size_t)n, limit, st.stage_bytes, want_stage);
     int max_stages = nsx_env_int("NSX_STAGES", NSX_MAX_STAGES);
     if (max_stages < 2) max_stages = 2;
@@ -1744,7 +1756,16 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         NSX_CUDA(cudaGetLastError());
     }
     void* kargs[] = {(void*)&ka};
-    NSX_CUDA(cudaLaunchCooperativeKernel((void*)nsx_resident_kernel, dim3(grid), dim3(NSX_THREADS), kargs, smem, stream));
+    // The kernel synchronises its CTAs through its own flags; the cooperative launch is only there for the guarantee
+    // that all of them are resident at once.  NSX_LAUNCH_PLAIN=1 (tests that run several ranks of a sharded solve as
+    // host threads on ONE device) uses an ordinary launch instead: the driver does not run two cooperative grids side by
+    // side, and grid <= SM count with one CTA per SM is co-resident on an otherwise idle device anyway.
+    if (nsx_env_int("NSX_LAUNCH_PLAIN", 0)) {
+        nsx_resident_kernel<<<dim3(grid), dim3(NSX_THREADS), smem, stream>>>(ka);
+        NSX_CUDA(cudaGetLastError());
+    } else {
+        NSX_CUDA(cudaLaunchCooperativeKernel((void*)nsx_resident_kernel, dim3(grid), dim3(NSX_THREADS), kargs, smem, stream));
+    }
     NSX_CUDA(cudaEventRecord(ev[2], stream));
 
     // ---- results ----
@@ -1886,13 +1907,24 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     for (int64_t i = 0; i < count; ++i) if (problems[i].n_nodes - 1 > 65536) narrow = false;
     NsxStore layout;
     nsx_store_layout(layout, narrow ? NSX_NODE_U16 : NSX_NODE_I32, NSX_COST_F64, devex ? 1 : 0);
-    struct Off { size_t store; size_t tail, head, pert, upper, atail, ahead, aupper, flow, state, wgt, node, depth, pi, order, tmp, gph, gpt, garc2, gres, supply, ctl, trace; };
+    struct Off { size_t store; size_t tail, head, pert, upper, atail, ahead, aupper, flow, state, wgt, node, depth, pi, order, tmp, sidx, gph, gpt, garc2, gres, supply, ctl, trace; };
     std::vector<Off> off(count);
     int32_t max_n = 1;
+    const size_t fixed = nsx_smem_fixed();
+    const size_t limit_all = info.smem_optin - fixed;
+    const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
+    for (int64_t i = 0; i < count; ++i) if (problems[i].n_nodes > max_n) max_n = problems[i].n_nodes;
+    // shared memory of every CTA: sized for the largest instance (each CTA re-plans per instance within this size)
+    NsxSmemPlan plan = nsx_plan_pivot((size_t)max_n, limit_all, layout.stage_bytes, true, want_mode, want_stage);
+    if (plan.stages < 2) return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit");
+    int max_stages = nsx_env_int("NSX_BATCH_STAGES", 4);
+    if (max_stages < 2) max_stages = 2;
+    if (plan.stages > max_stages) plan.stages = max_stages;
+    const size_t dyn = nsx_plan_bytes(plan, layout.stage_bytes);
+    const size_t smem = fixed + dyn;
     for (int64_t i = 0; i < count; ++i) {
         const nsx_problem& p = problems[i];
         const size_t n = p.n_nodes, m = p.n_arcs, ma = m + n - 1, mpad = (size_t)nsx_pad_tiles((int64_t)m);
-        if ((int32_t)n > max_n) max_n = (int32_t)n;
         Off& o = off[i];
         o.tail = arena.plan((m + 4) * 4); o.head = arena.plan((m + 4) * 4);
         o.pert = arena.plan((m + 4) * 8); o.upper = arena.plan((m + 4) * 8);
@@ -1901,7 +1933,10 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         o.flow = arena.plan((ma + 4) * 8); o.state = arena.plan((ma > mpad ? ma : mpad) + 16);
         o.wgt = devex ? arena.plan(mpad * 4) : 0;
         o.node = arena.plan(n * sizeof(NsxNode)); o.depth = arena.plan(n * 4); o.pi = arena.plan(n * 8 + 16);
-        o.order = arena.plan(n * 4); o.tmp = arena.plan(n * 4); o.gph = arena.plan(n * 4); o.gpt = arena.plan(n * 4);
+        // (a tree too large for the CTA's shared memory keeps its preorder array in blocks: same plan as the kernel makes)
+        const bool in_hbm = nsx_plan_pivot(n, dyn, layout.stage_bytes, true, want_mode, want_stage).mode == NSX_RES_NONE;
+        o.order = arena.plan((in_hbm ? nsx_order_len(n) : n) * 4); o.tmp = arena.plan(n * 4); o.sidx = arena.plan(n * 4);
+        o.gph = arena.plan(n * 4); o.gpt = arena.plan(n * 4);
         o.garc2 = arena.plan((2 * n + 1) * 4); o.gres = arena.plan((2 * n + 1) * 8);
         o.supply = arena.plan(n * 8); o.ctl = arena.plan(sizeof(NsxCtl));
         o.trace = (results[i].entering_trace && opt->trace_capacity > 0) ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
@@ -1936,7 +1971,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.garc2 = arena.at<int32_t>(o.garc2); d.gres = arena.at<double>(o.gres);
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
         d.node_mask = nullptr; d.imbalance = nullptr;
-        d.lazy_pos = (n < (1u << 24)) ? nsx_env_int("NSX_LAZY", 1) : 0; d.log_cap = 32;
+        d.blk = nullptr; d.sidx = arena.at<int32_t>(o.sidx);
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);
         items[i].mpad = nsx_pad_tiles((int64_t)m);
@@ -1959,16 +1994,6 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     NSX_CUDA(cudaMemsetAsync(d_next, 0, 8, stream));
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
-    const size_t fixed = nsx_smem_fixed();
-    const size_t limit_all = info.smem_optin - fixed;
-    const int want_mode = nsx_env_int("NSX_RESIDENT", 2), want_stage = nsx_env_int("NSX_STAGE_PI", 1);
-    NsxSmemPlan plan = nsx_plan_pivot((size_t)max_n, limit_all, layout.stage_bytes, true, want_mode, want_stage);
-    if (plan.stages < 2) { arena.release(); return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit"); }
-    int max_stages = nsx_env_int("NSX_BATCH_STAGES", 4);
-    if (max_stages < 2) max_stages = 2;
-    if (plan.stages > max_stages) plan.stages = max_stages;
-    const size_t dyn = nsx_plan_bytes(plan, layout.stage_bytes);
-    const size_t smem = fixed + dyn;
     NSX_CUDA(cudaFuncSetAttribute(nsx_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_batch_kernel, NSX_THREADS, smem));

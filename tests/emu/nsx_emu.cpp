@@ -75,7 +75,21 @@ struct SerialSweep {
 static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, const nsx_warm_start* warm, nsx_result* res) {
     const int32_t n = pb->n_nodes;
     const int64_t m = pb->n_arcs, ma = m + n - 1;
-    std::vector<int32_t> atail(n), ahead(n), depth(n), order(n), tmp(n), gph(n), gpt(n), garc2(2 * (size_t)n + 1);
+    // NSX_EMU_BLOCKED=1: blocked preorder array (what the engine uses for trees that live in HBM); NSX_EMU_BLK_LG / NSX_EMU_BLK_NB
+    // shrink the blocks / the arena so that small instances split, merge and rebuild all the time
+    const char* bk = getenv("NSX_EMU_BLOCKED");
+    const bool blocked = bk && *bk && atoi(bk) != 0;
+    int32_t blk_lg = nsx_blk_lg(n), blk_nb = NSX_BLK_MAX;
+    if (blocked) {
+        const char* e1 = getenv("NSX_EMU_BLK_LG"); if (e1 && *e1) blk_lg = atoi(e1);
+        if (blk_lg < 1) blk_lg = 1;
+        while (((n + (1 << (blk_lg - 1)) - 1) >> (blk_lg - 1)) + 8 > NSX_BLK_MAX) ++blk_lg;  // (the directory has NSX_BLK_MAX slots)
+        const int32_t half = 1 << (blk_lg - 1), need = (n + half - 1) / half;
+        const char* e2 = getenv("NSX_EMU_BLK_NB"); if (e2 && *e2) blk_nb = need + atoi(e2);  // (value = spare blocks beyond a half-filled layout)
+        if (blk_nb > NSX_BLK_MAX) blk_nb = NSX_BLK_MAX;
+        if (blk_nb < need + 4) return -7;  // knobs leave no room
+    }
+    std::vector<int32_t> atail(n), ahead(n), depth(n), order(blocked ? ((size_t)blk_nb << blk_lg) + n : (size_t)n), tmp(n), sidx(n), gph(n), gpt(n), garc2(2 * (size_t)n + 1);
     std::vector<double> aupper(n), flow(ma), pi(n), gres(2 * (size_t)n + 1);
     std::vector<uint8_t> state(ma);
     std::vector<uint32_t> wgt(m > 0 ? m : 1);
@@ -88,9 +102,10 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     d.node = node.data(); d.depth = depth.data(); d.pi = pi.data(); d.pi_mirror = nullptr; d.order = order.data();
     d.tmp = tmp.data(); d.gpath_h = gph.data(); d.gpath_t = gpt.data(); d.garc2 = garc2.data();
     d.node_mask = opt->node_mask; d.imbalance = nullptr; d.gres = gres.data(); d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
-    { const char* lz = getenv("NSX_EMU_LAZY"); d.lazy_pos = lz && *lz ? atoi(lz) : 0;
-      const char* lc = getenv("NSX_EMU_LOG_CAP"); d.log_cap = lc && *lc ? atoi(lc) : NSX_LOG_CAP;
-      if (d.log_cap < 1 || d.log_cap > NSX_LOG_CAP) d.log_cap = NSX_LOG_CAP; }
+    d.sidx = sidx.data();
+    NsxBlk* blk = blocked ? new NsxBlk : nullptr;
+    if (blk) { memset(blk, 0, sizeof *blk); blk->lg = blk_lg; blk->nb = blk_nb; }
+    d.blk = blk;
 
     NsxCtl c;
     memset(&c, 0, sizeof c);
@@ -141,6 +156,8 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep);
 #endif
     delete L; delete s; delete ps;
+    const int32_t rebuilds = blk ? blk->rebuilds : 0;
+    delete blk;
 
     res->status = c.status;
     res->iterations = c.total;
@@ -157,6 +174,7 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     res->sum_cycle_len = c.sum_cycle; res->sum_subtree = c.sum_subtree; res->max_subtree = c.max_subtree;
     res->sum_rounds = c.sum_rounds; res->sum_window = c.sum_window;
     res->pricing_ms = (double)c.sum_window;  // emulation only: moved preorder entries, for design stats
+    res->pivot_ms = (double)rebuilds;        // emulation only: re-layouts of the blocked preorder array
     if (res->flow) memcpy(res->flow, flow.data(), ma * 8);
     if (res->potential) memcpy(res->potential, pi.data(), (size_t)n * 8);
     if (res->state) memcpy(res->state, state.data(), ma);

@@ -37,7 +37,7 @@ def test_cta_of_real_threads_neither_deadlocks_nor_races(tmp_path, lazy):
     lib = emu.build_mt(tmp_path / "libnsx_emu_tsan.so", sanitize=True)
     log = tmp_path / "tsan.log"
     proc = run_suite(lib, {"LD_PRELOAD": tsan, "TSAN_OPTIONS": f"report_signal_unsafe=0 exitcode=0 log_path={log}",
-                           "NSX_EMU_LAZY": lazy, "NSX_EMU_LOG_CAP": "3"}, tmp_path)
+                           "NSX_EMU_BLOCKED": lazy, "NSX_EMU_BLK_LG": "2" if lazy == "1" else "", "NSX_EMU_BLK_NB": "6" if lazy == "1" else ""}, tmp_path)
     if "unexpected memory mapping" in proc.stderr or "unexpected memory mapping" in proc.stdout:
         pytest.skip("ThreadSanitizer cannot map its shadow memory on this kernel (ASLR layout)")
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]  # a deadlock ends in the timeout above

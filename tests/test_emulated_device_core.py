@@ -86,13 +86,19 @@ def test_emulated_core_iteration_limits():
         assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
 
 
-@pytest.mark.parametrize("log_cap", [1, 3, 64])
+@pytest.mark.parametrize("lg,spare", [("", ""), ("1", "6"), ("2", "4"), ("3", "40"), ("5", "4")])
 @pytest.mark.parametrize("family,make,pricing", CASES[:6] + CASES[-2:])
-def test_emulated_core_lazy_positions(family, make, pricing, log_cap, monkeypatch):
-    """Lazy preorder positions (shift log + depth-synchronised cycle walk), the variant the engine
-    uses for trees that live in HBM, gives the same pivots as the oracle for every log capacity."""
-    monkeypatch.setenv("NSX_EMU_LAZY", "1")
-    monkeypatch.setenv("NSX_EMU_LOG_CAP", str(log_cap))
+def test_emulated_core_blocked_preorder(family, make, pricing, lg, spare, monkeypatch):
+    """Blocked preorder array (+ depth-synchronised cycle walk), the variant the engine uses for trees that live
+    in HBM, gives the same pivots as the oracle - with the production block size and with blocks of 2 / 4 / 8 / 32
+    slots and few spare blocks, where every pivot splits, empties or merges blocks and the array is laid out afresh
+    again and again."""
+    monkeypatch.setenv("NSX_EMU_BLOCKED", "1")
+    monkeypatch.setenv("NSX_EMU_BLK_LG", lg)
+    monkeypatch.setenv("NSX_EMU_BLK_NB", spare)
     cp = make().canonical()
     opts = engine_options(cp, pricing)
-    assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
+    got = emu.solve_canonical(cp, opts)
+    assert_same_solution(got, oracle.solve_canonical(cp, opts))
+    if lg in ("1", "2") and got.tree_updates > 50:
+        assert got.timing["pivot_ms"] > 0  # (emulation: number of re-layouts) the rebuild path ran

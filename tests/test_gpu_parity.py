@@ -131,11 +131,9 @@ def test_sweep_probe_prices_every_arc():
     assert r.status == 0 and r.arcs_priced == 10 * cp.n_arcs and r.stats["sweeps"] == 10
 
 
-@pytest.mark.parametrize("lazy,log_cap,par16", [(0, 64, 0), (1, 1, 1), (1, 5, 0), (1, 64, 1)])
-def test_engine_lazy_preorder_positions(lazy, log_cap, par16, monkeypatch):
-    """Trees that live in HBM: eager vs lazy (shift-log) preorder positions give identical pivots."""
-    monkeypatch.setenv("NSX_LAZY", str(lazy))
-    monkeypatch.setenv("NSX_LOG_CAP", str(log_cap))
+@pytest.mark.parametrize("par16", [0, 1])
+def test_engine_blocked_preorder_array(par16, monkeypatch):
+    """Trees that live in HBM (blocked preorder array, directory in shared memory) give the oracle's pivots."""
     monkeypatch.setenv("NSX_PAR16", str(par16))
     monkeypatch.setenv("NSX_GRID", "8")  # multi-CTA: the pivot CTA does not sweep and may mirror the parents
     monkeypatch.setenv("NSX_RESIDENT", "0")  # keep the tree out of shared memory

@@ -76,7 +76,7 @@ def run_ranks(cp, opts, world, boxes):
                                                 ("netgen", _capi.PRICING_DEVEX, 3), ("transport", _capi.PRICING_DANTZIG, 2),
                                                 ("netgen", _capi.PRICING_CANDIDATE_LIST, 2)])
 def test_every_rank_returns_the_single_gpu_solve(monkeypatch, kind, pricing, world):
-    monkeypatch.setenv("NSX_GRID", "24")  # 1 pivot CTA + 23 sweep CTAs per rank: `world` kernels fit the GPU side by side
+    monkeypatch.setenv("NSX_GRID", "24"); monkeypatch.setenv("NSX_LAUNCH_PLAIN", "1")  # 1 pivot CTA + 23 sweep CTAs per rank: `world` kernels fit the GPU side by side
     cp = instance(kind)
     opts = options(cp, pricing)
     single = _capi.solve_canonical(cp, opts)
@@ -104,7 +104,7 @@ def test_world_of_one_is_the_single_gpu_solve():
 
 
 def test_a_peer_that_never_comes_ends_in_an_error_not_a_hang(monkeypatch):
-    monkeypatch.setenv("NSX_GRID", "24")
+    monkeypatch.setenv("NSX_GRID", "24"); monkeypatch.setenv("NSX_LAUNCH_PLAIN", "1")
     cp = instance("netgen")
     opts = options(cp, _capi.PRICING_DANTZIG, spin_timeout_ms=400)
     boxes = Boxes(2)
@@ -120,7 +120,7 @@ def test_a_peer_that_never_comes_ends_in_an_error_not_a_hang(monkeypatch):
 
 
 def test_abort_word_releases_a_waiting_rank(monkeypatch):
-    monkeypatch.setenv("NSX_GRID", "24")
+    monkeypatch.setenv("NSX_GRID", "24"); monkeypatch.setenv("NSX_LAUNCH_PLAIN", "1")
     cp = instance("netgen")
     opts = options(cp, _capi.PRICING_DANTZIG, spin_timeout_ms=60000)
     boxes = Boxes(2)

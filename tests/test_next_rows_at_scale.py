@@ -84,8 +84,7 @@ WARM = [(4096, 16384, 21, _capi.PRICING_DANTZIG, 0), (4096, 16384, 21, _capi.PRI
 @pytest.mark.parametrize("lazy", ["0", "1"])
 @pytest.mark.parametrize("n,m,seed,pricing,drop_every", WARM)
 def test_emulated_core_agrees_with_oracle_on_warm_starts(n, m, seed, pricing, drop_every, lazy, monkeypatch):
-    monkeypatch.setenv("NSX_EMU_LAZY", lazy)
-    monkeypatch.setenv("NSX_EMU_LOG_CAP", "5")
+    monkeypatch.setenv("NSX_EMU_BLOCKED", lazy)
     cp, opts, warm, first = warm_case(n, m, seed, pricing, drop_every)
     assert warm is not None and warm.artificial_in_tree >= 1
     ref = oracle.solve_canonical(cp, opts, warm=warm)

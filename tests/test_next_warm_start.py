@@ -77,8 +77,9 @@ def test_oracle_warm_solve_matches_reference(name, i):
 @pytest.mark.parametrize("lazy", ["0", "1"])
 @pytest.mark.parametrize("name,i", SOLVED)
 def test_emulated_device_core_warm_solve_matches_reference(name, i, lazy, monkeypatch):
-    monkeypatch.setenv("NSX_EMU_LAZY", lazy)
-    monkeypatch.setenv("NSX_EMU_LOG_CAP", "3")
+    monkeypatch.setenv("NSX_EMU_BLOCKED", lazy)
+    monkeypatch.setenv("NSX_EMU_BLK_LG", "2" if lazy == "1" else "")
+    monkeypatch.setenv("NSX_EMU_BLK_NB", "8" if lazy == "1" else "")
     check(name, i, lambda cp, eng, warm: emu.solve_canonical(cp, eng, warm=warm))
 
 
