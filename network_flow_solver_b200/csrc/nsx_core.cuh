@@ -29,6 +29,7 @@
 #if defined(__CUDACC__) && !defined(NSX_HOST_EMU)
 #define NSX_ON_DEVICE 1
 #define NSX_FN __device__ __forceinline__
+#define NSX_FN_COLD __device__ __noinline__  /* kept out of the hot paths' register allocation */
 #define NSX_PAR_FOR(i, lo, hi) \
     for (int64_t i = (int64_t)(lo) + (int64_t)threadIdx.x; i < (int64_t)(hi); i += (int64_t)blockDim.x)
 // __syncwarp() first: bar.sync is an *aligned* barrier and nvcc may thread a preceding
@@ -62,6 +63,7 @@ extern int nsx_mt_nthreads;
 void nsx_mt_barrier();
 #define NSX_ON_DEVICE 0
 #define NSX_FN static inline
+#define NSX_FN_COLD static inline
 #define NSX_PAR_FOR(i, lo, hi) for (int64_t i = (int64_t)(lo) + nsx_mt_tid; i < (int64_t)(hi); i += nsx_mt_nthreads)
 #define NSX_SYNC() nsx_mt_barrier()
 #define NSX_SINGLE if (nsx_mt_tid == 0)
@@ -71,6 +73,7 @@ void nsx_mt_barrier();
 #else
 #define NSX_ON_DEVICE 0
 #define NSX_FN static inline
+#define NSX_FN_COLD static inline
 #define NSX_PAR_FOR(i, lo, hi) for (int64_t i = (int64_t)(lo); i < (int64_t)(hi); ++i)
 #define NSX_SYNC() ((void)0)
 #define NSX_SINGLE
@@ -502,7 +505,7 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32
 
 // ---- blocked preorder array: maintenance (all routines are called by every thread of the pivot CTA) ----
 // prefix[k] = entries in directory slots [0, k)
-NSX_FN void nsx_blk_scan(NsxBlk& B) {
+NSX_FN_COLD void nsx_blk_scan(NsxBlk& B) {
     NSX_SYNC();
 #if NSX_ON_DEVICE
     const int T = NSX_NTHREADS, tid = NSX_TID, nd = B.ndir;
@@ -543,7 +546,7 @@ NSX_FN void nsx_blk_scan(NsxBlk& B) {
     NSX_SYNC();
 }
 // dst[x - skip] = node of preorder rank x, x in [skip, n); with `sidx` also the inverse map (prefix must be valid)
-NSX_FN void nsx_blk_flatten(const NsxDev& d, const NsxBlk& B, int32_t* dst, int32_t skip, int32_t* sidx) {
+NSX_FN_COLD void nsx_blk_flatten(const NsxDev& d, const NsxBlk& B, int32_t* dst, int32_t skip, int32_t* sidx) {
     NSX_PAR_FOR(x, skip, d.n) {
         const int32_t v = d.order[nsx_blk_phys(B, (int32_t)x)];
         dst[x - skip] = v;
@@ -552,7 +555,7 @@ NSX_FN void nsx_blk_flatten(const NsxDev& d, const NsxBlk& B, int32_t* dst, int3
     NSX_SYNC();
 }
 // Lay the dense preorder sequence tmp[0 .. n) out in half-filled blocks: arena, stored positions, directory, free list.
-NSX_FN void nsx_blk_layout(const NsxDev& d, NsxBlk& B) {
+NSX_FN_COLD void nsx_blk_layout(const NsxDev& d, NsxBlk& B) {
     const int32_t lg = B.lg, F = 1 << (lg - 1);
     const int32_t nblk = (d.n + F - 1) / F;
     NSX_SYNC();
@@ -574,14 +577,14 @@ NSX_FN void nsx_blk_layout(const NsxDev& d, NsxBlk& B) {
     NSX_SYNC();
 }
 // first use: `order` still holds the dense preorder array the init kernel (or the warm-start layout) wrote
-NSX_FN void nsx_blk_init(const NsxDev& d, NsxBlk& B) {
+NSX_FN_COLD void nsx_blk_init(const NsxDev& d, NsxBlk& B) {
     NSX_SINGLE { B.rebuilds = 0; }
     NSX_PAR_FOR(x, 0, d.n) { d.tmp[x] = d.order[x]; }
     NSX_SYNC();
     nsx_blk_layout(d, B);
 }
 // the free list ran short: flatten and lay out afresh
-NSX_FN void nsx_blk_rebuild(const NsxDev& d, NsxBlk& B) {
+NSX_FN_COLD void nsx_blk_rebuild(const NsxDev& d, NsxBlk& B) {
     nsx_blk_scan(B);
     nsx_blk_flatten(d, B, d.tmp, 0, (int32_t*)0);
     nsx_blk_layout(d, B);
@@ -632,7 +635,7 @@ NSX_FN void nsx_blk_dirshift(NsxBlk& B, int32_t from, int32_t count, int32_t del
 }
 // Take the preorder ranks [S0, S0 + sz) out (their nodes have been copied elsewhere).  `prefix` must be valid on
 // entry and is stale afterwards.  Returns the number of entries that moved.
-NSX_FN int32_t nsx_blk_remove(const NsxDev& d, NsxBlk& B, int32_t S0, int32_t sz) {
+NSX_FN_COLD int32_t nsx_blk_remove(const NsxDev& d, NsxBlk& B, int32_t S0, int32_t sz) {
     const int32_t lg = B.lg;
     const int32_t k0 = nsx_blk_find(B, S0), k1 = nsx_blk_find(B, S0 + sz - 1);
     const int32_t b0 = B.dir[k0], b1 = B.dir[k1];
@@ -662,7 +665,7 @@ NSX_FN int32_t nsx_blk_remove(const NsxDev& d, NsxBlk& B, int32_t S0, int32_t sz
     return c1 - o1;
 }
 // Put the sz nodes tmp[0 .. sz) right behind node p in preorder.  Needs nfree >= (sz + CAP) / CAP + 1.
-NSX_FN int32_t nsx_blk_insert(const NsxDev& d, NsxBlk& B, int32_t p, int32_t sz) {
+NSX_FN_COLD int32_t nsx_blk_insert(const NsxDev& d, NsxBlk& B, int32_t p, int32_t sz) {
     const int32_t lg = B.lg, CAP = 1 << lg;
     const int32_t pp = d.node[p].pos;  // (p may have moved when S was taken out)
     const int32_t bp = pp >> lg, op = pp & (CAP - 1), kp = B.dirpos[bp], cp = B.cnt[bp];
@@ -703,8 +706,11 @@ NSX_FN int32_t nsx_blk_insert(const NsxDev& d, NsxBlk& B, int32_t p, int32_t sz)
     return t;
 }
 // Potentials of the whole tree (start of a phase): dense arrays walk `order`, the blocked array is flattened first.
+// BLK (here and below): the blocked-array code is compiled in; kernels for trees that fit the pivot CTA's shared memory are
+// instantiated without it (smaller register footprint of the latency-bound pivot code).
+template <bool BLK>
 NSX_FN void nsx_recompute_all_potentials(const NsxDev& d, int32_t phase, NsxPotScratch& ps) {
-    if (d.blk) {
+    if (BLK && d.blk) {
         nsx_blk_scan(*d.blk);
         nsx_blk_flatten(d, *d.blk, d.tmp, 1, d.sidx);
         nsx_recompute_potentials(d, phase, d.tmp, d.sidx, 0, (int64_t)d.n - 1, ps, (int64_t*)0);
@@ -789,6 +795,7 @@ NSX_FN void nsx_ratio_finish(const NsxRatio& rr, const double* res, const int32_
 // One pivot on entering arc e (direction dir = +1 forward / -1 backward).
 // Returns (block-uniform) 0 = ok, 3 = unbounded.
 // ------------------------------------------------------------------------------------------
+template <bool BLK>
 NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScratch& ps, int32_t e,
                      int32_t dir, int32_t want_weight) {
     const double tol = d.tol;
@@ -849,7 +856,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             const int32_t dj = d.depth[join];
             s.join = join; s.nh = dh - dj; s.nt = dt - dj;
         }
-    } else if (d.blk) {
+    } else if (BLK && d.blk) {
         // Depth-synchronised climb (no positions needed): lane 0 holds the head-side node, lane 1
         // the tail-side node; the deeper one climbs, both climb when level, until they meet.
         if (threadIdx.x < 32) {
@@ -884,7 +891,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     }
 #else
     NSX_HOST_SERIAL {
-    if (d.blk) {
+    if (BLK && d.blk) {
         int32_t u = h, v = t, du = d.depth[h], dv = d.depth[t], nh_ = 0, nt_ = 0;
         while (u != v) {
             const bool climb_u = du >= dv, climb_v = dv >= du;
@@ -1059,7 +1066,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const NsxNode rec_p = d.node[p];
     const int32_t sz = rec_r.size;
     const int32_t depth_q_new = d.depth[p] + 1;
-    if (d.blk) {
+    if (BLK && d.blk) {
         // (uniform: every thread reads the same shared-memory words) enough free blocks for the worst case of this update?
         if (d.blk->nfree < (sz >> d.blk->lg) + 3) nsx_blk_rebuild(d, *d.blk);
         nsx_blk_scan(*d.blk);  // preorder ranks of stored positions are valid from here until the array is edited
@@ -1072,9 +1079,9 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     int32_t* st_pred2 = spill ? ((int32_t*)d.gres) + d.n : s.arc2;
     NSX_SYNC();  // everyone has read arc2/res for the flow update before they are reused
     NSX_PAR_FOR(i, 0, kk + 2) {
-        if (i == kk + 1) { s.p_pos = nsx_lpos(d, d.node[p].pos); continue; }  // preorder rank of the new parent
+        if (i == kk + 1) { s.p_pos = BLK ? nsx_lpos(d, d.node[p].pos) : d.node[p].pos; continue; }  // preorder rank of the new parent
         NsxNode x = d.node[spath[i]];
-        st_pos[i] = nsx_lpos(d, x.pos); st_size[i] = x.size; st_pred2[i] = x.pred2;
+        st_pos[i] = BLK ? nsx_lpos(d, x.pos) : x.pos; st_size[i] = x.size; st_pred2[i] = x.pred2;
         st_depth[i] = d.depth[spath[i]];
     }
     // subtree-size bookkeeping of the untouched ancestors on both sides of the cycle
@@ -1098,7 +1105,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t k_stem = kk;
     // Blocked mode: only S is permuted (into tmp[0 .. sz), with the inverse map in sidx); the dense array also shifts
     // the entries between the old and the new place of S in the same pass.
-    const bool blocked = d.blk != nullptr;
+    const bool blocked = BLK && d.blk != nullptr;
     const int64_t w_lo = blocked ? S0 : lo, w_hi = blocked ? S1 : hi;
     {
         // four entries per thread and step: the loads of all four are issued before any store
@@ -1803,13 +1810,13 @@ NSX_FN void nsx_check_conservation(const NsxDev& d, NsxCtl& c) {
 // The resident loop of the pivot CTA.  `Sweep::run(cmd, dz, dx)` prices the arc range of `cmd`
 // (grid-wide on the device, serially in the emulation) and leaves the merged candidates in
 // dz / dx, visible to all threads of this CTA on return.  `Sweep::finish()` releases workers.
-template <class Sweep>
+template <bool BLK, class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
-    if (d.blk) nsx_blk_init(d, *d.blk);
+    if (BLK && d.blk) nsx_blk_init(d, *d.blk);
     NSX_SYNC();
     // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
-    nsx_recompute_all_potentials(d, c.phase, ps);
+    nsx_recompute_all_potentials<BLK>(d, c.phase, ps);
     NSX_SINGLE {
         L.drv.stage = 0; L.drv.final_check = 0; L.drv.bc = 1; L.drv.blocks_left = 0;
         L.drv.budget = c.maxit;
@@ -1838,7 +1845,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             nsx_special_scan(d, c, &L.cl_arc2, s);
             NSX_SINGLE { nsx_drv_on_special(c, L.drv, d.m, L.cl_arc2, L.cmd, L.act, trace); }
         } else if (kind == NSX_ACT_PIVOT) {
-            int32_t rc = nsx_pivot(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
+            int32_t rc = nsx_pivot<BLK>(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
             if (c.need_wfill) {  // Devex epoch tags wrapped: physically reset the weights
                 NSX_SYNC();
                 NSX_PAR_FOR(i, 0, d.m) { if (d.wgt) d.wgt[i] = 1u; }
@@ -1852,7 +1859,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             if (d.imbalance && c.phase == 1) nsx_check_conservation(d, c);
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
-            if (!L.drv.final_check) nsx_recompute_all_potentials(d, 2, ps);
+            if (!L.drv.final_check) nsx_recompute_all_potentials<BLK>(d, 2, ps);
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }
         } else {  // NSX_ACT_EXIT

@@ -21,7 +21,9 @@
 #include <string.h>
 
 #include <mutex>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef NSX_THREADS
@@ -1109,12 +1111,12 @@ __device__ __forceinline__ void nsx_init_barriers(NsxCtaShared& sh) {
 
 // Measurement aid (nsx_sweep_probe): `count` sweeps of the initial state through exactly the
 // command / arrival protocol of a solve, no pivots.
-template <class Sweep>
+template <bool BLK, class Sweep>
 __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
                                                NsxPotScratch& ps, Sweep& sweep, int32_t count) {
-    if (d.blk) nsx_blk_init(d, *d.blk);
+    if (BLK && d.blk) nsx_blk_init(d, *d.blk);
     NSX_SYNC();
-    nsx_recompute_all_potentials(d, 1, ps);
+    nsx_recompute_all_potentials<BLK>(d, 1, ps);
     for (int32_t k = 0; k < count; ++k) {
         NSX_SYNC();
         if (threadIdx.x == 0) {
@@ -1137,8 +1139,9 @@ __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLo
     sweep.finish();
 }
 
-extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
-nsx_resident_kernel(const NsxKernelArgs a) {
+// BLK = false: the tree fits the pivot CTA's shared memory (dense preorder array); true: it lives in HBM (blocked array).
+template <bool BLK>
+__device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
     unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
@@ -1158,8 +1161,8 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
         GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns};
-        if (a.probe_sweeps > 0) nsx_probe_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
-        else nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
+        if (a.probe_sweeps > 0) nsx_probe_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
+        else nsx_solve_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
         if (threadIdx.x == 0) {
             unsigned long long total = nsx_globaltimer() - t_begin;
@@ -1232,6 +1235,9 @@ nsx_resident_kernel(const NsxKernelArgs a) {
         }
     }
 }
+
+extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_resident_kernel(const NsxKernelArgs a) { nsx_resident_body<false>(a); }
+extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_resident_kernel_hbm(const NsxKernelArgs a) { nsx_resident_body<true>(a); }
 
 // Initial state: real arcs, nodes + artificial arcs, artificial-flow count.
 extern "C" __global__ void nsx_init_kernel(const NsxDev d, const double* supply, NsxCtl* ctl) {
@@ -1339,8 +1345,8 @@ struct LocalSweep {
 
 // The shared-memory plan of an item is made in the kernel from its node count; `limit_bytes` =
 // dynamic bytes available after the fixed part (sized by the host for the largest instance).
-extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
-nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes,
+template <bool BLK>
+__device__ __forceinline__ void nsx_batch_body(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes,
                  int want_mode, int want_stage) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
@@ -1385,10 +1391,19 @@ nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* n
         NsxSweepCtx cx{&item.st, (resident || plan.stage_pi) ? pis : nullptr, !resident && plan.stage_pi != 0,
                        dyn + plan.ring_off, plan.stages};
         LocalSweep sweep{d, sh, cx, stage_count, q0};
-        nsx_solve_loop(dl, sh.ctl, sh.L, sh.piv, sh.pot, item.trace, sweep);
+        nsx_solve_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, item.trace, sweep);
         NSX_SYNC();
         nsx_copy_ctl(item.ctl, &sh.ctl);
     }
+}
+// nsx_batch_kernel: every instance of the batch fits its CTA's shared memory (what the host checked); _hbm: some do not
+extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
+nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage) {
+    nsx_batch_body<false>(items, count, next, limit_bytes, want_mode, want_stage);
+}
+extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
+nsx_batch_kernel_hbm(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage) {
+    nsx_batch_body<true>(items, count, next, limit_bytes, want_mode, want_stage);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1732,9 +1747,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         arena.release(); inputs.release();
         return nsx_fail(NSX_ERR_INTERNAL, "shared memory plan exceeds the device limit");
     }
-    NSX_CUDA(cudaFuncSetAttribute(nsx_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto* resident_kernel = ka.plan.mode == NSX_RES_NONE ? nsx_resident_kernel_hbm : nsx_resident_kernel;
+    NSX_CUDA(cudaFuncSetAttribute(resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_resident_kernel, NSX_THREADS, smem));
+    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, resident_kernel, NSX_THREADS, smem));
     if (per_sm < 1) { arena.release(); inputs.release(); return nsx_fail(NSX_ERR_INTERNAL, "resident kernel does not fit on an SM"); }
 
     {
@@ -1761,10 +1777,20 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     // host threads on ONE device) uses an ordinary launch instead: the driver does not run two cooperative grids side by
     // side, and grid <= SM count with one CTA per SM is co-resident on an otherwise idle device anyway.
     if (nsx_env_int("NSX_LAUNCH_PLAIN", 0)) {
-        nsx_resident_kernel<<<dim3(grid), dim3(NSX_THREADS), smem, stream>>>(ka);
+        // Ranks as host threads on one device: a device allocation or memset issued by one thread while another thread's
+        // resident kernel is already spinning would wait for that kernel (implicit synchronisation) - which waits for this
+        // rank.  So every rank finishes its set-up, then all meet here (NSX_LAUNCH_PLAIN = number of ranks) and launch.
+        NSX_CUDA(cudaStreamSynchronize(stream));
+        static std::atomic<int> arrivals{0};
+        if (shard) {
+            const int ranks = nsx_env_int("NSX_LAUNCH_PLAIN", 1), ticket = arrivals.fetch_add(1);
+            const int target = (ticket / ranks + 1) * ranks;
+            while (arrivals.load() < target) std::this_thread::yield();
+        }
+        resident_kernel<<<dim3(grid), dim3(NSX_THREADS), smem, stream>>>(ka);
         NSX_CUDA(cudaGetLastError());
     } else {
-        NSX_CUDA(cudaLaunchCooperativeKernel((void*)nsx_resident_kernel, dim3(grid), dim3(NSX_THREADS), kargs, smem, stream));
+        NSX_CUDA(cudaLaunchCooperativeKernel((void*)resident_kernel, dim3(grid), dim3(NSX_THREADS), kargs, smem, stream));
     }
     NSX_CUDA(cudaEventRecord(ev[2], stream));
 
@@ -1922,6 +1948,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     if (plan.stages > max_stages) plan.stages = max_stages;
     const size_t dyn = nsx_plan_bytes(plan, layout.stage_bytes);
     const size_t smem = fixed + dyn;
+    bool any_hbm = false;
     for (int64_t i = 0; i < count; ++i) {
         const nsx_problem& p = problems[i];
         const size_t n = p.n_nodes, m = p.n_arcs, ma = m + n - 1, mpad = (size_t)nsx_pad_tiles((int64_t)m);
@@ -1935,6 +1962,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         o.node = arena.plan(n * sizeof(NsxNode)); o.depth = arena.plan(n * 4); o.pi = arena.plan(n * 8 + 16);
         // (a tree too large for the CTA's shared memory keeps its preorder array in blocks: same plan as the kernel makes)
         const bool in_hbm = nsx_plan_pivot(n, dyn, layout.stage_bytes, true, want_mode, want_stage).mode == NSX_RES_NONE;
+        any_hbm = any_hbm || in_hbm;
         o.order = arena.plan((in_hbm ? nsx_order_len(n) : n) * 4); o.tmp = arena.plan(n * 4); o.sidx = arena.plan(n * 4);
         o.gph = arena.plan(n * 4); o.gpt = arena.plan(n * 4);
         o.garc2 = arena.plan((2 * n + 1) * 4); o.gres = arena.plan((2 * n + 1) * 8);
@@ -1994,13 +2022,14 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
     NSX_CUDA(cudaMemsetAsync(d_next, 0, 8, stream));
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
-    NSX_CUDA(cudaFuncSetAttribute(nsx_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto* batch_kernel = any_hbm ? nsx_batch_kernel_hbm : nsx_batch_kernel;
+    NSX_CUDA(cudaFuncSetAttribute(batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nsx_batch_kernel, NSX_THREADS, smem));
+    NSX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, batch_kernel, NSX_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)info.sms * per_sm;
     if (grid > count) grid = count;
-    nsx_batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, dyn, want_mode, want_stage);
+    batch_kernel<<<(int)grid, NSX_THREADS, smem, stream>>>(d_items, count, d_next, dyn, want_mode, want_stage);
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(ev[2], stream));
     for (int64_t i = 0; i < count; ++i) {

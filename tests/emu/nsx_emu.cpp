@@ -5,6 +5,7 @@
 // machine) on machines without a GPU.  Not linked into libnsx_b200.so, not importable from the
 // package; the product has no host execution path.
 #define NSX_HOST_EMU 1
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -27,9 +28,49 @@ void nsx_mt_barrier() { pthread_barrier_wait(&nsx_mt_bar); }
 
 namespace {
 
+// Design statistics (NSX_EMU_INCSTATS=1, Dantzig full sweeps): how much of a sweep an incremental scheme would have to
+// redo - arcs incident to nodes whose potential changed since the previous sweep, and tail groups ("rows") whose cached
+// best arc points into such a node.
+struct IncStats {
+    bool on = false;
+    std::vector<double> prev_pi;
+    std::vector<int32_t> row_best;   // per tail node: arc of the row's best candidate at the previous sweep, -1 none
+    std::vector<int64_t> row_begin;  // CSR by tail (arcs are sorted by tail)
+    std::vector<int32_t> indeg;
+    long long sweeps = 0, dirty_nodes = 0, star_arcs = 0, rescan_rows = 0, rescan_arcs = 0, total_arcs = 0;
+};
+static IncStats g_inc;
+
 struct SerialSweep {
     const NsxDev& d;
     SerialSweep(const NsxDev& dev) : d(dev) {}
+    void inc_stats(const NsxCmd& cmd) {
+        IncStats& I = g_inc;
+        const int32_t n = d.n; const int64_t m = d.m;
+        if (I.prev_pi.empty()) {
+            I.prev_pi.assign(d.pi, d.pi + n); I.row_best.assign(n, -1); I.row_begin.assign(n + 1, 0); I.indeg.assign(n, 0);
+            for (int64_t i = 0; i < m; ++i) { I.row_begin[d.tail[i] + 1]++; I.indeg[d.head[i]]++; }
+            for (int32_t v = 0; v < n; ++v) I.row_begin[v + 1] += I.row_begin[v];
+        } else {
+            std::vector<uint8_t> dirty(n, 0);
+            for (int32_t v = 0; v < n; ++v) if (d.pi[v] != I.prev_pi[v]) { dirty[v] = 1; I.dirty_nodes++; I.star_arcs += (I.row_begin[v + 1] - I.row_begin[v]) + I.indeg[v]; }
+            for (int32_t v = 1; v < n; ++v) {
+                if (dirty[v]) continue;
+                const int32_t b = I.row_best[v];
+                if (b >= 0 && (dirty[d.head[b]] || (d.state[b] & NSX_ARC_IN_TREE))) { I.rescan_rows++; I.rescan_arcs += I.row_begin[v + 1] - I.row_begin[v]; }
+            }
+            I.sweeps++; I.total_arcs += m;
+            memcpy(I.prev_pi.data(), d.pi, (size_t)n * 8);
+        }
+        for (int32_t v = 1; v < n; ++v) {  // row bests of this sweep
+            NsxCand k; nsx_cand_init(k);
+            for (int64_t i = I.row_begin[v]; i < I.row_begin[v + 1]; ++i) {
+                double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
+                nsx_price_dantzig(k, (int32_t)i, d.state[i], rc, d.tol);
+            }
+            I.row_best[v] = k.arc2 >= 0 ? (k.arc2 >> 1) : -1;
+        }
+    }
     void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         NSX_SYNC();
         NSX_SINGLE { run_serial(cmd, dz, dx, c); }  // the grid sweep is not what this emulation is about
@@ -54,6 +95,7 @@ struct SerialSweep {
             for (int32_t k = 0; k < c.cl_count; ++k) c.cl_list[k] = cands[k].second;
             return;
         }
+        if (g_inc.on && cmd.kind == NSX_CMD_DANTZIG && cmd.lo == 0 && cmd.hi == d.m) inc_stats(cmd);
         if (cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO) {
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
                 double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
@@ -136,6 +178,7 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     }
     c.art_with_flow = art;
 
+    { const char* e = getenv("NSX_EMU_INCSTATS"); g_inc = IncStats(); g_inc.on = e && *e && atoi(e) != 0; }
     NsxLoopShared* L = new NsxLoopShared;
     NsxPivotScratch* s = new NsxPivotScratch;
     NsxPotScratch* ps = new NsxPotScratch;
@@ -148,14 +191,20 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
         pthread_barrier_init(&nsx_mt_bar, nullptr, (unsigned)nsx_mt_nthreads);
         std::vector<std::thread> team;
         for (int t = 0; t < nsx_mt_nthreads; ++t)
-            team.emplace_back([&, t] { nsx_mt_tid = t; nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep); });
+            team.emplace_back([&, t] { nsx_mt_tid = t; nsx_solve_loop<true>(d, c, *L, *s, *ps, res->entering_trace, sweep); });
         for (auto& th : team) th.join();
         pthread_barrier_destroy(&nsx_mt_bar);
     }
 #else
-    nsx_solve_loop(d, c, *L, *s, *ps, res->entering_trace, sweep);
+    if (blk) nsx_solve_loop<true>(d, c, *L, *s, *ps, res->entering_trace, sweep);
+    else nsx_solve_loop<false>(d, c, *L, *s, *ps, res->entering_trace, sweep);
 #endif
     delete L; delete s; delete ps;
+    if (g_inc.on && g_inc.sweeps > 0)
+        fprintf(stderr, "incstats: sweeps %lld  dirty nodes/sweep %.1f  star arcs/sweep %.0f (%.2f%% of m)  rescan rows/sweep %.1f  rescan arcs/sweep %.0f (%.2f%% of m)\n",
+                g_inc.sweeps, (double)g_inc.dirty_nodes / g_inc.sweeps, (double)g_inc.star_arcs / g_inc.sweeps,
+                100.0 * g_inc.star_arcs / g_inc.total_arcs, (double)g_inc.rescan_rows / g_inc.sweeps,
+                (double)g_inc.rescan_arcs / g_inc.sweeps, 100.0 * g_inc.rescan_arcs / g_inc.total_arcs);
     const int32_t rebuilds = blk ? blk->rebuilds : 0;
     delete blk;
 

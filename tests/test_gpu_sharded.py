@@ -76,7 +76,8 @@ def run_ranks(cp, opts, world, boxes):
                                                 ("netgen", _capi.PRICING_DEVEX, 3), ("transport", _capi.PRICING_DANTZIG, 2),
                                                 ("netgen", _capi.PRICING_CANDIDATE_LIST, 2)])
 def test_every_rank_returns_the_single_gpu_solve(monkeypatch, kind, pricing, world):
-    monkeypatch.setenv("NSX_GRID", "24"); monkeypatch.setenv("NSX_LAUNCH_PLAIN", "1")  # 1 pivot CTA + 23 sweep CTAs per rank: `world` kernels fit the GPU side by side
+    monkeypatch.setenv("NSX_GRID", "24")  # 1 pivot CTA + 23 sweep CTAs per rank: `world` kernels fit the GPU side by side
+    monkeypatch.setenv("NSX_LAUNCH_PLAIN", str(world))  # ordinary launches, all ranks set up before any of them launches
     cp = instance(kind)
     opts = options(cp, pricing)
     single = _capi.solve_canonical(cp, opts)
