@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define NSX_ABI_VERSION 3 /* 2: nsx_options.node_mask, NSX_SPECIAL_*, NSX_PRICING_DEVEX_LOOP, nsx_solve_warm, NSX_ARC_STALE
+#define NSX_ABI_VERSION 4 /* 4: nsx_result.star_* / blk_rebuilds
+                             2: nsx_options.node_mask, NSX_SPECIAL_*, NSX_PRICING_DEVEX_LOOP, nsx_solve_warm, NSX_ARC_STALE
                              3: nsx_options.spin_timeout_ms, nsx_options.flags reserved (NSX_FLAG_FAST_POTENTIALS removed),
                                 nsx_mailbox_abort, nsx_result.fault */
 
@@ -165,7 +166,13 @@ typedef struct nsx_result {
                                      tiles done, reduced, arrived; pivot CTA saw all arrivals, merged */
     int32_t fault;                /* 0, or why the resident kernel gave up (the call then returns NSX_ERR_INTERNAL):
                                      1 a sweep worker did not answer, 2 a peer GPU did not deliver its candidate,
-                                     3 a peer GPU raised its abort word, 4 a worker saw no command, 5 bad node id */
+                                     3 a peer GPU raised its abort word, 4 a worker saw no command, 5 bad node id,
+                                     6 a sweep worker did not reach the barrier of a star-pricing update */
+    int32_t star_pricing;         /* 1: the Dantzig rule was priced from the row cache (star pricing) */
+    int64_t star_updates;         /* pricing steps that brought the row cache up to date after a pivot */
+    int64_t star_builds;          /* pricing steps that priced every row afresh (start, phase switch, large subtrees) */
+    int64_t star_rescans;         /* rows priced afresh because their cached arc got worse */
+    int64_t blk_rebuilds;         /* blocked preorder array: fresh layouts (trees in HBM) */
 } nsx_result;
 
 /* Solve one instance on one GPU; all nsx_problem / nsx_result pointers are HOST memory. */

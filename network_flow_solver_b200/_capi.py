@@ -17,7 +17,7 @@ import numpy as np
 from .canonical import CanonicalProblem
 from .exceptions import DeviceEngineError
 
-ABI_VERSION = 3  # NSX_ABI_VERSION of include/nsx_b200.h these declarations mirror
+ABI_VERSION = 4  # NSX_ABI_VERSION of include/nsx_b200.h these declarations mirror
 PRICING_DANTZIG = 0
 PRICING_DEVEX = 1
 PRICING_CANDIDATE_LIST = 2  # also what pricing_strategy="adaptive" (the reference's default) amounts to
@@ -125,6 +125,11 @@ class NsxResult(C.Structure):
         ("phase_cycles", C.c_int64 * 12),
         ("handshake_ns", C.c_int64 * 8),
         ("fault", C.c_int32),
+        ("star_pricing", C.c_int32),
+        ("star_updates", C.c_int64),
+        ("star_builds", C.c_int64),
+        ("star_rescans", C.c_int64),
+        ("blk_rebuilds", C.c_int64),
     ]
 
 
@@ -285,6 +290,8 @@ class CallFrame:
                 "sum_rounds": int(r.sum_rounds),
                 "sum_window": int(r.sum_window),
                 "phase_cycles": [int(x) for x in r.phase_cycles],
+                "star_pricing": int(r.star_pricing), "star_updates": int(r.star_updates), "star_builds": int(r.star_builds),
+                "star_rescans": int(r.star_rescans), "blk_rebuilds": int(r.blk_rebuilds),
                 "handshake_ns": [int(x) for x in r.handshake_ns],
             },
         )

@@ -125,6 +125,15 @@ struct alignas(16) NsxNode {
     int32_t size;    // subtree size (node included): subtree = order[pos .. pos+size)
 };
 
+// Star pricing (Dantzig rule without full sweeps).  The arcs are sorted by tail, so the out-arcs of a node are one
+// index range ("row").  rc[v] caches the best improving arc of row v - smallest key, lowest arc*2+dir on ties, exactly
+// the order of nsx_dantzig_improving.  A pivot changes the potentials of the re-hung subtree S only, so only arcs with
+// an endpoint in S can change their reduced cost: the rows of S are priced afresh, the in-arcs of S (CSC copy of the
+// arcs, grouped by head) propose themselves to the rows of their tails, a row whose cached arc got worse is priced
+// afresh too, and the entering arc is the minimum over the row cache.  Same arc as a full sweep, ~|S| * degree arcs
+// examined instead of m.
+struct alignas(16) NsxRC { double key; int32_t arc2; int32_t pad; };  // arc2 < 0: the row has no improving arc
+
 struct NsxDev {
     int32_t n;   // nodes incl. root
     int64_t m;   // real arcs
@@ -160,6 +169,14 @@ struct NsxDev {
     const uint8_t* node_mask;  // [n] NSX_SPECIAL_SHORTEST_PATH: node reachable from the source (HBM), else null
     double* imbalance;         // [n] warm starts only (else null): flow that clamping to a bound added at / removed from
                                // each node - the reference checks conservation after Phase 1 (simplex.py:1575-1598)
+    // star pricing (null / unused when it is off)
+    NsxRC* rc;             // [n] row cache
+    int32_t* dlist;        // [n] nodes whose potential the last pivot changed (its re-hung subtree)
+    int32_t* dstamp;       // [n] star round in which the node was last in dlist
+    const int32_t* row_begin;  // [n+1] out-arcs of v = arcs row_begin[v] .. row_begin[v+1]
+    const int32_t* col_begin;  // [n+1] in-arcs of v = entries col_begin[v] .. col_begin[v+1] of the CSC copy
+    int32_t* csc_pos;      // [m] arc -> its entry in the CSC copy (the state byte is written in both places)
+    uint8_t* csc_state;    // [m] state bytes in CSC order
     struct NsxBlk* blk; // trees that live in HBM: the preorder array is kept in blocks with slack (see NsxBlk); `order` is
                         // then the block arena (NSX_BLK_MAX << blk->lg entries) and node.pos a physical index into it
     int32_t* sidx;      // [n] blocked mode: index of a node inside the sequence nsx_recompute_potentials runs over
@@ -191,6 +208,12 @@ struct NsxCtl {
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     int32_t warm;         // started from a caller-supplied tree (nsx_solve_warm): NSX_ARC_STALE bits may be set
     int32_t unbalanced;   // warm start: some node's balance is off by more than tol after Phase 1 (simplex.py:1575-1598)
+    // star pricing: on for this solve / row cache consistent with the state before the pending pivot / pivots since the
+    // cache was last brought up to date / current round (stamp) / nodes in dlist / row of the entering arc
+    int32_t star_on, star_valid, star_pending, star_round, star_nd, star_extra;
+    int64_t star_evaluated;   // arcs examined by the last star command (reported by the sweep workers)
+    int64_t star_updates, star_builds, star_rescans;
+    int64_t blk_rebuilds;     // blocked preorder array: fresh layouts
     // statistics
     int64_t degenerate, tree_updates, resets, arcs_priced, sweeps;
     int64_t avg_cycle;    // running mean of the cycle length * 16 (chooses the cycle-walk variant)
@@ -803,6 +826,18 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t h = dir == 1 ? d.head[e] : d.tail[e];
 
     long long tph = NSX_CLOCK();
+    // star pricing: this pivot opens a new round; its re-hung subtree (recorded after the potential recompute) and the
+    // row of the entering arc are what the next pricing step has to look at
+    NSX_SINGLE {
+        if (c.star_on) {
+            if (c.star_pending >= 1) c.star_valid = 0;  // two pivots without a pricing step in between
+            c.star_pending++;
+            c.star_round++;
+            c.star_nd = 0;
+            c.star_extra = d.tail[e];
+            if (c.star_valid) { NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0; d.rc[d.tail[e]] = none; }
+        }
+    }
     // ---- 1. walk both sides up to the join ------------------------------------------------
 #if NSX_ON_DEVICE
     if (d.scan_walk && c.avg_cycle > 40 * 16) {
@@ -1027,6 +1062,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             d.flow[a] = f;
             st = (uint8_t)((st & (NSX_ARC_IN_TREE | NSX_ARC_TOUCHED)) | nsx_bounds_bits(f, up, tol));
             d.state[a] = st;
+            if (d.csc_state && a < d.m) d.csc_state[d.csc_pos[a]] = st;
             if (a >= d.m) {
                 int had = old > tol, has = f > tol;
                 if (had != has) NSX_ATOMIC_ADD_I32(&s.art_delta, has - had);
@@ -1068,7 +1104,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t depth_q_new = d.depth[p] + 1;
     if (BLK && d.blk) {
         // (uniform: every thread reads the same shared-memory words) enough free blocks for the worst case of this update?
-        if (d.blk->nfree < (sz >> d.blk->lg) + 3) nsx_blk_rebuild(d, *d.blk);
+        if (d.blk->nfree < (sz >> d.blk->lg) + 3) { nsx_blk_rebuild(d, *d.blk); NSX_SINGLE { c.blk_rebuilds++; } }
         nsx_blk_scan(*d.blk);  // preorder ranks of stored positions are valid from here until the array is edited
     }
     // stem snapshot (old pos / size / depth / pred2): shared scratch reusing res[] / arc2[], or the
@@ -1185,6 +1221,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_SINGLE {
         d.state[e] |= NSX_ARC_IN_TREE;
         d.state[leave] &= (uint8_t)~NSX_ARC_IN_TREE;
+        if (d.csc_state) {
+            d.csc_state[d.csc_pos[e]] = d.state[e];
+            if (leave < d.m) d.csc_state[d.csc_pos[leave]] = d.state[leave];
+        }
         c.tree_updates++;
         c.sum_subtree += sz;
         if (sz > c.max_subtree) c.max_subtree = sz;
@@ -1196,6 +1236,23 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
     if (blocked) nsx_recompute_potentials(d, c.phase, d.tmp, d.sidx, 0, sz, ps, &c.sum_rounds);
     else nsx_recompute_potentials(d, c.phase, d.order, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds);
+    const bool star_record = c.star_on && c.star_valid;  // (block-uniform: written by thread 0 before several barriers)
+    if (star_record) {
+        NSX_SYNC();  // every thread has read the flags before thread 0 may change them
+        if ((int64_t)sz * 4 > d.n) {
+            NSX_SINGLE { c.star_valid = 0; }  // a large part of the tree moved: pricing every row afresh is cheaper
+        } else {
+            const int32_t* seq = blocked ? d.tmp : d.order + s_base;
+            const int32_t round = c.star_round;
+            NSX_PAR_FOR(j, 0, sz) {
+                const int32_t v = seq[j];
+                NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0;
+                d.dlist[j] = v; d.dstamp[v] = round; d.rc[v] = none;
+            }
+            NSX_SINGLE { c.star_nd = sz; }
+        }
+        NSX_SYNC();
+    }
     NSX_PH(c, 8, tph);
 
     // ---- 7. reset cadence (simplex.py:1373-1425) -------------------------------------------
@@ -1430,6 +1487,22 @@ NSX_FN void nsx_devex_merge(NsxDevexCand& a, const NsxDevexCand& b) {
 }
 
 // DantzigPricing.select_entering_arc body for one arc (simplex_pricing.py:110-135)
+// ---- star pricing: one arc's candidate, and the order of the row cache (same as nsx_dantzig_improving / nsx_cand_merge) ----
+// returns arc*2 + (backward) with its key, or -1 when the arc is not an improving candidate
+NSX_FN int32_t nsx_star_candidate(int64_t a, uint32_t st, double rc, double tol, double* key) {
+    if (st & NSX_ARC_IN_TREE) return -1;
+    if ((st & NSX_ARC_CAN_FWD) && rc < -tol) { *key = rc; return (int32_t)(a * 2); }
+    if ((st & NSX_ARC_CAN_BWD) && rc > tol) { *key = -rc; return (int32_t)(a * 2 + 1); }
+    return -1;
+}
+NSX_FN bool nsx_rc_better(double key, int32_t arc2, const NsxRC& cur) {
+    return cur.arc2 < 0 || key < cur.key || (key == cur.key && arc2 < cur.arc2);
+}
+// pricing cost of a real arc from its perturbed Phase-2 cost (nsx_arc_cost without the array access)
+NSX_FN double nsx_phase_cost(int32_t phase, double pert, int64_t a) {
+    return phase == 1 ? NSX_SUB(NSX_SUB(pert, 1.0), NSX_MUL(1e-6, (double)a)) : pert;
+}
+
 NSX_FN void nsx_price_dantzig(NsxCand& k, int32_t i, uint8_t st, double rc, double tol) {
     if (st & NSX_ARC_IN_TREE) return;
     if ((st & NSX_ARC_CAN_FWD) && rc < -tol) {
@@ -1537,7 +1610,10 @@ NSX_FN int nsx_init_arc_warm(const NsxDev& d, int64_t a, const double* supply, c
 // the same range found nothing): the hot sweeps then carry no zero bookkeeping.
 // NSX_CMD_TOPK refreshes the candidate list: the NSX_CL_SIZE improving arcs of largest |rc| (ties: larger index).
 enum { NSX_CMD_EXIT = 0, NSX_CMD_DANTZIG = 1, NSX_CMD_DEVEX = 2, NSX_CMD_DANTZIG_ZERO = 3, NSX_CMD_DEVEX_ZERO = 4,
-       NSX_CMD_TOPK = 5 };
+       NSX_CMD_TOPK = 5,
+       // star pricing: NSX_CMD_STAR_BUILD prices every row afresh (cache invalid), NSX_CMD_STAR brings the cache up to
+       // date after one pivot: lo = nodes in dlist, hi = round stamp, excluded = row of the entering arc (-1 none)
+       NSX_CMD_STAR = 6, NSX_CMD_STAR_BUILD = 7 };
 enum { NSX_ST_ROWSCAN = 1, NSX_ST_DANTZIG = 2, NSX_ST_DEVEX = 3, NSX_ST_DANTZIG_ZERO = 4, NSX_ST_DEVEX_ZERO = 5,
        // candidate list (CandidateListPricing.select_entering_arc, simplex_pricing.py:418-458): quick scan of the
        // list, scan after the (optional) periodic refresh, forced refresh, scan after the forced refresh
@@ -1625,6 +1701,19 @@ NSX_FN void nsx_drv_devex_loop_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cm
     nsx_drv_devex_loop_block(c, m, cmd, act);
 }
 
+// full-range Dantzig pricing: a sweep of all arcs, or - star pricing - an update / rebuild of the row cache
+NSX_FN void nsx_drv_dantzig_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
+    cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
+    cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+    if (!c.star_on) return;
+    if (c.star_valid && c.star_pending <= 1) {
+        cmd.kind = NSX_CMD_STAR;
+        cmd.lo = c.star_pending ? c.star_nd : 0; cmd.hi = c.star_round;
+        cmd.excluded = c.star_pending ? c.star_extra : -1;
+    } else {
+        cmd.kind = NSX_CMD_STAR_BUILD;
+    }
+}
 // top of an iteration: first sweep command, or phase end when the budget is used up
 NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxAction& act) {
     if (!v.final_check && c.it >= v.budget) { act.kind = NSX_ACT_PHASE_END; return; }
@@ -1632,8 +1721,7 @@ NSX_FN void nsx_drv_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd, NsxActio
     act.kind = NSX_ACT_SWEEP;
     if (c.row_scan_first || c.pricing == NSX_PRICING_DANTZIG) {
         v.stage = c.row_scan_first ? NSX_ST_ROWSCAN : NSX_ST_DANTZIG;
-        cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
-        cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+        nsx_drv_dantzig_cmd(c, m, cmd);
     } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
         nsx_drv_cl_begin(c, v, m, cmd, act);
     } else if (c.pricing == NSX_PRICING_DEVEX_LOOP) {
@@ -1691,8 +1779,7 @@ NSX_FN void nsx_drv_on_special(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, Ns
     act.kind = NSX_ACT_SWEEP;
     if (c.pricing == NSX_PRICING_DANTZIG) {
         v.stage = NSX_ST_DANTZIG;
-        cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
-        cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+        nsx_drv_dantzig_cmd(c, m, cmd);
     } else if (c.pricing == NSX_PRICING_CANDIDATE_LIST) {
         nsx_drv_cl_begin(c, v, m, cmd, act);
     } else if (c.pricing == NSX_PRICING_DEVEX_LOOP) {
@@ -1714,7 +1801,14 @@ NSX_FN void nsx_drv_on_block(NsxCtl& c, NsxDrv& v, int64_t m, int32_t arc2, int3
 NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz,
                               const NsxDevexCand& dx, NsxCmd& cmd, NsxAction& act, int32_t* trace) {
     const int allow_zero = (c.phase == 1) && !v.final_check;
-    c.arcs_priced += cmd.hi - cmd.lo;
+    if (cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD) {  // the row cache is up to date again
+        c.arcs_priced += c.star_evaluated;
+        if (cmd.kind == NSX_CMD_STAR) c.star_updates++; else c.star_builds++;
+        c.star_valid = 1; c.star_pending = 0;
+        cmd.lo = 0; cmd.hi = m; cmd.excluded = -1;  // (a zero-candidate pass may follow: it sweeps the arc range)
+    } else {
+        c.arcs_priced += cmd.hi - cmd.lo;
+    }
     c.sweeps++;
     if (v.stage == NSX_ST_CL_REFRESH || v.stage == NSX_ST_CL_FORCED) {  // the list has just been refreshed
         c.cl_since = 0;
@@ -1859,7 +1953,10 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             if (d.imbalance && c.phase == 1) nsx_check_conservation(d, c);
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
-            if (!L.drv.final_check) nsx_recompute_all_potentials<BLK>(d, 2, ps);
+            if (!L.drv.final_check) {
+                nsx_recompute_all_potentials<BLK>(d, 2, ps);
+                NSX_SINGLE { c.star_valid = 0; }  // Phase-2 costs: every reduced cost changed
+            }
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }
         } else {  // NSX_ACT_EXIT

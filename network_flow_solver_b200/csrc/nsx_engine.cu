@@ -22,6 +22,8 @@
 
 #include <mutex>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <string>
 #include <thread>
 #include <vector>
@@ -868,6 +870,297 @@ __device__ __forceinline__ void nsx_tk_publish_list(NsxCtaShared& sh, NsxCtl& c)
     NSX_SYNC();
 }
 
+// ------------------------------------------------------------------------------------------
+// Star pricing on the sweep workers (see NsxRC in nsx_core.cuh for the scheme; the serial restatement the CPU tests
+// check against the oracle is SerialSweep::run_star in tests/emu/nsx_emu.cpp).
+//   NSX_CMD_STAR_BUILD  every worker prices the rows of its slice of the node range afresh.
+//   NSX_CMD_STAR        phase A: the rows of the nodes in dlist (and the row of the entering arc) are priced afresh,
+//                       the in-arcs of those nodes propose themselves to the rows of their tails, a row whose cached
+//                       arc got worse is emptied and queued;  barrier over the workers;  phase B: every worker prices
+//                       the queued rows of its slice afresh.
+//   Both end with the minimum over the worker's slice of the row cache, delivered like a sweep candidate.
+// Rows are updated with 128-bit compare-and-swap (key + arc): a proposal only ever lowers a row in the order of
+// nsx_rc_better, so the result does not depend on the order in which proposals arrive.
+// ------------------------------------------------------------------------------------------
+struct NsxStar {
+    int32_t on;
+    int32_t cost_i32;           // csc_cost holds int32 (every cost an exact integer) instead of float64
+    const int32_t* csc_arc;     // [m] arc ids grouped by head
+    const int32_t* csc_tail;    // [m] tail of that arc
+    const void* csc_cost;       // [m] its perturbed Phase-2 cost
+    int32_t* rq;                // [n] rows whose cached arc got worse
+    int32_t* rq_n;              // entries in rq (reset by the pivot CTA before each NSX_CMD_STAR)
+    unsigned int* bar;          // arrivals at the workers' barrier, cumulative
+};
+#define NSX_STAR_CH 256         // arcs per work item of phase A (one warp)
+#define NSX_STAR_BATCH 2048     // nodes of dlist whose work items are indexed at a time (prefix sums in shared memory)
+
+__device__ __forceinline__ NsxRC nsx_rc_load(const NsxRC* p) {
+    const int4 v = __ldcg(reinterpret_cast<const int4*>(p));
+    NsxRC r;
+    r.key = __longlong_as_double(((long long)(uint32_t)v.y << 32) | (uint32_t)v.x);
+    r.arc2 = v.z; r.pad = v.w;
+    return r;
+}
+__device__ __forceinline__ bool nsx_rc_cas(NsxRC* addr, const NsxRC& expect, const NsxRC& desired, NsxRC& old) {
+    const unsigned long long e0 = (unsigned long long)__double_as_longlong(expect.key);
+    const unsigned long long e1 = ((unsigned long long)(uint32_t)expect.pad << 32) | (uint32_t)expect.arc2;
+    const unsigned long long d0 = (unsigned long long)__double_as_longlong(desired.key);
+    const unsigned long long d1 = ((unsigned long long)(uint32_t)desired.pad << 32) | (uint32_t)desired.arc2;
+    unsigned long long o0, o1;
+    asm volatile("{\n\t.reg .b128 e, d, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(o0), "=l"(o1) : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "l"(addr) : "memory");
+    old.key = __longlong_as_double((long long)o0); old.arc2 = (int32_t)(uint32_t)o1; old.pad = (int32_t)(o1 >> 32);
+    return o0 == e0 && o1 == e1;
+}
+__device__ __forceinline__ NsxRC nsx_rc_none() { NsxRC r; r.key = 0.0; r.arc2 = -1; r.pad = 0; return r; }
+// lower the row to (key, arc2) unless it already holds something at least as good
+__device__ __forceinline__ void nsx_rc_propose(NsxRC* row, double key, int32_t arc2, NsxRC cur) {
+    for (;;) {
+        if (!nsx_rc_better(key, arc2, cur)) return;
+        NsxRC want; want.key = key; want.arc2 = arc2; want.pad = 0;
+        NsxRC old;
+        if (nsx_rc_cas(row, cur, want, old)) return;
+        cur = old;
+    }
+}
+// Out-arcs [lo, hi) of node v, spread over `nth` threads (this thread is `t`): the thread's best candidate in (key, arc2).
+__device__ __forceinline__ void nsx_star_price_row_part(const NsxDev& d, int32_t phase, double pv, int64_t lo, int64_t hi,
+                                                        int t, int nth, double& key, int32_t& arc2) {
+    const double tol = d.tol;
+    for (int64_t a0 = lo + t; a0 < hi; a0 += 4 * (int64_t)nth) {
+        int32_t hd[4]; double ct[4]; uint32_t st[4]; double ph[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t a = a0 + (int64_t)u * nth;
+            const bool in = a < hi;
+            hd[u] = in ? __ldcs(d.head + a) : 0;
+            ct[u] = in ? __ldcs(d.pert + a) : 0.0;
+            st[u] = in ? (uint32_t)__ldcg(d.state + a) : (uint32_t)NSX_ARC_IN_TREE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ph[u] = __ldcg(d.pi + hd[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t a = a0 + (int64_t)u * nth;
+            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a), pv), ph[u]);
+            double k2 = 0.0;
+            const int32_t c2 = nsx_star_candidate(a, st[u], rc, tol, &k2);
+            if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
+        }
+    }
+}
+__device__ __forceinline__ void nsx_star_warp_min(double& key, int32_t& arc2) {
+    __syncwarp();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double k2 = __shfl_down_sync(0xffffffffu, key, off);
+        const int32_t c2 = __shfl_down_sync(0xffffffffu, arc2, off);
+        if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
+    }
+}
+// Price row v afresh (its cache entry has been emptied): rows of at least `wide` arcs by the whole CTA (every warp
+// proposes its own best), shorter ones by the calling warp alone.  `whole_cta`: all threads of the CTA are calling.
+__device__ __forceinline__ void nsx_star_price_row(const NsxDev& d, int32_t phase, int32_t v, bool whole_cta, int64_t& evaluated) {
+    const int64_t lo = d.row_begin[v], hi = d.row_begin[v + 1];
+    if (hi <= lo) return;
+    const double pv = __ldcg(d.pi + v);
+    double key = 0.0; int32_t arc2 = -1;
+    if (whole_cta) nsx_star_price_row_part(d, phase, pv, lo, hi, (int)threadIdx.x, (int)blockDim.x, key, arc2);
+    else nsx_star_price_row_part(d, phase, pv, lo, hi, (int)(threadIdx.x & 31), 32, key, arc2);
+    nsx_star_warp_min(key, arc2);
+    if ((threadIdx.x & 31) == 0) {
+        if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
+        if (!whole_cta || threadIdx.x == 0) evaluated += hi - lo;
+    }
+}
+// Rows [r0, r1) of this worker's slice that `pick(v)` selects are priced afresh: short rows warp by warp, long rows
+// by the whole CTA.  Called by every thread of the CTA.
+template <class Pick>
+__device__ __forceinline__ void nsx_star_price_rows(const NsxDev& d, int32_t phase, int32_t r0, int32_t r1, Pick pick,
+                                                    int64_t& evaluated) {
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int32_t wide = 1024;
+    for (int32_t v = r0 + warp; v < r1; v += nwarp) {
+        if (!pick(v)) continue;
+        if (d.row_begin[v + 1] - d.row_begin[v] < wide) nsx_star_price_row(d, phase, v, false, evaluated);
+    }
+    for (int32_t v = r0; v < r1; ++v) {  // (block-uniform control flow)
+        if (!pick(v)) continue;
+        if (d.row_begin[v + 1] - d.row_begin[v] >= wide) nsx_star_price_row(d, phase, v, true, evaluated);
+    }
+}
+
+// One star command on a worker CTA.  Returns the worker's candidate in thread 0's dz; `evaluated` = arcs examined by
+// this thread's warp (lane 0) - summed by the caller.  `fault` is set when the barrier ran past its deadline.
+__device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp, const NsxCmd& cmd, int worker, int nworkers,
+                                             unsigned char* dyn, NsxCtaShared& sh, uint32_t& bar_rounds,
+                                             unsigned long long spin_ns, NsxCand& dz, int64_t& evaluated, int32_t& fault) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int32_t phase = cmd.phase;
+    const double tol = d.tol;
+    if (tid == 0) sh.x_fault = 0;
+    // this worker's slice of the rows
+    const int32_t per = (d.n + nworkers - 1) / nworkers;
+    const int32_t r0 = worker * per < d.n ? worker * per : d.n;
+    const int32_t r1 = r0 + per < d.n ? r0 + per : d.n;
+    NSX_SYNC();
+    if (cmd.kind == NSX_CMD_STAR_BUILD) {
+        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) d.rc[v] = nsx_rc_none();
+        NSX_SYNC();
+        nsx_star_price_rows(d, phase, r0 > 1 ? r0 : 1, r1, [](int32_t) { return true; }, evaluated);
+    } else {
+        const int32_t nd = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+        const bool extra_row = extra >= 0 && __ldcg(d.dstamp + extra) != round;
+        const int32_t nitems_nodes = nd + (extra_row ? 1 : 0);
+        int32_t* pfx = reinterpret_cast<int32_t*>(dyn);  // [2 * NSX_STAR_BATCH + 1] work-item prefix sums
+        const int gw = worker * nwarp + warp, GW = nworkers * nwarp;
+        // ---- phase A ----
+        for (int32_t b0 = 0; b0 < nitems_nodes; b0 += NSX_STAR_BATCH) {
+            const int32_t bn = nitems_nodes - b0 < NSX_STAR_BATCH ? nitems_nodes - b0 : NSX_STAR_BATCH;
+            NSX_SYNC();
+            // entry 2k: out-chunks of node k of the batch, entry 2k+1: its in-chunks (none for the extra row)
+            for (int32_t q = tid; q < 2 * bn; q += blockDim.x) {
+                const int32_t k = b0 + (q >> 1);
+                const int32_t v = k < nd ? __ldcg(d.dlist + k) : extra;
+                int32_t cnt;
+                if (q & 1) cnt = k < nd ? (d.col_begin[v + 1] - d.col_begin[v] + NSX_STAR_CH - 1) / NSX_STAR_CH : 0;
+                else cnt = (d.row_begin[v + 1] - d.row_begin[v] + NSX_STAR_CH - 1) / NSX_STAR_CH;
+                pfx[q + 1] = cnt;
+            }
+            if (tid == 0) pfx[0] = 0;
+            NSX_SYNC();
+            // inclusive scan of pfx[1 .. 2bn] (<= 4096 entries): 8 per thread, then the thread totals
+            {
+                const int32_t per_t = (2 * bn + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+                const int32_t q0 = 1 + tid * per_t, q1 = q0 + per_t < 2 * bn + 1 ? q0 + per_t : 2 * bn + 1;
+                int32_t sum = 0;
+                for (int32_t q = q0; q < q1; ++q) sum += pfx[q];
+                int32_t incl = sum;
+                __syncwarp();
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+                int32_t* wsum = reinterpret_cast<int32_t*>(sh.dz_buf);  // (32 ints of scratch)
+                if (lane == 31) wsum[warp] = incl;
+                NSX_SYNC();
+                if (warp == 0) {
+                    const int32_t w = lane < nwarp ? wsum[lane] : 0;
+                    int32_t wi = w;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += o; }
+                    wsum[lane] = wi - w;
+                }
+                NSX_SYNC();
+                int32_t run = wsum[warp] + incl - sum;
+                for (int32_t q = q0; q < q1; ++q) { run += pfx[q]; pfx[q] = run; }
+            }
+            NSX_SYNC();
+            const int32_t total = pfx[2 * bn];
+            for (int32_t item = gw; item < total; item += GW) {
+                // entry q with pfx[q] <= item < pfx[q + 1]
+                int32_t lo_q = 0, hi_q = 2 * bn - 1;
+                while (lo_q < hi_q) { const int32_t mid = (lo_q + hi_q + 1) >> 1; if (pfx[mid] <= item) lo_q = mid; else hi_q = mid - 1; }
+                const int32_t q = lo_q, c = item - pfx[q], k = b0 + (q >> 1);
+                const int32_t v = k < nd ? __ldcg(d.dlist + k) : extra;
+                if (!(q & 1)) {  // a chunk of the row of v
+                    const int64_t rb = d.row_begin[v], re = d.row_begin[v + 1];
+                    const int64_t lo = rb + (int64_t)c * NSX_STAR_CH, hi = lo + NSX_STAR_CH < re ? lo + NSX_STAR_CH : re;
+                    const double pv = __ldcg(d.pi + v);
+                    double key = 0.0; int32_t arc2 = -1;
+                    nsx_star_price_row_part(d, phase, pv, lo, hi, lane, 32, key, arc2);
+                    nsx_star_warp_min(key, arc2);
+                    if (lane == 0) {
+                        if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
+                        evaluated += hi - lo;
+                    }
+                } else {        // a chunk of the in-arcs of v
+                    const int32_t cb = d.col_begin[v], ce = d.col_begin[v + 1];
+                    const int32_t lo = cb + c * NSX_STAR_CH, hi = lo + NSX_STAR_CH < ce ? lo + NSX_STAR_CH : ce;
+                    const double pv = __ldcg(d.pi + v);
+                    for (int32_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
+                        int32_t a[4], i[4]; double ct[4]; uint32_t st[4]; double pt[4]; int32_t ds[4]; NsxRC cur[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int32_t e = e0 + u * 32;
+                            const bool in = e < hi;
+                            a[u] = in ? __ldcs(sp.csc_arc + e) : -1;
+                            i[u] = in ? __ldcs(sp.csc_tail + e) : 0;
+                            ct[u] = !in ? 0.0 : sp.cost_i32 ? (double)__ldcs(reinterpret_cast<const int32_t*>(sp.csc_cost) + e)
+                                                            : __ldcs(reinterpret_cast<const double*>(sp.csc_cost) + e);
+                            st[u] = in ? (uint32_t)__ldcg(d.csc_state + e) : (uint32_t)NSX_ARC_IN_TREE;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { pt[u] = __ldcg(d.pi + i[u]); ds[u] = __ldcg(d.dstamp + i[u]); cur[u] = nsx_rc_load(d.rc + i[u]); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (a[u] < 0 || ds[u] == round || i[u] == extra) continue;  // (that row is priced afresh anyway)
+                            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a[u]), pt[u]), pv);
+                            double key = 0.0;
+                            const int32_t arc2 = nsx_star_candidate(a[u], st[u], rc, tol, &key);
+                            NsxRC* row = d.rc + i[u];
+                            if (cur[u].arc2 >= 0 && (cur[u].arc2 >> 1) == a[u]) {
+                                // the cached arc of the row: still the best when it did not get worse, else the row starts over
+                                NsxRC old;
+                                if (arc2 >= 0 && key <= cur[u].key) {
+                                    NsxRC want; want.key = key; want.arc2 = arc2; want.pad = 0;
+                                    if (!nsx_rc_cas(row, cur[u], want, old)) nsx_rc_propose(row, key, arc2, old);
+                                } else if (nsx_rc_cas(row, cur[u], nsx_rc_none(), old)) {
+                                    sp.rq[atomicAdd(sp.rq_n, 1)] = i[u];
+                                } else if (arc2 >= 0) {
+                                    nsx_rc_propose(row, key, arc2, old);  // somebody lowered the row in between: it needs no fresh start
+                                }
+                            } else if (arc2 >= 0) {
+                                nsx_rc_propose(row, key, arc2, cur[u]);
+                            }
+                        }
+                        if (lane == 0) evaluated += (hi - e0 < 128 ? hi - e0 : 128);
+                    }
+                }
+            }
+        }
+        // ---- every proposal of phase A is in the row cache before anybody reads its slice ----
+        __threadfence();
+        NSX_SYNC();
+        ++bar_rounds;
+        if (tid == 0) {
+            atomicAdd(sp.bar, 1u);
+            const unsigned int target = bar_rounds * (unsigned int)nworkers;
+            const unsigned long long t0 = nsx_globaltimer();
+            uint32_t spins = 0;
+            while ((unsigned int)nsx_ld_acquire(reinterpret_cast<const int32_t*>(sp.bar)) < target) {
+                if ((++spins & 1023u) == 0 && nsx_globaltimer() - t0 > spin_ns) { sh.x_fault = 6; break; }
+            }
+        }
+        NSX_SYNC();
+        if (sh.x_fault == 6) fault = 6;
+        // ---- phase B: queued rows of this slice ----
+        const int32_t nq = __ldcg(sp.rq_n);
+        if (nq > 0) {
+            // mark the queued rows of this slice in shared memory (slice bitmap), then price them
+            uint32_t* bits = reinterpret_cast<uint32_t*>(dyn);
+            const int32_t words = (r1 - r0 + 31) / 32;
+            for (int32_t w = tid; w < words; w += blockDim.x) bits[w] = 0u;
+            NSX_SYNC();
+            for (int32_t k = tid; k < nq; k += blockDim.x) {
+                const int32_t v = __ldcg(sp.rq + k);
+                if (v >= r0 && v < r1) atomicOr(&bits[(v - r0) >> 5], 1u << ((v - r0) & 31));
+            }
+            NSX_SYNC();
+            nsx_star_price_rows(d, phase, r0, r1, [bits, r0](int32_t v) { return ((bits[(v - r0) >> 5] >> ((v - r0) & 31)) & 1u) != 0u; }, evaluated);
+        }
+    }
+    // ---- minimum over this worker's slice of the row cache ----
+    __threadfence();
+    NSX_SYNC();
+    nsx_cand_init(dz);
+    for (int32_t v = r0 + tid; v < r1; v += blockDim.x) {
+        const NsxRC r = nsx_rc_load(d.rc + v);
+        if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) { dz.key = r.key; dz.arc2 = r.arc2; }
+    }
+    nsx_block_reduce(dz, sh.dz_buf);
+}
+
 // Sweep functor of CTA 0.
 struct GridSweep {
     const NsxDev& d;      // global view (state bytes, weights, global potentials)
@@ -884,6 +1177,7 @@ struct GridSweep {
     const NsxShard& shd;
     unsigned long long xseq, t_xchg;
     unsigned long long spin_ns;  // deadline of every wait in this functor
+    const NsxStar& star;
 
     // Candidates of the other GPUs.  Called by ALL threads of the pivot CTA; thread 0 holds the local best in kz / kx
     // and receives the merged best.  A deadline or a raised abort word ends in c.fault (and tells the peers).
@@ -1020,12 +1314,16 @@ struct GridSweep {
             NSX_SYNC();
             return;
         }
+        const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
+        if (starcmd && threadIdx.x == 0) { *star.rq_n = 0; *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull; }  // (x_recs: idle on one GPU, holds the evaluated-arc count)
+        if (starcmd) NSX_SYNC();
         publish(cmd);
         unsigned long long t1 = 0;
         if (threadIdx.x == 0) t1 = nsx_globaltimer();
         // every worker's candidate: thread b polls slot b until it carries this command's number
         NsxDevexCand kx; nsx_devex_init(kx);
         NsxCand kz; nsx_cand_init(kz);
+        unsigned long long ev = 0ull;
         for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
             const NsxSlot* sl = slots + b;
             uint32_t spins = 0;
@@ -1043,14 +1341,20 @@ struct GridSweep {
                 union { NsxCand c; int4 v; } tmp;
                 tmp.v = __ldcg(&sl->v[0]);
                 nsx_cand_merge(kz, tmp.c);
+                if (starcmd) { const int4 w = __ldcg(&sl->v[1]); ev += ((unsigned long long)(uint32_t)w.y << 32) | (uint32_t)w.x; if (w.z) c.fault = w.z; }
             }
         }
+        if (starcmd && ev) atomicAdd(reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]), ev);
         NSX_SYNC();
         if (c.fault) {  // a worker never answered (block-uniform after the barrier): tell the peers, the loop ends
             if (threadIdx.x == 0 && shd.world > 1) nsx_raise_peer_aborts(shd);
             return;
         }
         if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; g->tl[6] += nsx_globaltimer() - g->t_pub; }
+        if (starcmd && threadIdx.x == 0) {
+            c.star_evaluated = (int64_t)*reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]);
+            if (cmd.kind == NSX_CMD_STAR) c.star_rescans += __ldcg(star.rq_n);
+        }
         if (cmd.kind == NSX_CMD_TOPK) {
             merge_topk(c);
             if (threadIdx.x == 0) t_price += nsx_globaltimer() - t0;
@@ -1088,6 +1392,7 @@ struct NsxKernelArgs {
     NsxSmemPlan wplan;   // sweep workers
     int32_t probe_sweeps;  // > 0: measurement aid, run this many sweeps of the initial state and stop
     NsxShard shard;        // world == 1: single GPU
+    NsxStar star;          // star pricing (on == 0: full sweeps)
     unsigned long long spin_ns;  // deadline of device-side waits (nsx_options.spin_timeout_ms)
 };
 
@@ -1160,7 +1465,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns};
+        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns, a.star};
         if (a.probe_sweeps > 0) nsx_probe_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -1180,6 +1485,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
     double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     unsigned char* ring = dyn + a.wplan.ring_off;
     int32_t seen = 0;
+    uint32_t bar_rounds = 0;
     for (;;) {
         if (threadIdx.x == 0) {
             int32_t s;
@@ -1207,6 +1513,25 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         const NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
+        const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
+        if (starcmd) {
+            int64_t evaluated = 0; int32_t fault = 0;
+            nsx_cta_star(d, a.star, cmd, (int)blockIdx.x - 1, (int)gridDim.x - 1, dyn, sh, bar_rounds, a.spin_ns, dz, evaluated, fault);
+            // arcs examined by this CTA (lane 0 of every warp counted its warp's): summed through shared memory
+            if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull;
+            NSX_SYNC();
+            if (evaluated) atomicAdd(reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]), (unsigned long long)evaluated);
+            NSX_SYNC();
+            if (threadIdx.x == 0) {
+                const unsigned long long ev = *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]);
+                NsxSlot* sl = a.slots + blockIdx.x;
+                union { NsxCand c; int4 v; } tmp; tmp.c = dz;
+                sl->v[0] = tmp.v;
+                sl->v[1] = make_int4((int)(uint32_t)ev, (int)(uint32_t)(ev >> 32), fault, 0);
+                nsx_st_release(&sl->seq, seen);
+            }
+            continue;
+        }
         nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
                       a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
         if (cmd.kind == NSX_CMD_TOPK) {  // this CTA's sorted list -> HBM (the slot release below orders it)
@@ -1276,8 +1601,42 @@ extern "C" __global__ void nsx_classify_costs_kernel(const double* pert, const i
         else if (fabs(c) > 32767.0) f |= 2u;
         const int32_t tl = tail[i], hd = head[i];
         if (tl < 1 || tl >= n || hd < 1 || hd >= n) f |= 4u;
+        if (i + 1 < m && tail[i + 1] < tl) f |= 8u;  // not grouped by ascending tail: no rows, no star pricing
     }
     if (f) atomicOr(flags, f);
+}
+
+// ---- star pricing: CSR offsets of the rows and the CSC copy of the arcs (built once per solve) ----
+extern "C" __global__ void nsx_star_count_kernel(const int32_t* tail, const int32_t* head, int64_t m, int32_t* row_cnt, int32_t* col_cnt) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = g; i < m; i += T) { atomicAdd(row_cnt + tail[i] + 1, 1); atomicAdd(col_cnt + head[i] + 1, 1); }
+}
+// in-place inclusive scan of two arrays of n + 1 counters (element 0 is 0): one CTA, chunk per thread
+extern "C" __global__ void nsx_star_scan_kernel(int32_t* a, int32_t* b, int32_t* cursor, int32_t n1) {
+    __shared__ int32_t part[2][1024];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int32_t per = (n1 + T - 1) / T, lo = t * per < n1 ? t * per : n1, hi = lo + per < n1 ? lo + per : n1;
+    int32_t sa = 0, sb = 0;
+    for (int32_t i = lo; i < hi; ++i) { sa += a[i]; sb += b[i]; }
+    part[0][t] = sa; part[1][t] = sb;
+    __syncthreads();
+    if (t == 0) { int32_t ra = 0, rb = 0; for (int k = 0; k < T; ++k) { int32_t x = part[0][k]; part[0][k] = ra; ra += x; x = part[1][k]; part[1][k] = rb; rb += x; } }
+    __syncthreads();
+    int32_t ra = part[0][t], rb = part[1][t];
+    for (int32_t i = lo; i < hi; ++i) { ra += a[i]; a[i] = ra; rb += b[i]; b[i] = rb; }
+    __syncthreads();
+    for (int32_t i = lo; i < hi; ++i) if (i + 1 < n1) cursor[i] = b[i];  // fill cursor of column i = col_begin[i]
+}
+extern "C" __global__ void nsx_star_fill_kernel(const int32_t* tail, const int32_t* head, const double* pert, const uint8_t* state,
+                                                int64_t m, int32_t* cursor, int32_t* csc_arc, int32_t* csc_tail, void* csc_cost,
+                                                int32_t cost_i32, int32_t* csc_pos, uint8_t* csc_state) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = g; i < m; i += T) {
+        const int32_t e = atomicAdd(cursor + head[i], 1);  // (the order inside a column is free: proposals commute)
+        csc_arc[e] = (int32_t)i; csc_tail[e] = tail[i]; csc_pos[i] = e; csc_state[e] = state[i];
+        if (cost_i32) reinterpret_cast<int32_t*>(csc_cost)[e] = (int32_t)pert[i];
+        else reinterpret_cast<double*>(csc_cost)[e] = pert[i];
+    }
 }
 
 // Canonical arrays (int32 tail / head, float64 perturbed cost) -> tile-padded pricing store.
@@ -1524,6 +1883,9 @@ static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
     res->sync_ms = (double)c.clk_sync * 1e-6;
     res->exchange_ms = (double)c.clk_xchg * 1e-6;
     for (int i = 0; i < 12; ++i) res->phase_cycles[i] = c.ph[i];
+    res->star_pricing = c.star_on;
+    res->star_updates = c.star_updates; res->star_builds = c.star_builds; res->star_rescans = c.star_rescans;
+    res->blk_rebuilds = c.blk_rebuilds;
 }
 
 struct DeviceInfo { int sms = 0; int coop = 0; size_t smem_optin = 0; bool ok = false; };
@@ -1660,6 +2022,20 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     NsxStore& st = ka.st;
     nsx_choose_layout(n, cost_flags & 3u, devex, st);
 
+    // ---- launch shape: one pivot CTA + sweep workers; small instances are priced by the pivot CTA alone ----
+    int64_t arcs_per_cta = nsx_env_int("NSX_ARCS_PER_CTA", 8192);
+    int64_t workers = (m + arcs_per_cta - 1) / arcs_per_cta;
+    if (workers > info.sms - 1) workers = info.sms - 1;
+    int grid = m < nsx_env_int("NSX_SINGLE_CTA_ARCS", 65536) || workers < 2 ? 1 : (int)workers + 1;
+    int forced = nsx_env_int("NSX_GRID", 0);
+    if (forced > 0) grid = forced < info.sms ? forced : info.sms;
+    // Star pricing (row cache instead of full Dantzig sweeps): whenever the driver prices with the Dantzig rule over the
+    // whole arc range - Dantzig pricing, or the transportation row scan in front of any rule - on a multi-CTA grid of one
+    // GPU, cold start, arcs grouped by tail.  NSX_STAR=0 keeps the full sweeps (what the sweep roofline is quoted on).
+    const bool star = nsx_env_int("NSX_STAR", 1) != 0 && grid > 1 && !shard && !warm && probe_sweeps == 0 && m > 0 && m < (1ll << 30) &&
+                      !(cost_flags & 8u) && (opt->pricing == NSX_PRICING_DANTZIG || opt->row_scan_first == NSX_SPECIAL_ROW_SCAN);
+    const bool star_i32 = !(cost_flags & 1u);  // every cost an exact int32
+
     // ---- engine-owned device memory ----
     const size_t state_len = (size_t)(ma > mpad ? ma : mpad) + 16;
     size_t o_store = arena.plan((size_t)(mpad / NSX_TILE) * st.tile_bytes);
@@ -1677,6 +2053,15 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_topk = arena.plan(sizeof(NsxTopkOut) * 160);
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     size_t o_imb = warm ? arena.plan((size_t)n * 8) : 0;
+    size_t o_rc = 0, o_dlist = 0, o_dstamp = 0, o_rowb = 0, o_colb = 0, o_cursor = 0, o_cpos = 0, o_cstate = 0, o_carc = 0, o_ctail = 0,
+           o_ccost = 0, o_rq = 0, o_rqn = 0;
+    if (star) {
+        o_rc = arena.plan((size_t)n * sizeof(NsxRC)); o_dlist = arena.plan((size_t)n * 4); o_dstamp = arena.plan((size_t)n * 4);
+        o_rowb = arena.plan(((size_t)n + 2) * 4); o_colb = arena.plan(((size_t)n + 2) * 4); o_cursor = arena.plan(((size_t)n + 2) * 4);
+        o_cpos = arena.plan((size_t)m * 4); o_cstate = arena.plan((size_t)m + 16); o_carc = arena.plan((size_t)m * 4);
+        o_ctail = arena.plan((size_t)m * 4); o_ccost = arena.plan((size_t)m * (star_i32 ? 4 : 8));
+        o_rq = arena.plan((size_t)n * 4); o_rqn = arena.plan(256);
+    }
     NSX_CUDA(arena.commit());
 
     st.base = arena.at<unsigned char>(o_store);
@@ -1686,6 +2071,18 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi); d.pi_mirror = nullptr;
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.sidx = arena.at<int32_t>(o_sidx); d.blk = nullptr;  // (the pivot CTA points blk at its shared memory)
+    d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    memset(&ka.star, 0, sizeof ka.star);
+    if (star) {
+        d.rc = arena.at<NsxRC>(o_rc); d.dlist = arena.at<int32_t>(o_dlist); d.dstamp = arena.at<int32_t>(o_dstamp);
+        d.row_begin = arena.at<int32_t>(o_rowb); d.col_begin = arena.at<int32_t>(o_colb);
+        d.csc_pos = arena.at<int32_t>(o_cpos); d.csc_state = arena.at<uint8_t>(o_cstate);
+        ka.star.on = 1; ka.star.cost_i32 = star_i32 ? 1 : 0;
+        ka.star.csc_arc = arena.at<int32_t>(o_carc); ka.star.csc_tail = arena.at<int32_t>(o_ctail);
+        ka.star.csc_cost = arena.at<unsigned char>(o_ccost);
+        ka.star.rq = arena.at<int32_t>(o_rq); ka.star.rq_n = arena.at<int32_t>(o_rqn);
+        ka.star.bar = reinterpret_cast<unsigned int*>(arena.at<int32_t>(o_rqn) + 16);
+    }
     d.gpath_h = arena.at<int32_t>(o_gph); d.gpath_t = arena.at<int32_t>(o_gpt);
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
     d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
@@ -1710,6 +2107,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     NsxCtl hctl;
     nsx_fill_ctl(hctl, opt, want_trace);
     if (warm) { hctl.warm = 1; hctl.phase = warm->start_phase; }
+    hctl.star_on = star ? 1 : 0;
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
     NSX_CUDA(cudaMemsetAsync(ka.slots, 0, sizeof(NsxSlot) * 1024, stream));
@@ -1719,14 +2117,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     NSX_CUDA(cudaGetLastError());
     NSX_CUDA(cudaEventRecord(ev[1], stream));
 
-    // ---- launch shape ----
-    // one pivot CTA + sweep workers; small instances are priced by the pivot CTA alone
-    int64_t arcs_per_cta = nsx_env_int("NSX_ARCS_PER_CTA", 8192);
-    int64_t workers = (m + arcs_per_cta - 1) / arcs_per_cta;
-    if (workers > info.sms - 1) workers = info.sms - 1;
-    int grid = m < nsx_env_int("NSX_SINGLE_CTA_ARCS", 65536) || workers < 2 ? 1 : (int)workers + 1;
-    int forced = nsx_env_int("NSX_GRID", 0);
-    if (forced > 0) grid = forced < info.sms ? forced : info.sms;
+    // ---- launch shape (grid: chosen above) ----
     const size_t fixed = nsx_smem_fixed();
     if (fixed + 2 * (size_t)st.stage_bytes > info.smem_optin) { arena.release(); inputs.release(); return nsx_fail(NSX_ERR_INTERNAL, "tile ring does not fit in shared memory"); }
     const size_t limit = info.smem_optin - fixed;
@@ -1770,6 +2161,18 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
             nsx_init_kernel<<<ib, 1024, 0, stream>>>(d, d_supply, ka.ctl);
         }
         NSX_CUDA(cudaGetLastError());
+        if (star) {  // rows / CSC copy / empty stamps (after the init kernel: the CSC copy takes the initial state bytes)
+            NSX_CUDA(cudaMemsetAsync((void*)d.row_begin, 0, ((size_t)n + 2) * 4, stream));
+            NSX_CUDA(cudaMemsetAsync((void*)d.col_begin, 0, ((size_t)n + 2) * 4, stream));
+            NSX_CUDA(cudaMemsetAsync(d.dstamp, 0, (size_t)n * 4, stream));
+            NSX_CUDA(cudaMemsetAsync(ka.star.rq_n, 0, 256, stream));
+            nsx_star_count_kernel<<<util_blocks, 256, 0, stream>>>(d.tail, d.head, m, (int32_t*)d.row_begin, (int32_t*)d.col_begin);
+            nsx_star_scan_kernel<<<1, 1024, 0, stream>>>((int32_t*)d.row_begin, (int32_t*)d.col_begin, arena.at<int32_t>(o_cursor), n + 1);
+            nsx_star_fill_kernel<<<util_blocks, 256, 0, stream>>>(d.tail, d.head, d.pert, d.state, m, arena.at<int32_t>(o_cursor),
+                                                                 (int32_t*)ka.star.csc_arc, (int32_t*)ka.star.csc_tail, (void*)ka.star.csc_cost,
+                                                                 ka.star.cost_i32, d.csc_pos, d.csc_state);
+            NSX_CUDA(cudaGetLastError());
+        }
     }
     void* kargs[] = {(void*)&ka};
     // The kernel synchronises its CTAs through its own flags; the cooperative launch is only there for the guarantee
@@ -1781,11 +2184,16 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
         // resident kernel is already spinning would wait for that kernel (implicit synchronisation) - which waits for this
         // rank.  So every rank finishes its set-up, then all meet here (NSX_LAUNCH_PLAIN = number of ranks) and launch.
         NSX_CUDA(cudaStreamSynchronize(stream));
-        static std::atomic<int> arrivals{0};
         if (shard) {
-            const int ranks = nsx_env_int("NSX_LAUNCH_PLAIN", 1), ticket = arrivals.fetch_add(1);
-            const int target = (ticket / ranks + 1) * ranks;
-            while (arrivals.load() < target) std::this_thread::yield();
+            static std::mutex mu;
+            static std::condition_variable cv;
+            static int waiting = 0;
+            static unsigned generation = 0;
+            const int ranks = nsx_env_int("NSX_LAUNCH_PLAIN", 1);
+            std::unique_lock<std::mutex> lock(mu);
+            const unsigned mine = generation;
+            if (++waiting >= ranks) { waiting = 0; ++generation; cv.notify_all(); }
+            else cv.wait_for(lock, std::chrono::seconds(120), [&] { return generation != mine; });
         }
         resident_kernel<<<dim3(grid), dim3(NSX_THREADS), smem, stream>>>(ka);
         NSX_CUDA(cudaGetLastError());

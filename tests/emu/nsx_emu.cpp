@@ -43,7 +43,58 @@ static IncStats g_inc;
 
 struct SerialSweep {
     const NsxDev& d;
+    const int32_t* csc_arc = nullptr;  // star pricing: arc ids grouped by head (the emulation's CSC copy)
     SerialSweep(const NsxDev& dev) : d(dev) {}
+    // Star pricing, serial restatement of what the sweep workers do (nsx_engine.cu, NSX_CMD_STAR / NSX_CMD_STAR_BUILD):
+    // same row cache, same marking rule, same order of the phases.
+    void price_row(int32_t v, int32_t phase, int64_t& evaluated) {
+        for (int64_t a = d.row_begin[v]; a < d.row_begin[v + 1]; ++a) {
+            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, d.pert[a], a), d.pi[v]), d.pi[d.head[a]]);
+            double key = 0.0;
+            const int32_t arc2 = nsx_star_candidate(a, d.state[a], rc, d.tol, &key);
+            ++evaluated;
+            if (arc2 >= 0 && nsx_rc_better(key, arc2, d.rc[v])) { d.rc[v].key = key; d.rc[v].arc2 = arc2; }
+        }
+    }
+    void run_star(const NsxCmd& cmd, NsxCand& dz, NsxCtl& c) {
+        int64_t evaluated = 0;
+        NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0;
+        if (cmd.kind == NSX_CMD_STAR_BUILD) {
+            for (int32_t v = 1; v < d.n; ++v) { d.rc[v] = none; price_row(v, cmd.phase, evaluated); }
+        } else {
+            const int32_t nd = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+            for (int32_t k = 0; k < nd; ++k) price_row(d.dlist[k], cmd.phase, evaluated);  // (reset by the pivot)
+            if (extra >= 0 && d.dstamp[extra] != round) price_row(extra, cmd.phase, evaluated);
+            std::vector<int32_t> rq;
+            for (int32_t k = 0; k < nd; ++k) {
+                const int32_t v = d.dlist[k];
+                for (int32_t e = d.col_begin[v]; e < d.col_begin[v + 1]; ++e) {
+                    const int64_t a = csc_arc[e];
+                    const int32_t i = d.tail[a];
+                    if (d.dstamp[i] == round || i == extra) continue;  // that row is priced afresh anyway
+                    const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(cmd.phase, d.pert[a], a), d.pi[i]), d.pi[v]);
+                    double key = 0.0;
+                    const int32_t arc2 = nsx_star_candidate(a, d.csc_state[e], rc, d.tol, &key);
+                    ++evaluated;
+                    const NsxRC cur = d.rc[i];
+                    if (cur.arc2 >= 0 && (cur.arc2 >> 1) == a) {  // the cached arc of the row changed its reduced cost
+                        if (arc2 >= 0 && key <= cur.key) { d.rc[i].key = key; d.rc[i].arc2 = arc2; }
+                        else { d.rc[i] = none; rq.push_back(i); }
+                    } else if (arc2 >= 0 && nsx_rc_better(key, arc2, cur)) {
+                        d.rc[i].key = key; d.rc[i].arc2 = arc2;
+                    }
+                }
+            }
+            for (int32_t i : rq) price_row(i, cmd.phase, evaluated);
+            c.star_rescans += (int64_t)rq.size();
+        }
+        nsx_cand_init(dz);
+        for (int32_t v = 1; v < d.n; ++v) {
+            const NsxRC r = d.rc[v];
+            if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) { dz.key = r.key; dz.arc2 = r.arc2; }
+        }
+        c.star_evaluated = evaluated;
+    }
     void inc_stats(const NsxCmd& cmd) {
         IncStats& I = g_inc;
         const int32_t n = d.n; const int64_t m = d.m;
@@ -79,6 +130,7 @@ struct SerialSweep {
     void run_serial(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         nsx_cand_init(dz);
         nsx_devex_init(dx);
+        if (cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD) { run_star(cmd, dz, c); return; }
         if (cmd.kind == NSX_CMD_TOPK) {  // candidate-list refresh (simplex_pricing.py:507-536)
             std::vector<std::pair<double, int32_t>> cands;
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
@@ -157,6 +209,24 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     c.pricing = opt->pricing; c.row_scan_first = opt->row_scan_first;
     c.trace_cap = res->entering_trace ? opt->trace_capacity : 0;
     c.unbounded_arc = -1;
+    // NSX_EMU_STAR=1: star pricing (row cache + CSC copy), as the engine runs Dantzig pricing on multi-CTA grids
+    const char* sp = getenv("NSX_EMU_STAR");
+    const bool star = sp && *sp && atoi(sp) != 0 && !warm;
+    std::vector<NsxRC> rcache(star ? n : 0);
+    std::vector<int32_t> dlist(star ? n : 0), dstamp(star ? n : 0, 0), row_begin(star ? n + 1 : 0, 0), col_begin(star ? n + 1 : 0, 0),
+        csc_pos(star ? (size_t)m : 0), csc_arc(star ? (size_t)m : 0);
+    std::vector<uint8_t> csc_state(star ? (size_t)m : 0);
+    d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    if (star) {
+        for (int64_t a = 0; a + 1 < m; ++a) if (pb->tail[a] > pb->tail[a + 1]) return -8;  // rows need arcs sorted by tail
+        for (int64_t a = 0; a < m; ++a) { row_begin[pb->tail[a] + 1]++; col_begin[pb->head[a] + 1]++; }
+        for (int32_t v = 0; v < n; ++v) { row_begin[v + 1] += row_begin[v]; col_begin[v + 1] += col_begin[v]; }
+        std::vector<int32_t> cur(col_begin.begin(), col_begin.end() - 1);
+        for (int64_t a = 0; a < m; ++a) { const int32_t e = cur[pb->head[a]]++; csc_arc[e] = (int32_t)a; csc_pos[a] = e; }
+        d.rc = rcache.data(); d.dlist = dlist.data(); d.dstamp = dstamp.data(); d.row_begin = row_begin.data();
+        d.col_begin = col_begin.data(); d.csc_pos = csc_pos.data(); d.csc_state = csc_state.data();
+        c.star_on = 1;
+    }
 
     int64_t art = 0;
     std::vector<double> imbalance(warm ? (size_t)n : 0, 0.0);
@@ -182,7 +252,9 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     NsxLoopShared* L = new NsxLoopShared;
     NsxPivotScratch* s = new NsxPivotScratch;
     NsxPotScratch* ps = new NsxPotScratch;
+    if (star) for (int64_t a = 0; a < m; ++a) csc_state[csc_pos[a]] = state[a];  // (the engine fills it when it builds the CSC copy)
     SerialSweep sweep(d);
+    sweep.csc_arc = star ? csc_arc.data() : nullptr;
 #ifdef NSX_HOST_MT
     {
         const char* nt = getenv("NSX_EMU_THREADS");
@@ -224,6 +296,9 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     res->sum_rounds = c.sum_rounds; res->sum_window = c.sum_window;
     res->pricing_ms = (double)c.sum_window;  // emulation only: moved preorder entries, for design stats
     res->pivot_ms = (double)rebuilds;        // emulation only: re-layouts of the blocked preorder array
+    res->sync_ms = (double)c.star_updates;   // emulation only: star-pricing updates / rebuilds / rows priced afresh
+    res->exchange_ms = (double)c.star_builds;
+    res->h2d_ms = (double)c.star_rescans;
     if (res->flow) memcpy(res->flow, flow.data(), ma * 8);
     if (res->potential) memcpy(res->potential, pi.data(), (size_t)n * 8);
     if (res->state) memcpy(res->state, state.data(), ma);

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     abi, arch = ctypes.c_int32(), ctypes.c_int32()
     lib.nsx_version(ctypes.byref(abi), ctypes.byref(arch))
-    assert (abi.value, arch.value) == (_capi.ABI_VERSION, 100) == (3, 100)
+    assert (abi.value, arch.value) == (_capi.ABI_VERSION, 100) == (4, 100)
 
 
 def test_ctypes_structs_match_the_header(tmp_path):

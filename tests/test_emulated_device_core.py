@@ -102,3 +102,31 @@ def test_emulated_core_blocked_preorder(family, make, pricing, lg, spare, monkey
     assert_same_solution(got, oracle.solve_canonical(cp, opts))
     if lg in ("1", "2") and got.tree_updates > 50:
         assert got.timing["pivot_ms"] > 0  # (emulation: number of re-layouts) the rebuild path ran
+
+
+STAR_CASES = [
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), 0, 0),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), 0, 0),
+    ("netgen_caps", lambda: gen.netgen_like(512, 8192, n_sources=32, n_sinks=32, supply_each=3000, cap_max=50, seed=12), 0, 0),
+    ("transport", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 0, 1),
+    ("transport_ties", lambda: gen.transportation(64, 64, cost_max=3, seed=17), 0, 1),
+    ("transport_devex_fallthrough", lambda: gen.transportation(48, 80, cost_max=50, seed=27), 1, 1),
+    ("goto", lambda: gen.goto_like(32, seed=8), 0, 0),
+    ("gridgen", lambda: gen.gridgen_like(32, 8200, seed=9), 0, 0),
+]
+
+
+@pytest.mark.parametrize("blocked", ["0", "1"])
+@pytest.mark.parametrize("family,make,pricing,eps0", STAR_CASES)
+def test_emulated_core_star_pricing(family, make, pricing, eps0, blocked, monkeypatch):
+    """Star pricing (row cache kept up to date from the re-hung subtree of each pivot instead of sweeping all arcs)
+    enters exactly the arcs the full Dantzig sweep enters - with and without cost perturbation (ties), with capacities
+    (backward candidates, bound flips), through Phase 1 zero-candidate passes and the phase switch."""
+    monkeypatch.setenv("NSX_EMU_STAR", "1")
+    monkeypatch.setenv("NSX_EMU_BLOCKED", blocked)
+    cp = make().canonical(eps_base=0.0) if eps0 else make().canonical()
+    opts = engine_options(cp, pricing)
+    got = emu.solve_canonical(cp, opts)
+    assert_same_solution(got, oracle.solve_canonical(cp, opts))
+    assert got.timing["sync_ms"] > 0  # (emulation: number of star updates) the incremental path ran
+    assert got.arcs_priced < 0.7 * got.iterations * cp.n_arcs
