@@ -317,11 +317,21 @@ def sharded_leg(name: str, rank: int, world: int, device: int, dist, barrier, pe
                              and g["flow_sha"] == mine["flow"] and g["pi_sha"] == mine["pi"] and g["state_sha"] == mine["state"])
         single_ok = None
         single_ms = None
-        if world > 1:  # the same prefix on one GPU (rank 0; the others wait at the barrier)
+        single_rec = None
+        # the same prefix as an ordinary single-GPU solve (rank 0; the others wait at the barrier): the parity anchor of the
+        # sharded run and - under the Dantzig rule, where one GPU prices from the row cache (star pricing) instead of sweeping
+        # all arcs - the figure the sharded sweeps have to be read against
+        if world > 1 or not devex:
             if rank == 0:
                 single = _capi.solve_resident(cp, opts, ptrs)
                 single_ok = bool((single.status, single.iterations, solution_hashes(single)) == sigs[0][:3])
                 single_ms = single.timing["solve_ms"]
+                single_rec = {"solve_ms": single_ms, "pivots_per_s": single.iterations / (single_ms * 1e-3),
+                              "us_per_pivot": {"total": 1e3 * single_ms / max(single.iterations, 1),
+                                               "pricing": 1e3 * single.timing["pricing_ms"] / max(single.iterations, 1),
+                                               "pivot_and_tree": 1e3 * single.timing["pivot_ms"] / max(single.iterations, 1)},
+                              "arcs_priced_per_pivot": single.arcs_priced / max(single.iterations, 1),
+                              "star_pricing": {k: single.stats[k] for k in ("star_pricing", "star_updates", "star_builds", "star_rescans")}}
             barrier()
         t = torch.tensor([r.timing["solve_ms"], r.timing["pricing_ms"], r.timing["exchange_ms"], r.timing["sync_ms"],
                           r.timing["pivot_ms"]], dtype=torch.float64, device=f"cuda:{device}")
@@ -350,7 +360,7 @@ def sharded_leg(name: str, rank: int, world: int, device: int, dist, barrier, pe
                 r.stats["phase_cycles"])},
             "avg_rehung_subtree": r.stats["sum_subtree"] / max(r.tree_updates, 1),
             "hashes": mine, "ranks_agree": ranks_agree, "repeatable": repeatable, "matches_oracle_prefix_record": golden_ok,
-            "matches_single_gpu": single_ok, "single_gpu_solve_ms": single_ms,
+            "matches_single_gpu": single_ok, "single_gpu_solve_ms": single_ms, "single_gpu": single_rec,
             "parity_ok": bool(ranks_agree and repeatable and golden_ok is not False and single_ok is not False
                               and (golden_ok is True or single_ok is True)),
         })
@@ -669,6 +679,8 @@ def main() -> int:
             "pivot_phase_us": {k: round(v / 1.9e3 / max(last.iterations, 1), 3) for k, v in zip(
                 ["walk", "residuals", "ratio", "flow", "bookkeeping", "snapshot", "window", "copy_stem",
                  "potentials", "cadence"], last.stats["phase_cycles"])},
+            "star_pricing": {k: last.stats[k] for k in ("star_pricing", "star_updates", "star_builds", "star_rescans")},
+            "blk_rebuilds": last.stats["blk_rebuilds"],
             "e2e_device_events_ms_per_step": e2e_dev_ms / args.steps,
             "exchange_ms_per_step": last.timing.get("exchange_ms", 0.0),
             "exchange_us_per_sweep": 1e3 * last.timing.get("exchange_ms", 0.0) / max(last.stats["sweeps"], 1),

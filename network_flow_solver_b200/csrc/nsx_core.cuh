@@ -132,7 +132,8 @@ struct alignas(16) NsxNode {
 // arcs, grouped by head) propose themselves to the rows of their tails, a row whose cached arc got worse is priced
 // afresh too, and the entering arc is the minimum over the row cache.  Same arc as a full sweep, ~|S| * degree arcs
 // examined instead of m.
-struct alignas(16) NsxRC { double key; int32_t arc2; int32_t pad; };  // arc2 < 0: the row has no improving arc
+struct alignas(16) NsxRC { double key; int32_t arc2; int32_t pad; };  // arc2 < 0: the row has no improving arc; pad = star round in
+                                                                     // which the pivot last emptied the row (it is priced afresh then)
 
 struct NsxDev {
     int32_t n;   // nodes incl. root
@@ -173,6 +174,8 @@ struct NsxDev {
     NsxRC* rc;             // [n] row cache
     int32_t* dlist;        // [n] nodes whose potential the last pivot changed (its re-hung subtree)
     int32_t* dstamp;       // [n] star round in which the node was last in dlist
+    int32_t* dinfo;        // [8 (n + 1)] per listed node {node, first out-arc, out-degree, first CSC entry, in-degree, -, -, -}: what
+                           // the sweep workers turn into work items (the row of the entering arc is appended with in-degree 0)
     const int32_t* row_begin;  // [n+1] out-arcs of v = arcs row_begin[v] .. row_begin[v+1]
     const int32_t* col_begin;  // [n+1] in-arcs of v = entries col_begin[v] .. col_begin[v+1] of the CSC copy
     int32_t* csc_pos;      // [m] arc -> its entry in the CSC copy (the state byte is written in both places)
@@ -211,6 +214,7 @@ struct NsxCtl {
     // star pricing: on for this solve / row cache consistent with the state before the pending pivot / pivots since the
     // cache was last brought up to date / current round (stamp) / nodes in dlist / row of the entering arc
     int32_t star_on, star_valid, star_pending, star_round, star_nd, star_extra;
+    int32_t star_ne, star_pad;   // entries of dinfo for the next update (star_nd, + 1 when the row of the entering arc is not among them)
     int64_t star_evaluated;   // arcs examined by the last star command (reported by the sweep workers)
     int64_t star_updates, star_builds, star_rescans;
     int64_t blk_rebuilds;     // blocked preorder array: fresh layouts
@@ -818,6 +822,19 @@ NSX_FN void nsx_ratio_finish(const NsxRatio& rr, const double* res, const int32_
 // One pivot on entering arc e (direction dir = +1 forward / -1 backward).
 // Returns (block-uniform) 0 = ok, 3 = unbounded.
 // ------------------------------------------------------------------------------------------
+// star pricing, end of a pivot (one thread): the row of the entering arc joins the work list unless its node is in it already
+NSX_FN void nsx_star_close(const NsxDev& d, NsxCtl& c) {
+    if (!c.star_on || !c.star_valid) return;
+    const int32_t x = c.star_extra;
+    c.star_ne = c.star_nd;
+    if (x >= 0 && d.dstamp[x] != c.star_round) {
+        int32_t* info = d.dinfo + 8 * c.star_nd;
+        const int32_t rb = d.row_begin[x];
+        info[0] = x; info[1] = rb; info[2] = d.row_begin[x + 1] - rb; info[3] = 0; info[4] = 0;
+        c.star_ne = c.star_nd + 1;
+    }
+}
+
 template <bool BLK>
 NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScratch& ps, int32_t e,
                      int32_t dir, int32_t want_weight) {
@@ -835,7 +852,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             c.star_round++;
             c.star_nd = 0;
             c.star_extra = d.tail[e];
-            if (c.star_valid) { NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0; d.rc[d.tail[e]] = none; }
+            if (c.star_valid) { NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = c.star_round; d.rc[d.tail[e]] = none; }
         }
     }
     // ---- 1. walk both sides up to the join ------------------------------------------------
@@ -1086,7 +1103,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     }
     NSX_SYNC();
     NSX_PH(c, 4, tph);
-    if (leave == e) return 0;  // tree unchanged
+    if (leave == e) {  // tree unchanged
+        NSX_SINGLE { nsx_star_close(d, c); }
+        return 0;
+    }
 
     // ---- 5. tree update: re-hang the subtree below the leaving arc under the entering arc --
     // stem s_0 = q (entering endpoint inside the cut subtree) ... s_k = r (its pred arc leaves)
@@ -1246,12 +1266,16 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             const int32_t round = c.star_round;
             NSX_PAR_FOR(j, 0, sz) {
                 const int32_t v = seq[j];
-                NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0;
+                NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = round;
                 d.dlist[j] = v; d.dstamp[v] = round; d.rc[v] = none;
+                int32_t* info = d.dinfo + 8 * j;
+                const int32_t rb = d.row_begin[v], cb = d.col_begin[v];
+                info[0] = v; info[1] = rb; info[2] = d.row_begin[v + 1] - rb; info[3] = cb; info[4] = d.col_begin[v + 1] - cb;
             }
             NSX_SINGLE { c.star_nd = sz; }
         }
         NSX_SYNC();
+        NSX_SINGLE { nsx_star_close(d, c); }
     }
     NSX_PH(c, 8, tph);
 
@@ -1708,7 +1732,7 @@ NSX_FN void nsx_drv_dantzig_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
     if (!c.star_on) return;
     if (c.star_valid && c.star_pending <= 1) {
         cmd.kind = NSX_CMD_STAR;
-        cmd.lo = c.star_pending ? c.star_nd : 0; cmd.hi = c.star_round;
+        cmd.lo = c.star_pending ? c.star_ne : 0; cmd.hi = c.star_round;
         cmd.excluded = c.star_pending ? c.star_extra : -1;
     } else {
         cmd.kind = NSX_CMD_STAR_BUILD;

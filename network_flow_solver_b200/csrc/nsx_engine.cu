@@ -914,12 +914,12 @@ __device__ __forceinline__ bool nsx_rc_cas(NsxRC* addr, const NsxRC& expect, con
     old.key = __longlong_as_double((long long)o0); old.arc2 = (int32_t)(uint32_t)o1; old.pad = (int32_t)(o1 >> 32);
     return o0 == e0 && o1 == e1;
 }
-__device__ __forceinline__ NsxRC nsx_rc_none() { NsxRC r; r.key = 0.0; r.arc2 = -1; r.pad = 0; return r; }
+__device__ __forceinline__ NsxRC nsx_rc_none(int32_t pad) { NsxRC r; r.key = 0.0; r.arc2 = -1; r.pad = pad; return r; }
 // lower the row to (key, arc2) unless it already holds something at least as good
 __device__ __forceinline__ void nsx_rc_propose(NsxRC* row, double key, int32_t arc2, NsxRC cur) {
     for (;;) {
         if (!nsx_rc_better(key, arc2, cur)) return;
-        NsxRC want; want.key = key; want.arc2 = arc2; want.pad = 0;
+        NsxRC want; want.key = key; want.arc2 = arc2; want.pad = cur.pad;
         NsxRC old;
         if (nsx_rc_cas(row, cur, want, old)) return;
         cur = old;
@@ -960,199 +960,198 @@ __device__ __forceinline__ void nsx_star_warp_min(double& key, int32_t& arc2) {
         if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
     }
 }
-// Price row v afresh (its cache entry has been emptied): rows of at least `wide` arcs by the whole CTA (every warp
-// proposes its own best), shorter ones by the calling warp alone.  `whole_cta`: all threads of the CTA are calling.
-__device__ __forceinline__ void nsx_star_price_row(const NsxDev& d, int32_t phase, int32_t v, bool whole_cta, int64_t& evaluated) {
-    const int64_t lo = d.row_begin[v], hi = d.row_begin[v + 1];
-    if (hi <= lo) return;
-    const double pv = __ldcg(d.pi + v);
-    double key = 0.0; int32_t arc2 = -1;
-    if (whole_cta) nsx_star_price_row_part(d, phase, pv, lo, hi, (int)threadIdx.x, (int)blockDim.x, key, arc2);
-    else nsx_star_price_row_part(d, phase, pv, lo, hi, (int)(threadIdx.x & 31), 32, key, arc2);
-    nsx_star_warp_min(key, arc2);
-    if ((threadIdx.x & 31) == 0) {
-        if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
-        if (!whole_cta || threadIdx.x == 0) evaluated += hi - lo;
+// Work entries of one batch in shared memory: entry q is a row (out-arcs of ent_v[q]: arc indices) or a column (in-arcs:
+// indices into the CSC copy), ent_lo / ent_n its index range; pfx[q] = work items (chunks of NSX_STAR_CH) before entry q.
+struct NsxStarTab {
+    int32_t* v; int32_t* lo; int32_t* n; int32_t* pfx;  // [NSX_STAR_ENT], pfx [NSX_STAR_ENT + 1]; column entries carry v | 0x80000000
+};
+#define NSX_STAR_ENT (2 * NSX_STAR_BATCH)
+// pfx[1 .. E] holds the chunk counts on entry: turn them into inclusive sums (pfx[0] = 0).  All threads of the CTA.
+__device__ __forceinline__ void nsx_star_scan(int32_t* pfx, int32_t E, NsxCtaShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int32_t per_t = (E + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+    const int32_t q0 = 1 + tid * per_t, q1 = q0 + per_t < E + 1 ? q0 + per_t : E + 1;
+    int32_t sum = 0;
+    for (int32_t q = q0; q < q1; ++q) sum += pfx[q];
+    int32_t incl = sum;
+    __syncwarp();
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+    int32_t* wsum = reinterpret_cast<int32_t*>(sh.dz_buf);  // (32 ints of scratch)
+    if (lane == 31) wsum[warp] = incl;
+    NSX_SYNC();
+    if (warp == 0) {
+        const int32_t w = lane < nwarp ? wsum[lane] : 0;
+        int32_t wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += o; }
+        wsum[lane] = wi - w;
+    }
+    NSX_SYNC();
+    int32_t run = wsum[warp] + incl - sum;
+    for (int32_t q = q0; q < q1; ++q) { run += pfx[q]; pfx[q] = run; }
+    NSX_SYNC();
+}
+// The work items of the E entries in `tab`, dealt to the warps gw, gw + GW, ... (phase A / B: all warps of all workers;
+// build: the warps of this CTA).  Rows propose their chunk's best to the row cache; in-arcs follow the marking rule.
+__device__ __forceinline__ void nsx_star_items(const NsxDev& d, const NsxStar& sp, const NsxStarTab& tab, int32_t E, int32_t phase,
+                                               int32_t round, int32_t extra, int gw, int GW, int64_t& evaluated) {
+    const int lane = threadIdx.x & 31;
+    const double tol = d.tol;
+    const int32_t total = tab.pfx[E];
+    for (int32_t item = gw; item < total; item += GW) {
+        int32_t lo_q = 0, hi_q = E - 1;  // entry q with pfx[q] <= item < pfx[q + 1]
+        while (lo_q < hi_q) { const int32_t mid = (lo_q + hi_q + 1) >> 1; if (tab.pfx[mid] <= item) lo_q = mid; else hi_q = mid - 1; }
+        const int32_t q = lo_q, c = item - tab.pfx[q];
+        const int32_t vraw = tab.v[q], v = vraw & 0x7fffffff;
+        const int32_t lo = tab.lo[q] + c * NSX_STAR_CH, end = tab.lo[q] + tab.n[q], hi = lo + NSX_STAR_CH < end ? lo + NSX_STAR_CH : end;
+        const double pv = __ldcg(d.pi + v);
+        if (vraw >= 0) {  // a chunk of the row of v
+            double key = 0.0; int32_t arc2 = -1;
+            nsx_star_price_row_part(d, phase, pv, lo, hi, lane, 32, key, arc2);
+            nsx_star_warp_min(key, arc2);
+            if (lane == 0) {
+                if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
+                evaluated += hi - lo;
+            }
+        } else {          // a chunk of the in-arcs of v
+            for (int32_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
+                int32_t a[4], i[4]; double ct[4]; uint32_t st[4]; double pt[4]; NsxRC cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t e = e0 + u * 32;
+                    const bool in = e < hi;
+                    a[u] = in ? __ldcs(sp.csc_arc + e) : -1;
+                    i[u] = in ? __ldcs(sp.csc_tail + e) : 0;
+                    ct[u] = !in ? 0.0 : sp.cost_i32 ? (double)__ldcs(reinterpret_cast<const int32_t*>(sp.csc_cost) + e)
+                                                    : __ldcs(reinterpret_cast<const double*>(sp.csc_cost) + e);
+                    st[u] = in ? (uint32_t)__ldcg(d.csc_state + e) : (uint32_t)NSX_ARC_IN_TREE;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { pt[u] = __ldcg(d.pi + i[u]); cur[u] = nsx_rc_load(d.rc + i[u]); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (a[u] < 0 || cur[u].pad == round) continue;  // (the pivot emptied that row this round: it is priced afresh anyway)
+                    const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a[u]), pt[u]), pv);
+                    double key = 0.0;
+                    const int32_t arc2 = nsx_star_candidate(a[u], st[u], rc, tol, &key);
+                    NsxRC* row = d.rc + i[u];
+                    if (cur[u].arc2 >= 0 && (cur[u].arc2 >> 1) == a[u]) {
+                        // the cached arc of the row: still the best when it did not get worse, else the row starts over
+                        NsxRC old;
+                        if (arc2 >= 0 && key <= cur[u].key) {
+                            NsxRC want; want.key = key; want.arc2 = arc2; want.pad = cur[u].pad;
+                            if (!nsx_rc_cas(row, cur[u], want, old)) nsx_rc_propose(row, key, arc2, old);
+                        } else if (nsx_rc_cas(row, cur[u], nsx_rc_none(cur[u].pad), old)) {
+                            sp.rq[atomicAdd(sp.rq_n, 1)] = i[u];
+                        } else if (arc2 >= 0) {
+                            nsx_rc_propose(row, key, arc2, old);  // somebody lowered the row in between: it needs no fresh start
+                        }
+                    } else if (arc2 >= 0) {
+                        nsx_rc_propose(row, key, arc2, cur[u]);
+                    }
+                }
+                if (lane == 0) evaluated += (hi - e0 < 128 ? hi - e0 : 128);
+            }
+        }
     }
 }
-// Rows [r0, r1) of this worker's slice that `pick(v)` selects are priced afresh: short rows warp by warp, long rows
-// by the whole CTA.  Called by every thread of the CTA.
-template <class Pick>
-__device__ __forceinline__ void nsx_star_price_rows(const NsxDev& d, int32_t phase, int32_t r0, int32_t r1, Pick pick,
-                                                    int64_t& evaluated) {
-    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int32_t wide = 1024;
-    for (int32_t v = r0 + warp; v < r1; v += nwarp) {
-        if (!pick(v)) continue;
-        if (d.row_begin[v + 1] - d.row_begin[v] < wide) nsx_star_price_row(d, phase, v, false, evaluated);
+// barrier over the worker CTAs (thread 0 arrives with a release and acquires the count); false when the deadline passed
+__device__ __forceinline__ bool nsx_star_barrier(const NsxStar& sp, NsxCtaShared& sh, uint32_t& bar_rounds, int nworkers,
+                                                 unsigned long long spin_ns) {
+    NSX_SYNC();
+    ++bar_rounds;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sp.bar) : "memory");
+        const unsigned int target = bar_rounds * (unsigned int)nworkers;
+        const unsigned long long t0 = nsx_globaltimer();
+        uint32_t spins = 0;
+        while ((unsigned int)nsx_ld_acquire(reinterpret_cast<const int32_t*>(sp.bar)) < target) {
+            if ((++spins & 1023u) == 0 && nsx_globaltimer() - t0 > spin_ns) { sh.x_fault = 6; break; }
+        }
+        sh.tk_cnt = __ldcg(sp.rq_n);  // (tk_cnt: idle during star commands) rows queued so far, the same number on every worker
     }
-    for (int32_t v = r0; v < r1; ++v) {  // (block-uniform control flow)
-        if (!pick(v)) continue;
-        if (d.row_begin[v + 1] - d.row_begin[v] >= wide) nsx_star_price_row(d, phase, v, true, evaluated);
-    }
+    NSX_SYNC();
+    return sh.x_fault != 6;
 }
 
 // One star command on a worker CTA.  Returns the worker's candidate in thread 0's dz; `evaluated` = arcs examined by
-// this thread's warp (lane 0) - summed by the caller.  `fault` is set when the barrier ran past its deadline.
+// this thread's warp (lane 0) - summed by the caller.  `fault` is set when a barrier ran past its deadline.
 __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp, const NsxCmd& cmd, int worker, int nworkers,
                                              unsigned char* dyn, NsxCtaShared& sh, uint32_t& bar_rounds,
                                              unsigned long long spin_ns, NsxCand& dz, int64_t& evaluated, int32_t& fault) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int32_t phase = cmd.phase;
-    const double tol = d.tol;
     if (tid == 0) sh.x_fault = 0;
+    NsxStarTab tab;
+    tab.v = reinterpret_cast<int32_t*>(dyn); tab.lo = tab.v + NSX_STAR_ENT; tab.n = tab.lo + NSX_STAR_ENT; tab.pfx = tab.n + NSX_STAR_ENT;
     // this worker's slice of the rows
     const int32_t per = (d.n + nworkers - 1) / nworkers;
     const int32_t r0 = worker * per < d.n ? worker * per : d.n;
     const int32_t r1 = r0 + per < d.n ? r0 + per : d.n;
+    const int gw = worker * nwarp + warp, GW = nworkers * nwarp;
     NSX_SYNC();
     if (cmd.kind == NSX_CMD_STAR_BUILD) {
-        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) d.rc[v] = nsx_rc_none();
-        NSX_SYNC();
-        nsx_star_price_rows(d, phase, r0 > 1 ? r0 : 1, r1, [](int32_t) { return true; }, evaluated);
+        // every row of the slice, emptied first; the chunks of a batch of rows are dealt to the warps of this CTA
+        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) d.rc[v] = nsx_rc_none(0);
+        __threadfence();  // (rare command) the plain stores are in L2 before any proposal - an L2 atomic - of another thread
+        for (int32_t b0 = r0; b0 < r1; b0 += NSX_STAR_ENT) {
+            const int32_t E = r1 - b0 < NSX_STAR_ENT ? r1 - b0 : NSX_STAR_ENT;
+            NSX_SYNC();
+            for (int32_t q = tid; q < E; q += blockDim.x) {
+                const int32_t rb = d.row_begin[b0 + q], re = d.row_begin[b0 + q + 1];
+                tab.v[q] = b0 + q; tab.lo[q] = rb; tab.n[q] = re - rb; tab.pfx[q + 1] = (re - rb + NSX_STAR_CH - 1) / NSX_STAR_CH;
+            }
+            if (tid == 0) tab.pfx[0] = 0;
+            NSX_SYNC();
+            nsx_star_scan(tab.pfx, E, sh);
+            nsx_star_items(d, sp, tab, E, phase, 0, -1, warp, nwarp, evaluated);
+        }
     } else {
-        const int32_t nd = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
-        const bool extra_row = extra >= 0 && __ldcg(d.dstamp + extra) != round;
-        const int32_t nitems_nodes = nd + (extra_row ? 1 : 0);
-        int32_t* pfx = reinterpret_cast<int32_t*>(dyn);  // [2 * NSX_STAR_BATCH + 1] work-item prefix sums
-        const int gw = worker * nwarp + warp, GW = nworkers * nwarp;
-        // ---- phase A ----
-        for (int32_t b0 = 0; b0 < nitems_nodes; b0 += NSX_STAR_BATCH) {
-            const int32_t bn = nitems_nodes - b0 < NSX_STAR_BATCH ? nitems_nodes - b0 : NSX_STAR_BATCH;
+        const int32_t ne = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+        const int4* info = reinterpret_cast<const int4*>(d.dinfo);
+        // ---- phase A: rows and in-arcs of the listed nodes (the pivot CTA wrote their index ranges to dinfo) ----
+        for (int32_t b0 = 0; b0 < ne; b0 += NSX_STAR_BATCH) {
+            const int32_t bn = ne - b0 < NSX_STAR_BATCH ? ne - b0 : NSX_STAR_BATCH;
             NSX_SYNC();
-            // entry 2k: out-chunks of node k of the batch, entry 2k+1: its in-chunks (none for the extra row)
-            for (int32_t q = tid; q < 2 * bn; q += blockDim.x) {
-                const int32_t k = b0 + (q >> 1);
-                const int32_t v = k < nd ? __ldcg(d.dlist + k) : extra;
-                int32_t cnt;
-                if (q & 1) cnt = k < nd ? (d.col_begin[v + 1] - d.col_begin[v] + NSX_STAR_CH - 1) / NSX_STAR_CH : 0;
-                else cnt = (d.row_begin[v + 1] - d.row_begin[v] + NSX_STAR_CH - 1) / NSX_STAR_CH;
-                pfx[q + 1] = cnt;
+            for (int32_t k = tid; k < bn; k += blockDim.x) {
+                const int4 x = __ldcg(info + 2 * (b0 + k)), y = __ldcg(info + 2 * (b0 + k) + 1);  // {v, row lo, row n, col lo} {col n, ...}
+                tab.v[2 * k] = x.x; tab.lo[2 * k] = x.y; tab.n[2 * k] = x.z; tab.pfx[2 * k + 1] = (x.z + NSX_STAR_CH - 1) / NSX_STAR_CH;
+                tab.v[2 * k + 1] = x.x | (int32_t)0x80000000; tab.lo[2 * k + 1] = x.w; tab.n[2 * k + 1] = y.x;
+                tab.pfx[2 * k + 2] = (y.x + NSX_STAR_CH - 1) / NSX_STAR_CH;
             }
-            if (tid == 0) pfx[0] = 0;
+            if (tid == 0) tab.pfx[0] = 0;
             NSX_SYNC();
-            // inclusive scan of pfx[1 .. 2bn] (<= 4096 entries): 8 per thread, then the thread totals
-            {
-                const int32_t per_t = (2 * bn + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
-                const int32_t q0 = 1 + tid * per_t, q1 = q0 + per_t < 2 * bn + 1 ? q0 + per_t : 2 * bn + 1;
-                int32_t sum = 0;
-                for (int32_t q = q0; q < q1; ++q) sum += pfx[q];
-                int32_t incl = sum;
-                __syncwarp();
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-                int32_t* wsum = reinterpret_cast<int32_t*>(sh.dz_buf);  // (32 ints of scratch)
-                if (lane == 31) wsum[warp] = incl;
-                NSX_SYNC();
-                if (warp == 0) {
-                    const int32_t w = lane < nwarp ? wsum[lane] : 0;
-                    int32_t wi = w;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) { const int32_t o = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += o; }
-                    wsum[lane] = wi - w;
-                }
-                NSX_SYNC();
-                int32_t run = wsum[warp] + incl - sum;
-                for (int32_t q = q0; q < q1; ++q) { run += pfx[q]; pfx[q] = run; }
-            }
-            NSX_SYNC();
-            const int32_t total = pfx[2 * bn];
-            for (int32_t item = gw; item < total; item += GW) {
-                // entry q with pfx[q] <= item < pfx[q + 1]
-                int32_t lo_q = 0, hi_q = 2 * bn - 1;
-                while (lo_q < hi_q) { const int32_t mid = (lo_q + hi_q + 1) >> 1; if (pfx[mid] <= item) lo_q = mid; else hi_q = mid - 1; }
-                const int32_t q = lo_q, c = item - pfx[q], k = b0 + (q >> 1);
-                const int32_t v = k < nd ? __ldcg(d.dlist + k) : extra;
-                if (!(q & 1)) {  // a chunk of the row of v
-                    const int64_t rb = d.row_begin[v], re = d.row_begin[v + 1];
-                    const int64_t lo = rb + (int64_t)c * NSX_STAR_CH, hi = lo + NSX_STAR_CH < re ? lo + NSX_STAR_CH : re;
-                    const double pv = __ldcg(d.pi + v);
-                    double key = 0.0; int32_t arc2 = -1;
-                    nsx_star_price_row_part(d, phase, pv, lo, hi, lane, 32, key, arc2);
-                    nsx_star_warp_min(key, arc2);
-                    if (lane == 0) {
-                        if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
-                        evaluated += hi - lo;
-                    }
-                } else {        // a chunk of the in-arcs of v
-                    const int32_t cb = d.col_begin[v], ce = d.col_begin[v + 1];
-                    const int32_t lo = cb + c * NSX_STAR_CH, hi = lo + NSX_STAR_CH < ce ? lo + NSX_STAR_CH : ce;
-                    const double pv = __ldcg(d.pi + v);
-                    for (int32_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
-                        int32_t a[4], i[4]; double ct[4]; uint32_t st[4]; double pt[4]; int32_t ds[4]; NsxRC cur[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int32_t e = e0 + u * 32;
-                            const bool in = e < hi;
-                            a[u] = in ? __ldcs(sp.csc_arc + e) : -1;
-                            i[u] = in ? __ldcs(sp.csc_tail + e) : 0;
-                            ct[u] = !in ? 0.0 : sp.cost_i32 ? (double)__ldcs(reinterpret_cast<const int32_t*>(sp.csc_cost) + e)
-                                                            : __ldcs(reinterpret_cast<const double*>(sp.csc_cost) + e);
-                            st[u] = in ? (uint32_t)__ldcg(d.csc_state + e) : (uint32_t)NSX_ARC_IN_TREE;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { pt[u] = __ldcg(d.pi + i[u]); ds[u] = __ldcg(d.dstamp + i[u]); cur[u] = nsx_rc_load(d.rc + i[u]); }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (a[u] < 0 || ds[u] == round || i[u] == extra) continue;  // (that row is priced afresh anyway)
-                            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a[u]), pt[u]), pv);
-                            double key = 0.0;
-                            const int32_t arc2 = nsx_star_candidate(a[u], st[u], rc, tol, &key);
-                            NsxRC* row = d.rc + i[u];
-                            if (cur[u].arc2 >= 0 && (cur[u].arc2 >> 1) == a[u]) {
-                                // the cached arc of the row: still the best when it did not get worse, else the row starts over
-                                NsxRC old;
-                                if (arc2 >= 0 && key <= cur[u].key) {
-                                    NsxRC want; want.key = key; want.arc2 = arc2; want.pad = 0;
-                                    if (!nsx_rc_cas(row, cur[u], want, old)) nsx_rc_propose(row, key, arc2, old);
-                                } else if (nsx_rc_cas(row, cur[u], nsx_rc_none(), old)) {
-                                    sp.rq[atomicAdd(sp.rq_n, 1)] = i[u];
-                                } else if (arc2 >= 0) {
-                                    nsx_rc_propose(row, key, arc2, old);  // somebody lowered the row in between: it needs no fresh start
-                                }
-                            } else if (arc2 >= 0) {
-                                nsx_rc_propose(row, key, arc2, cur[u]);
-                            }
-                        }
-                        if (lane == 0) evaluated += (hi - e0 < 128 ? hi - e0 : 128);
-                    }
-                }
-            }
+            nsx_star_scan(tab.pfx, 2 * bn, sh);
+            nsx_star_items(d, sp, tab, 2 * bn, phase, round, extra, gw, GW, evaluated);
         }
-        // ---- every proposal of phase A is in the row cache before anybody reads its slice ----
-        __threadfence();
-        NSX_SYNC();
-        ++bar_rounds;
-        if (tid == 0) {
-            atomicAdd(sp.bar, 1u);
-            const unsigned int target = bar_rounds * (unsigned int)nworkers;
-            const unsigned long long t0 = nsx_globaltimer();
-            uint32_t spins = 0;
-            while ((unsigned int)nsx_ld_acquire(reinterpret_cast<const int32_t*>(sp.bar)) < target) {
-                if ((++spins & 1023u) == 0 && nsx_globaltimer() - t0 > spin_ns) { sh.x_fault = 6; break; }
+        if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
+        // ---- every proposal of phase A is in the row cache (L2 atomics; the CTA barrier plus thread 0's release publish
+        // them to whoever acquires the counter - a per-thread fence here costs tens of microseconds) ----
+        if (!nsx_star_barrier(sp, sh, bar_rounds, nworkers, spin_ns)) fault = 6;
+        if (sh.tl_grid) NSX_TL(sh.tl_grid, 3);
+        // ---- phase B: the queued rows (emptied when they were queued) are priced afresh by all workers ----
+        const int32_t nq = sh.tk_cnt;
+        if (nq > 0 && !fault) {
+            for (int32_t b0 = 0; b0 < nq; b0 += NSX_STAR_ENT) {
+                const int32_t E = nq - b0 < NSX_STAR_ENT ? nq - b0 : NSX_STAR_ENT;
+                NSX_SYNC();
+                for (int32_t q = tid; q < E; q += blockDim.x) {
+                    const int32_t v = __ldcg(sp.rq + b0 + q);
+                    const int32_t rb = d.row_begin[v], re = d.row_begin[v + 1];
+                    tab.v[q] = v; tab.lo[q] = rb; tab.n[q] = re - rb; tab.pfx[q + 1] = (re - rb + NSX_STAR_CH - 1) / NSX_STAR_CH;
+                }
+                if (tid == 0) tab.pfx[0] = 0;
+                NSX_SYNC();
+                nsx_star_scan(tab.pfx, E, sh);
+                nsx_star_items(d, sp, tab, E, phase, round, extra, gw, GW, evaluated);
             }
-        }
-        NSX_SYNC();
-        if (sh.x_fault == 6) fault = 6;
-        // ---- phase B: queued rows of this slice ----
-        const int32_t nq = __ldcg(sp.rq_n);
-        if (nq > 0) {
-            // mark the queued rows of this slice in shared memory (slice bitmap), then price them
-            uint32_t* bits = reinterpret_cast<uint32_t*>(dyn);
-            const int32_t words = (r1 - r0 + 31) / 32;
-            for (int32_t w = tid; w < words; w += blockDim.x) bits[w] = 0u;
-            NSX_SYNC();
-            for (int32_t k = tid; k < nq; k += blockDim.x) {
-                const int32_t v = __ldcg(sp.rq + k);
-                if (v >= r0 && v < r1) atomicOr(&bits[(v - r0) >> 5], 1u << ((v - r0) & 31));
-            }
-            NSX_SYNC();
-            nsx_star_price_rows(d, phase, r0, r1, [bits, r0](int32_t v) { return ((bits[(v - r0) >> 5] >> ((v - r0) & 31)) & 1u) != 0u; }, evaluated);
+            if (!nsx_star_barrier(sp, sh, bar_rounds, nworkers, spin_ns)) fault = 6;
         }
     }
     // ---- minimum over this worker's slice of the row cache ----
-    __threadfence();
     NSX_SYNC();
+    if (sh.tl_grid) NSX_TL(sh.tl_grid, 4);
     nsx_cand_init(dz);
     for (int32_t v = r0 + tid; v < r1; v += blockDim.x) {
         const NsxRC r = nsx_rc_load(d.rc + v);
@@ -1178,6 +1177,7 @@ struct GridSweep {
     unsigned long long xseq, t_xchg;
     unsigned long long spin_ns;  // deadline of every wait in this functor
     const NsxStar& star;
+    int timeline;   // accumulate the handshake timeline (two global read-modify-writes per sweep on the critical path)
 
     // Candidates of the other GPUs.  Called by ALL threads of the pivot CTA; thread 0 holds the local best in kz / kx
     // and receives the merged best.  A deadline or a raised abort word ends in c.fault (and tells the peers).
@@ -1350,7 +1350,7 @@ struct GridSweep {
             if (threadIdx.x == 0 && shd.world > 1) nsx_raise_peer_aborts(shd);
             return;
         }
-        if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; g->tl[6] += nsx_globaltimer() - g->t_pub; }
+        if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; if (timeline) g->tl[6] += nsx_globaltimer() - g->t_pub; }
         if (starcmd && threadIdx.x == 0) {
             c.star_evaluated = (int64_t)*reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]);
             if (cmd.kind == NSX_CMD_STAR) c.star_rescans += __ldcg(star.rq_n);
@@ -1363,7 +1363,7 @@ struct GridSweep {
         if (devex) nsx_block_reduce(kx, sh.dx_buf); else nsx_block_reduce(kz, sh.dz_buf);
         if (shd.world > 1) exchange_all(devex, kz, kx, c);
         if (threadIdx.x == 0) { if (devex) out_dx = kx; else out_dz = kz; }
-        if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; g->tl[7] += nsx_globaltimer() - g->t_pub; }
+        if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; if (timeline) g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
     }
     __device__ __forceinline__ void finish() {
@@ -1393,6 +1393,7 @@ struct NsxKernelArgs {
     int32_t probe_sweeps;  // > 0: measurement aid, run this many sweeps of the initial state and stop
     NsxShard shard;        // world == 1: single GPU
     NsxStar star;          // star pricing (on == 0: full sweeps)
+    int32_t timeline;      // measurement aid: record the handshake timeline (nsx_result.handshake_ns); sweep probes and NSX_TIMELINE=1
     unsigned long long spin_ns;  // deadline of device-side waits (nsx_options.spin_timeout_ms)
 };
 
@@ -1465,7 +1466,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns, a.star};
+        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns, a.star, a.timeline};
         if (a.probe_sweeps > 0) nsx_probe_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -1481,7 +1482,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         return;
     }
     // worker CTAs: wait for a command, price, deliver, repeat
-    if (threadIdx.x == 0) sh.tl_grid = a.grid;
+    if (threadIdx.x == 0) sh.tl_grid = a.timeline ? a.grid : nullptr;
     double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     unsigned char* ring = dyn + a.wplan.ring_off;
     int32_t seen = 0;
@@ -1502,7 +1503,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
                 sh.cmd.kind = NSX_CMD_EXIT;
             } else {
                 seen = s;
-                NSX_TL(a.grid, 0);
+                if (a.timeline) NSX_TL(a.grid, 0);
                 union { NsxCmd c; int4 v[3]; } tmp;
                 const int4* src = reinterpret_cast<const int4*>(&a.grid->cmd);
                 tmp.v[0] = __ldcg(src); tmp.v[1] = __ldcg(src + 1); tmp.v[2] = __ldcg(src + 2);
@@ -1529,6 +1530,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
                 sl->v[0] = tmp.v;
                 sl->v[1] = make_int4((int)(uint32_t)ev, (int)(uint32_t)(ev >> 32), fault, 0);
                 nsx_st_release(&sl->seq, seen);
+                if (a.timeline) NSX_TL(a.grid, 5);
             }
             continue;
         }
@@ -1546,7 +1548,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             NSX_SYNC();
         }
         if (threadIdx.x == 0) {
-            NSX_TL(a.grid, 4);
+            if (a.timeline) NSX_TL(a.grid, 4);
             NsxSlot* sl = a.slots + blockIdx.x;
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) {
                 union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx;
@@ -1556,7 +1558,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
                 sl->v[0] = tmp.v;
             }
             nsx_st_release(&sl->seq, seen);  // the payload above is ordered before the sequence number
-            NSX_TL(a.grid, 5);
+            if (a.timeline) NSX_TL(a.grid, 5);
         }
     }
 }
@@ -2032,7 +2034,12 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     // Star pricing (row cache instead of full Dantzig sweeps): whenever the driver prices with the Dantzig rule over the
     // whole arc range - Dantzig pricing, or the transportation row scan in front of any rule - on a multi-CTA grid of one
     // GPU, cold start, arcs grouped by tail.  NSX_STAR=0 keeps the full sweeps (what the sweep roofline is quoted on).
-    const bool star = nsx_env_int("NSX_STAR", 1) != 0 && grid > 1 && !shard && !warm && probe_sweeps == 0 && m > 0 && m < (1ll << 30) &&
+    // Default: on when the average degree is moderate (m / n <= 512) - on dense instances (config 3: 2048 arcs per node, ~470
+    // re-hung nodes per pivot) an update touches a tenth of the arcs at several times the bytes per arc and the TMA sweep
+    // of the packed store is as fast; NSX_STAR=1 / 0 forces it on / off.
+    const int star_env = nsx_env_int("NSX_STAR", -1);
+    const bool star_wanted = star_env >= 0 ? star_env != 0 : m / (n > 0 ? n : 1) <= 512;
+    const bool star = star_wanted && grid > 1 && !shard && !warm && probe_sweeps == 0 && m > 0 && m < (1ll << 30) &&
                       !(cost_flags & 8u) && (opt->pricing == NSX_PRICING_DANTZIG || opt->row_scan_first == NSX_SPECIAL_ROW_SCAN);
     const bool star_i32 = !(cost_flags & 1u);  // every cost an exact int32
 
@@ -2054,13 +2061,13 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     size_t o_imb = warm ? arena.plan((size_t)n * 8) : 0;
     size_t o_rc = 0, o_dlist = 0, o_dstamp = 0, o_rowb = 0, o_colb = 0, o_cursor = 0, o_cpos = 0, o_cstate = 0, o_carc = 0, o_ctail = 0,
-           o_ccost = 0, o_rq = 0, o_rqn = 0;
+           o_ccost = 0, o_rq = 0, o_rqn = 0, o_dinfo = 0;
     if (star) {
         o_rc = arena.plan((size_t)n * sizeof(NsxRC)); o_dlist = arena.plan((size_t)n * 4); o_dstamp = arena.plan((size_t)n * 4);
         o_rowb = arena.plan(((size_t)n + 2) * 4); o_colb = arena.plan(((size_t)n + 2) * 4); o_cursor = arena.plan(((size_t)n + 2) * 4);
         o_cpos = arena.plan((size_t)m * 4); o_cstate = arena.plan((size_t)m + 16); o_carc = arena.plan((size_t)m * 4);
         o_ctail = arena.plan((size_t)m * 4); o_ccost = arena.plan((size_t)m * (star_i32 ? 4 : 8));
-        o_rq = arena.plan((size_t)n * 4); o_rqn = arena.plan(256);
+        o_rq = arena.plan((size_t)n * 4); o_rqn = arena.plan(256); o_dinfo = arena.plan(((size_t)n + 1) * 32);
     }
     NSX_CUDA(arena.commit());
 
@@ -2071,9 +2078,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi); d.pi_mirror = nullptr;
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.sidx = arena.at<int32_t>(o_sidx); d.blk = nullptr;  // (the pivot CTA points blk at its shared memory)
-    d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
     memset(&ka.star, 0, sizeof ka.star);
     if (star) {
+        d.dinfo = arena.at<int32_t>(o_dinfo);
         d.rc = arena.at<NsxRC>(o_rc); d.dlist = arena.at<int32_t>(o_dlist); d.dstamp = arena.at<int32_t>(o_dstamp);
         d.row_begin = arena.at<int32_t>(o_rowb); d.col_begin = arena.at<int32_t>(o_colb);
         d.csc_pos = arena.at<int32_t>(o_cpos); d.csc_state = arena.at<uint8_t>(o_cstate);
@@ -2092,6 +2100,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     ka.topk = arena.at<NsxTopkOut>(o_topk);
     ka.trace = want_trace ? arena.at<int32_t>(o_trace) : nullptr;
     ka.probe_sweeps = probe_sweeps;
+    ka.timeline = (probe_sweeps > 0 || nsx_env_int("NSX_TIMELINE", 0)) ? 1 : 0;
     ka.spin_ns = nsx_spin_ns(opt);
     memset(&ka.shard, 0, sizeof ka.shard);
     ka.shard.rank = 0; ka.shard.world = 1;
@@ -2132,6 +2141,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     if (ka.plan.stages > max_stages) ka.plan.stages = max_stages;
     if (ka.wplan.stages > max_stages) ka.wplan.stages = max_stages;
     size_t dyn = nsx_plan_bytes(ka.plan, st.stage_bytes);
+    if (star && dyn < (size_t)(4 * NSX_STAR_ENT + 1) * 4 + 64) dyn = (size_t)(4 * NSX_STAR_ENT + 1) * 4 + 64;  // star work tables of a worker
     if (grid > 1 && nsx_plan_bytes(ka.wplan, st.stage_bytes) > dyn) dyn = nsx_plan_bytes(ka.wplan, st.stage_bytes);
     const size_t smem = fixed + dyn;
     if (smem > info.smem_optin || (grid == 1 ? ka.plan.stages : ka.wplan.stages) < 2) {
@@ -2408,6 +2418,8 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.penalty = p.penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
         d.node_mask = nullptr; d.imbalance = nullptr;
         d.blk = nullptr; d.sidx = arena.at<int32_t>(o.sidx);
+        d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr;
+        d.csc_pos = nullptr; d.csc_state = nullptr;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);
         items[i].mpad = nsx_pad_tiles((int64_t)m);

@@ -11,24 +11,23 @@ if str(ROOT) not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: longer CPU-only checks")
-    config.addinivalue_line("markers", "gpu_unverified: GPU test of device code that has not run on hardware yet; ordered last")
 
 
-# Order of the GPU run (pytest -x stops at the first failure): first the suites that have been green on a B200, oldest
-# evidence first; then suites that feed new INPUTS to device code already validated on hardware; last (marker
-# gpu_unverified) the tests of device code that could not be run on a B200 in the round it was written, so that a failure
-# there cannot mask the results before it.
-HARDWARE_PROVEN = ["test_gpu_parity", "test_gpu_full_size", "test_dimacs", "test_next_candidate_list", "test_next_scaling",
-                   "test_io_and_adapter", "test_properties"]
+# Order of the GPU run (pytest -x stops at the first failure): the suites with the longest record on B200s first (every GPU
+# test of round 1 - 396 of them - passed on hardware in the driver's round-end run, GPUTEST_r01.json), the newest device code
+# (sharded ranks on one device, star pricing) last, so that a failure there cannot mask the results before it.
+ORDER = ["test_gpu_parity", "test_gpu_full_size", "test_dimacs", "test_next_candidate_list", "test_next_scaling",
+         "test_io_and_adapter", "test_properties"]
+NEWEST = ["test_gpu_star_pricing", "test_gpu_sharded"]
 
 
 def pytest_collection_modifyitems(config, items):
     def rank(it):
-        if it.get_closest_marker("gpu_unverified"):
-            return len(HARDWARE_PROVEN) + 1
         if not it.get_closest_marker("gpu"):
             return -1  # CPU tests keep their place in front
         name = it.module.__name__.split(".")[-1]
-        return HARDWARE_PROVEN.index(name) if name in HARDWARE_PROVEN else len(HARDWARE_PROVEN)
+        if name in NEWEST:
+            return len(ORDER) + 1 + NEWEST.index(name)
+        return ORDER.index(name) if name in ORDER else len(ORDER)
 
     items.sort(key=rank)  # stable

@@ -62,7 +62,14 @@ struct SerialSweep {
         if (cmd.kind == NSX_CMD_STAR_BUILD) {
             for (int32_t v = 1; v < d.n; ++v) { d.rc[v] = none; price_row(v, cmd.phase, evaluated); }
         } else {
-            const int32_t nd = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+            const int32_t ne = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+            const int32_t nd = (extra >= 0 && d.dstamp[extra] != round) ? ne - 1 : ne;  // (the last entry is the row of the entering arc)
+            for (int32_t k = 0; k < ne; ++k) {  // the work list the pivot wrote for the sweep workers
+                const int32_t* info = d.dinfo + 8 * k;
+                const int32_t v = k < nd ? d.dlist[k] : extra;
+                if (info[0] != v || info[1] != d.row_begin[v] || info[2] != d.row_begin[v + 1] - d.row_begin[v] ||
+                    info[4] != (k < nd ? d.col_begin[v + 1] - d.col_begin[v] : 0) || (k < nd && info[3] != d.col_begin[v])) abort();
+            }
             for (int32_t k = 0; k < nd; ++k) price_row(d.dlist[k], cmd.phase, evaluated);  // (reset by the pivot)
             if (extra >= 0 && d.dstamp[extra] != round) price_row(extra, cmd.phase, evaluated);
             std::vector<int32_t> rq;
@@ -71,7 +78,8 @@ struct SerialSweep {
                 for (int32_t e = d.col_begin[v]; e < d.col_begin[v + 1]; ++e) {
                     const int64_t a = csc_arc[e];
                     const int32_t i = d.tail[a];
-                    if (d.dstamp[i] == round || i == extra) continue;  // that row is priced afresh anyway
+                    if (d.rc[i].pad == round) continue;  // the pivot emptied that row (its node is listed, or it is the row of the entering arc): priced afresh anyway
+                    if (d.dstamp[i] == round || i == extra) abort();  // (the two ways of saying it agree)
                     const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(cmd.phase, d.pert[a], a), d.pi[i]), d.pi[v]);
                     double key = 0.0;
                     const int32_t arc2 = nsx_star_candidate(a, d.csc_state[e], rc, d.tol, &key);
@@ -79,7 +87,7 @@ struct SerialSweep {
                     const NsxRC cur = d.rc[i];
                     if (cur.arc2 >= 0 && (cur.arc2 >> 1) == a) {  // the cached arc of the row changed its reduced cost
                         if (arc2 >= 0 && key <= cur.key) { d.rc[i].key = key; d.rc[i].arc2 = arc2; }
-                        else { d.rc[i] = none; rq.push_back(i); }
+                        else { d.rc[i].key = 0.0; d.rc[i].arc2 = -1; rq.push_back(i); }
                     } else if (arc2 >= 0 && nsx_rc_better(key, arc2, cur)) {
                         d.rc[i].key = key; d.rc[i].arc2 = arc2;
                     }
@@ -213,16 +221,18 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     const char* sp = getenv("NSX_EMU_STAR");
     const bool star = sp && *sp && atoi(sp) != 0 && !warm;
     std::vector<NsxRC> rcache(star ? n : 0);
+    std::vector<int32_t> dinfo(star ? 8 * ((size_t)n + 1) : 0);
     std::vector<int32_t> dlist(star ? n : 0), dstamp(star ? n : 0, 0), row_begin(star ? n + 1 : 0, 0), col_begin(star ? n + 1 : 0, 0),
         csc_pos(star ? (size_t)m : 0), csc_arc(star ? (size_t)m : 0);
     std::vector<uint8_t> csc_state(star ? (size_t)m : 0);
-    d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
     if (star) {
         for (int64_t a = 0; a + 1 < m; ++a) if (pb->tail[a] > pb->tail[a + 1]) return -8;  // rows need arcs sorted by tail
         for (int64_t a = 0; a < m; ++a) { row_begin[pb->tail[a] + 1]++; col_begin[pb->head[a] + 1]++; }
         for (int32_t v = 0; v < n; ++v) { row_begin[v + 1] += row_begin[v]; col_begin[v + 1] += col_begin[v]; }
         std::vector<int32_t> cur(col_begin.begin(), col_begin.end() - 1);
         for (int64_t a = 0; a < m; ++a) { const int32_t e = cur[pb->head[a]]++; csc_arc[e] = (int32_t)a; csc_pos[a] = e; }
+        d.dinfo = dinfo.data();
         d.rc = rcache.data(); d.dlist = dlist.data(); d.dstamp = dstamp.data(); d.row_begin = row_begin.data();
         d.col_begin = col_begin.data(); d.csc_pos = csc_pos.data(); d.csc_state = csc_state.data();
         c.star_on = 1;

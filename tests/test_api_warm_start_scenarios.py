@@ -12,7 +12,7 @@ from oracle import oracle
 
 BACKENDS = [
     "oracle",
-    pytest.param("engine", marks=[pytest.mark.gpu, pytest.mark.gpu_unverified, pytest.mark.timeout(300, method="thread")]),
+    pytest.param("engine", marks=[pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]),
 ]
 
 

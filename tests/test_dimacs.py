@@ -109,7 +109,6 @@ def test_engine_reproduces_reference_on_dimacs_instances(name, i):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("name,i", [r for r in solvable_runs() if CASES[r[0]]["runs"][r[1]]["network_type"] in STRUCTURE_RULES])
 def test_engine_reproduces_reference_on_dimacs_instances_with_structure_rules(name, i):

@@ -33,6 +33,7 @@ def test_star_pricing_enters_the_arcs_of_the_full_sweeps(family, make, pricing, 
     cp = make().canonical(eps_base=0.0) if eps0 else make().canonical()
     opts = engine_options(cp, pricing)
     want = oracle.solve_canonical(cp, opts, threads=4)
+    monkeypatch.setenv("NSX_STAR", "1")  # (the default turns it on for sparse instances only)
     got = _capi.solve_canonical(cp, opts)
     assert got.stats["grid"] > 1 and got.stats["star_pricing"] == 1
     assert got.stats["star_updates"] > 0 and got.stats["star_builds"] >= 1
@@ -44,7 +45,8 @@ def test_star_pricing_enters_the_arcs_of_the_full_sweeps(family, make, pricing, 
     assert_same_solution(full, want)
 
 
-def test_star_pricing_iteration_limits_and_repeatability():
+def test_star_pricing_iteration_limits_and_repeatability(monkeypatch):
+    monkeypatch.setenv("NSX_STAR", "1")
     cp = gen.netgen_like(4096, 1 << 17, n_sources=32, n_sinks=32, seed=21).canonical()
     full = oracle.solve_canonical(cp, engine_options(cp, 0), threads=4)
     for limit in (1, 5, full.phase1_iterations, full.phase1_iterations + 1, full.iterations - 1):

@@ -43,7 +43,6 @@ def test_emulated_device_core_matches_reference(name, i):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("name,i", RUNS)
 def test_engine_matches_reference(name, i):

@@ -40,7 +40,6 @@ def test_emulated_device_core_reproduces_the_record(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(1800, method="thread")
 @pytest.mark.parametrize("name", NAMES)
 def test_engine_reproduces_the_record(name):

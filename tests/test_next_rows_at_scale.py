@@ -97,7 +97,6 @@ def test_emulated_core_agrees_with_oracle_on_warm_starts(n, m, seed, pricing, dr
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(600, method="thread")
 @pytest.mark.parametrize("name,make,pricing", SCANS)
 def test_engine_agrees_with_oracle_on_scan_rules(name, make, pricing):
@@ -105,7 +104,6 @@ def test_engine_agrees_with_oracle_on_scan_rules(name, make, pricing):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(600, method="thread")
 @pytest.mark.parametrize("n,m,seed,pricing,drop_every", WARM)
 def test_engine_agrees_with_oracle_on_warm_starts(n, m, seed, pricing, drop_every):

@@ -121,7 +121,6 @@ def test_emulated_device_core_matches_reference(name, i):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("name,i", RUNS)
 def test_engine_matches_reference(name, i):
@@ -130,7 +129,6 @@ def test_engine_matches_reference(name, i):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 def test_public_api_picks_the_rule_by_itself(capsys):
     for name in ("assignment_16", "max_flow_48_unit_cost", "shortest_path_96"):

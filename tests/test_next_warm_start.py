@@ -119,7 +119,6 @@ def test_c_abi_rejects_malformed_warm_starts():
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("name,i", SOLVED)
 def test_engine_warm_solve_matches_reference(name, i):
@@ -127,7 +126,6 @@ def test_engine_warm_solve_matches_reference(name, i):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 @pytest.mark.parametrize("grid", ["2", "7"])
 def test_engine_warm_solve_on_a_multi_cta_grid(grid, monkeypatch):
@@ -137,7 +135,6 @@ def test_engine_warm_solve_on_a_multi_cta_grid(grid, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_unverified
 @pytest.mark.timeout(300, method="thread")
 def test_public_api_incremental_resolve(capsys):
     """solve -> edit costs -> solve(warm_start_basis=previous.basis), as in examples/incremental_resolving_example.py."""
