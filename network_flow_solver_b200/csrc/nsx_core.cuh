@@ -171,7 +171,8 @@ struct NsxDev {
     double* imbalance;         // [n] warm starts only (else null): flow that clamping to a bound added at / removed from
                                // each node - the reference checks conservation after Phase 1 (simplex.py:1575-1598)
     // star pricing (null / unused when it is off)
-    NsxRC* rc;             // [n] row cache
+    NsxRC* rc;             // [n] row cache; Devex: [2n], forward candidates first (key = -merit), backward candidates from n on
+    uint32_t* csc_wgt;     // [m] Devex weights in CSC order (written together with wgt), star pricing under Devex only
     int32_t* dlist;        // [n] nodes whose potential the last pivot changed (its re-hung subtree)
     int32_t* dstamp;       // [n] star round in which the node was last in dlist
     int32_t* dinfo;        // [8 (n + 1)] per listed node {node, first out-arc, out-degree, first CSC entry, in-degree, -, -, -}: what
@@ -211,10 +212,11 @@ struct NsxCtl {
     int32_t need_wfill;   // epoch wrapped: weights must be physically refilled
     int32_t warm;         // started from a caller-supplied tree (nsx_solve_warm): NSX_ARC_STALE bits may be set
     int32_t unbalanced;   // warm start: some node's balance is off by more than tol after Phase 1 (simplex.py:1575-1598)
-    // star pricing: on for this solve / row cache consistent with the state before the pending pivot / pivots since the
+    // star pricing: on for this solve (1 Dantzig rule, 2 Devex with a single block) / row cache consistent with the state before the pending pivot / pivots since the
     // cache was last brought up to date / current round (stamp) / nodes in dlist / row of the entering arc
     int32_t star_on, star_valid, star_pending, star_round, star_nd, star_extra;
-    int32_t star_ne, star_pad;   // entries of dinfo for the next update (star_nd, + 1 when the row of the entering arc is not among them)
+    int32_t star_ne;             // entries of dinfo for the next update (star_nd, + 1 when the row of the entering arc is not among them)
+    int32_t star_excl_prev;      // Devex: arc the last star command left out of the cache (DevexPricing.last_degenerate_arc), -1 none
     int64_t star_evaluated;   // arcs examined by the last star command (reported by the sweep workers)
     int64_t star_updates, star_builds, star_rescans;
     int64_t blk_rebuilds;     // blocked preorder array: fresh layouts
@@ -852,7 +854,11 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             c.star_round++;
             c.star_nd = 0;
             c.star_extra = d.tail[e];
-            if (c.star_valid) { NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = c.star_round; d.rc[d.tail[e]] = none; }
+            if (c.star_valid) {
+                NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = c.star_round;
+                d.rc[d.tail[e]] = none;
+                if (c.star_on == 2) d.rc[d.n + d.tail[e]] = none;
+            }
         }
     }
     // ---- 1. walk both sides up to the join ------------------------------------------------
@@ -1095,7 +1101,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         c.avg_cycle += ncyc - (c.avg_cycle >> 4);  // running mean of the cycle length, scaled by 16
         // Devex weight := number of tree arcs on the tail-head path, written by pricing before
         // the pivot in the reference (simplex_pricing.py:350-352)
-        if (want_weight && e < d.m) d.wgt[e] = (c.wepoch << 24) | (uint32_t)(nh + nt);
+        if (want_weight && e < d.m) {
+            d.wgt[e] = (c.wepoch << 24) | (uint32_t)(nh + nt);
+            if (d.csc_wgt) d.csc_wgt[d.csc_pos[e]] = d.wgt[e];
+        }
         int is_deg = (leave == e) || (fabs(theta) < tol);  // simplex.py:1317
         c.tuner_total++;
         if (is_deg) c.tuner_deg++;
@@ -1268,6 +1277,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                 const int32_t v = seq[j];
                 NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = round;
                 d.dlist[j] = v; d.dstamp[v] = round; d.rc[v] = none;
+                if (c.star_on == 2) d.rc[d.n + v] = none;
                 int32_t* info = d.dinfo + 8 * j;
                 const int32_t rb = d.row_begin[v], cb = d.col_begin[v];
                 info[0] = v; info[1] = rb; info[2] = d.row_begin[v + 1] - rb; info[3] = cb; info[4] = d.col_begin[v + 1] - cb;
@@ -1288,6 +1298,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             c.resets++;
             c.wepoch = (c.wepoch + 1) & 0xffu;
             if (c.wepoch == 0) c.need_wfill = 1;  // epoch tags wrapped: refill physically
+            if (c.star_on == 2) c.star_valid = 0;  // every weight is 1 again: every cached merit is stale
         } else {
             c.ftc++;
         }
@@ -1681,6 +1692,21 @@ NSX_FN void nsx_drv_devex_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
     int64_t en = st + c.bs < m ? st + c.bs : m;
     cmd.kind = NSX_CMD_DEVEX; cmd.phase = c.phase; cmd.lo = st; cmd.hi = en;
     cmd.excluded = c.last_deg; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
+    cmd.pad[0] = 0;
+    if (c.star_on == 2 && c.bs >= m) {
+        // one block = all arcs: the search is an arg-max over everything, kept in the row cache (star pricing).  pad[0] = 1
+        // marks the Devex flavour, pad[1] = arc left out (last_degenerate_arc), pad[2] = arc to put back in (left out by
+        // the previous command, not any more)
+        const int32_t back = (c.star_excl_prev >= 0 && c.star_excl_prev != c.last_deg) ? c.star_excl_prev : -1;
+        cmd.pad[0] = 1; cmd.pad[1] = c.last_deg; cmd.pad[2] = back;
+        if (c.star_valid && c.star_pending <= 1) {
+            cmd.kind = NSX_CMD_STAR;
+            cmd.lo = c.star_pending ? c.star_ne : 0; cmd.hi = c.star_round;
+            cmd.excluded = c.star_pending ? c.star_extra : -1;
+        } else {
+            cmd.kind = NSX_CMD_STAR_BUILD;
+        }
+    }
 }
 NSX_FN void nsx_drv_devex_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cmd) {
     v.stage = NSX_ST_DEVEX;
@@ -1729,7 +1755,8 @@ NSX_FN void nsx_drv_devex_loop_begin(NsxCtl& c, NsxDrv& v, int64_t m, NsxCmd& cm
 NSX_FN void nsx_drv_dantzig_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
     cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
     cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
-    if (!c.star_on) return;
+    cmd.pad[0] = 0;
+    if (c.star_on != 1) return;
     if (c.star_valid && c.star_pending <= 1) {
         cmd.kind = NSX_CMD_STAR;
         cmd.lo = c.star_pending ? c.star_ne : 0; cmd.hi = c.star_round;
@@ -1829,7 +1856,9 @@ NSX_FN void nsx_drv_on_result(NsxCtl& c, NsxDrv& v, int64_t m, const NsxCand& dz
         c.arcs_priced += c.star_evaluated;
         if (cmd.kind == NSX_CMD_STAR) c.star_updates++; else c.star_builds++;
         c.star_valid = 1; c.star_pending = 0;
-        cmd.lo = 0; cmd.hi = m; cmd.excluded = -1;  // (a zero-candidate pass may follow: it sweeps the arc range)
+        cmd.lo = 0; cmd.hi = m;  // (a zero-candidate pass may follow: it sweeps the arc range)
+        cmd.excluded = cmd.pad[0] ? cmd.pad[1] : -1;
+        if (cmd.pad[0]) c.star_excl_prev = cmd.pad[1];
     } else {
         c.arcs_priced += cmd.hi - cmd.lo;
     }
@@ -1944,6 +1973,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
     for (;;) {
         NSX_SYNC();
         const int32_t kind = L.act.kind;
+        sweep.alive();
         NSX_SYNC();
         if (kind == NSX_ACT_SWEEP) {
             sweep.run(L.cmd, L.dz, L.dx, c);
@@ -1966,7 +1996,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             int32_t rc = nsx_pivot<BLK>(d, c, s, ps, L.act.arc, L.act.dir, L.act.want_weight);
             if (c.need_wfill) {  // Devex epoch tags wrapped: physically reset the weights
                 NSX_SYNC();
-                NSX_PAR_FOR(i, 0, d.m) { if (d.wgt) d.wgt[i] = 1u; }
+                NSX_PAR_FOR(i, 0, d.m) { if (d.wgt) d.wgt[i] = 1u; if (d.csc_wgt) d.csc_wgt[i] = 1u; }
                 NSX_SYNC();
                 NSX_SINGLE { c.need_wfill = 0; }
             }

@@ -50,7 +50,8 @@ struct alignas(64) NsxSlot {
 struct NsxGridCtl {
     int32_t seq;  // command sequence number, release-published by CTA 0
     int32_t abort;  // raised by a sweep worker that saw no command before its deadline (fault 4)
-    unsigned long long arrived;  // CTAs (other than 0) that delivered their candidate, cumulative
+    unsigned long long arrived;  // heartbeat of the pivot CTA: bumped once per step of its loop, so that workers waiting for a
+                                 // command can tell "the pivot CTA is busy" (rule scans, long pivots) from "it is gone"
     NsxCmd cmd;
     unsigned long long t_pub;    // globaltimer at the publication of the current command
     unsigned long long tl[8];    // handshake timeline of worker 1, ns after t_pub, accumulated over sweeps
@@ -925,12 +926,35 @@ __device__ __forceinline__ void nsx_rc_propose(NsxRC* row, double key, int32_t a
         cur = old;
     }
 }
-// Out-arcs [lo, hi) of node v, spread over `nth` threads (this thread is `t`): the thread's best candidate in (key, arc2).
-__device__ __forceinline__ void nsx_star_price_row_part(const NsxDev& d, int32_t phase, double pv, int64_t lo, int64_t hi,
-                                                        int t, int nth, double& key, int32_t& arc2) {
-    const double tol = d.tol;
+// One arc under the rule of the command: which cache it is a candidate for (0: the Dantzig cache / Devex forward, 1: Devex
+// backward, -1: none), with its key (Dantzig: the reduced-cost key; Devex: -merit) and arc*2 + (backward).
+struct NsxStarRule {
+    int32_t devex, phase, excluded; uint32_t wepoch; double tol;
+};
+__device__ __forceinline__ int nsx_star_eval(const NsxStarRule& R, int64_t a, uint32_t st, double pert, double pt, double ph,
+                                             uint32_t wraw, double& key, int32_t& arc2) {
+    if (R.devex) {
+        if ((st & NSX_ARC_IN_TREE) || (int32_t)a == R.excluded) return -1;
+        const double rc = NSX_SUB(NSX_ADD(pert, pt), ph);  // Devex prices with the Phase-2 cost in both phases
+        const bool fv = (st & NSX_ARC_CAN_FWD) && rc < -R.tol, bv = (st & NSX_ARC_CAN_BWD) && rc > R.tol;
+        if (!(fv || bv)) return -1;
+        const double w = (wraw >> 24) == R.wepoch ? (double)(wraw & 0xffffffu) : 1.0;
+        key = -NSX_DIV(NSX_MUL(rc, rc), w);
+        arc2 = (int32_t)(a * 2 + (fv ? 0 : 1));
+        return fv ? 0 : 1;
+    }
+    const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(R.phase, pert, a), pt), ph);
+    arc2 = nsx_star_candidate(a, st, rc, R.tol, &key);
+    return arc2 >= 0 ? 0 : -1;
+}
+__device__ __forceinline__ void nsx_star_take(double k2, int32_t c2, double& key, int32_t& arc2) {
+    if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
+}
+// Out-arcs [lo, hi) of node v, spread over `nth` threads (this thread is `t`): the thread's best candidate per cache.
+__device__ __forceinline__ void nsx_star_price_row_part(const NsxDev& d, const NsxStarRule& R, double pv, int64_t lo, int64_t hi,
+                                                        int t, int nth, double (&key)[2], int32_t (&arc2)[2]) {
     for (int64_t a0 = lo + t; a0 < hi; a0 += 4 * (int64_t)nth) {
-        int32_t hd[4]; double ct[4]; uint32_t st[4]; double ph[4];
+        int32_t hd[4]; double ct[4]; uint32_t st[4], wr[4]; double ph[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t a = a0 + (int64_t)u * nth;
@@ -938,16 +962,17 @@ __device__ __forceinline__ void nsx_star_price_row_part(const NsxDev& d, int32_t
             hd[u] = in ? __ldcs(d.head + a) : 0;
             ct[u] = in ? __ldcs(d.pert + a) : 0.0;
             st[u] = in ? (uint32_t)__ldcg(d.state + a) : (uint32_t)NSX_ARC_IN_TREE;
+            wr[u] = (in && R.devex) ? __ldcg(d.wgt + a) : 1u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) ph[u] = __ldcg(d.pi + hd[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t a = a0 + (int64_t)u * nth;
-            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a), pv), ph[u]);
-            double k2 = 0.0;
-            const int32_t c2 = nsx_star_candidate(a, st[u], rc, tol, &k2);
-            if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
+            double k2 = 0.0; int32_t c2 = -1;
+            const int x = nsx_star_eval(R, a, st[u], ct[u], pv, ph[u], wr[u], k2, c2);
+            if (x == 0) nsx_star_take(k2, c2, key[0], arc2[0]);
+            else if (x == 1) nsx_star_take(k2, c2, key[1], arc2[1]);
         }
     }
 }
@@ -957,7 +982,7 @@ __device__ __forceinline__ void nsx_star_warp_min(double& key, int32_t& arc2) {
     for (int off = 16; off > 0; off >>= 1) {
         const double k2 = __shfl_down_sync(0xffffffffu, key, off);
         const int32_t c2 = __shfl_down_sync(0xffffffffu, arc2, off);
-        if (c2 >= 0 && (arc2 < 0 || k2 < key || (k2 == key && c2 < arc2))) { key = k2; arc2 = c2; }
+        nsx_star_take(k2, c2, key, arc2);
     }
 }
 // Work entries of one batch in shared memory: entry q is a row (out-arcs of ent_v[q]: arc indices) or a column (in-arcs:
@@ -994,10 +1019,10 @@ __device__ __forceinline__ void nsx_star_scan(int32_t* pfx, int32_t E, NsxCtaSha
 }
 // The work items of the E entries in `tab`, dealt to the warps gw, gw + GW, ... (phase A / B: all warps of all workers;
 // build: the warps of this CTA).  Rows propose their chunk's best to the row cache; in-arcs follow the marking rule.
-__device__ __forceinline__ void nsx_star_items(const NsxDev& d, const NsxStar& sp, const NsxStarTab& tab, int32_t E, int32_t phase,
-                                               int32_t round, int32_t extra, int gw, int GW, int64_t& evaluated) {
+__device__ __forceinline__ void nsx_star_items(const NsxDev& d, const NsxStar& sp, const NsxStarTab& tab, int32_t E, const NsxStarRule& R,
+                                               int32_t round, int gw, int GW, int64_t& evaluated) {
     const int lane = threadIdx.x & 31;
-    const double tol = d.tol;
+    const int ncache = R.devex ? 2 : 1;
     const int32_t total = tab.pfx[E];
     for (int32_t item = gw; item < total; item += GW) {
         int32_t lo_q = 0, hi_q = E - 1;  // entry q with pfx[q] <= item < pfx[q + 1]
@@ -1007,16 +1032,18 @@ __device__ __forceinline__ void nsx_star_items(const NsxDev& d, const NsxStar& s
         const int32_t lo = tab.lo[q] + c * NSX_STAR_CH, end = tab.lo[q] + tab.n[q], hi = lo + NSX_STAR_CH < end ? lo + NSX_STAR_CH : end;
         const double pv = __ldcg(d.pi + v);
         if (vraw >= 0) {  // a chunk of the row of v
-            double key = 0.0; int32_t arc2 = -1;
-            nsx_star_price_row_part(d, phase, pv, lo, hi, lane, 32, key, arc2);
-            nsx_star_warp_min(key, arc2);
+            double key[2] = {0.0, 0.0}; int32_t arc2[2] = {-1, -1};
+            nsx_star_price_row_part(d, R, pv, lo, hi, lane, 32, key, arc2);
+            nsx_star_warp_min(key[0], arc2[0]);
+            if (R.devex) nsx_star_warp_min(key[1], arc2[1]);
             if (lane == 0) {
-                if (arc2 >= 0) nsx_rc_propose(d.rc + v, key, arc2, nsx_rc_load(d.rc + v));
+                if (arc2[0] >= 0) nsx_rc_propose(d.rc + v, key[0], arc2[0], nsx_rc_load(d.rc + v));
+                if (R.devex && arc2[1] >= 0) nsx_rc_propose(d.rc + d.n + v, key[1], arc2[1], nsx_rc_load(d.rc + d.n + v));
                 evaluated += hi - lo;
             }
         } else {          // a chunk of the in-arcs of v
             for (int32_t e0 = lo + lane; e0 < hi; e0 += 4 * 32) {
-                int32_t a[4], i[4]; double ct[4]; uint32_t st[4]; double pt[4]; NsxRC cur[4];
+                int32_t a[4], i[4]; double ct[4]; uint32_t st[4], wr[4]; double pt[4]; NsxRC cur[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int32_t e = e0 + u * 32;
@@ -1026,29 +1053,34 @@ __device__ __forceinline__ void nsx_star_items(const NsxDev& d, const NsxStar& s
                     ct[u] = !in ? 0.0 : sp.cost_i32 ? (double)__ldcs(reinterpret_cast<const int32_t*>(sp.csc_cost) + e)
                                                     : __ldcs(reinterpret_cast<const double*>(sp.csc_cost) + e);
                     st[u] = in ? (uint32_t)__ldcg(d.csc_state + e) : (uint32_t)NSX_ARC_IN_TREE;
+                    wr[u] = (in && R.devex) ? __ldcg(d.csc_wgt + e) : 1u;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { pt[u] = __ldcg(d.pi + i[u]); cur[u] = nsx_rc_load(d.rc + i[u]); }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (a[u] < 0 || cur[u].pad == round) continue;  // (the pivot emptied that row this round: it is priced afresh anyway)
-                    const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, ct[u], a[u]), pt[u]), pv);
-                    double key = 0.0;
-                    const int32_t arc2 = nsx_star_candidate(a[u], st[u], rc, tol, &key);
-                    NsxRC* row = d.rc + i[u];
-                    if (cur[u].arc2 >= 0 && (cur[u].arc2 >> 1) == a[u]) {
-                        // the cached arc of the row: still the best when it did not get worse, else the row starts over
-                        NsxRC old;
-                        if (arc2 >= 0 && key <= cur[u].key) {
-                            NsxRC want; want.key = key; want.arc2 = arc2; want.pad = cur[u].pad;
-                            if (!nsx_rc_cas(row, cur[u], want, old)) nsx_rc_propose(row, key, arc2, old);
-                        } else if (nsx_rc_cas(row, cur[u], nsx_rc_none(cur[u].pad), old)) {
-                            sp.rq[atomicAdd(sp.rq_n, 1)] = i[u];
-                        } else if (arc2 >= 0) {
-                            nsx_rc_propose(row, key, arc2, old);  // somebody lowered the row in between: it needs no fresh start
+                    double key = 0.0; int32_t arc2 = -1;
+                    const int x = nsx_star_eval(R, a[u], st[u], ct[u], pt[u], pv, wr[u], key, arc2);
+                    bool queued = false;
+                    for (int k = 0; k < ncache; ++k) {
+                        NsxRC* row = d.rc + (size_t)k * d.n + i[u];
+                        const NsxRC have = k == 0 ? cur[u] : nsx_rc_load(row);
+                        if (have.arc2 >= 0 && (have.arc2 >> 1) == a[u]) {
+                            // the cached arc of the row: still the best when it did not get worse, else the row starts over
+                            NsxRC old;
+                            if (x == k && key <= have.key) {
+                                NsxRC want; want.key = key; want.arc2 = arc2; want.pad = have.pad;
+                                if (!nsx_rc_cas(row, have, want, old)) nsx_rc_propose(row, key, arc2, old);
+                            } else if (nsx_rc_cas(row, have, nsx_rc_none(have.pad), old)) {
+                                if (!queued) sp.rq[atomicAdd(sp.rq_n, 1)] = i[u];
+                                queued = true;
+                            } else if (x == k) {
+                                nsx_rc_propose(row, key, arc2, old);  // somebody lowered the row in between: it needs no fresh start
+                            }
+                        } else if (x == k) {
+                            nsx_rc_propose(row, key, arc2, have);
                         }
-                    } else if (arc2 >= 0) {
-                        nsx_rc_propose(row, key, arc2, cur[u]);
                     }
                 }
                 if (lane == 0) evaluated += (hi - e0 < 128 ? hi - e0 : 128);
@@ -1079,9 +1111,12 @@ __device__ __forceinline__ bool nsx_star_barrier(const NsxStar& sp, NsxCtaShared
 // this thread's warp (lane 0) - summed by the caller.  `fault` is set when a barrier ran past its deadline.
 __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp, const NsxCmd& cmd, int worker, int nworkers,
                                              unsigned char* dyn, NsxCtaShared& sh, uint32_t& bar_rounds,
-                                             unsigned long long spin_ns, NsxCand& dz, int64_t& evaluated, int32_t& fault) {
+                                             unsigned long long spin_ns, NsxCand& dz, NsxDevexCand& dx, int64_t& evaluated,
+                                             int32_t& fault) {
     const int tid = threadIdx.x, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int32_t phase = cmd.phase;
+    NsxStarRule R;
+    R.devex = cmd.pad[0]; R.phase = cmd.phase; R.excluded = cmd.pad[0] ? cmd.pad[1] : -1; R.wepoch = cmd.wepoch; R.tol = d.tol;
+    const int ncache = R.devex ? 2 : 1;
     if (tid == 0) sh.x_fault = 0;
     NsxStarTab tab;
     tab.v = reinterpret_cast<int32_t*>(dyn); tab.lo = tab.v + NSX_STAR_ENT; tab.n = tab.lo + NSX_STAR_ENT; tab.pfx = tab.n + NSX_STAR_ENT;
@@ -1093,7 +1128,7 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
     NSX_SYNC();
     if (cmd.kind == NSX_CMD_STAR_BUILD) {
         // every row of the slice, emptied first; the chunks of a batch of rows are dealt to the warps of this CTA
-        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) d.rc[v] = nsx_rc_none(0);
+        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) { d.rc[v] = nsx_rc_none(0); if (R.devex) d.rc[d.n + v] = nsx_rc_none(0); }
         __threadfence();  // (rare command) the plain stores are in L2 before any proposal - an L2 atomic - of another thread
         for (int32_t b0 = r0; b0 < r1; b0 += NSX_STAR_ENT) {
             const int32_t E = r1 - b0 < NSX_STAR_ENT ? r1 - b0 : NSX_STAR_ENT;
@@ -1105,10 +1140,10 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
             if (tid == 0) tab.pfx[0] = 0;
             NSX_SYNC();
             nsx_star_scan(tab.pfx, E, sh);
-            nsx_star_items(d, sp, tab, E, phase, 0, -1, warp, nwarp, evaluated);
+            nsx_star_items(d, sp, tab, E, R, 0, warp, nwarp, evaluated);
         }
     } else {
-        const int32_t ne = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
+        const int32_t ne = (int32_t)cmd.lo, round = (int32_t)cmd.hi;
         const int4* info = reinterpret_cast<const int4*>(d.dinfo);
         // ---- phase A: rows and in-arcs of the listed nodes (the pivot CTA wrote their index ranges to dinfo) ----
         for (int32_t b0 = 0; b0 < ne; b0 += NSX_STAR_BATCH) {
@@ -1123,7 +1158,16 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
             if (tid == 0) tab.pfx[0] = 0;
             NSX_SYNC();
             nsx_star_scan(tab.pfx, 2 * bn, sh);
-            nsx_star_items(d, sp, tab, 2 * bn, phase, round, extra, gw, GW, evaluated);
+            nsx_star_items(d, sp, tab, 2 * bn, R, round, gw, GW, evaluated);
+        }
+        if (R.devex && cmd.pad[2] >= 0 && gw == 0 && (tid & 31) == 0) {
+            // Devex: the arc the previous command left out (last degenerate arc) is a candidate again
+            const int64_t a = cmd.pad[2];
+            const int32_t tl = d.tail[a], hd = d.head[a];
+            double key = 0.0; int32_t arc2 = -1;
+            const int x = nsx_star_eval(R, a, (uint32_t)__ldcg(d.state + a), d.pert[a], __ldcg(d.pi + tl), __ldcg(d.pi + hd), __ldcg(d.wgt + a), key, arc2);
+            if (x >= 0) { NsxRC* row = d.rc + (size_t)x * d.n + tl; nsx_rc_propose(row, key, arc2, nsx_rc_load(row)); }
+            evaluated += 1;
         }
         if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
         // ---- every proposal of phase A is in the row cache (L2 atomics; the CTA barrier plus thread 0's release publish
@@ -1144,7 +1188,7 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
                 if (tid == 0) tab.pfx[0] = 0;
                 NSX_SYNC();
                 nsx_star_scan(tab.pfx, E, sh);
-                nsx_star_items(d, sp, tab, E, phase, round, extra, gw, GW, evaluated);
+                nsx_star_items(d, sp, tab, E, R, round, gw, GW, evaluated);
             }
             if (!nsx_star_barrier(sp, sh, bar_rounds, nworkers, spin_ns)) fault = 6;
         }
@@ -1153,11 +1197,19 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
     NSX_SYNC();
     if (sh.tl_grid) NSX_TL(sh.tl_grid, 4);
     nsx_cand_init(dz);
+    nsx_devex_init(dx);
     for (int32_t v = r0 + tid; v < r1; v += blockDim.x) {
         const NsxRC r = nsx_rc_load(d.rc + v);
-        if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) { dz.key = r.key; dz.arc2 = r.arc2; }
+        if (!R.devex) {
+            if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) { dz.key = r.key; dz.arc2 = r.arc2; }
+        } else {
+            if (r.arc2 >= 0 && (dx.fi < 0 || -r.key > dx.fm || (-r.key == dx.fm && (r.arc2 >> 1) < dx.fi))) { dx.fm = -r.key; dx.fi = r.arc2 >> 1; }
+            const NsxRC b = nsx_rc_load(d.rc + d.n + v);
+            if (b.arc2 >= 0 && (dx.bi < 0 || -b.key > dx.bm || (-b.key == dx.bm && (b.arc2 >> 1) < dx.bi))) { dx.bm = -b.key; dx.bi = b.arc2 >> 1; }
+        }
     }
-    nsx_block_reduce(dz, sh.dz_buf);
+    if (R.devex) nsx_block_reduce(dx, sh.dx_buf); else nsx_block_reduce(dz, sh.dz_buf);
+    (void)ncache;
 }
 
 // Sweep functor of CTA 0.
@@ -1178,6 +1230,7 @@ struct GridSweep {
     unsigned long long spin_ns;  // deadline of every wait in this functor
     const NsxStar& star;
     int timeline;   // accumulate the handshake timeline (two global read-modify-writes per sweep on the critical path)
+    unsigned long long beat;
 
     // Candidates of the other GPUs.  Called by ALL threads of the pivot CTA; thread 0 holds the local best in kz / kx
     // and receives the merged best.  A deadline or a raised abort word ends in c.fault (and tells the peers).
@@ -1295,7 +1348,8 @@ struct GridSweep {
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
         const NsxCmd cmd = cmd_in;
-        const bool devex = cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO;
+        const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
+        const bool devex = cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO || (starcmd && cmd.pad[0]);
         if (gridDim.x == 1) {  // alone: this CTA prices everything itself
             NsxCand dz; NsxDevexCand dx;
             if (threadIdx.x == 0) __threadfence();
@@ -1314,7 +1368,6 @@ struct GridSweep {
             NSX_SYNC();
             return;
         }
-        const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
         if (starcmd && threadIdx.x == 0) { *star.rq_n = 0; *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull; }  // (x_recs: idle on one GPU, holds the evaluated-arc count)
         if (starcmd) NSX_SYNC();
         publish(cmd);
@@ -1337,11 +1390,12 @@ struct GridSweep {
                 union { NsxDevexCand c; int4 v[2]; } tmp;
                 tmp.v[0] = __ldcg(&sl->v[0]); tmp.v[1] = __ldcg(&sl->v[1]);
                 nsx_devex_merge(kx, tmp.c);
+                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); }
             } else {
                 union { NsxCand c; int4 v; } tmp;
                 tmp.v = __ldcg(&sl->v[0]);
                 nsx_cand_merge(kz, tmp.c);
-                if (starcmd) { const int4 w = __ldcg(&sl->v[1]); ev += ((unsigned long long)(uint32_t)w.y << 32) | (uint32_t)w.x; if (w.z) c.fault = w.z; }
+                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); }
             }
         }
         if (starcmd && ev) atomicAdd(reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]), ev);
@@ -1365,6 +1419,10 @@ struct GridSweep {
         if (threadIdx.x == 0) { if (devex) out_dx = kx; else out_dz = kz; }
         if (threadIdx.x == 0) { t_price += nsx_globaltimer() - t0; if (timeline) g->tl[7] += nsx_globaltimer() - g->t_pub; }
         NSX_SYNC();
+    }
+    // once per step of the pivot loop: tells the waiting workers that this CTA is alive
+    __device__ __forceinline__ void alive() {
+        if (threadIdx.x == 0 && gridDim.x > 1) *reinterpret_cast<volatile unsigned long long*>(&g->arrived) = ++beat;
     }
     __device__ __forceinline__ void finish() {
         NsxCmd cmd;
@@ -1466,7 +1524,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         const bool resident = a.plan.mode != NSX_RES_NONE;
         NsxSweepCtx cx{&a.st, (resident || a.plan.stage_pi) ? pis : nullptr, !resident && a.plan.stage_pi != 0,
                        dyn + a.plan.ring_off, a.plan.stages};
-        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns, a.star, a.timeline};
+        GridSweep sweep{d, a.grid, a.slots, a.topk, sh, cx, stage_count, q0, 0, 0ull, 0ull, 0ull, a.shard, 0ull, 0ull, a.spin_ns, a.star, a.timeline, 0ull};
         if (a.probe_sweeps > 0) nsx_probe_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, sweep, a.probe_sweeps);
         else nsx_solve_loop<BLK>(dl, sh.ctl, sh.L, sh.piv, sh.pot, a.trace, sweep);
         NSX_SYNC();
@@ -1492,11 +1550,16 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             int32_t s;
             uint32_t spins = 0;
             bool lost = false;
-            const unsigned long long t_wait = nsx_globaltimer();
-            // the pivot CTA may itself be waiting for a peer GPU (up to spin_ns) between two commands
+            unsigned long long t_wait = nsx_globaltimer(), beat = 0ull;
+            // the deadline runs from the last sign of life of the pivot CTA (it may be waiting for a peer GPU - up to
+            // spin_ns - or scanning arcs itself for a long time between two commands)
             while ((s = nsx_ld_acquire(&a.grid->seq)) == seen) {
                 __nanosleep(20);
-                if ((++spins & 4095u) == 0 && nsx_globaltimer() - t_wait > 4ull * a.spin_ns) { lost = true; break; }
+                if ((++spins & 4095u) == 0) {
+                    const unsigned long long b = *reinterpret_cast<volatile unsigned long long*>(&a.grid->arrived);
+                    if (b != beat) { beat = b; t_wait = nsx_globaltimer(); }
+                    else if (nsx_globaltimer() - t_wait > 4ull * a.spin_ns) { lost = true; break; }
+                }
             }
             if (lost) {
                 atomicExch(&a.grid->abort, 4);
@@ -1517,7 +1580,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
         if (starcmd) {
             int64_t evaluated = 0; int32_t fault = 0;
-            nsx_cta_star(d, a.star, cmd, (int)blockIdx.x - 1, (int)gridDim.x - 1, dyn, sh, bar_rounds, a.spin_ns, dz, evaluated, fault);
+            nsx_cta_star(d, a.star, cmd, (int)blockIdx.x - 1, (int)gridDim.x - 1, dyn, sh, bar_rounds, a.spin_ns, dz, dx, evaluated, fault);
             // arcs examined by this CTA (lane 0 of every warp counted its warp's): summed through shared memory
             if (threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull;
             NSX_SYNC();
@@ -1526,9 +1589,9 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             if (threadIdx.x == 0) {
                 const unsigned long long ev = *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]);
                 NsxSlot* sl = a.slots + blockIdx.x;
-                union { NsxCand c; int4 v; } tmp; tmp.c = dz;
-                sl->v[0] = tmp.v;
-                sl->v[1] = make_int4((int)(uint32_t)ev, (int)(uint32_t)(ev >> 32), fault, 0);
+                if (cmd.pad[0]) { union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx; sl->v[0] = tmp.v[0]; sl->v[1] = tmp.v[1]; }
+                else { union { NsxCand c; int4 v; } tmp; tmp.c = dz; sl->v[0] = tmp.v; }
+                sl->pad[0] = (int32_t)(uint32_t)ev; sl->pad[1] = (int32_t)(uint32_t)(ev >> 32); sl->pad[2] = fault;
                 nsx_st_release(&sl->seq, seen);
                 if (a.timeline) NSX_TL(a.grid, 5);
             }
@@ -1631,11 +1694,12 @@ extern "C" __global__ void nsx_star_scan_kernel(int32_t* a, int32_t* b, int32_t*
 }
 extern "C" __global__ void nsx_star_fill_kernel(const int32_t* tail, const int32_t* head, const double* pert, const uint8_t* state,
                                                 int64_t m, int32_t* cursor, int32_t* csc_arc, int32_t* csc_tail, void* csc_cost,
-                                                int32_t cost_i32, int32_t* csc_pos, uint8_t* csc_state) {
+                                                int32_t cost_i32, int32_t* csc_pos, uint8_t* csc_state, uint32_t* csc_wgt) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, T = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = g; i < m; i += T) {
         const int32_t e = atomicAdd(cursor + head[i], 1);  // (the order inside a column is free: proposals commute)
         csc_arc[e] = (int32_t)i; csc_tail[e] = tail[i]; csc_pos[i] = e; csc_state[e] = state[i];
+        if (csc_wgt) csc_wgt[e] = 1u;  // epoch 0, weight 1 (nsx_init_real_arc)
         if (cost_i32) reinterpret_cast<int32_t*>(csc_cost)[e] = (int32_t)pert[i];
         else reinterpret_cast<double*>(csc_cost)[e] = pert[i];
     }
@@ -1701,6 +1765,7 @@ struct LocalSweep {
         }
         NSX_SYNC();
     }
+    __device__ void alive() {}
     __device__ void finish() {}
 };
 
@@ -2040,7 +2105,10 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     const int star_env = nsx_env_int("NSX_STAR", -1);
     const bool star_wanted = star_env >= 0 ? star_env != 0 : m / (n > 0 ? n : 1) <= 512;
     const bool star = star_wanted && grid > 1 && !shard && !warm && probe_sweeps == 0 && m > 0 && m < (1ll << 30) &&
-                      !(cost_flags & 8u) && (opt->pricing == NSX_PRICING_DANTZIG || opt->row_scan_first == NSX_SPECIAL_ROW_SCAN);
+                      !(cost_flags & 8u) && (opt->pricing == NSX_PRICING_DANTZIG || opt->row_scan_first == NSX_SPECIAL_ROW_SCAN ||
+                                             (opt->pricing == NSX_PRICING_DEVEX && opt->row_scan_first == 0));
+    // Devex (vectorised, no structure rule in front): the row cache holds arg-max candidates whenever one block covers all arcs
+    const bool star_devex = star && opt->pricing == NSX_PRICING_DEVEX && opt->row_scan_first == 0;
     const bool star_i32 = !(cost_flags & 1u);  // every cost an exact int32
 
     // ---- engine-owned device memory ----
@@ -2061,9 +2129,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     size_t o_imb = warm ? arena.plan((size_t)n * 8) : 0;
     size_t o_rc = 0, o_dlist = 0, o_dstamp = 0, o_rowb = 0, o_colb = 0, o_cursor = 0, o_cpos = 0, o_cstate = 0, o_carc = 0, o_ctail = 0,
-           o_ccost = 0, o_rq = 0, o_rqn = 0, o_dinfo = 0;
+           o_ccost = 0, o_rq = 0, o_rqn = 0, o_dinfo = 0, o_cwgt = 0;
     if (star) {
-        o_rc = arena.plan((size_t)n * sizeof(NsxRC)); o_dlist = arena.plan((size_t)n * 4); o_dstamp = arena.plan((size_t)n * 4);
+        o_rc = arena.plan((size_t)n * sizeof(NsxRC) * 2); o_cwgt = star_devex ? arena.plan((size_t)m * 4) : 0; o_dlist = arena.plan((size_t)n * 4); o_dstamp = arena.plan((size_t)n * 4);
         o_rowb = arena.plan(((size_t)n + 2) * 4); o_colb = arena.plan(((size_t)n + 2) * 4); o_cursor = arena.plan(((size_t)n + 2) * 4);
         o_cpos = arena.plan((size_t)m * 4); o_cstate = arena.plan((size_t)m + 16); o_carc = arena.plan((size_t)m * 4);
         o_ctail = arena.plan((size_t)m * 4); o_ccost = arena.plan((size_t)m * (star_i32 ? 4 : 8));
@@ -2078,10 +2146,11 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.node = arena.at<NsxNode>(o_node); d.depth = arena.at<int32_t>(o_depth); d.pi = arena.at<double>(o_pi); d.pi_mirror = nullptr;
     d.order = arena.at<int32_t>(o_order); d.tmp = arena.at<int32_t>(o_tmp);
     d.sidx = arena.at<int32_t>(o_sidx); d.blk = nullptr;  // (the pivot CTA points blk at its shared memory)
-    d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    d.csc_wgt = nullptr; d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
     memset(&ka.star, 0, sizeof ka.star);
     if (star) {
         d.dinfo = arena.at<int32_t>(o_dinfo);
+        d.csc_wgt = star_devex ? arena.at<uint32_t>(o_cwgt) : nullptr;
         d.rc = arena.at<NsxRC>(o_rc); d.dlist = arena.at<int32_t>(o_dlist); d.dstamp = arena.at<int32_t>(o_dstamp);
         d.row_begin = arena.at<int32_t>(o_rowb); d.col_begin = arena.at<int32_t>(o_colb);
         d.csc_pos = arena.at<int32_t>(o_cpos); d.csc_state = arena.at<uint8_t>(o_cstate);
@@ -2116,7 +2185,8 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     NsxCtl hctl;
     nsx_fill_ctl(hctl, opt, want_trace);
     if (warm) { hctl.warm = 1; hctl.phase = warm->start_phase; }
-    hctl.star_on = star ? 1 : 0;
+    hctl.star_on = star ? (star_devex ? 2 : 1) : 0;
+    hctl.star_excl_prev = -1;
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
     NSX_CUDA(cudaMemsetAsync(ka.slots, 0, sizeof(NsxSlot) * 1024, stream));
@@ -2180,7 +2250,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
             nsx_star_scan_kernel<<<1, 1024, 0, stream>>>((int32_t*)d.row_begin, (int32_t*)d.col_begin, arena.at<int32_t>(o_cursor), n + 1);
             nsx_star_fill_kernel<<<util_blocks, 256, 0, stream>>>(d.tail, d.head, d.pert, d.state, m, arena.at<int32_t>(o_cursor),
                                                                  (int32_t*)ka.star.csc_arc, (int32_t*)ka.star.csc_tail, (void*)ka.star.csc_cost,
-                                                                 ka.star.cost_i32, d.csc_pos, d.csc_state);
+                                                                 ka.star.cost_i32, d.csc_pos, d.csc_state, d.csc_wgt);
             NSX_CUDA(cudaGetLastError());
         }
     }
@@ -2419,7 +2489,7 @@ extern "C" int nsx_solve_batch(int64_t count, const nsx_problem* problems, const
         d.node_mask = nullptr; d.imbalance = nullptr;
         d.blk = nullptr; d.sidx = arena.at<int32_t>(o.sidx);
         d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr;
-        d.csc_pos = nullptr; d.csc_state = nullptr;
+        d.csc_pos = nullptr; d.csc_state = nullptr; d.csc_wgt = nullptr;
         items[i].st = layout;
         items[i].st.base = arena.at<unsigned char>(o.store);
         items[i].mpad = nsx_pad_tiles((int64_t)m);

@@ -46,21 +46,46 @@ struct SerialSweep {
     const int32_t* csc_arc = nullptr;  // star pricing: arc ids grouped by head (the emulation's CSC copy)
     SerialSweep(const NsxDev& dev) : d(dev) {}
     // Star pricing, serial restatement of what the sweep workers do (nsx_engine.cu, NSX_CMD_STAR / NSX_CMD_STAR_BUILD):
-    // same row cache, same marking rule, same order of the phases.
-    void price_row(int32_t v, int32_t phase, int64_t& evaluated) {
+    // same row cache(s), same marking rule, same order of the phases.  Dantzig rule: one cache (key = reduced-cost key);
+    // Devex with a single block (cmd.pad[0]): a forward and a backward cache (key = -merit), arc cmd.pad[1] left out,
+    // arc cmd.pad[2] put back in.
+    struct Ev { int cache; double key; int32_t arc2; };  // cache < 0: not a candidate
+    Ev eval(const NsxCmd& cmd, int64_t a, uint32_t st, int32_t tl, int32_t hd, uint32_t wraw) {
+        Ev ev; ev.cache = -1; ev.key = 0.0; ev.arc2 = -1;
+        if (cmd.pad[0]) {
+            if (a == cmd.pad[1] || (st & NSX_ARC_IN_TREE)) return ev;
+            const double rc = NSX_SUB(NSX_ADD(d.pert[a], d.pi[tl]), d.pi[hd]);
+            const bool fv = (st & NSX_ARC_CAN_FWD) && rc < -d.tol, bv = (st & NSX_ARC_CAN_BWD) && rc > d.tol;
+            if (!(fv || bv)) return ev;
+            const double w = (wraw >> 24) == cmd.wepoch ? (double)(wraw & 0xffffffu) : 1.0;
+            ev.key = -NSX_DIV(NSX_MUL(rc, rc), w);
+            ev.cache = fv ? 0 : 1; ev.arc2 = (int32_t)(a * 2 + (fv ? 0 : 1));
+        } else {
+            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(cmd.phase, d.pert[a], a), d.pi[tl]), d.pi[hd]);
+            ev.arc2 = nsx_star_candidate(a, st, rc, d.tol, &ev.key);
+            ev.cache = ev.arc2 >= 0 ? 0 : -1;
+        }
+        return ev;
+    }
+    void propose(int32_t row, const Ev& ev) {
+        NsxRC& r = d.rc[(size_t)ev.cache * d.n + row];
+        if (nsx_rc_better(ev.key, ev.arc2, r)) { r.key = ev.key; r.arc2 = ev.arc2; }
+    }
+    void price_row(const NsxCmd& cmd, int32_t v, int64_t& evaluated) {
         for (int64_t a = d.row_begin[v]; a < d.row_begin[v + 1]; ++a) {
-            const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(phase, d.pert[a], a), d.pi[v]), d.pi[d.head[a]]);
-            double key = 0.0;
-            const int32_t arc2 = nsx_star_candidate(a, d.state[a], rc, d.tol, &key);
+            const Ev ev = eval(cmd, a, d.state[a], v, d.head[a], d.wgt ? d.wgt[a] : 1u);
             ++evaluated;
-            if (arc2 >= 0 && nsx_rc_better(key, arc2, d.rc[v])) { d.rc[v].key = key; d.rc[v].arc2 = arc2; }
+            if (ev.cache >= 0) propose(v, ev);
         }
     }
-    void run_star(const NsxCmd& cmd, NsxCand& dz, NsxCtl& c) {
+    void run_star(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         int64_t evaluated = 0;
-        NsxRC none; none.key = 0.0; none.arc2 = -1; none.pad = 0;
+        const int ncache = cmd.pad[0] ? 2 : 1;
         if (cmd.kind == NSX_CMD_STAR_BUILD) {
-            for (int32_t v = 1; v < d.n; ++v) { d.rc[v] = none; price_row(v, cmd.phase, evaluated); }
+            for (int32_t v = 1; v < d.n; ++v) {
+                for (int x = 0; x < ncache; ++x) { NsxRC& r = d.rc[(size_t)x * d.n + v]; r.key = 0.0; r.arc2 = -1; r.pad = 0; }
+                price_row(cmd, v, evaluated);
+            }
         } else {
             const int32_t ne = (int32_t)cmd.lo, round = (int32_t)cmd.hi, extra = cmd.excluded;
             const int32_t nd = (extra >= 0 && d.dstamp[extra] != round) ? ne - 1 : ne;  // (the last entry is the row of the entering arc)
@@ -70,8 +95,8 @@ struct SerialSweep {
                 if (info[0] != v || info[1] != d.row_begin[v] || info[2] != d.row_begin[v + 1] - d.row_begin[v] ||
                     info[4] != (k < nd ? d.col_begin[v + 1] - d.col_begin[v] : 0) || (k < nd && info[3] != d.col_begin[v])) abort();
             }
-            for (int32_t k = 0; k < nd; ++k) price_row(d.dlist[k], cmd.phase, evaluated);  // (reset by the pivot)
-            if (extra >= 0 && d.dstamp[extra] != round) price_row(extra, cmd.phase, evaluated);
+            for (int32_t k = 0; k < nd; ++k) price_row(cmd, d.dlist[k], evaluated);  // (emptied by the pivot)
+            if (nd < ne) price_row(cmd, extra, evaluated);
             std::vector<int32_t> rq;
             for (int32_t k = 0; k < nd; ++k) {
                 const int32_t v = d.dlist[k];
@@ -80,26 +105,40 @@ struct SerialSweep {
                     const int32_t i = d.tail[a];
                     if (d.rc[i].pad == round) continue;  // the pivot emptied that row (its node is listed, or it is the row of the entering arc): priced afresh anyway
                     if (d.dstamp[i] == round || i == extra) abort();  // (the two ways of saying it agree)
-                    const double rc = NSX_SUB(NSX_ADD(nsx_phase_cost(cmd.phase, d.pert[a], a), d.pi[i]), d.pi[v]);
-                    double key = 0.0;
-                    const int32_t arc2 = nsx_star_candidate(a, d.csc_state[e], rc, d.tol, &key);
+                    const Ev ev = eval(cmd, a, d.csc_state[e], i, v, d.csc_wgt ? d.csc_wgt[e] : 1u);
                     ++evaluated;
-                    const NsxRC cur = d.rc[i];
-                    if (cur.arc2 >= 0 && (cur.arc2 >> 1) == a) {  // the cached arc of the row changed its reduced cost
-                        if (arc2 >= 0 && key <= cur.key) { d.rc[i].key = key; d.rc[i].arc2 = arc2; }
-                        else { d.rc[i].key = 0.0; d.rc[i].arc2 = -1; rq.push_back(i); }
-                    } else if (arc2 >= 0 && nsx_rc_better(key, arc2, cur)) {
-                        d.rc[i].key = key; d.rc[i].arc2 = arc2;
+                    bool queued = false;
+                    for (int x = 0; x < ncache; ++x) {
+                        NsxRC& cur = d.rc[(size_t)x * d.n + i];
+                        if (cur.arc2 >= 0 && (cur.arc2 >> 1) == a) {  // the cached arc of the row changed its reduced cost
+                            if (ev.cache == x && ev.key <= cur.key) { cur.key = ev.key; cur.arc2 = ev.arc2; }
+                            else { cur.key = 0.0; cur.arc2 = -1; if (!queued) rq.push_back(i); queued = true; }
+                        } else if (ev.cache == x) {
+                            propose(i, ev);
+                        }
                     }
                 }
             }
-            for (int32_t i : rq) price_row(i, cmd.phase, evaluated);
+            if (cmd.pad[0] && cmd.pad[2] >= 0) {  // Devex: the arc left out by the previous command is a candidate again
+                const int64_t a = cmd.pad[2];
+                const Ev ev = eval(cmd, a, d.state[a], d.tail[a], d.head[a], d.wgt[a]);
+                ++evaluated;
+                if (ev.cache >= 0) propose(d.tail[a], ev);
+            }
+            for (int32_t i : rq) price_row(cmd, i, evaluated);
             c.star_rescans += (int64_t)rq.size();
         }
         nsx_cand_init(dz);
+        nsx_devex_init(dx);
         for (int32_t v = 1; v < d.n; ++v) {
             const NsxRC r = d.rc[v];
-            if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) { dz.key = r.key; dz.arc2 = r.arc2; }
+            if (cmd.pad[0]) {
+                if (r.arc2 >= 0 && (dx.fi < 0 || -r.key > dx.fm || (-r.key == dx.fm && (r.arc2 >> 1) < dx.fi))) { dx.fm = -r.key; dx.fi = r.arc2 >> 1; }
+                const NsxRC b = d.rc[(size_t)d.n + v];
+                if (b.arc2 >= 0 && (dx.bi < 0 || -b.key > dx.bm || (-b.key == dx.bm && (b.arc2 >> 1) < dx.bi))) { dx.bm = -b.key; dx.bi = b.arc2 >> 1; }
+            } else if (r.arc2 >= 0 && (dz.arc2 < 0 || r.key < dz.key || (r.key == dz.key && r.arc2 < dz.arc2))) {
+                dz.key = r.key; dz.arc2 = r.arc2;
+            }
         }
         c.star_evaluated = evaluated;
     }
@@ -138,7 +177,7 @@ struct SerialSweep {
     void run_serial(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
         nsx_cand_init(dz);
         nsx_devex_init(dx);
-        if (cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD) { run_star(cmd, dz, c); return; }
+        if (cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD) { run_star(cmd, dz, dx, c); return; }
         if (cmd.kind == NSX_CMD_TOPK) {  // candidate-list refresh (simplex_pricing.py:507-536)
             std::vector<std::pair<double, int32_t>> cands;
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
@@ -169,6 +208,7 @@ struct SerialSweep {
             }
         }
     }
+    void alive() {}
     void finish() {}
 };
 
@@ -220,12 +260,13 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
     // NSX_EMU_STAR=1: star pricing (row cache + CSC copy), as the engine runs Dantzig pricing on multi-CTA grids
     const char* sp = getenv("NSX_EMU_STAR");
     const bool star = sp && *sp && atoi(sp) != 0 && !warm;
-    std::vector<NsxRC> rcache(star ? n : 0);
+    std::vector<NsxRC> rcache(star ? 2 * (size_t)n : 0);
+    std::vector<uint32_t> csc_wgt(star && opt->pricing == NSX_PRICING_DEVEX ? (size_t)m : 0, 1u);
     std::vector<int32_t> dinfo(star ? 8 * ((size_t)n + 1) : 0);
     std::vector<int32_t> dlist(star ? n : 0), dstamp(star ? n : 0, 0), row_begin(star ? n + 1 : 0, 0), col_begin(star ? n + 1 : 0, 0),
         csc_pos(star ? (size_t)m : 0), csc_arc(star ? (size_t)m : 0);
     std::vector<uint8_t> csc_state(star ? (size_t)m : 0);
-    d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
+    d.csc_wgt = nullptr; d.dinfo = nullptr; d.rc = nullptr; d.dlist = nullptr; d.dstamp = nullptr; d.row_begin = nullptr; d.col_begin = nullptr; d.csc_pos = nullptr; d.csc_state = nullptr;
     if (star) {
         for (int64_t a = 0; a + 1 < m; ++a) if (pb->tail[a] > pb->tail[a + 1]) return -8;  // rows need arcs sorted by tail
         for (int64_t a = 0; a < m; ++a) { row_begin[pb->tail[a] + 1]++; col_begin[pb->head[a] + 1]++; }
@@ -235,7 +276,9 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
         d.dinfo = dinfo.data();
         d.rc = rcache.data(); d.dlist = dlist.data(); d.dstamp = dstamp.data(); d.row_begin = row_begin.data();
         d.col_begin = col_begin.data(); d.csc_pos = csc_pos.data(); d.csc_state = csc_state.data();
-        c.star_on = 1;
+        d.csc_wgt = csc_wgt.empty() ? nullptr : csc_wgt.data();
+        c.star_on = opt->pricing == NSX_PRICING_DEVEX && !opt->row_scan_first ? 2 : 1;
+        c.star_excl_prev = -1;
     }
 
     int64_t art = 0;

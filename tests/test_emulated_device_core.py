@@ -130,3 +130,30 @@ def test_emulated_core_star_pricing(family, make, pricing, eps0, blocked, monkey
     assert_same_solution(got, oracle.solve_canonical(cp, opts))
     assert got.timing["sync_ms"] > 0  # (emulation: number of star updates) the incremental path ran
     assert got.arcs_priced < 0.7 * got.iterations * cp.n_arcs
+
+
+DEVEX_STAR_CASES = [
+    ("netgen", lambda: gen.netgen_like(2048, 16384, n_sources=8, n_sinks=8, seed=5), False),
+    ("netgen_deep", lambda: gen.netgen_like(4096, 8192, n_sources=16, n_sinks=16, seed=6), False),
+    ("netgen_caps", lambda: gen.netgen_like(512, 8192, n_sources=32, n_sinks=32, supply_each=3000, cap_max=50, seed=12), False),
+    ("netgen_caps_ties", lambda: gen.netgen_like(256, 4096, n_sources=32, n_sinks=32, supply_each=2000, cap_max=20, cost_max=4, seed=13), True),
+    ("goto", lambda: gen.goto_like(32, seed=8), False),
+    ("gridgen", lambda: gen.gridgen_like(32, 8200, seed=9), False),
+]
+
+
+@pytest.mark.parametrize("blocks", ["one_block", "adaptive", "short_cadence"])
+@pytest.mark.parametrize("family,make,eps0", DEVEX_STAR_CASES)
+def test_emulated_core_star_pricing_devex(family, make, eps0, blocks, monkeypatch):
+    """Devex block pricing while its block covers all arcs (what the block adaptation grows it to on degenerate runs) is an
+    arg-max over everything: kept in a forward and a backward row cache, with the last degenerate arc left out and put back,
+    the caches rebuilt at every weight reset.  Same pivots as the oracle's block sweeps."""
+    monkeypatch.setenv("NSX_EMU_STAR", "1")
+    cp = make().canonical(eps_base=0.0) if eps0 else make().canonical()
+    kw = {"one_block": dict(block_size=cp.n_arcs, auto_block=False), "adaptive": {},
+          "short_cadence": dict(block_size=cp.n_arcs, auto_block=False, ft_update_limit=3)}[blocks]
+    opts = engine_options(cp, 1, **kw)
+    got = emu.solve_canonical(cp, opts)
+    assert_same_solution(got, oracle.solve_canonical(cp, opts))
+    if blocks != "adaptive":
+        assert got.timing["sync_ms"] > 0 and got.timing["exchange_ms"] >= 1  # (emulation: star updates / rebuilds)
