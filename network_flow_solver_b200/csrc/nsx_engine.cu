@@ -1127,15 +1127,45 @@ __device__ __forceinline__ void nsx_cta_star(const NsxDev& d, const NsxStar& sp,
     const int gw = worker * nwarp + warp, GW = nworkers * nwarp;
     NSX_SYNC();
     if (cmd.kind == NSX_CMD_STAR_BUILD) {
-        // every row of the slice, emptied first; the chunks of a batch of rows are dealt to the warps of this CTA
-        for (int32_t v = r0 + tid; v < r1; v += blockDim.x) { d.rc[v] = nsx_rc_none(0); if (R.devex) d.rc[d.n + v] = nsx_rc_none(0); }
+        // Every row of the slice (nobody else touches these rows during a build).  Short rows: an 8-lane group prices a
+        // whole row - four rows in flight per warp - and stores the result directly.  Wide rows: emptied, then their chunks
+        // are dealt to the warps of this CTA, which propose.
+        const int32_t wide = 512;
+        {
+            const int lane = tid & 31, grp = lane >> 3, gl = lane & 7;
+            for (int32_t v0 = r0 + warp * 4; v0 < r1; v0 += nwarp * 4) {
+                const int32_t v = v0 + grp;
+                int64_t lo = 0, hi = 0;
+                if (v < r1) { lo = d.row_begin[v]; hi = d.row_begin[v + 1]; }
+                const bool mine = v < r1 && hi - lo < wide;
+                double key[2] = {0.0, 0.0}; int32_t arc2[2] = {-1, -1};
+                if (mine && hi > lo) nsx_star_price_row_part(d, R, __ldcg(d.pi + v), lo, hi, gl, 8, key, arc2);
+                __syncwarp();
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {
+                    const double k0 = __shfl_down_sync(0xffffffffu, key[0], off, 8), k1 = __shfl_down_sync(0xffffffffu, key[1], off, 8);
+                    const int32_t c0 = __shfl_down_sync(0xffffffffu, arc2[0], off, 8), c1 = __shfl_down_sync(0xffffffffu, arc2[1], off, 8);
+                    nsx_star_take(k0, c0, key[0], arc2[0]);
+                    nsx_star_take(k1, c1, key[1], arc2[1]);
+                }
+                if (mine && gl == 0) {
+                    NsxRC f; f.key = arc2[0] >= 0 ? key[0] : 0.0; f.arc2 = arc2[0]; f.pad = 0;
+                    d.rc[v] = f;
+                    if (R.devex) { NsxRC b; b.key = arc2[1] >= 0 ? key[1] : 0.0; b.arc2 = arc2[1]; b.pad = 0; d.rc[d.n + v] = b; }
+                    evaluated += hi - lo;
+                }
+            }
+        }
+        for (int32_t v = r0 + tid; v < r1; v += blockDim.x)
+            if (d.row_begin[v + 1] - d.row_begin[v] >= wide) { d.rc[v] = nsx_rc_none(0); if (R.devex) d.rc[d.n + v] = nsx_rc_none(0); }
         __threadfence();  // (rare command) the plain stores are in L2 before any proposal - an L2 atomic - of another thread
         for (int32_t b0 = r0; b0 < r1; b0 += NSX_STAR_ENT) {
             const int32_t E = r1 - b0 < NSX_STAR_ENT ? r1 - b0 : NSX_STAR_ENT;
             NSX_SYNC();
             for (int32_t q = tid; q < E; q += blockDim.x) {
                 const int32_t rb = d.row_begin[b0 + q], re = d.row_begin[b0 + q + 1];
-                tab.v[q] = b0 + q; tab.lo[q] = rb; tab.n[q] = re - rb; tab.pfx[q + 1] = (re - rb + NSX_STAR_CH - 1) / NSX_STAR_CH;
+                tab.v[q] = b0 + q; tab.lo[q] = rb; tab.n[q] = re - rb;
+                tab.pfx[q + 1] = re - rb >= wide ? (re - rb + NSX_STAR_CH - 1) / NSX_STAR_CH : 0;
             }
             if (tid == 0) tab.pfx[0] = 0;
             NSX_SYNC();
