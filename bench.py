@@ -281,7 +281,7 @@ def sharded_leg(name: str, rank: int, world: int, device: int, dist, barrier, pe
     wl = WORKLOADS[name]
     pivots = SHARDED_PREFIX[name]
     t0 = time.perf_counter()
-    cp = cached_canonical(wl, name, rank, barrier)
+    cp = cached_canonical(wl, name.rsplit("_", 1)[0], rank, barrier)  # (the Devex and the Dantzig leg price the same instance)
     t_build = time.perf_counter() - t0
     m = cp.n_arcs
     opts = wl.engine_options(cp, device=device, max_iterations=pivots, trace_capacity=pivots)
@@ -321,7 +321,7 @@ def sharded_leg(name: str, rank: int, world: int, device: int, dist, barrier, pe
         # the same prefix as an ordinary single-GPU solve (rank 0; the others wait at the barrier): the parity anchor of the
         # sharded run and - under the Dantzig rule, where one GPU prices from the row cache (star pricing) instead of sweeping
         # all arcs - the figure the sharded sweeps have to be read against
-        if world > 1 or not devex:
+        if True:
             if rank == 0:
                 single = _capi.solve_resident(cp, opts, ptrs)
                 single_ok = bool((single.status, single.iterations, solution_hashes(single)) == sigs[0][:3])
