@@ -252,6 +252,12 @@ struct NsxPivotScratch {
     int32_t pending;
     int32_t p_pos;             // preorder position of the new parent p (tree update)
     int32_t jkey;              // scan walk: min over common ancestors of (size << 16 | node)
+    // Tree bookkeeping the next pricing step does not need is deferred (nsx_pivot_flush): it runs while the sweep workers
+    // price, or at the latest before the next reader of the preorder array.  def_kind 1: dense array - shift the entries
+    // between the old and the new place of S into tmp and copy the window back; 2: blocked array - take S out, put it back.
+    int32_t def_kind, def_p, def_sz, def_pad;
+    int64_t def_lo, def_hi, def_S0, def_S1, def_xshift;
+    int64_t def_moved;
     int32_t sp_any;            // rule scan: number of the last round in which some thread saw an arc that beats the incumbent
     int32_t sp_best, sp_zero;  // rule scan: incumbent arc*2 + (dir<0) / first zero-reduced-cost candidate, -1 none
     double theta;
@@ -370,8 +376,9 @@ NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
 // Blocked mode: the sequence is a flattened copy (d.tmp) and `sidx` maps a node to its index in it; the first entry
 // hangs below a node outside the sequence, and so does every child of the root (whole-tree recompute).
 NSX_FN int32_t nsx_seq_parent(const NsxDev& d, const int32_t* sidx, int64_t x, int64_t lo, int32_t parent) {
+    if (x == lo) return -1;  // (dense arrays too: the stored position of that node may still await the deferred window shift)
     if (!sidx) return d.node[parent].pos;
-    return (x == lo || parent == 0) ? -1 : sidx[parent];
+    return parent == 0 ? -1 : sidx[parent];
 }
 
 struct NsxPotScratch {
@@ -824,6 +831,46 @@ NSX_FN void nsx_ratio_finish(const NsxRatio& rr, const double* res, const int32_
 // One pivot on entering arc e (direction dir = +1 forward / -1 backward).
 // Returns (block-uniform) 0 = ok, 3 = unbounded.
 // ------------------------------------------------------------------------------------------
+// Deferred tree bookkeeping of the last pivot (all threads of the pivot CTA; a no-op when nothing is pending).
+template <bool BLK>
+NSX_FN void nsx_pivot_flush(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s) {
+    const int32_t kind = s.def_kind;
+    if (!kind) return;
+    int64_t moved;
+    if (BLK && kind == 2) {
+        moved = s.def_sz + nsx_blk_remove(d, *d.blk, (int32_t)s.def_S0, s.def_sz);
+        moved += nsx_blk_insert(d, *d.blk, s.def_p, s.def_sz);
+    } else {
+        const int64_t lo = s.def_lo, hi = s.def_hi, S0 = s.def_S0, S1 = s.def_S1, xshift = s.def_xshift;
+        const int64_t T = NSX_NTHREADS;
+        NSX_SYNC();
+        // entries between the old and the new place of S move by +-|S| (into tmp, next to the permuted S) ...
+        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+            int32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = (x < hi && !(x >= S0 && x < S1)) ? d.order[x] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int64_t x = x0 + u * T;
+                if (v[u] >= 0) { d.tmp[x + xshift] = v[u]; d.node[v[u]].pos = (int32_t)(x + xshift); }
+            }
+        }
+        NSX_SYNC();
+        // ... and the window goes back to the preorder array
+        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
+            int32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.tmp[x] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < hi) d.order[x] = v[u]; }
+        }
+        moved = hi - lo;
+    }
+    NSX_SYNC();
+    NSX_SINGLE { s.def_kind = 0; c.sum_window += moved; }
+    NSX_SYNC();
+}
+
 // star pricing, end of a pivot (one thread): the row of the entering arc joins the work list unless its node is in it already
 NSX_FN void nsx_star_close(const NsxDev& d, NsxCtl& c) {
     if (!c.star_on || !c.star_valid) return;
@@ -844,6 +891,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     const int32_t t = dir == 1 ? d.tail[e] : d.head[e];
     const int32_t h = dir == 1 ? d.head[e] : d.tail[e];
 
+    nsx_pivot_flush<BLK>(d, c, s);  // (usually done already, while the sweep workers priced)
     long long tph = NSX_CLOCK();
     // star pricing: this pivot opens a new round; its re-hung subtree (recorded after the potential recompute) and the
     // row of the entering arc are what the next pricing step has to look at
@@ -1171,7 +1219,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     // Blocked mode: only S is permuted (into tmp[0 .. sz), with the inverse map in sidx); the dense array also shifts
     // the entries between the old and the new place of S in the same pass.
     const bool blocked = BLK && d.blk != nullptr;
-    const int64_t w_lo = blocked ? S0 : lo, w_hi = blocked ? S1 : hi;
+    const int64_t w_lo = S0, w_hi = S1;  // (the entries between the old and the new place of S: nsx_pivot_flush)
     {
         // four entries per thread and step: the loads of all four are issued before any store
         const int64_t T = NSX_NTHREADS;
@@ -1216,23 +1264,13 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             }
         }
     }
+    NSX_SINGLE {
+        s.def_kind = blocked ? 2 : 1; s.def_p = p; s.def_sz = sz;
+        s.def_lo = lo; s.def_hi = hi; s.def_S0 = S0; s.def_S1 = S1; s.def_xshift = xshift;
+    }
+    const int64_t moved = 0;  // (counted by nsx_pivot_flush)
     NSX_SYNC();
-    int64_t moved = hi - lo;
-    if (blocked) {
-        moved = sz + nsx_blk_remove(d, *d.blk, (int32_t)S0, sz);
-        moved += nsx_blk_insert(d, *d.blk, p, sz);
-    }
     NSX_PH(c, 6, tph);
-    if (!blocked) {
-        const int64_t T = NSX_NTHREADS;
-        for (int64_t x0 = lo + NSX_TID; x0 < hi; x0 += 4 * T) {
-            int32_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; v[u] = x < hi ? d.tmp[x] : -1; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { int64_t x = x0 + u * T; if (x < hi) d.order[x] = v[u]; }
-        }
-    }
     // stem: reverse parent pointers, new subtree sizes
     NSX_PAR_FOR(i, 0, k_stem + 1) {
         int32_t v = spath[i];
@@ -1263,15 +1301,16 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     NSX_PH(c, 7, tph);
 
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
+    // (the dense array has S in tmp at its final place; `order` catches up in nsx_pivot_flush)
     if (blocked) nsx_recompute_potentials(d, c.phase, d.tmp, d.sidx, 0, sz, ps, &c.sum_rounds);
-    else nsx_recompute_potentials(d, c.phase, d.order, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds);
+    else nsx_recompute_potentials(d, c.phase, d.tmp, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds);
     const bool star_record = c.star_on && c.star_valid;  // (block-uniform: written by thread 0 before several barriers)
     if (star_record) {
         NSX_SYNC();  // every thread has read the flags before thread 0 may change them
         if ((int64_t)sz * 4 > d.n) {
             NSX_SINGLE { c.star_valid = 0; }  // a large part of the tree moved: pricing every row afresh is cheaper
         } else {
-            const int32_t* seq = blocked ? d.tmp : d.order + s_base;
+            const int32_t* seq = blocked ? d.tmp : d.tmp + s_base;
             const int32_t round = c.star_round;
             NSX_PAR_FOR(j, 0, sz) {
                 const int32_t v = seq[j];
@@ -1960,6 +1999,7 @@ NSX_FN void nsx_check_conservation(const NsxDev& d, NsxCtl& c) {
 template <bool BLK, class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
+    NSX_SINGLE { s.def_kind = 0; }
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
     NSX_SYNC();
     // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
@@ -1976,7 +2016,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
         sweep.alive();
         NSX_SYNC();
         if (kind == NSX_ACT_SWEEP) {
-            sweep.run(L.cmd, L.dz, L.dx, c);
+            sweep.run(L.cmd, L.dz, L.dx, c, [&]() { nsx_pivot_flush<BLK>(d, c, s); });
             NSX_SYNC();
             if (c.fault) {  // (block-uniform: written before the barrier) a worker / peer GPU never answered
                 sweep.finish();
@@ -2007,6 +2047,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             if (d.imbalance && c.phase == 1) nsx_check_conservation(d, c);
             NSX_SINGLE { nsx_drv_phase_end(c, L.drv, L.act); }
         } else if (kind == NSX_ACT_RECOMPUTE) {
+            nsx_pivot_flush<BLK>(d, c, s);
             if (!L.drv.final_check) {
                 nsx_recompute_all_potentials<BLK>(d, 2, ps);
                 NSX_SINGLE { c.star_valid = 0; }  // Phase-2 costs: every reduced cost changed

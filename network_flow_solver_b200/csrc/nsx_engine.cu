@@ -1373,9 +1373,13 @@ struct GridSweep {
         if (shd.world > 1) { exchange_topk(c); if (c.fault) return; }
         nsx_tk_publish_list(sh, c);
     }
-    __device__ __forceinline__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
+    // `deferred`: tree bookkeeping of the last pivot that pricing does not need (nsx_pivot_flush) - run by this CTA while
+    // the workers price
+    template <class Deferred>
+    __device__ __forceinline__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c, Deferred deferred) {
         unsigned long long t0 = 0;
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
+        if (gridDim.x == 1) deferred();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
         const NsxCmd cmd = cmd_in;
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
@@ -1401,6 +1405,7 @@ struct GridSweep {
         if (starcmd && threadIdx.x == 0) { *star.rq_n = 0; *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull; }  // (x_recs: idle on one GPU, holds the evaluated-arc count)
         if (starcmd) NSX_SYNC();
         publish(cmd);
+        deferred();
         unsigned long long t1 = 0;
         if (threadIdx.x == 0) t1 = nsx_globaltimer();
         // every worker's candidate: thread b polls slot b until it carries this command's number
@@ -1526,7 +1531,7 @@ __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLo
             c.sweeps++;
         }
         NSX_SYNC();
-        sweep.run(L.cmd, L.dz, L.dx, c);
+        sweep.run(L.cmd, L.dz, L.dx, c, []() {});
     }
     NSX_SYNC();
     if (threadIdx.x == 0) { c.status = NSX_STATUS_OPTIMAL; c.total = 0; }
@@ -1783,9 +1788,11 @@ struct LocalSweep {
     NsxSweepCtx cx;
     uint32_t& stage_count;
     uint32_t& q0;
-    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c) {
+    template <class Deferred>
+    __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c, Deferred deferred) {
         const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
+        deferred();  // (one CTA does everything: nothing to overlap with)
         NSX_SYNC();
         if (threadIdx.x == 0) __threadfence();  // this CTA's own state / potential writes reach L2 before the bulk reads
         nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
@@ -2376,10 +2383,24 @@ extern "C" int nsx_sweep_probe_sharded(const nsx_problem* problem_dev, const nsx
     return nsx_solve_impl(problem_dev, options, result, true, sweeps, shard);
 }
 extern "C" int64_t nsx_mailbox_bytes(void) { return (int64_t)sizeof(NsxMailbox); }
+// the pinned word and the stream nsx_mailbox_abort copies from / on: made when a mailbox is created or opened, because a
+// page-locked allocation issued while a resident kernel spins would wait for that kernel (implicit synchronisation)
+static std::mutex g_abort_mu;
+static unsigned long long* g_abort_word = nullptr;
+static cudaStream_t g_abort_stream = nullptr;  // (of the device current at the first call: one device per process, one process per GPU)
+static cudaError_t nsx_abort_prepare() {
+    std::lock_guard<std::mutex> lock(g_abort_mu);
+    if (g_abort_word) return cudaSuccess;
+    cudaError_t e = cudaMallocHost((void**)&g_abort_word, 8);
+    if (e == cudaSuccess) *g_abort_word = 1ull;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_abort_stream, cudaStreamNonBlocking);
+    return e;
+}
 extern "C" int nsx_mailbox_create(int32_t device, void** mailbox, unsigned char handle[64]) {
     if (!mailbox || !handle) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = nsx_abort_prepare();
     if (e == cudaSuccess) e = cudaMalloc(mailbox, sizeof(NsxMailbox));
     if (e == cudaSuccess) e = cudaMemset(*mailbox, 0, sizeof(NsxMailbox));
     cudaIpcMemHandle_t h;
@@ -2406,15 +2427,14 @@ extern "C" int nsx_mailbox_reset(int32_t device, void* mailbox) {
 }
 extern "C" int nsx_mailbox_abort(int32_t device, void* mailbox) {
     if (!mailbox) return nsx_fail(NSX_ERR_INVALID_ARGUMENT, "null argument");
-    const unsigned long long one = 1ull;
     cudaError_t e = cudaSetDevice(device);
-    // (plain copy on the legacy stream would wait for a running resident kernel: use a private non-blocking stream)
-    cudaStream_t st = nullptr;
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(mailbox) + offsetof(NsxMailbox, abort), &one, 8,
-                                              cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (st) cudaStreamDestroy(st);
+    // A resident kernel is spinning on this device: the word has to get there by DMA alone - from PINNED memory (a pageable
+    // source is staged through the driver and was seen to wait for the kernel), on a private non-blocking stream (the legacy
+    // stream would wait as well).
+    if (e == cudaSuccess) e = nsx_abort_prepare();  // (normally done by nsx_mailbox_create / _open)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(mailbox) + offsetof(NsxMailbox, abort), g_abort_word, 8,
+                                              cudaMemcpyHostToDevice, g_abort_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_abort_stream);
     if (e != cudaSuccess) return nsx_fail(NSX_ERR_CUDA, std::string("nsx_mailbox_abort: ") + cudaGetErrorString(e));
     return 0;
 }

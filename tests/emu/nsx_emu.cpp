@@ -169,7 +169,12 @@ struct SerialSweep {
             I.row_best[v] = k.arc2 >= 0 ? (k.arc2 >> 1) : -1;
         }
     }
-    void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c) {
+    template <class Deferred>
+    void run(const NsxCmd& cmd, NsxCand& dz, NsxDevexCand& dx, NsxCtl& c, Deferred deferred) {
+        // NSX_EMU_DEFER=late leaves the deferred tree bookkeeping to the next reader of the preorder array (the engine's
+        // pivot CTA does it while the workers price: either order must give the same pivots)
+        const bool late = getenv("NSX_EMU_DEFER") && !strcmp(getenv("NSX_EMU_DEFER"), "late");
+        if (!late) deferred();
         NSX_SYNC();
         NSX_SINGLE { run_serial(cmd, dz, dx, c); }  // the grid sweep is not what this emulation is about
         NSX_SYNC();

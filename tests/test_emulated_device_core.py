@@ -157,3 +157,16 @@ def test_emulated_core_star_pricing_devex(family, make, eps0, blocks, monkeypatc
     assert_same_solution(got, oracle.solve_canonical(cp, opts))
     if blocks != "adaptive":
         assert got.timing["sync_ms"] > 0 and got.timing["exchange_ms"] >= 1  # (emulation: star updates / rebuilds)
+
+
+@pytest.mark.parametrize("blocked", ["0", "1"])
+@pytest.mark.parametrize("family,make,pricing", CASES[:6])
+def test_emulated_core_deferred_bookkeeping_can_wait_for_the_next_pivot(family, make, pricing, blocked, monkeypatch):
+    """The part of a tree update that pricing does not need (closing the gap the re-hung subtree left in the preorder array)
+    is deferred: the engine's pivot CTA does it while the sweep workers price.  Here it is left until the next pivot needs the
+    array - the latest possible moment - and the pivots must not change."""
+    monkeypatch.setenv("NSX_EMU_DEFER", "late")
+    monkeypatch.setenv("NSX_EMU_BLOCKED", blocked)
+    cp = make().canonical()
+    opts = engine_options(cp, pricing)
+    assert_same_solution(emu.solve_canonical(cp, opts), oracle.solve_canonical(cp, opts))
