@@ -1412,6 +1412,7 @@ struct GridSweep {
         NsxDevexCand kx; nsx_devex_init(kx);
         NsxCand kz; nsx_cand_init(kz);
         unsigned long long ev = 0ull;
+        int32_t nq_seen = 0;  // star update: rows that were queued, as reported by the worker whose slot this thread polls
         for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
             const NsxSlot* sl = slots + b;
             uint32_t spins = 0;
@@ -1425,12 +1426,12 @@ struct GridSweep {
                 union { NsxDevexCand c; int4 v[2]; } tmp;
                 tmp.v[0] = __ldcg(&sl->v[0]); tmp.v[1] = __ldcg(&sl->v[1]);
                 nsx_devex_merge(kx, tmp.c);
-                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); }
+                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); nq_seen = __ldcg(&sl->pad[3]); }
             } else {
                 union { NsxCand c; int4 v; } tmp;
                 tmp.v = __ldcg(&sl->v[0]);
                 nsx_cand_merge(kz, tmp.c);
-                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); }
+                if (starcmd) { ev += ((unsigned long long)(uint32_t)__ldcg(&sl->pad[1]) << 32) | (uint32_t)__ldcg(&sl->pad[0]); if (__ldcg(&sl->pad[2])) c.fault = __ldcg(&sl->pad[2]); nq_seen = __ldcg(&sl->pad[3]); }
             }
         }
         if (starcmd && ev) atomicAdd(reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]), ev);
@@ -1442,7 +1443,7 @@ struct GridSweep {
         if (threadIdx.x == 0) { t_sync += nsx_globaltimer() - t1; if (timeline) g->tl[6] += nsx_globaltimer() - g->t_pub; }
         if (starcmd && threadIdx.x == 0) {
             c.star_evaluated = (int64_t)*reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]);
-            if (cmd.kind == NSX_CMD_STAR) c.star_rescans += __ldcg(star.rq_n);
+            if (cmd.kind == NSX_CMD_STAR) c.star_rescans += nq_seen;  // (thread 0 polled worker 1's slot; the count is the same on every worker)
         }
         if (cmd.kind == NSX_CMD_TOPK) {
             merge_topk(c);
@@ -1627,6 +1628,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
                 if (cmd.pad[0]) { union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx; sl->v[0] = tmp.v[0]; sl->v[1] = tmp.v[1]; }
                 else { union { NsxCand c; int4 v; } tmp; tmp.c = dz; sl->v[0] = tmp.v; }
                 sl->pad[0] = (int32_t)(uint32_t)ev; sl->pad[1] = (int32_t)(uint32_t)(ev >> 32); sl->pad[2] = fault;
+                sl->pad[3] = cmd.kind == NSX_CMD_STAR ? sh.tk_cnt : 0;  // rows that were queued (the same count on every worker)
                 nsx_st_release(&sl->seq, seen);
                 if (a.timeline) NSX_TL(a.grid, 5);
             }
