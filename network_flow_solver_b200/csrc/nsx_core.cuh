@@ -232,7 +232,9 @@ struct NsxCtl {
     int64_t ph[12];       // SM-clock cycles per pivot phase (thread 0): walk, residuals, ratio, flow,
                           // bookkeeping, snapshot+sizes, window, copy+stem, potentials, cadence, driver
     int32_t fault;        // a device-side wait ran past its deadline or met an abort word (nsx_result.fault); the loop ends
-    int32_t fault_pad;
+    int32_t n_special;    // real arcs outside the tree whose residual bits are anything but "forward only" (nsx_special): while
+                          // there is none - e.g. for the whole solve of an uncapacitated instance - the Dantzig sweep needs no
+                          // state bytes (nsx_price_tile_dz).  Counted once by nsx_count_special, kept up to date by nsx_pivot.
 };
 // bar.sync blocks lazily (at the next access to barrier-protected state): touch shared memory first
 // so that the clock is read after the barrier has really been passed
@@ -256,6 +258,7 @@ struct NsxPivotScratch {
     // price, or at the latest before the next reader of the preorder array.  def_kind 1: dense array - shift the entries
     // between the old and the new place of S into tmp and copy the window back; 2: blocked array - take S out, put it back.
     int32_t def_kind, def_p, def_sz, def_pad;
+    int32_t spec_e0;           // nsx_special() of the entering arc before the pivot touched it
     int64_t def_lo, def_hi, def_S0, def_S1, def_xshift;
     int64_t def_moved;
     int32_t sp_any;            // rule scan: number of the last round in which some thread saw an arc that beats the incumbent
@@ -349,6 +352,10 @@ NSX_FN int64_t nsx_blk_phys(const NsxBlk& B, int32_t x) {
     return ((int64_t)B.dir[k] << B.lg) + (x - B.prefix[k]);
 }
 
+// 1 for an arc outside the tree that the Dantzig rule cannot treat as "candidate iff rc < -tol" (NsxCtl::n_special)
+NSX_FN int32_t nsx_special(uint8_t st) {
+    return (!(st & NSX_ARC_IN_TREE) && (st & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD)) != NSX_ARC_CAN_FWD) ? 1 : 0;
+}
 NSX_FN uint8_t nsx_bounds_bits(double f, double up, double tol) {
     uint8_t b = 0;
     if (nsx_isinf(up) || NSX_SUB(up, f) > tol) b |= NSX_ARC_CAN_FWD;
@@ -896,6 +903,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
     // star pricing: this pivot opens a new round; its re-hung subtree (recorded after the potential recompute) and the
     // row of the entering arc are what the next pricing step has to look at
     NSX_SINGLE {
+        s.spec_e0 = -1;  // (nsx_special of the entering arc before this pivot: set by the flow update when it runs)
         if (c.star_on) {
             if (c.star_pending >= 1) c.star_valid = 0;  // two pivots without a pricing step in between
             c.star_pending++;
@@ -1116,6 +1124,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
             double up = nsx_upper(d, a);
             double f = sign > 0 ? NSX_ADD(old, theta) : NSX_SUB(old, theta);
             uint8_t st = d.state[a];
+            if (k == ncyc - 1) s.spec_e0 = a < d.m ? nsx_special(st) : 0;  // (the entering arc is the last of the scan order)
             if (theta > 0.0) st |= NSX_ARC_TOUCHED;
             const double pushed = f;
             if (f < NSX_SUB(0.0, tol)) { f = 0.0; st &= (uint8_t)~NSX_ARC_TOUCHED; }
@@ -1156,7 +1165,10 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         int is_deg = (leave == e) || (fabs(theta) < tol);  // simplex.py:1317
         c.tuner_total++;
         if (is_deg) c.tuner_deg++;
-        if (leave == e) c.last_deg = e;  // bound flip (simplex.py:1320-1334)
+        if (leave == e) {  // bound flip (simplex.py:1320-1334)
+            c.last_deg = e;
+            if (e < d.m && s.spec_e0 >= 0) c.n_special += nsx_special(d.state[e]) - s.spec_e0;  // (no flow update: nothing changed)
+        }
     }
     NSX_SYNC();
     NSX_PH(c, 4, tph);
@@ -1286,12 +1298,16 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
     }
     NSX_SINGLE {
-        d.state[e] |= NSX_ARC_IN_TREE;
+        const uint8_t st_e = d.state[e];
+        if (s.spec_e0 < 0) s.spec_e0 = e < d.m ? nsx_special(st_e) : 0;  // no flow update ran: this IS the state before the pivot
+        d.state[e] = (uint8_t)(st_e | NSX_ARC_IN_TREE);
         d.state[leave] &= (uint8_t)~NSX_ARC_IN_TREE;
         if (d.csc_state) {
             d.csc_state[d.csc_pos[e]] = d.state[e];
             if (leave < d.m) d.csc_state[d.csc_pos[leave]] = d.state[leave];
         }
+        // (the entering arc is in the tree now, the leaving arc outside with the residual bits the flow update gave it)
+        c.n_special += (leave < d.m ? nsx_special(d.state[leave]) : 0) - s.spec_e0;
         c.tree_updates++;
         c.sum_subtree += sz;
         if (sz > c.max_subtree) c.max_subtree = sz;
@@ -1795,6 +1811,7 @@ NSX_FN void nsx_drv_dantzig_cmd(NsxCtl& c, int64_t m, NsxCmd& cmd) {
     cmd.kind = NSX_CMD_DANTZIG; cmd.phase = c.phase; cmd.lo = 0; cmd.hi = m;
     cmd.excluded = -1; cmd.wepoch = c.wepoch; cmd.reverse ^= 1;
     cmd.pad[0] = 0;
+    cmd.pad[1] = c.n_special == 0;  // the sweep may skip the state bytes (nsx_price_tile_dz)
     if (c.star_on != 1) return;
     if (c.star_valid && c.star_pending <= 1) {
         cmd.kind = NSX_CMD_STAR;
@@ -1996,11 +2013,40 @@ NSX_FN void nsx_check_conservation(const NsxDev& d, NsxCtl& c) {
 // The resident loop of the pivot CTA.  `Sweep::run(cmd, dz, dx)` prices the arc range of `cmd`
 // (grid-wide on the device, serially in the emulation) and leaves the merged candidates in
 // dz / dx, visible to all threads of this CTA on return.  `Sweep::finish()` releases workers.
+// NsxCtl::n_special of the initial state (cold or warm), once per solve
+NSX_FN void nsx_count_special(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s) {
+    NSX_SINGLE { s.spec_e0 = 0; }
+    NSX_SYNC();
+    int32_t cnt = 0;
+#if NSX_ON_DEVICE
+    // sixteen state bytes per load while the pointer allows it
+    const int64_t m16 = ((reinterpret_cast<uintptr_t>(d.state) & 15) == 0) ? (d.m >> 4) : 0;
+    const uint4* s16 = reinterpret_cast<const uint4*>(d.state);
+    for (int64_t i = threadIdx.x; i < m16; i += blockDim.x) {
+        const uint4 v = s16[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cnt += nsx_special((uint8_t)(w[k] >> (8 * b)));
+        }
+    }
+    NSX_PAR_FOR(i, m16 << 4, d.m) { cnt += nsx_special(d.state[i]); }
+#else
+    NSX_PAR_FOR(i, 0, d.m) { cnt += nsx_special(d.state[i]); }
+#endif
+    if (cnt) NSX_ATOMIC_ADD_I32(&s.spec_e0, cnt);
+    NSX_SYNC();
+    NSX_SINGLE { c.n_special = s.spec_e0; }
+    NSX_SYNC();
+}
+
 template <bool BLK, class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
     NSX_SINGLE { s.def_kind = 0; }
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
+    nsx_count_special(d, c, s);
     NSX_SYNC();
     // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
     nsx_recompute_all_potentials<BLK>(d, c.phase, ps);

@@ -289,6 +289,7 @@ struct NsxCtaShared {
     NsxDevexCand dx_buf[32];
     unsigned long long gate_bits;               // Dantzig sweep: raw bits of the best (most negative) key any
                                                 // thread of this CTA has found so far in the current sweep
+    int32_t gate_arc2;                          // ... and, after the sweep, the lowest arc*2+dir among the threads that hold it
     // candidate-list refresh (NSX_CMD_TOPK): entries in the top-k buffer and the (merit bits, arc) an arc has to
     // exceed to enter it; the buffer itself aliases piv.res (keys) and piv.arc2 (arcs), idle during sweeps
     int32_t tk_cnt;
@@ -520,6 +521,154 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
 #undef OFFU
 #undef IDXU
 
+// The improving sweep of the Dantzig rule / transportation row scan - the hot loop of BASELINE config 3 - in a form
+// that costs fewer issue slots per arc than the general routine above (same arithmetic, same candidates):
+//  * potentials in shared memory are read through a 32-bit shared address computed once per sweep (`pi_s`; no
+//    generic-pointer select and no per-arc index adjustment);
+//  * eligibility is three integer operations per arc; the gate test is one float64 compare per arc (keys are negative
+//    doubles: "raw bits of rc >= raw bits of gate" is "rc <= gate", and a non-negative rc never passes) accumulating the
+//    eligibility bits themselves;
+//  * the Phase-1 cost `(c - 1) - 1e-6 idx` (simplex.py:1162-1168) takes its `c - 1` as an integer subtraction when the
+//    store holds integer costs (exact either way: |c| < 2^31);
+//  * `ragged` = false: the tiles lie inside [lo, hi) (every tile of a worker but its first and last).
+__device__ __forceinline__ double nsx_lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// "some rc[u] <= g": one predicate-accumulating float64 compare per value (the C++ `||` chain compiles to a min chain
+// with NaN handling, eight instructions per value)
+template <int NA>
+__device__ __forceinline__ bool nsx_any_le(const double (&rc)[NA], double g) {
+    static_assert(NA == 4 || NA == 8, "four arcs per tile and thread");
+    uint32_t h;
+    if (NA == 4) {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.le.f64 p, %1, %5;\n\tsetp.le.or.f64 p, %2, %5, p;\n\tsetp.le.or.f64 p, %3, %5, p;\n\tsetp.le.or.f64 p, %4, %5, p;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(h) : "d"(rc[0]), "d"(rc[1]), "d"(rc[2]), "d"(rc[3]), "d"(g));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.le.f64 p, %1, %9;\n\tsetp.le.or.f64 p, %2, %9, p;\n\tsetp.le.or.f64 p, %3, %9, p;\n\tsetp.le.or.f64 p, %4, %9, p;\n\t"
+            "setp.le.or.f64 p, %5, %9, p;\n\tsetp.le.or.f64 p, %6, %9, p;\n\tsetp.le.or.f64 p, %7, %9, p;\n\tsetp.le.or.f64 p, %8, %9, p;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(h) : "d"(rc[0]), "d"(rc[1]), "d"(rc[2]), "d"(rc[3]), "d"(rc[NA - 4]), "d"(rc[NA - 3]), "d"(rc[NA - 2]), "d"(rc[NA - 1]), "d"(g));
+    }
+    return h != 0;
+}
+template <bool PHASE1, bool PISMEM, int Q>
+__device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStore& st, const double* pi1, uint32_t pi_s,
+                                                  const unsigned char* const (&spq)[Q], const int32_t (&tbq)[Q], bool ragged,
+                                                  bool plain, int32_t lo, int32_t hi, NsxCand& dz, NsxCtaShared& sh) {
+    const int tid = threadIdx.x;
+    constexpr int NA = 4 * Q;
+#define SPU(u) (spq[(u) >> 2])
+#define OFFU(u) (((u) & 3) * NSX_CONSUMERS + tid)
+#define IDXU(u) (tbq[(u) >> 2] + ((u) & 3) * NSX_CONSUMERS + tid)
+    // `plain` (block-uniform): the tiles lie inside [lo, hi) and NO arc outside the tree has anything but forward
+    // residual (NsxCtl::n_special == 0 - e.g. every pivot of an uncapacitated instance): the candidates are exactly the
+    // arcs with rc < -tol - tree arcs have |rc| ~ 0 - so the state bytes are only looked at when an arc reaches the gate.
+    uint32_t sb[NA];
+    uint32_t any = 0;
+    if (!plain) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) sb[u] = SPU(u)[st.off_state + OFFU(u)];
+        if (ragged) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                if (tbq[q] < lo || tbq[q] + NSX_TILE > hi) {
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int32_t i = tbq[q] + uu * NSX_CONSUMERS + tid;
+                        if (i < lo || i >= hi) sb[4 * q + uu] = 0;
+                    }
+                }
+            }
+        }
+        // residual forward / backward and not in the tree:  bits & 6 & ((bits & 1) - 1)
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            sb[u] &= ((sb[u] & NSX_ARC_IN_TREE) - 1u) & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD);
+            any |= sb[u];
+        }
+        if (!any) return;
+    }
+    int32_t tl[NA], hd[NA];
+    double c[NA];
+    if (st.node_kind == NSX_NODE_U16) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)];
+            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)];
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            tl[u] = reinterpret_cast<const int32_t*>(SPU(u))[OFFU(u)];
+            hd[u] = reinterpret_cast<const int32_t*>(SPU(u) + st.off_head)[OFFU(u)];
+        }
+    }
+    // c = cost (Phase 2) or cost - 1 (Phase 1)
+    if (st.cost_kind == NSX_COST_F64) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            c[u] = reinterpret_cast<const double*>(SPU(u) + st.off_cost)[OFFU(u)];
+            if (PHASE1) c[u] = NSX_SUB(c[u], 1.0);
+        }
+    } else if (st.cost_kind == NSX_COST_I32) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) c[u] = (double)(reinterpret_cast<const int32_t*>(SPU(u) + st.off_cost)[OFFU(u)] - (PHASE1 ? 1 : 0));
+    } else {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) c[u] = (double)((int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)] - (PHASE1 ? 1 : 0));
+    }
+    double rc[NA];
+    double i0[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) i0[q] = (double)(tbq[q] + tid);
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+        double cost = c[u];
+        // idx as a double: i0 + k T is exact (and i0 + 0.0 == i0: no -0.0 here)
+        if (PHASE1) cost = NSX_SUB(cost, NSX_MUL(1e-6, (u & 3) ? NSX_ADD(i0[u >> 2], (double)((u & 3) * NSX_CONSUMERS)) : i0[u >> 2]));
+        const double pt = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)tl[u]) : __ldcg(pi1 + tl[u]);
+        const double ph = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)hd[u]) : __ldcg(pi1 + hd[u]);
+        rc[u] = NSX_SUB(NSX_ADD(cost, pt), ph);
+    }
+    // gate: the best key found so far by ANY thread of the CTA (shared memory, atomicMax on the raw bits of negative
+    // doubles).  It only filters - the exact rule runs in nsx_dantzig_improving on the few arcs that reach it.
+    const double gd = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long*>(&sh.gate_bits));
+    uint32_t hit = 0, hitb = 0;
+    if (plain) {
+        if (!nsx_any_le(rc, gd)) return;
+        hit = NSX_ARC_CAN_FWD;
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            sb[u] = SPU(u)[st.off_state + OFFU(u)];
+            sb[u] &= ((sb[u] & NSX_ARC_IN_TREE) - 1u) & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) hit |= rc[u] <= gd ? sb[u] : 0u;
+        if (any & NSX_ARC_CAN_BWD) {  // arcs with flow to push back are rare
+#pragma unroll
+            for (int u = 0; u < NA; ++u) hitb |= rc[u] >= -gd ? sb[u] : 0u;
+        }
+    }
+    if ((hit & NSX_ARC_CAN_FWD) | (hitb & NSX_ARC_CAN_BWD)) {
+        const double tol = d.tol;
+        const int32_t before = dz.arc2;
+        const double kbefore = dz.key;
+#pragma unroll
+        for (int u = 0; u < NA; ++u) nsx_dantzig_improving(dz, IDXU(u), sb[u], rc[u], tol);
+        if (dz.arc2 >= 0 && (before < 0 || dz.key < kbefore))
+            atomicMax(&sh.gate_bits, (unsigned long long)__double_as_longlong(dz.key));
+    }
+}
+#undef SPU
+#undef OFFU
+#undef IDXU
+
 // ------------------------------------------------------------------------------------------
 // Candidate-list refresh (CandidateListPricing._refresh_candidate_list, simplex_pricing.py:507-536): the
 // NSX_CL_SIZE improving arcs of largest merit |rc|, ties to the LARGER arc index (Python sorts (merit, idx)
@@ -700,6 +849,9 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
             bar();
             nsx_tk_compact(sh, (int)threadIdx.x, NSX_CONSUMERS, bar);  // sorted list of this CTA
         }
+        // (Dantzig improving sweep: nsx_price_tile_dz) potentials base: node ids are stored zero-based from node 1 in the uint16 layout
+        const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
+        const uint32_t pi_s = PISMEM ? nsx_smem_addr(pi1) : 0u;
         if (MODE != NSX_MODE_TOPK && stages >= 4) {
             for (; j + 1 < my_n; j += 2) {  // two tiles per step
                 uint32_t s2 = s + 1, par2 = par;
@@ -708,7 +860,11 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
                 nsx_mbar_wait(&sh.full[s2], par2);
                 const unsigned char* const sp[2] = {ring + s * st.stage_bytes, ring + s2 * st.stage_bytes};
                 const int32_t tb[2] = {tile * NSX_TILE, (tile + step) * NSX_TILE};
-                nsx_price_tile<MODE, PHASE1, PISMEM, 2>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
+                if (MODE == NSX_MODE_DANTZIG) {
+                    const bool inner = j > 0 && j + 2 < my_n;  // neither the first nor the last tile of this worker
+                    nsx_price_tile_dz<PHASE1, PISMEM, 2>(d, st, pi1, pi_s, sp, tb, !inner, inner && cmd.pad[1] != 0, lo, hi, dz, sh);
+                }
+                else nsx_price_tile<MODE, PHASE1, PISMEM, 2>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
                 __syncwarp();
                 if (lane == 0) { nsx_mbar_arrive(&sh.empty[s]); nsx_mbar_arrive(&sh.empty[s2]); }
                 tile += 2 * step;
@@ -720,7 +876,8 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
             nsx_mbar_wait(&sh.full[s], par);
             const unsigned char* const sp[1] = {ring + s * st.stage_bytes};
             const int32_t tb[1] = {tile * NSX_TILE};
-            nsx_price_tile<MODE, PHASE1, PISMEM, 1>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
+            if (MODE == NSX_MODE_DANTZIG) nsx_price_tile_dz<PHASE1, PISMEM, 1>(d, st, pi1, pi_s, sp, tb, true, false, lo, hi, dz, sh);
+            else nsx_price_tile<MODE, PHASE1, PISMEM, 1>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
             __syncwarp();
             if (lane == 0) nsx_mbar_arrive(&sh.empty[s]);
             tile += step;
@@ -753,7 +910,7 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
     nsx_cand_init(dz);
     nsx_devex_init(dx);
     // first candidate must satisfy rc < -tol: start the gate at the largest double below -tol
-    if (threadIdx.x == 0) { sh.gate_bits = (unsigned long long)__double_as_longlong(-d.tol) + 1ull; nsx_tk_reset(sh, d.tol); }
+    if (threadIdx.x == 0) { sh.gate_bits = (unsigned long long)__double_as_longlong(-d.tol) + 1ull; sh.gate_arc2 = 0x7fffffff; nsx_tk_reset(sh, d.tol); }
     NSX_SYNC();  // the command is visible; reduction buffers / staged potentials are free again
     if (sh.tl_grid) NSX_TL(sh.tl_grid, 1);
     if (cmd.kind == NSX_CMD_TOPK) {
@@ -766,7 +923,17 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
     if (cmd.kind == NSX_CMD_DANTZIG) {
         if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
         else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
-        nsx_block_reduce(dz, sh.dz_buf);
+        // The CTA's best key IS the gate (every thread raised it to its own best key; it still holds its start value when
+        // nobody found a candidate): the threads that hold that key agree on the lowest arc with one shared-memory atomic -
+        // two barriers instead of a shuffle tree over 16 warps.
+        NSX_SYNC();
+        const unsigned long long gbest = sh.gate_bits;
+        if (dz.arc2 >= 0 && (unsigned long long)__double_as_longlong(dz.key) == gbest) atomicMin(&sh.gate_arc2, dz.arc2);
+        NSX_SYNC();
+        if (threadIdx.x == 0) {
+            nsx_cand_init(dz);
+            if (sh.gate_arc2 != 0x7fffffff) { dz.key = __longlong_as_double((long long)gbest); dz.arc2 = sh.gate_arc2; }
+        }
     } else if (cmd.kind == NSX_CMD_DEVEX) {
         nsx_sweep_ring_pi<NSX_MODE_DEVEX, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
         nsx_block_reduce(dx, sh.dx_buf);
@@ -1515,6 +1682,7 @@ template <bool BLK, class Sweep>
 __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
                                                NsxPotScratch& ps, Sweep& sweep, int32_t count) {
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
+    nsx_count_special(d, c, pv);
     NSX_SYNC();
     nsx_recompute_all_potentials<BLK>(d, 1, ps);
     for (int32_t k = 0; k < count; ++k) {
@@ -1526,6 +1694,7 @@ __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLo
                 cmd.kind = NSX_CMD_DEVEX; cmd.lo = st; cmd.hi = st + c.bs < d.m ? st + c.bs : d.m;
             } else {
                 cmd.kind = NSX_CMD_DANTZIG; cmd.lo = 0; cmd.hi = d.m;
+                cmd.pad[1] = c.n_special == 0;
             }
             cmd.phase = 1; cmd.excluded = -1; cmd.wepoch = 0; cmd.reverse = k & 1;
             c.arcs_priced += cmd.hi - cmd.lo;
@@ -1663,8 +1832,31 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
     }
 }
 
+#ifdef NSX_DEV_SWEEP_ONLY
+// Development aid (never part of the library): the worker side of a sweep alone, so that `nvcc -cubin -DNSX_DEV_SWEEP_ONLY`
+// plus `cuobjdump -sass` shows the pricing loop within seconds instead of a full build of the four resident kernels.
+extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_dev_sweep_kernel(const NsxKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NsxCtaShared& sh = *reinterpret_cast<NsxCtaShared*>(smem_raw);
+    unsigned char* dyn = smem_raw + nsx_align16(sizeof(NsxCtaShared));
+    nsx_init_barriers(sh);
+    uint32_t stage_count = 0, q0 = 0;
+    NSX_SYNC();
+    double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
+    NsxCand dz; NsxDevexCand dx;
+    const NsxCmd cmd = a.grid->cmd;
+    nsx_cta_sweep(a.d, a.st, cmd, pis, pis != nullptr, stage_count, dyn + a.wplan.ring_off, a.wplan.stages, q0, (int)blockIdx.x, (int)gridDim.x, sh, dz, dx);
+    if (threadIdx.x == 0) { union { NsxCand c; int4 v; } tmp; tmp.c = dz; a.slots[blockIdx.x].v[0] = tmp.v; }
+}
+extern "C" __global__ void nsx_resident_kernel(const NsxKernelArgs a);      // (declared for the host code below, not built)
+extern "C" __global__ void nsx_resident_kernel_hbm(const NsxKernelArgs a);
+struct NsxBatchItem;
+extern "C" __global__ void nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage);
+extern "C" __global__ void nsx_batch_kernel_hbm(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage);
+#else
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_resident_kernel(const NsxKernelArgs a) { nsx_resident_body<false>(a); }
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_resident_kernel_hbm(const NsxKernelArgs a) { nsx_resident_body<true>(a); }
+#endif
 
 // Initial state: real arcs, nodes + artificial arcs, artificial-flow count.
 extern "C" __global__ void nsx_init_kernel(const NsxDev d, const double* supply, NsxCtl* ctl) {
@@ -1861,6 +2053,7 @@ __device__ __forceinline__ void nsx_batch_body(const NsxBatchItem* items, int64_
         nsx_copy_ctl(item.ctl, &sh.ctl);
     }
 }
+#ifndef NSX_DEV_SWEEP_ONLY
 // nsx_batch_kernel: every instance of the batch fits its CTA's shared memory (what the host checked); _hbm: some do not
 extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
 nsx_batch_kernel(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage) {
@@ -1870,6 +2063,7 @@ extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1)
 nsx_batch_kernel_hbm(const NsxBatchItem* items, int64_t count, unsigned long long* next, size_t limit_bytes, int want_mode, int want_stage) {
     nsx_batch_body<true>(items, count, next, limit_bytes, want_mode, want_stage);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Host side: C ABI
@@ -1965,6 +2159,7 @@ static const char* nsx_fault_text(int fault) {
 }
 
 static void nsx_harvest(const NsxCtl& c, nsx_result* res) {
+    if (getenv("NSX_DEBUG")) fprintf(stderr, "[nsx] n_special at exit: %d\n", c.n_special);
     res->fault = c.fault;
     res->status = c.status;
     res->iterations = c.total;

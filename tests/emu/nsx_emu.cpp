@@ -200,6 +200,16 @@ struct SerialSweep {
             return;
         }
         if (g_inc.on && cmd.kind == NSX_CMD_DANTZIG && cmd.lo == 0 && cmd.hi == d.m) inc_stats(cmd);
+        if (cmd.kind == NSX_CMD_DANTZIG) {
+            // the count that lets the CUDA sweep skip the state bytes (NsxCtl::n_special) must match a recount at every sweep
+            int32_t cnt = 0;
+            for (int64_t i = 0; i < d.m; ++i) cnt += nsx_special(d.state[i]);
+            if (getenv("NSX_EMU_DEBUG") && cnt) fprintf(stderr, "nsx_emu: sweep %lld n_special %d\n", (long long)c.sweeps, cnt);
+            if (cnt != c.n_special || cmd.pad[1] != (cnt == 0 ? 1 : 0)) {
+                fprintf(stderr, "nsx_emu: n_special %d, recount %d, command flag %d\n", c.n_special, cnt, cmd.pad[1]);
+                abort();
+            }
+        }
         if (cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO) {
             for (int64_t i = cmd.lo; i < cmd.hi; ++i) {
                 double rc = NSX_SUB(NSX_ADD(nsx_arc_cost(d, cmd.phase, i), d.pi[d.tail[i]]), d.pi[d.head[i]]);
