@@ -135,6 +135,10 @@ struct alignas(16) NsxNode {
 struct alignas(16) NsxRC { double key; int32_t arc2; int32_t pad; };  // arc2 < 0: the row has no improving arc; pad = star round in
                                                                      // which the pivot last emptied the row (it is priced afresh then)
 
+// One changed potential, as the sweep workers patch it into their shared-memory copy (NsxDev::pi_delta)
+struct alignas(16) NsxPiDelta { int32_t node, pad; double pi; };
+#define NSX_PI_DELTA_CAP 2048
+
 struct NsxDev {
     int32_t n;   // nodes incl. root
     int64_t m;   // real arcs
@@ -184,6 +188,10 @@ struct NsxDev {
     struct NsxBlk* blk; // trees that live in HBM: the preorder array is kept in blocks with slack (see NsxBlk); `order` is
                         // then the block arena (NSX_BLK_MAX << blk->lg entries) and node.pos a physical index into it
     int32_t* sidx;      // [n] blocked mode: index of a node inside the sequence nsx_recompute_potentials runs over
+    // [NSX_PI_DELTA_CAP] grid kernel whose workers keep the potentials in shared memory, else null: the potentials the last
+    // pivot changed (its re-hung subtree).  A sweep command carries their number (NsxPivotScratch::pi_delta_n) and the
+    // workers patch their copy instead of copying all n potentials again.
+    NsxPiDelta* pi_delta = nullptr;
 };
 
 #define NSX_CL_SIZE 100    // candidate-list length (simplex.py:232)
@@ -259,6 +267,9 @@ struct NsxPivotScratch {
     // between the old and the new place of S into tmp and copy the window back; 2: blocked array - take S out, put it back.
     int32_t def_kind, def_p, def_sz, def_pad;
     int32_t spec_e0;           // nsx_special() of the entering arc before the pivot touched it
+    int32_t pi_delta_n;        // entries of NsxDev::pi_delta that describe ALL potential changes since the last sweep command
+                               // (0: none), or -1: the workers must copy all potentials (start, phase switch, two tree
+                               // updates without a command in between, a subtree larger than the buffer)
     int64_t def_lo, def_hi, def_S0, def_S1, def_xshift;
     int64_t def_moved;
     int32_t sp_any;            // rule scan: number of the last round in which some thread saw an arc that beats the incumbent
@@ -410,7 +421,7 @@ struct NsxPotScratch {
 #define NSX_POT_EMPTY 0x7ff8dead0badc0deLL
 #define NSX_HOP 8
 NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32_t* arr, const int32_t* sidx,
-                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
+                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out, NsxPiDelta* delta = nullptr) {
     int32_t rounds = 0;
     volatile long long* vbits = reinterpret_cast<volatile long long*>(s.val);
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
@@ -477,24 +488,20 @@ NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32
         if (active) {
             d.pi[v] = val;
             if (d.pi_mirror) d.pi_mirror[v] = val;
+            if (delta) { NsxPiDelta ent; ent.node = v; ent.pad = 0; ent.pi = val; delta[x - lo] = ent; }  // (for the sweep workers, NsxDev::pi_delta)
         }
     }
     NSX_SYNC();
-    if (rounds_out) {
-        // statistics only: polls of the slowest warp, summed over chunks
-        NSX_SINGLE { s.rounds = 0; }
-        NSX_SYNC();
-        if ((NSX_TID & 31) == 0) NSX_ATOMIC_MAX_I32(&s.rounds, rounds);
-        NSX_SYNC();
-        NSX_SINGLE { *rounds_out += s.rounds; }
-    }
+    // statistics only: polls of warp 0 (it holds the first entries of every chunk), summed over chunks - kept free of
+    // barriers: this runs once per pivot on the critical path
+    if (rounds_out) { NSX_SINGLE { *rounds_out += rounds; } }
 }
 #else
 // A chunk is finished level by level: a waiting node of depth L has its parent at depth L-1, which
 // is either outside the chunk (final), or final from the chunk set-up, or was computed in the
 // previous level step.  One barrier per tree level present in the chunk.
 NSX_FN void nsx_recompute_potentials(const NsxDev& d, int32_t phase, const int32_t* arr, const int32_t* sidx,
-                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out) {
+                                     int64_t lo, int64_t hi, NsxPotScratch& s, int64_t* rounds_out, NsxPiDelta* delta = nullptr) {
     NSX_SINGLE { s.rounds = 0; }
     for (int64_t c0 = lo; c0 < hi; c0 += NSX_CHUNK) {
         int64_t c1 = c0 + NSX_CHUNK < hi ? c0 + NSX_CHUNK : hi;
@@ -1318,8 +1325,12 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
 
     // ---- 6. potentials of the re-hung subtree, parent before child ------------------------
     // (the dense array has S in tmp at its final place; `order` catches up in nsx_pivot_flush)
-    if (blocked) nsx_recompute_potentials(d, c.phase, d.tmp, d.sidx, 0, sz, ps, &c.sum_rounds);
-    else nsx_recompute_potentials(d, c.phase, d.tmp, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds);
+    // (pi_delta_n is block-uniform here: last written before several barriers; the recompute ends with a barrier, so
+    // every thread has read it before thread 0 writes it)
+    const bool pd_fits = d.pi_delta && s.pi_delta_n == 0 && sz <= NSX_PI_DELTA_CAP;
+    if (blocked) nsx_recompute_potentials(d, c.phase, d.tmp, d.sidx, 0, sz, ps, &c.sum_rounds, pd_fits ? d.pi_delta : nullptr);
+    else nsx_recompute_potentials(d, c.phase, d.tmp, (const int32_t*)0, s_base, s_base + sz, ps, &c.sum_rounds, pd_fits ? d.pi_delta : nullptr);
+    if (d.pi_delta) { NSX_SINGLE { s.pi_delta_n = pd_fits ? sz : -1; } }
     const bool star_record = c.star_on && c.star_valid;  // (block-uniform: written by thread 0 before several barriers)
     if (star_record) {
         NSX_SYNC();  // every thread has read the flags before thread 0 may change them
@@ -2044,7 +2055,7 @@ NSX_FN void nsx_count_special(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s) {
 template <bool BLK, class Sweep>
 NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& s,
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
-    NSX_SINGLE { s.def_kind = 0; }
+    NSX_SINGLE { s.def_kind = 0; s.pi_delta_n = -1; }
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
     nsx_count_special(d, c, s);
     NSX_SYNC();
@@ -2096,7 +2107,7 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
             nsx_pivot_flush<BLK>(d, c, s);
             if (!L.drv.final_check) {
                 nsx_recompute_all_potentials<BLK>(d, 2, ps);
-                NSX_SINGLE { c.star_valid = 0; }  // Phase-2 costs: every reduced cost changed
+                NSX_SINGLE { c.star_valid = 0; s.pi_delta_n = -1; }  // Phase-2 costs: every reduced cost (and potential) changed
             }
             NSX_SYNC();
             NSX_SINGLE { nsx_drv_begin(c, L.drv, d.m, L.cmd, L.act); }

@@ -56,6 +56,7 @@ struct NsxGridCtl {
     unsigned long long t_pub;    // globaltimer at the publication of the current command
     unsigned long long tl[8];    // handshake timeline of worker 1, ns after t_pub, accumulated over sweeps
 };
+struct NsxCand;
 #define NSX_TL(grid, k) do { if (blockIdx.x == 1 && threadIdx.x == 0) (grid)->tl[k] += nsx_globaltimer() - (grid)->t_pub; } while (0)
 
 __device__ __forceinline__ int32_t nsx_ld_acquire(const int32_t* p) {
@@ -75,6 +76,29 @@ __device__ __forceinline__ void nsx_st_release(int32_t* p, int32_t v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // 1-D bulk copies global -> shared through the TMA unit (cp.async.bulk), completion on an mbarrier.
+// Candidate of a Dantzig-rule sweep, worker -> pivot CTA, as four self-validating 64-bit words {data : 32, command
+// number : 32} (the "LL" idea of NCCL): the reader needs ONE round trip to L2 - no sequence word to acquire first and
+// no second load for the payload - and accepts the record when all four words carry the number it waits for.  64-bit
+// elements of a vector access are single-copy atomic; nothing else the reader looks at is published with this record.
+__device__ __forceinline__ void nsx_ll_store(NsxSlot* sl, double key, int32_t arc2, int32_t zero2, int32_t seq) {
+    const unsigned long long s = (unsigned long long)(uint32_t)seq << 32;
+    const unsigned long long kb = (unsigned long long)__double_as_longlong(key);
+    const unsigned long long w0 = s | (kb & 0xffffffffull), w1 = s | (kb >> 32);
+    const unsigned long long w2 = s | (unsigned long long)(uint32_t)arc2, w3 = s | (unsigned long long)(uint32_t)zero2;
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(&sl->v[0]), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(&sl->v[1]), "l"(w2), "l"(w3) : "memory");
+}
+__device__ __forceinline__ bool nsx_ll_load(const NsxSlot* sl, int32_t seq, double& key, int32_t& arc2, int32_t& zero2) {
+    unsigned long long w0, w1, w2, w3;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(&sl->v[0]) : "memory");
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(&sl->v[1]) : "memory");
+    const uint32_t s = (uint32_t)seq;
+    if ((uint32_t)(w0 >> 32) != s || (uint32_t)(w1 >> 32) != s || (uint32_t)(w2 >> 32) != s || (uint32_t)(w3 >> 32) != s) return false;
+    key = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+    arc2 = (int32_t)(uint32_t)w2; zero2 = (int32_t)(uint32_t)w3;
+    return true;
+}
+
 __device__ __forceinline__ uint32_t nsx_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nsx_mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nsx_smem_addr(bar)), "r"(count) : "memory");
@@ -542,16 +566,18 @@ template <int NA>
 __device__ __forceinline__ bool nsx_any_le(const double (&rc)[NA], double g) {
     static_assert(NA == 4 || NA == 8, "four arcs per tile and thread");
     uint32_t h;
+    // pairs accumulate into separate predicates (dependent chains of length two, not NA), combined at the end
     if (NA == 4) {
-        asm("{\n\t.reg .pred p;\n\t"
-            "setp.le.f64 p, %1, %5;\n\tsetp.le.or.f64 p, %2, %5, p;\n\tsetp.le.or.f64 p, %3, %5, p;\n\tsetp.le.or.f64 p, %4, %5, p;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.le.f64 p, %1, %5;\n\tsetp.le.f64 q, %3, %5;\n\t"
+            "setp.le.or.f64 p, %2, %5, p;\n\tsetp.le.or.f64 q, %4, %5, q;\n\t"
+            "or.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(h) : "d"(rc[0]), "d"(rc[1]), "d"(rc[2]), "d"(rc[3]), "d"(g));
     } else {
-        asm("{\n\t.reg .pred p;\n\t"
-            "setp.le.f64 p, %1, %9;\n\tsetp.le.or.f64 p, %2, %9, p;\n\tsetp.le.or.f64 p, %3, %9, p;\n\tsetp.le.or.f64 p, %4, %9, p;\n\t"
-            "setp.le.or.f64 p, %5, %9, p;\n\tsetp.le.or.f64 p, %6, %9, p;\n\tsetp.le.or.f64 p, %7, %9, p;\n\tsetp.le.or.f64 p, %8, %9, p;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
+        asm("{\n\t.reg .pred p, q, r, s;\n\t"
+            "setp.le.f64 p, %1, %9;\n\tsetp.le.f64 q, %3, %9;\n\tsetp.le.f64 r, %5, %9;\n\tsetp.le.f64 s, %7, %9;\n\t"
+            "setp.le.or.f64 p, %2, %9, p;\n\tsetp.le.or.f64 q, %4, %9, q;\n\tsetp.le.or.f64 r, %6, %9, r;\n\tsetp.le.or.f64 s, %8, %9, s;\n\t"
+            "or.pred p, p, q;\n\tor.pred r, r, s;\n\tor.pred p, p, r;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(h) : "d"(rc[0]), "d"(rc[1]), "d"(rc[2]), "d"(rc[3]), "d"(rc[NA - 4]), "d"(rc[NA - 3]), "d"(rc[NA - 2]), "d"(rc[NA - 1]), "d"(g));
     }
     return h != 0;
@@ -812,13 +838,15 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
     const int32_t step = cmd.reverse ? -nworkers : nworkers;
     const int32_t first = t0 + worker + (cmd.reverse ? (my_n - 1) * nworkers : 0);
     uint32_t stage = pos & 0xffffu, parity = pos >> 16;
+    // cmd.pad[2] < 0: copy all potentials into shared memory; >= 0: the copy of the previous command is patched
+    const bool full_pi = stage_pi && cmd.pad[2] < 0;
     if (threadIdx.x >= NSX_CONSUMERS) {
         // ---- producer warp: one lane keeps the ring full ----
         if (lane == 0) {
             // writes of the pivot CTA (state bytes, weights, potentials) were acquired through the
             // generic proxy; the bulk copies below read them through the async proxy
             nsx_fence_proxy_async();
-            if (stage_pi) nsx_bulk_load(pis, d.pi, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
+            if (full_pi) nsx_bulk_load(pis, d.pi, (uint32_t)(((size_t)d.n * 8 + 15) & ~(size_t)15), &sh.mbar);
             int32_t tile = first;
             uint32_t s = stage, par = parity;
             for (int32_t j = 0; j < my_n; ++j) {
@@ -830,7 +858,17 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         }
     } else {
         // ---- consumer warps ----
-        if (stage_pi) nsx_mbar_wait(&sh.mbar, stage_count & 1u);  // potentials of this sweep have landed
+        if (full_pi) {
+            nsx_mbar_wait(&sh.mbar, stage_count & 1u);  // potentials of this sweep have landed
+        } else if (stage_pi && cmd.pad[2] > 0) {
+            // only the potentials the last pivot changed (its re-hung subtree, NsxDev::pi_delta): patch the copy
+            for (int32_t k = threadIdx.x; k < cmd.pad[2]; k += NSX_CONSUMERS) {
+                const int4 ent = __ldcg(reinterpret_cast<const int4*>(d.pi_delta + k));
+                pis[ent.x] = __hiloint2double(ent.w, ent.z);
+            }
+            NsxBarConsumers bar;
+            bar();
+        }
         if (sh.tl_grid) NSX_TL(sh.tl_grid, 2);
         int32_t tile = first;
         const int32_t lo = (int32_t)cmd.lo, hi = (int32_t)cmd.hi;
@@ -885,7 +923,7 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         }
         if (sh.tl_grid) NSX_TL(sh.tl_grid, 3);
     }
-    if (stage_pi) stage_count++;
+    if (full_pi) stage_count++;
     const uint32_t adv = stage + (uint32_t)my_n;
     pos = (adv % (uint32_t)stages) | ((parity ^ ((adv / (uint32_t)stages) & 1u)) << 16);
 }
@@ -1548,7 +1586,9 @@ struct GridSweep {
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         if (gridDim.x == 1) deferred();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
-        const NsxCmd cmd = cmd_in;
+        NsxCmd cmd = cmd_in;
+        // potentials: how many entries of pi_delta bring a worker's shared-memory copy up to date (-1: copy everything)
+        cmd.pad[2] = (gridDim.x > 1 && d.pi_delta) ? sh.piv.pi_delta_n : -1;
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
         const bool devex = cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO || (starcmd && cmd.pad[0]);
         if (gridDim.x == 1) {  // alone: this CTA prices everything itself
@@ -1572,6 +1612,7 @@ struct GridSweep {
         if (starcmd && threadIdx.x == 0) { *star.rq_n = 0; *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull; }  // (x_recs: idle on one GPU, holds the evaluated-arc count)
         if (starcmd) NSX_SYNC();
         publish(cmd);
+        if (threadIdx.x == 0) sh.piv.pi_delta_n = 0;  // (every thread read it before the barrier in front of publish)
         deferred();
         unsigned long long t1 = 0;
         if (threadIdx.x == 0) t1 = nsx_globaltimer();
@@ -1580,11 +1621,21 @@ struct GridSweep {
         NsxCand kz; nsx_cand_init(kz);
         unsigned long long ev = 0ull;
         int32_t nq_seen = 0;  // star update: rows that were queued, as reported by the worker whose slot this thread polls
+        const bool ll = cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO;  // (nsx_ll_store on the worker side)
         for (int b = 1 + threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
             const NsxSlot* sl = slots + b;
             uint32_t spins = 0;
             bool lost = false;
             const unsigned long long t_wait = nsx_globaltimer();
+            if (ll) {
+                NsxCand got; nsx_cand_init(got);
+                while (!nsx_ll_load(sl, seq, got.key, got.arc2, got.zero2)) {
+                    if ((++spins & 1023u) == 0 && (nsx_ld_acquire(&g->abort) != 0 || nsx_globaltimer() - t_wait > spin_ns)) { lost = true; break; }
+                }
+                if (lost) { c.fault = 1; break; }
+                nsx_cand_merge(kz, got);
+                continue;
+            }
             while (nsx_ld_acquire(&sl->seq) != seq) {
                 if ((++spins & 1023u) == 0 && (nsx_ld_acquire(&g->abort) != 0 || nsx_globaltimer() - t_wait > spin_ns)) { lost = true; break; }
             }
@@ -1696,6 +1747,7 @@ __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLo
                 cmd.kind = NSX_CMD_DANTZIG; cmd.lo = 0; cmd.hi = d.m;
                 cmd.pad[1] = c.n_special == 0;
             }
+            pv.pi_delta_n = -1;  // (a probe sweep copies all potentials, like the first sweep after a phase switch)
             cmd.phase = 1; cmd.excluded = -1; cmd.wepoch = 0; cmd.reverse = k & 1;
             c.arcs_priced += cmd.hi - cmd.lo;
             c.sweeps++;
@@ -1750,6 +1802,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
     unsigned char* ring = dyn + a.wplan.ring_off;
     int32_t seen = 0;
     uint32_t bar_rounds = 0;
+    bool pi_valid = false;  // the potentials in `pis` are those of the previous command (a star command overwrites them)
     for (;;) {
         if (threadIdx.x == 0) {
             int32_t s;
@@ -1779,11 +1832,12 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             }
         }
         NSX_SYNC();
-        const NsxCmd cmd = sh.cmd;
+        NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
         if (starcmd) {
+            pi_valid = false;
             int64_t evaluated = 0; int32_t fault = 0;
             nsx_cta_star(d, a.star, cmd, (int)blockIdx.x - 1, (int)gridDim.x - 1, dyn, sh, bar_rounds, a.spin_ns, dz, dx, evaluated, fault);
             // arcs examined by this CTA (lane 0 of every warp counted its warp's): summed through shared memory
@@ -1803,8 +1857,10 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             }
             continue;
         }
+        if (!pi_valid) cmd.pad[2] = -1;
         nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
                       a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
+        pi_valid = pis != nullptr;
         if (cmd.kind == NSX_CMD_TOPK) {  // this CTA's sorted list -> HBM (the slot release below orders it)
             NsxTopkOut* out = a.topk + blockIdx.x;
             const int32_t cnt = sh.tk_cnt;
@@ -1819,14 +1875,28 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
         if (threadIdx.x == 0) {
             if (a.timeline) NSX_TL(a.grid, 4);
             NsxSlot* sl = a.slots + blockIdx.x;
-            if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) {
-                union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx;
-                sl->v[0] = tmp.v[0]; sl->v[1] = tmp.v[1];
+            if (cmd.kind == NSX_CMD_DANTZIG || cmd.kind == NSX_CMD_DANTZIG_ZERO) {
+                nsx_ll_store(sl, dz.key, dz.arc2, dz.zero2, seen);  // self-validating words: no sequence word, no fence
+                if (dz.arc2 >= 0) {
+                    // If this candidate wins, the pivot CTA starts with dependent reads of its arc record (endpoints, then
+                    // flow / capacity / cost): pull those lines into L2 now (random HBM access -> L2 hit, ~0.4 us each)
+                    const int64_t arc = dz.arc2 >> 1;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.tail + arc));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.head + arc));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.flow + arc));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.upper + arc));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.pert + arc));
+                }
             } else {
-                union { NsxCand c; int4 v; } tmp; tmp.c = dz;
-                sl->v[0] = tmp.v;
+                if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) {
+                    union { NsxDevexCand c; int4 v[2]; } tmp; tmp.c = dx;
+                    sl->v[0] = tmp.v[0]; sl->v[1] = tmp.v[1];
+                } else {
+                    union { NsxCand c; int4 v; } tmp; tmp.c = dz;
+                    sl->v[0] = tmp.v;
+                }
+                nsx_st_release(&sl->seq, seen);  // the payload above is ordered before the sequence number
             }
-            nsx_st_release(&sl->seq, seen);  // the payload above is ordered before the sequence number
             if (a.timeline) NSX_TL(a.grid, 5);
         }
     }
@@ -1844,7 +1914,8 @@ extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_dev_sweep_kerne
     NSX_SYNC();
     double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     NsxCand dz; NsxDevexCand dx;
-    const NsxCmd cmd = a.grid->cmd;
+    NsxCmd cmd = a.grid->cmd;
+    cmd.pad[2] = -1;
     nsx_cta_sweep(a.d, a.st, cmd, pis, pis != nullptr, stage_count, dyn + a.wplan.ring_off, a.wplan.stages, q0, (int)blockIdx.x, (int)gridDim.x, sh, dz, dx);
     if (threadIdx.x == 0) { union { NsxCand c; int4 v; } tmp; tmp.c = dz; a.slots[blockIdx.x].v[0] = tmp.v; }
 }
@@ -1984,7 +2055,8 @@ struct LocalSweep {
     uint32_t& q0;
     template <class Deferred>
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c, Deferred deferred) {
-        const NsxCmd cmd = cmd_in;
+        NsxCmd cmd = cmd_in;
+        cmd.pad[2] = -1;  // (potentials are staged in full, if at all)
         NsxCand dz; NsxDevexCand dx;
         deferred();  // (one CTA does everything: nothing to overlap with)
         NSX_SYNC();
@@ -2362,6 +2434,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t o_topk = arena.plan(sizeof(NsxTopkOut) * 160);
     size_t o_trace = want_trace ? arena.plan((size_t)opt->trace_capacity * 4) : 0;
     size_t o_imb = warm ? arena.plan((size_t)n * 8) : 0;
+    size_t o_pidelta = arena.plan((size_t)NSX_PI_DELTA_CAP * sizeof(NsxPiDelta));
     size_t o_rc = 0, o_dlist = 0, o_dstamp = 0, o_rowb = 0, o_colb = 0, o_cursor = 0, o_cpos = 0, o_cstate = 0, o_carc = 0, o_ctail = 0,
            o_ccost = 0, o_rq = 0, o_rqn = 0, o_dinfo = 0, o_cwgt = 0;
     if (star) {
@@ -2398,6 +2471,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     d.garc2 = arena.at<int32_t>(o_garc2); d.gres = arena.at<double>(o_gres);
     d.penalty = pb->penalty; d.tol = opt->tolerance; d.scan_walk = 0; d.par16 = nullptr; d.root_bits = nullptr;
     d.imbalance = warm ? arena.at<double>(o_imb) : nullptr;
+    d.pi_delta = arena.at<NsxPiDelta>(o_pidelta);  // (used by grids whose workers stage the potentials; set to null below otherwise)
     ka.ctl = arena.at<NsxCtl>(o_ctl); ka.grid = arena.at<NsxGridCtl>(o_grid);
     ka.slots = arena.at<NsxSlot>(o_slots);
     ka.topk = arena.at<NsxTopkOut>(o_topk);
@@ -2447,6 +2521,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     size_t dyn = nsx_plan_bytes(ka.plan, st.stage_bytes);
     if (star && dyn < (size_t)(4 * NSX_STAR_ENT + 1) * 4 + 64) dyn = (size_t)(4 * NSX_STAR_ENT + 1) * 4 + 64;  // star work tables of a worker
     if (grid > 1 && nsx_plan_bytes(ka.wplan, st.stage_bytes) > dyn) dyn = nsx_plan_bytes(ka.wplan, st.stage_bytes);
+    if (grid == 1 || !ka.wplan.stage_pi || nsx_env_int("NSX_PI_DELTA", 1) == 0) d.pi_delta = nullptr;
     const size_t smem = fixed + dyn;
     if (smem > info.smem_optin || (grid == 1 ? ka.plan.stages : ka.wplan.stages) < 2) {
         arena.release(); inputs.release();
