@@ -934,13 +934,14 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         // their depths are fetched after the scan, all at once (depth[] may live in L2), so the scan
         // itself has no dependent load and no atomics.  The join is the common ancestor of smallest
         // size (warp-reduced, one shared-memory atomic per warp).
-        NSX_SINGLE { s.jkey = 0x7fffffff; }
+        NSX_SINGLE { s.jkey = 0x7fffffff; s.nh = 0; s.nt = 0; }
         const int32_t ph = d.node[h].pos, pt = d.node[t].pos;
         const int32_t dh = d.depth[h], dt = d.depth[t];
         NSX_SYNC();
         int32_t jk = 0x7fffffff;
         int32_t hit_w[2] = {-1, -1};
         bool hit_h[2] = {false, false};
+        int32_t cnt_h = 0, cnt_t = 0;  // path lengths = number of ancestors of exactly one endpoint (no depth[join] round trip)
         NSX_PAR_FOR(w, 0, d.n) {
             const NsxNode rec = d.node[w];
             const bool in_h = rec.pos <= ph && ph < rec.pos + rec.size;
@@ -949,6 +950,7 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
                 const int32_t key = (rec.size << 16) | (int32_t)w;
                 jk = key < jk ? key : jk;
             } else if (in_h || in_t) {
+                if (in_h) ++cnt_h; else ++cnt_t;
                 if (hit_w[0] < 0) { hit_w[0] = (int32_t)w; hit_h[0] = in_h; }
                 else if (hit_w[1] < 0) { hit_w[1] = (int32_t)w; hit_h[1] = in_h; }
                 else {  // a third hit in one thread (rare): place it right away
@@ -970,13 +972,15 @@ NSX_FN int nsx_pivot(const NsxDev& d, NsxCtl& c, NsxPivotScratch& s, NsxPotScrat
         }
         __syncwarp();
         jk = __reduce_min_sync(0xffffffffu, jk);
-        if ((threadIdx.x & 31) == 0 && jk != 0x7fffffff) NSX_ATOMIC_MIN_I32(&s.jkey, jk);
-        NSX_SYNC();
-        NSX_SINGLE {
-            const int32_t join = s.jkey & 0xffff;
-            const int32_t dj = d.depth[join];
-            s.join = join; s.nh = dh - dj; s.nt = dt - dj;
+        cnt_h = __reduce_add_sync(0xffffffffu, cnt_h);
+        cnt_t = __reduce_add_sync(0xffffffffu, cnt_t);
+        if ((threadIdx.x & 31) == 0) {
+            if (jk != 0x7fffffff) NSX_ATOMIC_MIN_I32(&s.jkey, jk);
+            if (cnt_h) NSX_ATOMIC_ADD_I32(&s.nh, cnt_h);
+            if (cnt_t) NSX_ATOMIC_ADD_I32(&s.nt, cnt_t);
         }
+        NSX_SYNC();
+        NSX_SINGLE { s.join = s.jkey & 0xffff; }
     } else if (BLK && d.blk) {
         // Depth-synchronised climb (no positions needed): lane 0 holds the head-side node, lane 1
         // the tail-side node; the deeper one climbs, both climb when level, until they meet.

@@ -208,8 +208,11 @@ __device__ __forceinline__ void nsx_block_reduce(T& k, T* buf) {
 #define NSX_TILE (4 * NSX_CONSUMERS)  // arcs per tile: four arcs per consumer thread
 #define NSX_MAX_STAGES 8
 
-enum { NSX_NODE_I32 = 0, NSX_NODE_U16 = 1 };
-enum { NSX_COST_F64 = 0, NSX_COST_I32 = 1, NSX_COST_I16 = 2 };
+// NSX_NODE_U16X8 / NSX_COST_I16M1 (always together; n - 1 <= 8192 and int16 costs - BASELINE config 3): the uint16 holds
+// (id - 1) * 8, i.e. the byte offset of the node's potential behind pi[1], and the int16 holds cost - 1 (the Phase-1 cost is
+// (cost - 1) - 1e-6 idx, simplex.py:1162-1168) - two address multiplies and one subtraction less per arc in the hot loop.
+enum { NSX_NODE_I32 = 0, NSX_NODE_U16 = 1, NSX_NODE_U16X8 = 2 };
+enum { NSX_COST_F64 = 0, NSX_COST_I32 = 1, NSX_COST_I16 = 2, NSX_COST_I16M1 = 3 };
 
 struct NsxStore {
     const unsigned char* base;  // [tiles][tail column | head column | cost column], tile_bytes each
@@ -220,7 +223,7 @@ struct NsxStore {
     int32_t has_wgt;
 };
 
-static inline __host__ __device__ uint32_t nsx_node_bytes(int kind) { return kind == NSX_NODE_U16 ? 2u : 4u; }
+static inline __host__ __device__ uint32_t nsx_node_bytes(int kind) { return kind == NSX_NODE_I32 ? 4u : 2u; }
 static inline __host__ __device__ uint32_t nsx_cost_bytes(int kind) {
     return kind == NSX_COST_F64 ? 8u : kind == NSX_COST_I32 ? 4u : 2u;
 }
@@ -437,11 +440,12 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
     // node ids are stored zero-based from node 1 (uint16 layout) - `pi1` points at pi[1]
     int32_t tl[NA], hd[NA];
     double c[NA];
-    if (st.node_kind == NSX_NODE_U16) {
+    if (st.node_kind != NSX_NODE_I32) {
+        const int sh8 = st.node_kind == NSX_NODE_U16X8 ? 3 : 0;
 #pragma unroll
         for (int u = 0; u < NA; ++u) {
-            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)];
-            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)];
+            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)] >> sh8;
+            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)] >> sh8;
         }
     } else {
 #pragma unroll
@@ -457,11 +461,12 @@ __device__ __forceinline__ void nsx_price_tile(const NsxDev& d, const NsxStore& 
 #pragma unroll
         for (int u = 0; u < NA; ++u) c[u] = (double)reinterpret_cast<const int32_t*>(SPU(u) + st.off_cost)[OFFU(u)];
     } else {
+        const int32_t bias = st.cost_kind == NSX_COST_I16M1 ? 1 : 0;
 #pragma unroll
-        for (int u = 0; u < NA; ++u) c[u] = (double)(int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)];
+        for (int u = 0; u < NA; ++u) c[u] = (double)((int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)] + bias);
     }
     const double tol = d.tol;
-    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
+    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind != NSX_NODE_I32 ? 1 : 0);
     // all four reduced costs first (independent dependency chains), decisions after
     double rc[NA];
     double i0[Q];
@@ -582,7 +587,9 @@ __device__ __forceinline__ bool nsx_any_le(const double (&rc)[NA], double g) {
     }
     return h != 0;
 }
-template <bool PHASE1, bool PISMEM, int Q>
+//  * LAYOUT = 1: the store is NSX_NODE_U16X8 + NSX_COST_I16M1 (known at compile time: no layout branches; the node
+//    columns ARE the byte offsets of the potentials, the cost column IS the Phase-1 `c - 1`); 0: read st.node_kind / cost_kind.
+template <bool PHASE1, bool PISMEM, int Q, int LAYOUT>
 __device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStore& st, const double* pi1, uint32_t pi_s,
                                                   const unsigned char* const (&spq)[Q], const int32_t (&tbq)[Q], bool ragged,
                                                   bool plain, int32_t lo, int32_t hi, NsxCand& dz, NsxCtaShared& sh) {
@@ -619,13 +626,14 @@ __device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStor
         }
         if (!any) return;
     }
-    int32_t tl[NA], hd[NA];
+    int32_t tl[NA], hd[NA];  // node index behind pi1 - LAYOUT 1: byte offset behind pi1
     double c[NA];
-    if (st.node_kind == NSX_NODE_U16) {
+    if (LAYOUT == 1 || st.node_kind != NSX_NODE_I32) {
+        const int sh8 = (LAYOUT != 1 && st.node_kind == NSX_NODE_U16X8) ? 3 : 0;
 #pragma unroll
         for (int u = 0; u < NA; ++u) {
-            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)];
-            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)];
+            tl[u] = reinterpret_cast<const uint16_t*>(SPU(u))[OFFU(u)] >> sh8;
+            hd[u] = reinterpret_cast<const uint16_t*>(SPU(u) + st.off_head)[OFFU(u)] >> sh8;
         }
     } else {
 #pragma unroll
@@ -635,7 +643,10 @@ __device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStor
         }
     }
     // c = cost (Phase 2) or cost - 1 (Phase 1)
-    if (st.cost_kind == NSX_COST_F64) {
+    if (LAYOUT == 1) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) c[u] = (double)((int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)] + (PHASE1 ? 0 : 1));
+    } else if (st.cost_kind == NSX_COST_F64) {
 #pragma unroll
         for (int u = 0; u < NA; ++u) {
             c[u] = reinterpret_cast<const double*>(SPU(u) + st.off_cost)[OFFU(u)];
@@ -645,8 +656,9 @@ __device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStor
 #pragma unroll
         for (int u = 0; u < NA; ++u) c[u] = (double)(reinterpret_cast<const int32_t*>(SPU(u) + st.off_cost)[OFFU(u)] - (PHASE1 ? 1 : 0));
     } else {
+        const int32_t adj = (st.cost_kind == NSX_COST_I16M1 ? 1 : 0) - (PHASE1 ? 1 : 0);
 #pragma unroll
-        for (int u = 0; u < NA; ++u) c[u] = (double)((int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)] - (PHASE1 ? 1 : 0));
+        for (int u = 0; u < NA; ++u) c[u] = (double)((int32_t)reinterpret_cast<const int16_t*>(SPU(u) + st.off_cost)[OFFU(u)] + adj);
     }
     double rc[NA];
     double i0[Q];
@@ -657,8 +669,14 @@ __device__ __forceinline__ void nsx_price_tile_dz(const NsxDev& d, const NsxStor
         double cost = c[u];
         // idx as a double: i0 + k T is exact (and i0 + 0.0 == i0: no -0.0 here)
         if (PHASE1) cost = NSX_SUB(cost, NSX_MUL(1e-6, (u & 3) ? NSX_ADD(i0[u >> 2], (double)((u & 3) * NSX_CONSUMERS)) : i0[u >> 2]));
-        const double pt = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)tl[u]) : __ldcg(pi1 + tl[u]);
-        const double ph = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)hd[u]) : __ldcg(pi1 + hd[u]);
+        double pt, ph;
+        if (LAYOUT == 1) {
+            pt = PISMEM ? nsx_lds_f64(pi_s + (uint32_t)tl[u]) : __ldcg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(pi1) + tl[u]));
+            ph = PISMEM ? nsx_lds_f64(pi_s + (uint32_t)hd[u]) : __ldcg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(pi1) + hd[u]));
+        } else {
+            pt = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)tl[u]) : __ldcg(pi1 + tl[u]);
+            ph = PISMEM ? nsx_lds_f64(pi_s + 8u * (uint32_t)hd[u]) : __ldcg(pi1 + hd[u]);
+        }
         rc[u] = NSX_SUB(NSX_ADD(cost, pt), ph);
     }
     // gate: the best key found so far by ANY thread of the CTA (shared memory, atomicMax on the raw bits of negative
@@ -784,7 +802,7 @@ __device__ __forceinline__ void nsx_topk_tile(const NsxDev& d, const NsxStore& s
                                               const unsigned char* sp, int32_t tile_base, NsxCtaShared& sh) {
     const int tid = threadIdx.x;
     const double tol = d.tol;
-    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
+    const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind != NSX_NODE_I32 ? 1 : 0);
     NsxBarConsumers bar;
 #pragma unroll 1
     for (int u = 0; u < 4; ++u) {
@@ -797,14 +815,15 @@ __device__ __forceinline__ void nsx_topk_tile(const NsxDev& d, const NsxStore& s
         if (sbits & (NSX_ARC_CAN_FWD | NSX_ARC_CAN_BWD)) {
             int32_t tl, hd;
             double cost;
-            if (st.node_kind == NSX_NODE_U16) {
-                tl = reinterpret_cast<const uint16_t*>(sp)[off]; hd = reinterpret_cast<const uint16_t*>(sp + st.off_head)[off];
+            if (st.node_kind != NSX_NODE_I32) {
+                const int sh8 = st.node_kind == NSX_NODE_U16X8 ? 3 : 0;
+                tl = reinterpret_cast<const uint16_t*>(sp)[off] >> sh8; hd = reinterpret_cast<const uint16_t*>(sp + st.off_head)[off] >> sh8;
             } else {
                 tl = reinterpret_cast<const int32_t*>(sp)[off]; hd = reinterpret_cast<const int32_t*>(sp + st.off_head)[off];
             }
             if (st.cost_kind == NSX_COST_F64) cost = reinterpret_cast<const double*>(sp + st.off_cost)[off];
             else if (st.cost_kind == NSX_COST_I32) cost = (double)reinterpret_cast<const int32_t*>(sp + st.off_cost)[off];
-            else cost = (double)(int32_t)reinterpret_cast<const int16_t*>(sp + st.off_cost)[off];
+            else cost = (double)((int32_t)reinterpret_cast<const int16_t*>(sp + st.off_cost)[off] + (st.cost_kind == NSX_COST_I16M1 ? 1 : 0));
             if (PHASE1) cost = NSX_SUB(NSX_SUB(cost, 1.0), NSX_MUL(1e-6, (double)i));
             const double pt = PISMEM ? pi1[tl] : __ldcg(pi1 + tl);
             const double ph = PISMEM ? pi1[hd] : __ldcg(pi1 + hd);
@@ -824,7 +843,7 @@ __device__ __forceinline__ void nsx_topk_tile(const NsxDev& d, const NsxStore& s
 // of the range, ascending or (cmd.reverse) descending.  `pos` is the ring position of this CTA
 // (register copy, identical in all threads): bits 0-15 = stage of the next tile, bit 16 = mbarrier
 // phase parity of that stage.
-template <int MODE, bool PHASE1, bool PISMEM>
+template <int MODE, bool PHASE1, bool PISMEM, int LAYOUT = 0>
 __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
                                                double* pis, unsigned char* ring, int stages,
                                                NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
@@ -888,7 +907,7 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
             nsx_tk_compact(sh, (int)threadIdx.x, NSX_CONSUMERS, bar);  // sorted list of this CTA
         }
         // (Dantzig improving sweep: nsx_price_tile_dz) potentials base: node ids are stored zero-based from node 1 in the uint16 layout
-        const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind == NSX_NODE_U16 ? 1 : 0);
+        const double* pi1 = (PISMEM ? pis : d.pi) + (st.node_kind != NSX_NODE_I32 ? 1 : 0);
         const uint32_t pi_s = PISMEM ? nsx_smem_addr(pi1) : 0u;
         if (MODE != NSX_MODE_TOPK && stages >= 4) {
             for (; j + 1 < my_n; j += 2) {  // two tiles per step
@@ -900,7 +919,7 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
                 const int32_t tb[2] = {tile * NSX_TILE, (tile + step) * NSX_TILE};
                 if (MODE == NSX_MODE_DANTZIG) {
                     const bool inner = j > 0 && j + 2 < my_n;  // neither the first nor the last tile of this worker
-                    nsx_price_tile_dz<PHASE1, PISMEM, 2>(d, st, pi1, pi_s, sp, tb, !inner, inner && cmd.pad[1] != 0, lo, hi, dz, sh);
+                    nsx_price_tile_dz<PHASE1, PISMEM, 2, LAYOUT>(d, st, pi1, pi_s, sp, tb, !inner, inner && cmd.pad[1] != 0, lo, hi, dz, sh);
                 }
                 else nsx_price_tile<MODE, PHASE1, PISMEM, 2>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
                 __syncwarp();
@@ -914,7 +933,7 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
             nsx_mbar_wait(&sh.full[s], par);
             const unsigned char* const sp[1] = {ring + s * st.stage_bytes};
             const int32_t tb[1] = {tile * NSX_TILE};
-            if (MODE == NSX_MODE_DANTZIG) nsx_price_tile_dz<PHASE1, PISMEM, 1>(d, st, pi1, pi_s, sp, tb, true, false, lo, hi, dz, sh);
+            if (MODE == NSX_MODE_DANTZIG) nsx_price_tile_dz<PHASE1, PISMEM, 1, LAYOUT>(d, st, pi1, pi_s, sp, tb, true, false, lo, hi, dz, sh);
             else nsx_price_tile<MODE, PHASE1, PISMEM, 1>(d, st, cmd, pis, sp, tb, lo, hi, dz, dx, sh);
             __syncwarp();
             if (lane == 0) nsx_mbar_arrive(&sh.empty[s]);
@@ -934,7 +953,10 @@ __device__ __forceinline__ void nsx_sweep_ring_pi(const NsxDev& d, const NsxStor
                                                   NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
                                                   bool wait_pi, uint32_t& stage_count, NsxCand& dz,
                                                   NsxDevexCand& dx) {
-    if (pis) nsx_sweep_ring<MODE, PHASE1, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
+    // (the improving Dantzig sweep over the pre-scaled store - config 3 - has its own instantiation without layout branches)
+    if (MODE == NSX_MODE_DANTZIG && pis && st.node_kind == NSX_NODE_U16X8 && st.cost_kind == NSX_COST_I16M1)
+        nsx_sweep_ring<MODE, PHASE1, true, 1>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
+    else if (pis) nsx_sweep_ring<MODE, PHASE1, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
     else nsx_sweep_ring<MODE, PHASE1, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
 }
 
@@ -2017,16 +2039,17 @@ __device__ __forceinline__ void nsx_pack_range(const int32_t* tail, const int32_
         const int64_t tile = i / NSX_TILE;
         const int32_t r = (int32_t)(i - tile * NSX_TILE);
         unsigned char* tb = base + (size_t)tile * st.tile_bytes;
-        if (st.node_kind == NSX_NODE_U16) {
-            reinterpret_cast<uint16_t*>(tb)[r] = (uint16_t)(tl - 1);
-            reinterpret_cast<uint16_t*>(tb + st.off_head)[r] = (uint16_t)(hd - 1);
+        if (st.node_kind != NSX_NODE_I32) {
+            const int sh8 = st.node_kind == NSX_NODE_U16X8 ? 3 : 0;
+            reinterpret_cast<uint16_t*>(tb)[r] = (uint16_t)((tl - 1) << sh8);
+            reinterpret_cast<uint16_t*>(tb + st.off_head)[r] = (uint16_t)((hd - 1) << sh8);
         } else {
             reinterpret_cast<int32_t*>(tb)[r] = tl;
             reinterpret_cast<int32_t*>(tb + st.off_head)[r] = hd;
         }
         if (st.cost_kind == NSX_COST_F64) reinterpret_cast<double*>(tb + st.off_cost)[r] = c;
         else if (st.cost_kind == NSX_COST_I32) reinterpret_cast<int32_t*>(tb + st.off_cost)[r] = (int32_t)c;
-        else reinterpret_cast<int16_t*>(tb + st.off_cost)[r] = (int16_t)c;
+        else reinterpret_cast<int16_t*>(tb + st.off_cost)[r] = (int16_t)((int32_t)c - (st.cost_kind == NSX_COST_I16M1 ? 1 : 0));
     }
 }
 extern "C" __global__ void nsx_pack_kernel(const int32_t* tail, const int32_t* head, const double* pert,
@@ -2297,6 +2320,10 @@ static void nsx_choose_layout(int32_t n, unsigned int cost_flags, bool devex, Ns
     const char* force = getenv("NSX_LAYOUT");
     if (force && !strcmp(force, "wide")) { node_kind = NSX_NODE_I32; cost_kind = NSX_COST_F64; }
     if (force && !strcmp(force, "i32")) { node_kind = NSX_NODE_I32; if (cost_kind == NSX_COST_I16) cost_kind = NSX_COST_I32; }
+    // pre-scaled ids + cost - 1 (see NSX_NODE_U16X8): (id - 1) * 8 fits a uint16 up to n - 1 = 8192; NSX_LAYOUT=plain16 keeps the plain columns
+    if (node_kind == NSX_NODE_U16 && cost_kind == NSX_COST_I16 && n - 1 <= 8192 && !(force && !strcmp(force, "plain16"))) {
+        node_kind = NSX_NODE_U16X8; cost_kind = NSX_COST_I16M1;
+    }
     nsx_store_layout(st, node_kind, cost_kind, devex ? 1 : 0);
 }
 

@@ -96,6 +96,13 @@ LAYOUT_CASES = [
     ("i32_f64_forced", lambda: gen.netgen_like(1024, 8192, n_sources=8, n_sinks=8, seed=15), 1e-10, 1, 17, "wide"),
     ("i32_i32_forced", lambda: gen.transportation(300, 300, cost_max=1000, seed=3), 0.0, 0, 13, "i32"),
     ("multi_cta_u16_i16", lambda: gen.transportation(384, 512, cost_max=1000, seed=4), 0.0, 0, 7, None),
+    # (n - 1 <= 8192 with int16 costs is stored pre-scaled - NSX_NODE_U16X8 / NSX_COST_I16M1; "plain16" forces the plain columns;
+    # capacitated arcs keep the sweep on the path that reads the state bytes, the uncapacitated cases above take the state-free one)
+    ("u16_i16_plain_forced", lambda: gen.transportation(96, 128, cost_max=100, supply_each=64, seed=7), 0.0, 0, 7, "plain16"),
+    ("multi_cta_u16_i16_plain_forced", lambda: gen.transportation(384, 512, cost_max=1000, seed=4), 0.0, 0, 7, "plain16"),
+    ("multi_cta_u16x8_capacitated", lambda: gen.transportation(256, 384, cost_max=1000, capacity=8.0, seed=5), 0.0, 0, 7, None),
+    ("multi_cta_u16x8_devex", lambda: gen.transportation(384, 512, cost_max=1000, seed=6), 0.0, 1, 7, None),
+    ("u16 above 8192 nodes", lambda: gen.netgen_like(9000, 1 << 16, n_sources=16, n_sinks=16, seed=23), 0.0, 0, 7, None),
 ]
 
 
