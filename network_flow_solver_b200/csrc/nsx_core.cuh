@@ -2061,7 +2061,8 @@ NSX_FN void nsx_solve_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivo
                            NsxPotScratch& ps, int32_t* trace, Sweep& sweep) {
     NSX_SINGLE { s.def_kind = 0; s.pi_delta_n = -1; }
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
-    nsx_count_special(d, c, s);
+    // (block-uniform; thread 0 writes the count only behind the first barrier inside, i.e. after every thread has tested it)
+    if (c.n_special < 0) nsx_count_special(d, c, s);
     NSX_SYNC();
     // Phase-1 costs on the initial star; a warm start may begin in Phase 2 (no artificial arc in its tree)
     nsx_recompute_all_potentials<BLK>(d, c.phase, ps);

@@ -847,7 +847,7 @@ template <int MODE, bool PHASE1, bool PISMEM, int LAYOUT = 0>
 __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
                                                double* pis, unsigned char* ring, int stages,
                                                NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
-                                               bool stage_pi, uint32_t& stage_count, NsxCand& dz,
+                                               bool stage_pi, int32_t pi_n, uint32_t& stage_count, NsxCand& dz,
                                                NsxDevexCand& dx) {
     const int32_t t0 = (int32_t)(cmd.lo / NSX_TILE), t1 = (int32_t)((cmd.hi + NSX_TILE - 1) / NSX_TILE);
     const int32_t ntiles = t1 - t0;
@@ -857,8 +857,8 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
     const int32_t step = cmd.reverse ? -nworkers : nworkers;
     const int32_t first = t0 + worker + (cmd.reverse ? (my_n - 1) * nworkers : 0);
     uint32_t stage = pos & 0xffffu, parity = pos >> 16;
-    // cmd.pad[2] < 0: copy all potentials into shared memory; >= 0: the copy of the previous command is patched
-    const bool full_pi = stage_pi && cmd.pad[2] < 0;
+    // pi_n < 0: copy all potentials into shared memory; >= 0: the copy of the previous command is patched with pi_n entries
+    const bool full_pi = stage_pi && pi_n < 0;
     if (threadIdx.x >= NSX_CONSUMERS) {
         // ---- producer warp: one lane keeps the ring full ----
         if (lane == 0) {
@@ -879,9 +879,9 @@ __device__ __forceinline__ void nsx_sweep_ring(const NsxDev& d, const NsxStore& 
         // ---- consumer warps ----
         if (full_pi) {
             nsx_mbar_wait(&sh.mbar, stage_count & 1u);  // potentials of this sweep have landed
-        } else if (stage_pi && cmd.pad[2] > 0) {
+        } else if (stage_pi && pi_n > 0) {
             // only the potentials the last pivot changed (its re-hung subtree, NsxDev::pi_delta): patch the copy
-            for (int32_t k = threadIdx.x; k < cmd.pad[2]; k += NSX_CONSUMERS) {
+            for (int32_t k = threadIdx.x; k < pi_n; k += NSX_CONSUMERS) {
                 const int4 ent = __ldcg(reinterpret_cast<const int4*>(d.pi_delta + k));
                 pis[ent.x] = __hiloint2double(ent.w, ent.z);
             }
@@ -951,20 +951,20 @@ template <int MODE, bool PHASE1>
 __device__ __forceinline__ void nsx_sweep_ring_pi(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
                                                   double* pis, unsigned char* ring, int stages,
                                                   NsxCtaShared& sh, uint32_t& pos, int worker, int nworkers,
-                                                  bool wait_pi, uint32_t& stage_count, NsxCand& dz,
+                                                  bool wait_pi, int32_t pi_n, uint32_t& stage_count, NsxCand& dz,
                                                   NsxDevexCand& dx) {
     // (the improving Dantzig sweep over the pre-scaled store - config 3 - has its own instantiation without layout branches)
     if (MODE == NSX_MODE_DANTZIG && pis && st.node_kind == NSX_NODE_U16X8 && st.cost_kind == NSX_COST_I16M1)
-        nsx_sweep_ring<MODE, PHASE1, true, 1>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
-    else if (pis) nsx_sweep_ring<MODE, PHASE1, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
-    else nsx_sweep_ring<MODE, PHASE1, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, stage_count, dz, dx);
+        nsx_sweep_ring<MODE, PHASE1, true, 1>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, pi_n, stage_count, dz, dx);
+    else if (pis) nsx_sweep_ring<MODE, PHASE1, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, pi_n, stage_count, dz, dx);
+    else nsx_sweep_ring<MODE, PHASE1, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, wait_pi, pi_n, stage_count, dz, dx);
 }
 
 // One sweep of this CTA: refresh the staged potentials (optional), price, block-reduce into
 // thread 0.  `stage_count` is the per-thread register copy of the number of potential copies this
 // CTA has issued (its low bit is the mbarrier phase to wait for).
 __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& st, const NsxCmd& cmd,
-                                              double* pis, bool stage, uint32_t& stage_count,
+                                              double* pis, bool stage, int32_t pi_n, uint32_t& stage_count,
                                               unsigned char* ring, int stages, uint32_t& pos, int worker,
                                               int nworkers, NsxCtaShared& sh, NsxCand& dz, NsxDevexCand& dx) {
     nsx_cand_init(dz);
@@ -975,14 +975,14 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
     if (sh.tl_grid) NSX_TL(sh.tl_grid, 1);
     if (cmd.kind == NSX_CMD_TOPK) {
         // (tk_cnt / threshold were reset by thread 0 before the barrier above)
-        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_TOPK, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
-        else nsx_sweep_ring_pi<NSX_MODE_TOPK, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_TOPK, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_TOPK, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
         NSX_SYNC();  // the sorted top list of this CTA is in piv.res / piv.arc2, its length in tk_cnt
         return;
     }
     if (cmd.kind == NSX_CMD_DANTZIG) {
-        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
-        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
         // The CTA's best key IS the gate (every thread raised it to its own best key; it still holds its start value when
         // nobody found a candidate): the threads that hold that key agree on the lowest arc with one shared-memory atomic -
         // two barriers instead of a shuffle tree over 16 warps.
@@ -995,14 +995,14 @@ __device__ __forceinline__ void nsx_cta_sweep(const NsxDev& d, const NsxStore& s
             if (sh.gate_arc2 != 0x7fffffff) { dz.key = __longlong_as_double((long long)gbest); dz.arc2 = sh.gate_arc2; }
         }
     } else if (cmd.kind == NSX_CMD_DEVEX) {
-        nsx_sweep_ring_pi<NSX_MODE_DEVEX, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_sweep_ring_pi<NSX_MODE_DEVEX, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
         nsx_block_reduce(dx, sh.dx_buf);
     } else if (cmd.kind == NSX_CMD_DANTZIG_ZERO) {
-        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
-        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        if (cmd.phase == 1) nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, true>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
+        else nsx_sweep_ring_pi<NSX_MODE_DANTZIG_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
         nsx_block_reduce(dz, sh.dz_buf);
     } else {
-        nsx_sweep_ring_pi<NSX_MODE_DEVEX_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, stage_count, dz, dx);
+        nsx_sweep_ring_pi<NSX_MODE_DEVEX_ZERO, false>(d, st, cmd, pis, ring, stages, sh, pos, worker, nworkers, stage, pi_n, stage_count, dz, dx);
         nsx_block_reduce(dx, sh.dx_buf);
     }
 }
@@ -1519,10 +1519,11 @@ struct GridSweep {
         }
     }
 
-    __device__ __forceinline__ void publish(const NsxCmd& cmd) {
+    __device__ __forceinline__ void publish(const NsxCmd& cmd, int32_t pi_n = -1) {
         if (threadIdx.x == 0) {
             union { NsxCmd c; int4 v[3]; } tmp;
             tmp.c = cmd;
+            tmp.c.pad[2] = pi_n;
             int4* dst = reinterpret_cast<int4*>(&g->cmd);
             dst[0] = tmp.v[0]; dst[1] = tmp.v[1]; dst[2] = tmp.v[2];
             g->t_pub = nsx_globaltimer();
@@ -1608,15 +1609,16 @@ struct GridSweep {
         if (threadIdx.x == 0) t0 = nsx_globaltimer();
         if (gridDim.x == 1) deferred();
         NSX_SYNC();  // pivot writes of all threads precede thread 0's fence + release
-        NsxCmd cmd = cmd_in;
-        // potentials: how many entries of pi_delta bring a worker's shared-memory copy up to date (-1: copy everything)
-        cmd.pad[2] = (gridDim.x > 1 && d.pi_delta) ? sh.piv.pi_delta_n : -1;
+        const NsxCmd cmd = cmd_in;
+        // potentials: how many entries of pi_delta bring a worker's shared-memory copy up to date (-1: copy everything);
+        // travels in pad[2] of the published command
+        const int32_t pi_n = (gridDim.x > 1 && d.pi_delta) ? sh.piv.pi_delta_n : -1;
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
         const bool devex = cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO || (starcmd && cmd.pad[0]);
         if (gridDim.x == 1) {  // alone: this CTA prices everything itself
             NsxCand dz; NsxDevexCand dx;
             if (threadIdx.x == 0) __threadfence();
-            nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, shd.rank, shd.world, sh, dz, dx);
+            nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, -1, stage_count, cx.ring, cx.stages, q0, shd.rank, shd.world, sh, dz, dx);
             if (cmd.kind == NSX_CMD_TOPK) {
                 if (shd.world > 1) { exchange_topk(c); if (c.fault) return; }
                 nsx_tk_publish_list(sh, c);
@@ -1633,7 +1635,7 @@ struct GridSweep {
         }
         if (starcmd && threadIdx.x == 0) { *star.rq_n = 0; *reinterpret_cast<unsigned long long*>(&sh.x_recs[0][0]) = 0ull; }  // (x_recs: idle on one GPU, holds the evaluated-arc count)
         if (starcmd) NSX_SYNC();
-        publish(cmd);
+        publish(cmd, pi_n);
         if (threadIdx.x == 0) sh.piv.pi_delta_n = 0;  // (every thread read it before the barrier in front of publish)
         deferred();
         unsigned long long t1 = 0;
@@ -1755,7 +1757,7 @@ template <bool BLK, class Sweep>
 __device__ __forceinline__ void nsx_probe_loop(const NsxDev& d, NsxCtl& c, NsxLoopShared& L, NsxPivotScratch& pv,
                                                NsxPotScratch& ps, Sweep& sweep, int32_t count) {
     if (BLK && d.blk) nsx_blk_init(d, *d.blk);
-    nsx_count_special(d, c, pv);
+    if (c.n_special < 0) nsx_count_special(d, c, pv);
     NSX_SYNC();
     nsx_recompute_all_potentials<BLK>(d, 1, ps);
     for (int32_t k = 0; k < count; ++k) {
@@ -1854,7 +1856,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             }
         }
         NSX_SYNC();
-        NsxCmd cmd = sh.cmd;
+        const NsxCmd cmd = sh.cmd;
         if (cmd.kind == NSX_CMD_EXIT) return;
         NsxCand dz; NsxDevexCand dx;
         const bool starcmd = cmd.kind == NSX_CMD_STAR || cmd.kind == NSX_CMD_STAR_BUILD;
@@ -1879,8 +1881,7 @@ __device__ __forceinline__ void nsx_resident_body(const NsxKernelArgs& a) {
             }
             continue;
         }
-        if (!pi_valid) cmd.pad[2] = -1;
-        nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, stage_count, ring, a.wplan.stages, q0,
+        nsx_cta_sweep(d, a.st, cmd, pis, pis != nullptr, pi_valid ? cmd.pad[2] : -1, stage_count, ring, a.wplan.stages, q0,
                       a.shard.rank * ((int)gridDim.x - 1) + (int)blockIdx.x - 1, a.shard.world * ((int)gridDim.x - 1), sh, dz, dx);
         pi_valid = pis != nullptr;
         if (cmd.kind == NSX_CMD_TOPK) {  // this CTA's sorted list -> HBM (the slot release below orders it)
@@ -1936,9 +1937,8 @@ extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_dev_sweep_kerne
     NSX_SYNC();
     double* pis = a.wplan.stage_pi ? reinterpret_cast<double*>(dyn) : nullptr;
     NsxCand dz; NsxDevexCand dx;
-    NsxCmd cmd = a.grid->cmd;
-    cmd.pad[2] = -1;
-    nsx_cta_sweep(a.d, a.st, cmd, pis, pis != nullptr, stage_count, dyn + a.wplan.ring_off, a.wplan.stages, q0, (int)blockIdx.x, (int)gridDim.x, sh, dz, dx);
+    const NsxCmd cmd = a.grid->cmd;
+    nsx_cta_sweep(a.d, a.st, cmd, pis, pis != nullptr, -1, stage_count, dyn + a.wplan.ring_off, a.wplan.stages, q0, (int)blockIdx.x, (int)gridDim.x, sh, dz, dx);
     if (threadIdx.x == 0) { union { NsxCand c; int4 v; } tmp; tmp.c = dz; a.slots[blockIdx.x].v[0] = tmp.v; }
 }
 extern "C" __global__ void nsx_resident_kernel(const NsxKernelArgs a);      // (declared for the host code below, not built)
@@ -1955,7 +1955,9 @@ extern "C" __global__ void __launch_bounds__(NSX_THREADS, 1) nsx_resident_kernel
 extern "C" __global__ void nsx_init_kernel(const NsxDev d, const double* supply, NsxCtl* ctl) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = g; i < d.m; i += T) nsx_init_real_arc(d, i);
+    int32_t special = 0;  // NsxCtl::n_special of the initial state (the host set it to 0: the pivot CTA need not count)
+    for (int64_t i = g; i < d.m; i += T) { nsx_init_real_arc(d, i); special += nsx_special(d.state[i]); }
+    if (special) atomicAdd(&ctl->n_special, special);
     unsigned long long art = 0;
     for (int64_t v = g; v < d.n; v += T) {
         nsx_init_node(d, (int32_t)v, supply[v]);
@@ -1969,7 +1971,12 @@ extern "C" __global__ void nsx_init_warm_kernel(const NsxDev d, const double* su
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
     unsigned long long art = 0;
-    for (int64_t a = g; a < d.ma; a += T) art += (unsigned long long)nsx_init_arc_warm(d, a, supply, in_tree);
+    int32_t special = 0;
+    for (int64_t a = g; a < d.ma; a += T) {
+        art += (unsigned long long)nsx_init_arc_warm(d, a, supply, in_tree);
+        if (a < d.m) special += nsx_special(d.state[a]);
+    }
+    if (special) atomicAdd(&ctl->n_special, special);
     if (g == 0) d.pi[0] = 0.0;
     if (art) atomicAdd((unsigned long long*)&ctl->art_with_flow, art);
 }
@@ -2078,13 +2085,12 @@ struct LocalSweep {
     uint32_t& q0;
     template <class Deferred>
     __device__ void run(const NsxCmd& cmd_in, NsxCand& out_dz, NsxDevexCand& out_dx, NsxCtl& c, Deferred deferred) {
-        NsxCmd cmd = cmd_in;
-        cmd.pad[2] = -1;  // (potentials are staged in full, if at all)
+        const NsxCmd cmd = cmd_in;
         NsxCand dz; NsxDevexCand dx;
         deferred();  // (one CTA does everything: nothing to overlap with)
         NSX_SYNC();
         if (threadIdx.x == 0) __threadfence();  // this CTA's own state / potential writes reach L2 before the bulk reads
-        nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);
+        nsx_cta_sweep(d, *cx.st, cmd, cx.pis, cx.stage, -1, stage_count, cx.ring, cx.stages, q0, 0, 1, sh, dz, dx);  // (potentials staged in full, if at all)
         if (cmd.kind == NSX_CMD_TOPK) { nsx_tk_publish_list(sh, c); return; }
         if (threadIdx.x == 0) {
             if (cmd.kind == NSX_CMD_DEVEX || cmd.kind == NSX_CMD_DEVEX_ZERO) out_dx = dx; else out_dz = dz;
@@ -2231,6 +2237,7 @@ static void nsx_fill_ctl(NsxCtl& c, const nsx_options* o, bool trace) {
     c.pricing = o->pricing; c.row_scan_first = o->row_scan_first;
     c.trace_cap = trace ? o->trace_capacity : 0;
     c.unbounded_arc = -1;
+    c.n_special = -1;  // "not counted yet": nsx_solve_loop counts it (batch kernel); nsx_solve_impl lets its init kernels count
 }
 
 static int nsx_env_int(const char* name, int dflt) {
@@ -2522,6 +2529,7 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     if (warm) { hctl.warm = 1; hctl.phase = warm->start_phase; }
     hctl.star_on = star ? (star_devex ? 2 : 1) : 0;
     hctl.star_excl_prev = -1;
+    hctl.n_special = 0;  // accumulated by nsx_init_kernel / nsx_init_warm_kernel
     NSX_CUDA(cudaMemcpyAsync(ka.ctl, &hctl, sizeof hctl, cudaMemcpyHostToDevice, stream));
     NSX_CUDA(cudaMemsetAsync(ka.grid, 0, sizeof(NsxGridCtl), stream));
     NSX_CUDA(cudaMemsetAsync(ka.slots, 0, sizeof(NsxSlot) * 1024, stream));

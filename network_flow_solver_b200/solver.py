@@ -11,6 +11,8 @@ ratio test, flow / tree / potential updates all run inside libnsx_b200.so on the
 from __future__ import annotations
 
 import logging
+import time
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -28,7 +30,7 @@ from .canonical import (
     initial_block_size,
     is_likely_goto,
 )
-from .data import Basis, FlowResult, NetworkProblem, ProgressCallback, SolverOptions
+from .data import Basis, FlowResult, NetworkProblem, ProgressCallback, ProgressInfo, SolverOptions
 from .exceptions import SolverConfigurationError, UnboundedProblemError
 
 _log = logging.getLogger(__name__)
@@ -295,11 +297,14 @@ def solve_min_cost_flow(
 ) -> FlowResult:
     """Solve a minimum-cost flow problem on the GPU; drop-in for the reference call
     (solver.py:13-104).  Raises DeviceEngineError when the CUDA engine is unavailable."""
+    t_start = time.time()
     if progress_callback is not None:
-        _log.info(
-            "progress_callback is not invoked: the pivot loop is device-resident with no host "
-            "round-trip per pivot"
-        )
+        # The reference calls back every `progress_interval` pivots (simplex.py:1143-1154).  Here the pivot loop is one
+        # device-resident kernel with no host round trip per pivot: the callback is invoked ONCE, after the solve, with the
+        # totals - enough for logging, not for cancellation.
+        warnings.warn(
+            "progress_callback is invoked once, after the solve (the pivot loop is device-resident; "
+            f"progress_interval={progress_interval} is not honoured)", RuntimeWarning, stacklevel=2)
     cp, plan, options = prepare(problem, options, max_iterations, device=device)
     warm = None
     if warm_start_basis is not None:  # simplex.py:1494-1530; None = basis rejected, cold start
@@ -311,6 +316,16 @@ def solve_min_cost_flow(
             _log.info("Warm-start failed, performing cold start")
     raw = _capi.solve_canonical(cp, plan.engine, warm=warm)
     result = finish(cp, raw, options, plan.scaling)
+    if progress_callback is not None:
+        in_phase_two = raw.iterations > raw.phase1_iterations or raw.status == _capi.STATUS_OPTIMAL
+        progress_callback(ProgressInfo(
+            iteration=int(raw.iterations),
+            max_iterations=int(plan.engine.max_iterations),
+            phase=2 if in_phase_two else 1,
+            phase_iterations=int(raw.iterations - raw.phase1_iterations) if in_phase_two else int(raw.iterations),
+            objective_estimate=float(result.objective),
+            elapsed_time=time.time() - t_start,
+        ))
     if raw.status in (_capi.STATUS_OPTIMAL, _capi.STATUS_ITERATION_LIMIT):
         rate = (raw.degenerate_pivots / raw.iterations * 100) if raw.iterations > 0 else 0.0
         # the reference prints this line unconditionally (simplex.py:1672-1674)

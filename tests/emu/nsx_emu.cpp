@@ -266,6 +266,7 @@ static int nsx_emu_solve_impl(const nsx_problem* pb, const nsx_options* opt, con
 
     NsxCtl c;
     memset(&c, 0, sizeof c);
+    c.n_special = -1;  // counted by nsx_solve_loop
     c.phase = 1; c.status = -1; c.maxit = opt->max_iterations;
     c.bs = opt->block_size > 0 ? opt->block_size : 1; c.pb = 0; c.last_deg = -1;
     c.ft_limit = opt->ft_update_limit; c.auto_block = opt->auto_block;

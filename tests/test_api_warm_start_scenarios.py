@@ -122,3 +122,16 @@ def test_basis_contents(solve):
     assert len(r.basis.tree_arcs) == 3 and set(r.basis.arc_flows) == r.basis.tree_arcs  # n - 1 arcs, no artificial ones left
     for key, f in r.basis.arc_flows.items():
         assert f == pytest.approx(r.flows.get(key, 0.0))
+
+
+def test_progress_callback_is_invoked_once_with_the_totals(solve):
+    """The reference calls back every `progress_interval` pivots (simplex.py:1143-1154); the device-resident loop has no
+    host round trip per pivot, so the callback fires once, after the solve, with the totals - and says so in a warning."""
+    p = problem({"s": 40, "a": 0, "b": 0, "t": -40}, DIAMOND)
+    seen = []
+    with pytest.warns(RuntimeWarning, match="progress_callback is invoked once"):
+        res = solve(p, progress_callback=seen.append, progress_interval=1)
+    assert len(seen) == 1
+    info = seen[0]
+    assert info.iteration == res.iterations and info.phase == 2 and info.objective_estimate == res.objective
+    assert 0 <= info.phase_iterations <= info.iteration <= info.max_iterations and info.elapsed_time >= 0.0

@@ -56,3 +56,4 @@ def test_adapter_solves_on_the_gpu():
     spec = load_golden("ref_textbook_transport")
     r = B200Adapter.solve(rebuild_problem(spec["problem"]))
     assert r.status == "optimal" and r.objective == 85.0 and r.iterations > 0 and r.solve_time_ms > 0
+
