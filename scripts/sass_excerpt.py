@@ -39,14 +39,28 @@ groups = []
 for i in idx:
     if not groups or i - groups[-1][-1] > 400: groups.append([i])
     else: groups[-1].append(i)
-eight = [g for g in groups if len(g) == 8 and not any("LDG" in ins[j][1] for j in range(g[0] - 200, g[-1] + 100))]
-g = eight[-1]
-s = g[0]
-while not ins[s][1].startswith("SYNCS.PHASECHK"): s -= 1
-for j in range(s - 1, s - 14, -1):
-    if ins[j][1].startswith("SYNCS.PHASECHK"): s = j
-e = g[-1]
-while "SYNCS.ARRIVE" not in ins[e][1]: e += 1
+def loop_of(g):
+    s = g[0]
+    while not ins[s][1].startswith("SYNCS.PHASECHK"): s -= 1
+    for j in range(s - 1, s - 14, -1):
+        if ins[j][1].startswith("SYNCS.PHASECHK"): s = j
+    e = g[-1]
+    while "SYNCS.ARRIVE" not in ins[e][1]: e += 1
+    return s, e
+
+
+# the instantiation for the pre-scaled store (LAYOUT = 1, two tiles per step, potentials in shared memory): int16 costs are
+# converted directly (I2F.F64.S16), potentials are gathered without an address multiply, nothing is loaded from global memory;
+# the last such loop in the kernel is the copy inlined into the worker CTAs
+picked = None
+for g in groups:
+    if len(g) < 7: continue
+    s, e = loop_of(g)
+    body = [t for _, t in ins[s:e]]
+    if any("LDG" in t for t in body) or not any(t.startswith("I2F.F64.S16") for t in body): continue
+    if any(re.match(r"IMAD R\d+, R\d+, 0x8, R\d+", t) for t in body): continue
+    picked = (s, e)
+s, e = picked
 print(f"## Pricing loop of the sweep workers, one step = 2 tiles x 4 arcs per thread (0x{ins[s][0]:x} .. 0x{ins[e + 1][0]:x})\n")
 print("Executed on the state-free fast path (`plain`): the loop head, the uint16 node-id loads, the int16 cost loads, the\n"
       "arithmetic block (8 x [I2F.F64, DMUL 1e-6*idx, 3 x DADD, 2 x LDS.64 potential gather, DSETP.LE.OR]), the arrive.\n```")
