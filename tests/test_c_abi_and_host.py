@@ -110,3 +110,28 @@ def test_unbalanced_problem_is_rejected_like_the_reference():
     with pytest.raises(InvalidProblemError):
         solve_min_cost_flow(build_problem(nodes, arcs, directed=True, tolerance=1e-6),
                             SolverOptions(pricing_strategy="dantzig", explicit_pricing_strategy=True, auto_scale=False))
+
+
+def test_library_is_sm100a_with_tma_and_mbarrier_in_the_resident_kernels():
+    """What the GPU box will load: an sm_100a cubin whose resident kernels move tiles with TMA bulk copies (UBLKCP) counted
+    on mbarriers (SYNCS) - not a PTX-only or an LDG-loop build - and no statically linked CUDA runtime entry points."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    lib = entry.build_engine()
+    elf = subprocess.run([cuobjdump, "-lelf", str(lib)], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "nsx_resident_kernel", str(lib)], capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP.S.G") >= 8 and sass.count("SYNCS.PHASECHK") >= 8 and "SYNCS.ARRIVE" in sass
+    assert "DSETP" in sass and "DADD" in sass  # float64 arithmetic of the reference, not a reduced-precision path
+    # -fmad=false: the reference's `(c + pi[t]) - pi[h]` is never contracted into a fused multiply-add.  The only DFMAs in
+    # the kernel are the Newton steps of the correctly rounded divisions (__ddiv_rn: Devex merit rc^2 / w), i.e. they sit
+    # next to a MUFU.RCP64H
+    lines = sass.splitlines()
+    rcp = [i for i, ln in enumerate(lines) if "MUFU.RCP64H" in ln]
+    stray = [i for i, ln in enumerate(lines) if "DFMA" in ln and not any(abs(i - r) <= 120 for r in rcp)]
+    assert rcp and not stray, f"{len(stray)} DFMA instructions outside division sequences"
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True).stdout
+    assert "cudaMemcpy" not in nm and "cudaLaunchKernel" not in nm
