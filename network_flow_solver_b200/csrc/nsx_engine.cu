@@ -2443,7 +2443,9 @@ static int nsx_solve_impl(const nsx_problem* pb, const nsx_options* opt, nsx_res
     // re-hung nodes per pivot) an update touches a tenth of the arcs at several times the bytes per arc and the TMA sweep
     // of the packed store is as fast; NSX_STAR=1 / 0 forces it on / off.
     const int star_env = nsx_env_int("NSX_STAR", -1);
-    const bool star_wanted = star_env >= 0 ? star_env != 0 : m / (n > 0 ? n : 1) <= 512;
+    // ... and only where a full sweep is expensive (m >= 4 M arcs): on the 1 M-arc config 2 a sweep costs ~20 us, the row
+    // cache ~22 us per step plus ~4 us of bookkeeping in the pivot (18.6 K against 19.4 K pivots/s over the whole solve)
+    const bool star_wanted = star_env >= 0 ? star_env != 0 : (m / (n > 0 ? n : 1) <= 512 && m >= (4ll << 20));
     const bool star = star_wanted && grid > 1 && !shard && !warm && probe_sweeps == 0 && m > 0 && m < (1ll << 30) &&
                       !(cost_flags & 8u) && (opt->pricing == NSX_PRICING_DANTZIG || opt->row_scan_first == NSX_SPECIAL_ROW_SCAN ||
                                              (opt->pricing == NSX_PRICING_DEVEX && opt->row_scan_first == 0));
